@@ -1,0 +1,92 @@
+"""Generate golden vectors by executing the reference's OWN source (test infrastructure).
+
+Runs /root/reference/dreamer4/dreamer4.py (unmodified; third-party deps replaced by oracle/shims)
+on small seeded cases and stores inputs + outputs under tests/golden/*.pt.  Build-container only:
+the GPU box has no /root/reference, so the fixtures are committed.
+
+    python oracle/make_golden.py            # regenerates every fixture
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_import import import_reference  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+# name -> (DynamicsWorldModel kwargs, generate kwargs)
+CASES = {
+    # default architecture shrunk: LQAP pools both sides, 1 time layer of 4, single discrete action
+    'tiny_default': (
+        dict(dim=32, dim_latent=8, num_latent_tokens=6, depth=4, time_block_every=4, attn_heads=2, attn_dim_head=16,
+             num_discrete_actions=4, predict_terminals=False),
+        dict(time_steps=6, batch_size=3),
+    ),
+    # two time layers, multi-discrete actions, GQA, same-length latent/spatial tokens (Linear in/out)
+    'tiny_gqa_multidiscrete': (
+        dict(dim=32, dim_latent=16, num_latent_tokens=2, num_spatial_tokens=2, depth=4, time_block_every=2,
+             attn_heads=2, attn_dim_head=16, attn_kwargs=dict(query_heads=4), num_discrete_actions=(3, 5),
+             num_register_tokens=3, predict_terminals=False,
+             reward_encoder_kwargs=dict(num_bins=20, reward_range=(-3., 3.)), value_encoder_kwargs=dict(num_bins=32)),
+        dict(time_steps=5, batch_size=2),
+    ),
+    # every layer a time layer + terminal head with early lens bookkeeping + GEGLU feed-forward
+    'tiny_terminals_geglu': (
+        dict(dim=32, dim_latent=8, num_latent_tokens=4, depth=2, time_block_every=1, attn_heads=2, attn_dim_head=16,
+             num_discrete_actions=4, predict_terminals=True, ff_kwargs=dict(activation='gelu')),
+        dict(time_steps=5, batch_size=4, return_terminals=True),
+    ),
+}
+
+
+def run_case(ref, name, model_kwargs, gen_kwargs, seed=7):
+    torch.manual_seed(seed)
+    model = ref.DynamicsWorldModel(**model_kwargs)
+    # default init leaves several gains at exactly 0/1 - perturb so every parameter matters
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('gamma') or n.endswith('norm.weight') or n.endswith('norm_context.weight') or '.1.weight' in n:
+                p.add_(torch.randn_like(p) * 0.1)
+            if 'unembed' in n or n.endswith('queries') or 'learned_embed' in n or n == 'register_tokens':
+                p.mul_(30.)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    gen_seed = seed + 1000
+    torch.manual_seed(gen_seed)
+    exp, time_cache = model.generate(
+        return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True,
+        return_time_cache=True, **gen_kwargs)
+
+    out = dict(
+        latents=exp.latents, agent_embed=exp.agent_embed, rewards=exp.rewards, values=exp.values,
+        actions=exp.actions.discrete, log_probs=exp.log_probs.discrete,
+        old_action_unembeds=exp.old_action_unembeds.discrete, lens=exp.lens, is_truncated=exp.is_truncated,
+        terminals=exp.terminals, episode_return=exp.episode_return, step_size=exp.step_size,
+        kv_cache=time_cache.main.next_kv_cache, token_count=time_cache.main.token_count,
+    )
+
+    # DreamTrainer marks the last frame as bootstrap-only via is_truncated (TR:1422-1423); generate already did.
+    model.zero_grad()
+    policy_loss, value_loss = model.learn_from_experience(exp)
+    policy_loss.backward(retain_graph=True)
+    value_loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    out.update(policy_loss=policy_loss.detach(), value_loss=value_loss.detach(), grads=grads)
+
+    fixture = dict(name=name, model_kwargs=model_kwargs, gen_kwargs=gen_kwargs, gen_seed=gen_seed,
+                   state_dict=sd, out={k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in out.items()},
+                   torch_version=torch.__version__)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, f'{name}.pt')
+    torch.save(fixture, path)
+    print(f'{name}: T={exp.latents.shape[1]} lens={exp.lens.tolist()} policy_loss={policy_loss.item():.6f} '
+          f'value_loss={value_loss.item():.6f} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)')
+
+
+if __name__ == '__main__':
+    ref = import_reference()
+    for name, (mk, gk) in CASES.items():
+        run_case(ref, name, mk, gk)

@@ -1,0 +1,2 @@
+class HNet:
+    def __init__(self, *a, **k): raise NotImplementedError

@@ -1,0 +1,62 @@
+"""The oracle (oracle/dreamer4_oracle.py) against golden vectors produced by executing the
+reference's own dreamer4.py (oracle/make_golden.py).  CPU only."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import dreamer4_oracle as O
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.pt')))
+
+
+def load(path):
+    return torch.load(path, map_location='cpu', weights_only=False)
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_generate_matches_reference(path):
+    fx = load(path)
+    cfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    gk = dict(fx['gen_kwargs'])
+    torch.manual_seed(fx['gen_seed'])
+    exp = O.generate(fx['state_dict'], cfg, gk.pop('time_steps'), gk.pop('batch_size'), **gk)
+    ref = fx['out']
+    assert exp.latents.shape == ref['latents'].shape
+    assert torch.equal(exp.actions, ref['actions'])                      # sampled indices: bit exact
+    assert torch.equal(exp.lens, ref['lens'])
+    assert torch.equal(exp.terminals, ref['terminals'])
+    assert torch.equal(exp.is_truncated, ref['is_truncated'])
+    assert exp.step_size == ref['step_size']
+    tol = dict(atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(exp.latents, ref['latents'], **tol)
+    torch.testing.assert_close(exp.agent_embed, ref['agent_embed'], **tol)
+    torch.testing.assert_close(exp.rewards, ref['rewards'], **tol)
+    torch.testing.assert_close(exp.values, ref['values'], **tol)
+    torch.testing.assert_close(exp.log_probs, ref['log_probs'], **tol)
+    torch.testing.assert_close(exp.old_action_unembeds, ref['old_action_unembeds'], **tol)
+    torch.testing.assert_close(exp.episode_return, ref['episode_return'], **tol)
+    # KV cache: reference layout (y, 2, b*S, h, T, d)  (D4:3255-3265)
+    kv = torch.stack([torch.stack(layer) for layer in exp.kv_cache])
+    assert kv.shape == ref['kv_cache'].shape
+    torch.testing.assert_close(kv, ref['kv_cache'], **tol)
+    assert ref['token_count'] == exp.latents.shape[1]
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_learn_matches_reference(path):
+    fx = load(path)
+    cfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    ref = fx['out']
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and k in ref['grads']) for k, v in fx['state_dict'].items()}
+    exp = O.OracleExperience(
+        latents=ref['latents'], agent_embed=ref['agent_embed'], rewards=ref['rewards'], values=ref['values'],
+        actions=ref['actions'], log_probs=ref['log_probs'], lens=ref['lens'], is_truncated=ref['is_truncated'],
+        terminals=ref['terminals'], step_size=ref['step_size'])
+    pl, vl, _ = O.learn_from_experience(sd, cfg, exp)
+    torch.testing.assert_close(pl.detach(), ref['policy_loss'], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(vl.detach(), ref['value_loss'], atol=1e-6, rtol=1e-5)
+    (pl + vl).backward()
+    for name, g in ref['grads'].items():
+        torch.testing.assert_close(sd[name].grad, g, atol=1e-6, rtol=1e-4, msg=lambda m, n=name: f'{n}: {m}')

@@ -1,0 +1,8 @@
+"""dreamer4_b200 — B200-native imagination hot path of Dreamer 4 (generate + learn_from_experience).
+
+Public names mirror the reference package (`dreamer4/__init__.py:1-15`, `dreamer4/dreamer4.py`) for the
+classes on this path."""
+from .experience import Actions, Experience, combine_experiences
+from .dynamics import DynamicsWorldModel, ModelConfig, exists, default
+
+__all__ = ['Actions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'ModelConfig', 'exists', 'default']

@@ -1,0 +1,373 @@
+// Attention kernels of the imagination pass.
+//
+//  small_attn_kernel : every attention on the path whose key set fits in shared memory (<= 64 keys):
+//      space attention over the S tokens of a frame (reference dreamer4.py:1968-2075 + naive_attend 1683-1756
+//      with softclamp, agent-token mask 1769-1783, value-residual lerp 2005-2012, belief projection 2049-2054),
+//      the learned-query latent<->spatial pools (2179-2210), the attention-residual pools over layer hiddens
+//      (2143-2177) and the final agent cross-attention (3227-3238).
+//  time_attn_kernel  : K1, the time-decode attention of one new frame over the growing KV cache
+//      (query length 1 per (token, head); reference dreamer4.py:2021-2035, 2848, 3010).  HBM-bound: it streams
+//      2*t*d*4 bytes per (token, kv head) and appends the new key/value in place on the clean pass.
+#include "kernels.h"
+#include <float.h>
+
+namespace {
+
+// torch.lerp(start, end, w) as ATen evaluates it (w < 0.5 ? start + w*(end-start) : end - (end-start)*(1-w))
+__device__ __forceinline__ float lerp_(float a, float b, float w) {
+    const float d = b - a;
+    return (w < 0.5f) ? a + w * d : b - d * (1.f - w);
+}
+
+// -------------------------------------------------------------------------------------------------
+// generic small attention
+
+constexpr int SA_WARPS = 4;
+
+__global__ void __launch_bounds__(SA_WARPS * 32) small_attn_kernel(SmallAttnArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * SA_WARPS + warp;
+    if (item >= (long long)a.nb * a.hkv) return;
+    const int b = (int)(item / a.hkv), hk = (int)(item % a.hkv);
+    const int d = a.d, n = a.n, kp = d + 4, d4 = d >> 2;
+    float* Ks = smem + (size_t)warp * 2 * n * kp;
+    float* Vs = Ks + (size_t)n * kp;
+
+    // stage K, V (value-residual lerp applied on the way in)
+    for (int idx = lane; idx < n * d4; idx += 32) {
+        const int j = idx / d4, c = (idx % d4) * 4;
+        const float4 kv = *reinterpret_cast<const float4*>(a.k + b * a.k_sb + j * a.k_sj + (long long)hk * d + c);
+        float4 vv = *reinterpret_cast<const float4*>(a.v + b * a.v_sb + j * a.v_sj + (long long)hk * d + c);
+        if (a.v0) {
+            const float4 rv = *reinterpret_cast<const float4*>(a.v0 + b * a.v0_sb + j * a.v0_sj + (long long)hk * d + c);
+            const float w = sigmoidf_(a.mix[b * a.mix_sb + j * a.mix_sj + hk]);
+            vv.x = lerp_(vv.x, rv.x, w); vv.y = lerp_(vv.y, rv.y, w); vv.z = lerp_(vv.z, rv.z, w); vv.w = lerp_(vv.w, rv.w, w);
+        }
+        *reinterpret_cast<float4*>(Ks + j * kp + c) = kv;
+        *reinterpret_cast<float4*>(Vs + j * kp + c) = vv;
+    }
+    __syncwarp();
+    // MultiHeadRMSNorm on keys: l2norm(k) * (gamma + 1) * sqrt(d)   (reference dreamer4.py:1663-1679)
+    const float sqrt_d = sqrtf((float)d);
+    for (int j = lane; j < n; j += 32) {
+        float* kr = Ks + j * kp;
+        float ss = 0.f;
+        for (int c = 0; c < d; c += 4) { const float4 t = *reinterpret_cast<const float4*>(kr + c); ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w; }
+        const float den = fmaxf(sqrtf(ss), D4_L2_EPS);
+        for (int c = 0; c < d; ++c) kr[c] = (kr[c] / den) * ((a.k_gamma[hk * d + c] + 1.f) * sqrt_d);
+    }
+    __syncwarp();
+
+    for (int gi = 0; gi < a.g; ++gi) {
+        const int hq = hk * a.g + gi;
+        for (int i = 0; i < a.nq; ++i) {
+            const float* qp = a.q + b * a.q_sb + i * a.q_si + (long long)hq * d;
+            float sc[2], p[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int j = lane + 32 * r;
+                float s = -INFINITY;
+                if (j < n) {
+                    const float* kr = Ks + j * kp;
+                    float acc = 0.f;
+                    for (int c = 0; c < d; c += 4) {
+                        const float4 qv = __ldg(reinterpret_cast<const float4*>(qp + c));
+                        const float4 kv = *reinterpret_cast<const float4*>(kr + c);
+                        acc = fmaf(qv.x, kv.x, acc); acc = fmaf(qv.y, kv.y, acc); acc = fmaf(qv.z, kv.z, acc); acc = fmaf(qv.w, kv.w, acc);
+                    }
+                    s = acc * a.scale;
+                    if (a.softclamp > 0.f) s = tanhf(s / a.softclamp) * a.softclamp;
+                    if (a.mask_agent && i < a.nq - 1 && j == n - 1) s = -FLT_MAX;
+                }
+                sc[r] = s;
+            }
+            const float mx = warp_max(fmaxf(sc[0], sc[1]));
+#pragma unroll
+            for (int r = 0; r < 2; ++r) p[r] = (lane + 32 * r < n) ? expf(sc[r] - mx) : 0.f;
+            const float inv = 1.f / warp_sum(p[0] + p[1]);
+            p[0] *= inv; p[1] *= inv;
+
+            // out[c] = sum_j p_j V[j][c]; lane owns c = lane + 32*e
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < n; ++j) {
+                const float pj = __shfl_sync(D4_FULL, (j < 32) ? p[0] : p[1], j & 31);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const int c = lane + 32 * e; if (c < d) o[e] = fmaf(pj, Vs[j * kp + c], o[e]); }
+            }
+            if (a.belief) {   // out -= (out . vhat) vhat,  vhat = l2norm(v_i)
+                float vv[4], ss = 0.f, dot = 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const int c = lane + 32 * e; vv[e] = (c < d) ? Vs[i * kp + c] : 0.f; ss += vv[e] * vv[e]; }
+                const float den = fmaxf(sqrtf(warp_sum(ss)), D4_L2_EPS);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { vv[e] = vv[e] / den; dot += o[e] * vv[e]; }
+                dot = warp_sum(dot);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = o[e] - dot * vv[e];
+            }
+            float gate = 1.f;
+            if (a.gate) gate = sigmoidf_(a.gate[b * a.gate_sb + i * a.gate_si + hq]);
+            float* op = a.out + b * a.out_sb + i * a.out_si + (long long)hq * d;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const int c = lane + 32 * e; if (c < d) op[c] = o[e] * gate; }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K1: time-decode attention.  One warp per (token, kv head) stream.  HALF = d/2 rotary pairs; lane p owns
+// elements (p, p + HALF) of every d-vector (the rotate-half partner lives in the same lane).
+
+template <int D, int G>
+struct TimeAttnSmem {
+    float tile[32 * D];     // one staged tile of 32 keys (or values), linear [key][d]
+    float q[G * D];         // rotated queries of the group
+};
+
+constexpr int TA_WARPS = 8;
+constexpr int TA_MAXTILES = 8;       // up to 256 cached frames
+
+template <int D, int G>
+__global__ void __launch_bounds__(TA_WARPS * 32) time_attn_kernel(TimeAttnArgs a) {
+    constexpr int HALF = D / 2;
+    constexpr int PPL = (HALF + 31) / 32;          // rotary pairs per lane
+    constexpr int C4 = D / 4;                      // float4 chunks per key
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * TA_WARPS + warp;
+    if (item >= (long long)a.M * a.hkv) return;
+    const int m = (int)(item / a.hkv), hk = (int)(item % a.hkv);
+    TimeAttnSmem<D, G>& sm = reinterpret_cast<TimeAttnSmem<D, G>*>(smem_raw)[warp];
+
+    const float* row = a.qkvgm + (long long)m * a.ld;
+    const float sqrt_d = sqrtf((float)D);
+
+    // ---- prologue: new k, v (lerp with value residual), key head-norm, rotary on q and k
+    float k1[PPL], k2[PPL], v1[PPL], v2[PPL], cs[PPL], sn[PPL];
+    const float mixw = sigmoidf_(row[a.off_m + hk]);
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < PPL; ++e) {
+        const int p = lane + 32 * e;
+        k1[e] = k2[e] = v1[e] = v2[e] = 0.f; cs[e] = 1.f; sn[e] = 0.f;
+        if (p < HALF) {
+            k1[e] = row[a.off_k + hk * D + p]; k2[e] = row[a.off_k + hk * D + p + HALF];
+            const float r1 = a.v0[(long long)m * a.ldv0 + hk * D + p], r2 = a.v0[(long long)m * a.ldv0 + hk * D + p + HALF];
+            v1[e] = lerp_(row[a.off_v + hk * D + p], r1, mixw);
+            v2[e] = lerp_(row[a.off_v + hk * D + p + HALF], r2, mixw);
+            ss += k1[e] * k1[e] + k2[e] * k2[e];
+            const float ang = (float)a.t * a.inv_freq[p];
+            sincosf(ang, &sn[e], &cs[e]);
+        }
+    }
+    const float kden = fmaxf(sqrtf(warp_sum(ss)), D4_L2_EPS);
+#pragma unroll
+    for (int e = 0; e < PPL; ++e) {
+        const int p = lane + 32 * e;
+        if (p < HALF) {
+            const float n1 = (k1[e] / kden) * ((a.k_gamma[hk * D + p] + 1.f) * sqrt_d);
+            const float n2 = (k2[e] / kden) * ((a.k_gamma[hk * D + p + HALF] + 1.f) * sqrt_d);
+            k1[e] = n1 * cs[e] + (-n2) * sn[e];
+            k2[e] = n2 * cs[e] + n1 * sn[e];
+        }
+    }
+    float self_s[G];
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+        const int hq = hk * G + gi;
+        float dot = 0.f;
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) {
+            const int p = lane + 32 * e;
+            if (p < HALF) {
+                const float q1 = row[hq * D + p], q2 = row[hq * D + p + HALF];
+                const float r1 = q1 * cs[e] + (-q2) * sn[e];
+                const float r2 = q2 * cs[e] + q1 * sn[e];
+                sm.q[gi * D + p] = r1; sm.q[gi * D + p + HALF] = r2;
+                dot += r1 * k1[e] + r2 * k2[e];
+            }
+        }
+        float s = warp_sum(dot) * a.scale;
+        if (a.softclamp > 0.f) s = tanhf(s / a.softclamp) * a.softclamp;
+        self_s[gi] = s;
+    }
+    __syncwarp();
+
+    // ---- scores over the cached keys: coalesced 128-bit loads -> smem tile -> lane-per-key dot products
+    const int t = a.t;
+    const int ntiles = (t + 31) / 32;
+    const float* kc = a.kcache + ((long long)m * a.hkv + hk) * (long long)a.Tmax * D;
+    const float* vc = a.vcache + ((long long)m * a.hkv + hk) * (long long)a.Tmax * D;
+    float sc[G][TA_MAXTILES];
+#pragma unroll
+    for (int ti = 0; ti < TA_MAXTILES; ++ti) {
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) sc[gi][ti] = -INFINITY;
+        if (ti < ntiles) {
+            const int nk = min(32, t - ti * 32);
+            const float4* src = reinterpret_cast<const float4*>(kc + (long long)ti * 32 * D);
+            float4* dst = reinterpret_cast<float4*>(sm.tile);
+            for (int idx = lane; idx < nk * C4; idx += 32) dst[idx] = __ldcs(src + idx);
+            __syncwarp();
+            if (lane < nk) {
+                float acc[G];
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) acc[gi] = 0.f;
+                // rotated chunk order keeps the linear [key][d] tile bank-conflict free for 128-bit reads
+#pragma unroll
+                for (int c = 0; c < C4; ++c) {
+                    const int cc = (c + lane) % C4;
+                    const float4 kv = *reinterpret_cast<const float4*>(sm.tile + lane * D + cc * 4);
+#pragma unroll
+                    for (int gi = 0; gi < G; ++gi) {
+                        const float4 qv = *reinterpret_cast<const float4*>(sm.q + gi * D + cc * 4);
+                        acc[gi] = fmaf(qv.x, kv.x, acc[gi]); acc[gi] = fmaf(qv.y, kv.y, acc[gi]);
+                        acc[gi] = fmaf(qv.z, kv.z, acc[gi]); acc[gi] = fmaf(qv.w, kv.w, acc[gi]);
+                    }
+                }
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    float s = acc[gi] * a.scale;
+                    if (a.softclamp > 0.f) s = tanhf(s / a.softclamp) * a.softclamp;
+                    sc[gi][ti] = s;
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- softmax over cached keys + self
+    float pself[G];
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+        float mx = self_s[gi];
+#pragma unroll
+        for (int ti = 0; ti < TA_MAXTILES; ++ti) mx = fmaxf(mx, sc[gi][ti]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int ti = 0; ti < TA_MAXTILES; ++ti) { const float e = (sc[gi][ti] == -INFINITY) ? 0.f : expf(sc[gi][ti] - mx); sc[gi][ti] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float es = expf(self_s[gi] - mx);
+        const float inv = 1.f / (sum + es);
+#pragma unroll
+        for (int ti = 0; ti < TA_MAXTILES; ++ti) sc[gi][ti] *= inv;
+        pself[gi] = es * inv;
+    }
+
+    // ---- AV: stream the cached values tile by tile
+    float o1[G][PPL], o2[G][PPL];
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) { o1[gi][e] = 0.f; o2[gi][e] = 0.f; }
+#pragma unroll
+    for (int ti = 0; ti < TA_MAXTILES; ++ti) {
+        if (ti < ntiles) {
+            const int nk = min(32, t - ti * 32);
+            const float4* src = reinterpret_cast<const float4*>(vc + (long long)ti * 32 * D);
+            float4* dst = reinterpret_cast<float4*>(sm.tile);
+            for (int idx = lane; idx < nk * C4; idx += 32) dst[idx] = __ldcs(src + idx);
+            __syncwarp();
+            for (int j = 0; j < nk; ++j) {
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    const float pj = __shfl_sync(D4_FULL, sc[gi][ti], j);
+#pragma unroll
+                    for (int e = 0; e < PPL; ++e) {
+                        const int p = lane + 32 * e;
+                        if (p < HALF) {
+                            o1[gi][e] = fmaf(pj, sm.tile[j * D + p], o1[gi][e]);
+                            o2[gi][e] = fmaf(pj, sm.tile[j * D + p + HALF], o2[gi][e]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- epilogue: + self, belief projection on the new value, head gate, store; append k/v on the clean pass
+    float vs = 0.f;
+#pragma unroll
+    for (int e = 0; e < PPL; ++e) vs += v1[e] * v1[e] + v2[e] * v2[e];
+    const float vden = fmaxf(sqrtf(warp_sum(vs)), D4_L2_EPS);
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+        const int hq = hk * G + gi;
+        float dot = 0.f;
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) {
+            o1[gi][e] = fmaf(pself[gi], v1[e], o1[gi][e]);
+            o2[gi][e] = fmaf(pself[gi], v2[e], o2[gi][e]);
+            dot += o1[gi][e] * (v1[e] / vden) + o2[gi][e] * (v2[e] / vden);
+        }
+        dot = warp_sum(dot);
+        const float gate = sigmoidf_(row[a.off_g + hq]);
+        float* op = a.out + (long long)m * a.ldo + hq * D;
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) {
+            const int p = lane + 32 * e;
+            if (p < HALF) {
+                op[p] = (o1[gi][e] - dot * (v1[e] / vden)) * gate;
+                op[p + HALF] = (o2[gi][e] - dot * (v2[e] / vden)) * gate;
+            }
+        }
+    }
+    if (a.commit) {
+        float* kd = a.kcache + (((long long)m * a.hkv + hk) * a.Tmax + t) * D;
+        float* vd = a.vcache + (((long long)m * a.hkv + hk) * a.Tmax + t) * D;
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) {
+            const int p = lane + 32 * e;
+            if (p < HALF) { kd[p] = k1[e]; kd[p + HALF] = k2[e]; vd[p] = v1[e]; vd[p + HALF] = v2[e]; }
+        }
+    }
+}
+
+template <int D, int G>
+int launch_time_attn(const TimeAttnArgs& a, cudaStream_t s) {
+    const size_t smem = sizeof(TimeAttnSmem<D, G>) * TA_WARPS;
+    static bool configured = false;
+    if (!configured) {
+        D4_CUDA_OK(cudaFuncSetAttribute(time_attn_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long items = (long long)a.M * a.hkv;
+    time_attn_kernel<D, G><<<(unsigned)((items + TA_WARPS - 1) / TA_WARPS), TA_WARPS * 32, smem, s>>>(a);
+    D4_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int d4_time_attn_bulk(const TimeAttnArgs& a, cudaStream_t s);   // attn_bulk.cu
+
+int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s) {
+    if (a.nb <= 0) return 0;
+    if (a.n > 64 || a.n < 1) return d4_fail("small_attn: %d keys unsupported (1..64)", a.n);
+    if (a.d % 4 != 0 || a.d > 128) return d4_fail("small_attn: head dim %d unsupported", a.d);
+    if (a.belief && a.nq != a.n) return d4_fail("small_attn: belief projection needs nq == n");
+    const size_t smem = (size_t)SA_WARPS * 2 * a.n * (a.d + 4) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        D4_CUDA_OK(cudaFuncSetAttribute(small_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const long long items = (long long)a.nb * a.hkv;
+    small_attn_kernel<<<(unsigned)((items + SA_WARPS - 1) / SA_WARPS), SA_WARPS * 32, smem, s>>>(a);
+    D4_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int d4_time_attn(const TimeAttnArgs& a, cudaStream_t s) {
+    if (a.M <= 0) return 0;
+    if (a.t < 0 || a.t >= a.Tmax) return d4_fail("time_attn: t=%d outside the KV buffer (Tmax=%d)", a.t, a.Tmax);
+    if (a.t > 32 * TA_MAXTILES) return d4_fail("time_attn: context %d > %d unsupported", a.t, 32 * TA_MAXTILES);
+    if (a.variant == 1) return d4_time_attn_bulk(a, s);
+#define D4_TA_CASE(DD, GG) if (a.d == DD && a.g == GG) return launch_time_attn<DD, GG>(a, s);
+    D4_TA_CASE(64, 1) D4_TA_CASE(64, 2) D4_TA_CASE(32, 1) D4_TA_CASE(32, 2) D4_TA_CASE(16, 1) D4_TA_CASE(16, 2) D4_TA_CASE(128, 1)
+#undef D4_TA_CASE
+    return d4_fail("time_attn: (dim_head=%d, query groups=%d) has no kernel instantiation", a.d, a.g);
+}

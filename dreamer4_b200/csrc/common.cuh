@@ -1,0 +1,77 @@
+// Shared device/host helpers for the dreamer4_b200 CUDA path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define D4_WARP 32
+#define D4_FULL 0xffffffffu
+
+// fp32 machine epsilon: nn.RMSNorm(eps=None) resolves to torch.finfo(float32).eps
+// (reference dreamer4/dreamer4.py:1906, 2089, 2822).
+#define D4_RMS_EPS 1.1920928955078125e-07f
+// F.normalize(p=2) eps (reference dreamer4/dreamer4.py:521-522)
+#define D4_L2_EPS 1e-12f
+// nn.LayerNorm default eps (x-mlps normed MLP)
+#define D4_LN_EPS 1e-5f
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(D4_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(D4_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float geluf_(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// row remap used by the GEMMs and the row-wise kernels: compact row m -> physical row
+//   grp == 0 : m
+//   else     : (m / grp) * gstride + goff + (m % grp)
+struct RowMap {
+    int grp, gstride, goff;
+    __host__ __device__ __forceinline__ long long operator()(int m) const {
+        if (grp == 0) return m;
+        return (long long)(m / grp) * gstride + goff + (m % grp);
+    }
+};
+static inline RowMap rowmap_identity() { RowMap r; r.grp = 0; r.gstride = 0; r.goff = 0; return r; }
+static inline RowMap rowmap(int grp, int gstride, int goff) { RowMap r; r.grp = grp; r.gstride = gstride; r.goff = goff; return r; }
+
+enum { D4_ACT_NONE = 0, D4_ACT_GLU_SILU = 1, D4_ACT_GLU_GELU = 2, D4_ACT_SILU = 3 };
+
+// One linear layer  C = epi( rowscale[m] * (A @ W^T) + bias )  (+ residual)
+// A (M,K) fp32 row-major with leading dim lda (rows through amap); W (N,K) fp32 (nn.Linear layout, leading dim ldw).
+// act GLU_*: W rows are interleaved [x0,g0,x1,g1,...]; output has N/2 columns  x_j * act(g_j).
+struct GemmArgs {
+    const float* A; long long lda;
+    const float* W; long long ldw;
+    const float* W_lo;            // low words of W for the tf32x3 path (nullptr otherwise)
+    float* C; long long ldc;
+    int M, N, K;
+    const float* bias;
+    const float* row_scale;
+    const float* residual; long long ldr;
+    int act;
+    RowMap amap, cmap;
+    // operand layouts (exact-fp32 path only; used by the learn_from_experience backward GEMMs):
+    //   transA: A is stored (K, M) — element (m,k) at A[k*lda + m];  transW: W is stored (K, N) — element (n,k) at W[k*ldw + n]
+    int transA, transW;
+};
+
+static inline GemmArgs gemm_args(const float* A, long long lda, const float* W, long long ldw, float* C, long long ldc,
+                                 int M, int N, int K) {
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.W_lo = nullptr; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+    g.bias = nullptr; g.row_scale = nullptr; g.residual = nullptr; g.ldr = 0; g.act = D4_ACT_NONE;
+    g.amap = rowmap_identity(); g.cmap = rowmap_identity(); g.transA = 0; g.transW = 0;
+    return g;
+}
+
+#define D4_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return d4_fail_cuda(e__, #expr, __FILE__, __LINE__); } while (0)
+int d4_fail_cuda(cudaError_t e, const char* what, const char* file, int line);
+int d4_fail(const char* fmt, ...);

@@ -1,0 +1,609 @@
+// The imagination engine: one transformer pass for the newest frame over the in-place time-KV cache, the
+// per-frame denoise loop + heads, and the C-ABI entry points declared in include/d4b200.h.
+//
+// Data layout in HBM (fp32, row-major; M = B*S tokens of the new frame, S = tokens per frame):
+//   hid      (2L+1, M, D)   residual-stream snapshots [input, post-attn_0, post-ff_0, ...] — the context of
+//                           the attention-residual pools (reference dreamer4.py:3040, 3172, 3216)
+//   hid_rstd (2L+1, M)      their RMS statistics (gamma is folded into the consuming GEMM's weight)
+//   qkvgm    (M, ldq)       fused projection row [q | k | v | gate logits | value-residual mix logits]
+//   kv cache (y, 2, Mmax, h, Tmax, d)  reference next_kv_cache layout (dreamer4.py:3255-3265), time axis preallocated
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include "engine.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+int d4_fail(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return -1;
+}
+int d4_fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return -2;
+}
+extern "C" const char* d4_last_error(void) { return g_err; }
+extern "C" int d4_version(void) { return 100; }
+
+#define D4_TRY(expr) do { int rc__ = (expr); if (rc__ != 0) return rc__; } while (0)
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------ ctx
+extern "C" int d4_ctx_create(const d4_config* cfg, d4_ctx** out) {
+    if (!cfg || !out) return d4_fail("d4_ctx_create: null argument");
+    d4_ctx* c = new d4_ctx();
+    c->cfg = *cfg;
+    c->D = cfg->dim; c->Dl = cfg->dim_latent; c->N = cfg->num_latent_tokens; c->nsp = cfg->num_spatial_tokens;
+    c->nreg = cfg->num_register_tokens; c->L = cfg->depth; c->h = cfg->heads; c->hq = cfg->query_heads; c->d = cfg->dim_head;
+    c->hp = cfg->pool_heads; c->dp = cfg->pool_dim_head; c->Dp = c->hp * c->dp;
+    c->Dq = c->hq * c->d; c->Dkv = c->h * c->d;
+    c->inner = cfg->ff_inner; c->inner_pad = cfg->ff_inner_pad;
+    c->na = cfg->num_action_types; c->has_actions = c->na > 0;
+    c->A_total = 0;
+    for (int i = 0; i < c->na; ++i) { c->act_off[i] = c->A_total; c->A_total += cfg->action_sizes[i]; }
+    c->S = 1 + c->nsp + c->nreg + c->has_actions + 1;
+    c->same_len = (c->nsp == c->N);
+    c->n_hid = 2 * c->L + 1;
+    c->y = 0;
+    for (int i = 0; i < c->L; ++i) { const int it = ((i + 1) % cfg->time_block_every) == 0; c->is_time.push_back(it); c->y += it; }
+    c->NQ = c->Dq + 2 * c->Dkv + c->hq + c->h; c->ldq = round_up(c->NQ, 4);
+    c->ldpq = round_up(c->Dp + c->hp, 4);
+    c->ldfa = round_up(c->Dq + c->hq, 4);
+    c->ldlog = round_up(c->A_total > 0 ? c->A_total : 1, 4);
+    const char* bad = nullptr;
+    if (c->hq % c->h != 0) bad = "query_heads must be a multiple of heads";
+    else if (c->d % 4 != 0 || c->d > 128) bad = "dim_head must be a multiple of 4, <= 128";
+    else if (c->D % 4 != 0) bad = "dim must be a multiple of 4";
+    else if (c->S > 32) bad = "more than 32 tokens per frame unsupported";
+    else if (c->N > 64 || c->nsp > 64) bad = "more than 64 latent / spatial tokens unsupported";
+    else if (c->n_hid > 64) bad = "depth > 31 unsupported";
+    else if (c->na > D4_MAX_ACTION_TYPES) bad = "too many action types";
+    else if (c->inner_pad < c->inner || c->inner_pad % 4 != 0) bad = "ff_inner_pad must be >= ff_inner and a multiple of 4";
+    else if (cfg->max_batch < 1 || cfg->max_time < 1) bad = "max_batch / max_time must be positive";
+    else if (cfg->policy_layers > D4_MAX_MLP_LAYERS || cfg->value_layers > D4_MAX_MLP_LAYERS || cfg->terminal_layers > D4_MAX_MLP_LAYERS) bad = "MLP too deep";
+    if (bad) { delete c; return d4_fail("d4_ctx_create: %s", bad); }
+    d4_engine_plan(c);
+    *out = c;
+    return 0;
+}
+extern "C" void d4_ctx_destroy(d4_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& r : ctx->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    delete ctx;
+}
+
+extern "C" int d4_set_weight(d4_ctx* c, const char* name, const float* p, int64_t numel) {
+    if (!c || !name) return d4_fail("d4_set_weight: null argument");
+    c->table[name] = std::make_pair(p, numel);
+    c->bound = false;
+    return 0;
+}
+
+int d4_engine_plan(d4_ctx* c) {
+    const long long B = c->cfg.max_batch, M = B * c->S;
+    long long off = 0;
+    auto take = [&](long long nfloats) { long long o = off; off += (nfloats * 4 + 255) / 256 * 256; return o; };
+    struct { float** p; long long n; } items[] = {
+        {&c->b.lat_x, B * c->N * c->Dl}, {&c->b.lat_rstd, B * c->N}, {&c->b.kv_l, B * c->N * 2 * c->Dkv}, {&c->b.att_l, B * c->nsp * c->Dq},
+        {&c->b.hid, (long long)c->n_hid * M * c->D}, {&c->b.hid_rstd, (long long)c->n_hid * M}, {&c->b.x_cur, M * c->D}, {&c->b.x_rstd, M},
+        {&c->b.qkvgm, M * c->ldq}, {&c->b.v0, M * c->Dkv}, {&c->b.attn_o, M * c->Dq}, {&c->b.ff_mid, M * c->inner_pad},
+        {&c->b.pool_qg, M * c->ldpq}, {&c->b.pool_kv, (long long)c->n_hid * M * 2 * c->Dp}, {&c->b.pool_att, M * c->Dp},
+        {&c->b.fa_kv, M * 2 * c->Dkv}, {&c->b.fa_q, B * c->ldfa}, {&c->b.fa_att, B * c->Dq}, {&c->b.ag_rstd, B},
+        {&c->b.sp_n, B * c->nsp * c->D}, {&c->b.sp_n2, B * c->nsp * c->D}, {&c->b.sp_kv, B * c->nsp * 2 * c->Dkv},
+        {&c->b.lp_att, B * c->N * c->Dq}, {&c->b.pred, B * c->N * c->Dl},
+        {&c->b.hbuf0, B * (long long)std::max(std::max(c->cfg.policy_hidden, c->cfg.value_hidden), std::max(c->cfg.terminal_hidden, 4))},
+        {&c->b.hbuf1, B * (long long)std::max(std::max(c->cfg.policy_hidden, c->cfg.value_hidden), std::max(c->cfg.terminal_hidden, 4))},
+        {&c->b.logits, B * c->ldlog}, {&c->b.bins, B * (long long)std::max(std::max(c->cfg.reward_bins, c->cfg.value_bins), 4)},
+        {&c->b.agent, B * c->D}, {&c->b.term_in, B * c->Dl},
+    };
+    for (auto& it : items) *it.p = reinterpret_cast<float*>(take(it.n));   // offsets for now; rebased in d4_set_buffers
+    c->b.sizes_offs = reinterpret_cast<int*>(take(2 * D4_MAX_ACTION_TYPES));
+    c->ws_need = off;
+    return 0;
+}
+
+extern "C" int64_t d4_workspace_bytes(const d4_ctx* c) { return c ? c->ws_need : 0; }
+extern "C" int64_t d4_kv_bytes(const d4_ctx* c) {
+    if (!c) return 0;
+    return (int64_t)std::max(c->y, 1) * 2 * c->cfg.max_batch * c->S * c->h * (int64_t)c->cfg.max_time * c->d * 4;
+}
+
+extern "C" int d4_set_buffers(d4_ctx* c, void* workspace, int64_t workspace_bytes, float* kv, int64_t kv_bytes) {
+    if (!c) return d4_fail("d4_set_buffers: null ctx");
+    if (workspace_bytes < c->ws_need) return d4_fail("d4_set_buffers: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)c->ws_need);
+    if (kv_bytes < d4_kv_bytes(c)) return d4_fail("d4_set_buffers: kv buffer %lld < %lld bytes", (long long)kv_bytes, (long long)d4_kv_bytes(c));
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(kv) & 15)) return d4_fail("d4_set_buffers: buffers must be 256-byte aligned");
+    if (c->ws) return d4_fail("d4_set_buffers: buffers already set");
+    d4_engine_plan(c);
+    unsigned char* base = static_cast<unsigned char*>(workspace);
+    float** ptrs = reinterpret_cast<float**>(&c->b);
+    const int nptr = (int)(offsetof(decltype(c->b), sizes_offs) / sizeof(float*));
+    for (int i = 0; i < nptr; ++i) ptrs[i] = reinterpret_cast<float*>(base + reinterpret_cast<uintptr_t>(ptrs[i]));
+    c->b.sizes_offs = reinterpret_cast<int*>(base + reinterpret_cast<uintptr_t>(c->b.sizes_offs));
+    c->ws = base; c->ws_bytes = workspace_bytes; c->kv = kv; c->kv_bytes_ = kv_bytes;
+    // ff_mid pad columns must read as zero (they meet zero-padded weight columns)
+    D4_CUDA_OK(cudaMemset(c->b.ff_mid, 0, (size_t)c->cfg.max_batch * c->S * c->inner_pad * 4));
+    int so[2 * D4_MAX_ACTION_TYPES] = {0};
+    for (int i = 0; i < c->na; ++i) { so[i] = c->cfg.action_sizes[i]; so[c->na + i] = c->act_off[i]; }
+    D4_CUDA_OK(cudaMemcpy(c->b.sizes_offs, so, sizeof(so), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ binding
+namespace {
+struct Binder {
+    d4_ctx* c; const char* missing = nullptr; std::string miss_store;
+    const float* get(const std::string& name, int64_t numel, bool optional = false) {
+        auto it = c->table.find(name);
+        if (it == c->table.end() || it->second.first == nullptr) {
+            if (!optional && !missing) { miss_store = name; missing = miss_store.c_str(); }
+            return nullptr;
+        }
+        if (numel >= 0 && it->second.second != numel && !missing) {
+            miss_store = name + " (numel " + std::to_string(it->second.second) + " != expected " + std::to_string(numel) + ")";
+            missing = miss_store.c_str();
+        }
+        return it->second.first;
+    }
+    LinW lin(const std::string& name, int64_t numel) {
+        LinW w; w.w = get(name, numel);
+        const bool optional = c->cfg.precision != D4_PREC_TF32X3;
+        w.hi = get(name + ".hi", numel, optional);
+        w.lo = get(name + ".lo", numel, optional);
+        return w;
+    }
+};
+}  // namespace
+
+extern "C" int d4_bind(d4_ctx* c) {
+    if (!c) return d4_fail("d4_bind: null ctx");
+    Binder B{c};
+    const int D = c->D, Dl = c->Dl, Dq = c->Dq, Dkv = c->Dkv, h = c->h, hq = c->hq, d = c->d, Dp = c->Dp, hp = c->hp;
+    const int half = D / 2;
+    c->sig_emb = B.get("sig_emb", (int64_t)c->cfg.max_steps * half);
+    c->step_emb = B.get("step_emb", -1);
+    c->registers = B.get("registers", (int64_t)c->nreg * D, c->nreg == 0);
+    c->agent_embed = B.get("agent_embed", D);
+    c->action_learned = B.get("action_learned", D, !c->has_actions);
+    c->action_emb = B.get("action_emb", (int64_t)c->A_total * D, !c->has_actions);
+    c->task_emb = B.get("task_emb", -1, true);
+    if (c->same_len) {
+        c->l2s_w = B.lin("l2s.w", (int64_t)D * Dl); c->l2s_b = B.get("l2s.b", D);
+        c->lp_w = B.lin("lp.w", (int64_t)Dl * D);
+    } else {
+        c->l2s_w_kv = B.lin("l2s.w_kv", (int64_t)2 * Dkv * Dl); c->l2s_w_out = B.lin("l2s.w_out", (int64_t)D * Dq);
+        c->l2s_q = B.get("l2s.q", (int64_t)c->nsp * Dq); c->l2s_gate = B.get("l2s.gate", (int64_t)c->nsp * hq);
+        c->l2s_k_gamma = B.get("l2s.k_gamma", (int64_t)h * d);
+        c->lp_norm_ctx = B.get("lp.norm_ctx", D); c->lp_w_kv = B.lin("lp.w_kv", (int64_t)2 * Dkv * D);
+        c->lp_q = B.get("lp.q", (int64_t)c->N * Dq); c->lp_gate = B.get("lp.gate", (int64_t)c->N * hq);
+        c->lp_k_gamma = B.get("lp.k_gamma", (int64_t)h * d); c->lp_w_comb = B.lin("lp.w_comb", (int64_t)Dl * Dq);
+    }
+    c->lp_norm0 = B.get("lp.norm0", D);
+    c->vr_w = B.lin("vr.w", (int64_t)Dkv * D);
+    c->inv_freq = B.get("inv_freq", d / 2);
+    auto bind_ff = [&](const std::string& p, FFW& f) {
+        f.w_in = B.lin(p + ".w_in", (int64_t)2 * c->inner * D); f.b_in = B.get(p + ".b_in", 2 * c->inner);
+        f.w_out = B.lin(p + ".w_out", (int64_t)D * c->inner_pad); f.b_out = B.get(p + ".b_out", D);
+    };
+    auto bind_pool = [&](const std::string& p, PoolW& w) {
+        w.w_qg = B.lin(p + ".w_qg", (int64_t)(Dp + hp) * D); w.w_kv = B.lin(p + ".w_kv", (int64_t)2 * Dp * D);
+        w.k_gamma = B.get(p + ".k_gamma", (int64_t)hp * c->dp); w.w_out = B.lin(p + ".w_out", (int64_t)D * Dp);
+    };
+    c->attn.assign(c->L, AttnLayerW()); c->ff.assign(c->L, FFW()); c->pools.assign(c->L > 0 ? c->L - 1 : 0, PoolW());
+    for (int i = 0; i < c->L; ++i) {
+        const std::string p = "L" + std::to_string(i);
+        c->attn[i].w = B.lin(p + ".attn.w", (int64_t)c->NQ * D); c->attn[i].b = B.get(p + ".attn.b", c->NQ);
+        c->attn[i].k_gamma = B.get(p + ".attn.k_gamma", (int64_t)h * d); c->attn[i].w_out = B.lin(p + ".attn.w_out", (int64_t)D * Dq);
+        bind_ff(p + ".ff", c->ff[i]);
+        if (i != c->L - 1) bind_pool("P" + std::to_string(i), c->pools[i]);
+    }
+    bind_pool("PF", c->pool_final);
+    c->fa.w_qg = B.lin("FA.w_qg", (int64_t)(Dq + hq) * D); c->fa.w_kv = B.lin("FA.w_kv", (int64_t)2 * Dkv * D);
+    c->fa.k_gamma = B.get("FA.k_gamma", (int64_t)h * d); c->fa.w_out = B.lin("FA.w_out", (int64_t)D * Dq);
+    bind_ff("FAFF", c->fa_ff);
+    c->reward_w = B.get("reward.w", (int64_t)c->cfg.reward_bins * D);
+    c->reward_centers = B.get("reward.centers", c->cfg.reward_bins);
+    auto bind_mlp = [&](const std::string& p, MlpW& m, int layers, int din, int hidden, int dout) {
+        m.layers = layers;
+        for (int l = 0; l <= layers; ++l) m.dims[l] = (l == 0) ? din : (l == layers ? dout : hidden);
+        for (int l = 0; l < layers; ++l) {
+            const std::string q = p + "." + std::to_string(l);
+            m.w[l] = B.get(q + ".w", (int64_t)m.dims[l + 1] * m.dims[l]); m.b[l] = B.get(q + ".b", m.dims[l + 1]);
+            if (l < layers - 1) { m.lnw[l] = B.get(q + ".lnw", m.dims[l + 1]); m.lnb[l] = B.get(q + ".lnb", m.dims[l + 1]); }
+            else { m.lnw[l] = m.lnb[l] = nullptr; }
+        }
+    };
+    if (c->has_actions) {
+        bind_mlp("policy", c->policy, c->cfg.policy_layers, D, c->cfg.policy_hidden, c->cfg.policy_hidden);
+        bind_mlp("value", c->value, c->cfg.value_layers, D, c->cfg.value_hidden, c->cfg.value_bins);
+        c->value_centers = B.get("value.centers", c->cfg.value_bins);
+        auto it = c->table.find("unembed");
+        if (it == c->table.end()) { if (!B.missing) B.missing = "unembed"; }
+        else { c->unembed = it->second.first; c->unembed_ld = it->second.second; }   // numel slot carries the row stride
+    }
+    if (c->cfg.predict_terminals) bind_mlp("terminal", c->terminal, c->cfg.terminal_layers, Dl, c->cfg.terminal_hidden, 1);
+    if (B.missing) return d4_fail("d4_bind: weight '%s' missing or mis-sized", B.missing);
+    c->bound = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ profiling
+int d4_prof_begin(d4_ctx* c, int cls, double work, cudaStream_t s) {
+    if (!c->prof_on) return -1;
+    d4_ctx::ProfRec r;
+    if (!c->prof_pool.empty()) { r = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else {
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+    }
+    r.cls = cls; r.work = work;
+    cudaEventRecord(r.a, s);
+    c->prof.push_back(r);
+    return (int)c->prof.size() - 1;
+}
+void d4_prof_end(d4_ctx* c, int handle, cudaStream_t s) {
+    if (handle >= 0) cudaEventRecord(c->prof[handle].b, s);
+}
+extern "C" int d4_profile(d4_ctx* c, int enable) {
+    if (!c) return d4_fail("d4_profile: null ctx");
+    c->prof_on = enable != 0;
+    return 0;
+}
+extern "C" int d4_profile_read(d4_ctx* c, double* out) {
+    if (!c || !out) return d4_fail("d4_profile_read: null argument");
+    for (int i = 0; i < D4_PROF_CLASSES * 3; ++i) out[i] = 0.0;
+    for (auto& r : c->prof) {
+        D4_CUDA_OK(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        D4_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+        out[r.cls * 3 + 0] += ms; out[r.cls * 3 + 1] += 1.0; out[r.cls * 3 + 2] += r.work;
+        c->prof_pool.push_back(r);
+    }
+    c->prof.clear();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM dispatch
+int d4_engine_gemm(d4_ctx* c, GemmArgs g, const LinW& w, int force_fp32, cudaStream_t s) {
+    g.W = w.w;
+    const int prec = force_fp32 ? D4_PREC_FP32 : c->cfg.precision;
+    const int ph = d4_prof_begin(c, D4_CLS_GEMM, 2.0 * g.M * g.N * g.K, s);
+    int rc;
+    if (prec != D4_PREC_FP32 && d4_gemm_tc_supported(g)) {
+        if (prec == D4_PREC_TF32X3 && w.hi && w.lo) { g.W = w.hi; g.W_lo = w.lo; rc = d4_gemm_tc(g, 3, s); }
+        else rc = d4_gemm_tc(g, 1, s);
+    } else {
+        rc = d4_gemm_simt(g, s);
+    }
+    d4_prof_end(c, ph, s);
+    return rc;
+}
+
+static inline LinW plain(const float* w) { LinW l; l.w = w; return l; }
+
+// x-mlps normed MLP forward (Linear -> LayerNorm -> SiLU)* -> Linear, exact fp32.
+int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, int M, float* buf0, float* buf1, float* out, long long ldo,
+                   cudaStream_t s) {
+    const float* cur = x; long long ldc = ldx;
+    for (int l = 0; l < mlp.layers; ++l) {
+        const bool last = (l == mlp.layers - 1);
+        float* dst = last ? out : ((l & 1) ? buf1 : buf0);
+        const long long ldd = last ? ldo : mlp.dims[l + 1];
+        GemmArgs g = gemm_args(cur, ldc, mlp.w[l], mlp.dims[l], dst, ldd, M, mlp.dims[l + 1], mlp.dims[l]);
+        g.bias = mlp.b[l];
+        D4_TRY(d4_engine_gemm(c, g, plain(mlp.w[l]), 1, s));
+        if (!last) D4_TRY(d4_ln_act_rows(dst, ldd, mlp.lnw[l], mlp.lnb[l], M, mlp.dims[l + 1], dst, ldd, D4_ACT_SILU, nullptr, nullptr, s));
+        cur = dst; ldc = ldd;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ the pass
+namespace {
+
+int run_pool(d4_ctx* c, const PoolW& P, int M, const float* xq, const float* xq_rstd, int n, float* out, cudaStream_t s) {
+    const int D = c->D, Dp = c->Dp, hp = c->hp, dp = c->dp;
+    {   // query + gate logits from the normed token
+        GemmArgs g = gemm_args(xq, D, nullptr, D, c->b.pool_qg, c->ldpq, M, Dp + hp, D);
+        g.row_scale = xq_rstd;
+        D4_TRY(d4_engine_gemm(c, g, P.w_qg, 0, s));
+    }
+    {   // keys / values of all hiddens so far, re-projected by this pool (reference dreamer4.py:2164-2177)
+        GemmArgs g = gemm_args(c->b.hid, D, nullptr, D, c->b.pool_kv, 2 * Dp, n * M, 2 * Dp, D);
+        g.row_scale = c->b.hid_rstd;
+        D4_TRY(d4_engine_gemm(c, g, P.w_kv, 0, s));
+    }
+    SmallAttnArgs a; memset(&a, 0, sizeof(a));
+    a.nb = M; a.hkv = hp; a.g = 1; a.d = dp; a.nq = 1; a.n = n;
+    a.q = c->b.pool_qg; a.q_sb = c->ldpq; a.q_si = 0;
+    a.k = c->b.pool_kv; a.k_sb = 2 * Dp; a.k_sj = (long long)M * 2 * Dp;
+    a.v = c->b.pool_kv + Dp; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+    a.k_gamma = P.k_gamma;
+    a.gate = c->b.pool_qg + Dp; a.gate_sb = c->ldpq; a.gate_si = 0;
+    a.out = c->b.pool_att; a.out_sb = Dp; a.out_si = 0;
+    a.scale = 1.f / sqrtf((float)dp);
+    { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+    GemmArgs g = gemm_args(c->b.pool_att, Dp, nullptr, Dp, out, D, M, D, Dp);
+    g.residual = xq; g.ldr = D;
+    return d4_engine_gemm(c, g, P.w_out, 0, s);
+}
+
+int run_ff(d4_ctx* c, const FFW& F, int M, const float* x, long long ldx, RowMap xmap, const float* x_rstd, float* out, long long ldo, RowMap omap,
+           cudaStream_t s) {
+    const int D = c->D;
+    GemmArgs g = gemm_args(x, ldx, nullptr, D, c->b.ff_mid, c->inner_pad, M, 2 * c->inner, D);
+    g.amap = xmap; g.row_scale = x_rstd; g.bias = F.b_in; g.act = c->cfg.ff_act == 1 ? D4_ACT_GLU_GELU : D4_ACT_GLU_SILU;
+    D4_TRY(d4_engine_gemm(c, g, F.w_in, 0, s));
+    GemmArgs g2 = gemm_args(c->b.ff_mid, c->inner_pad, nullptr, c->inner_pad, out, ldo, M, D, c->inner_pad);
+    g2.bias = F.b_out; g2.residual = x; g2.ldr = ldx; g2.cmap = omap;
+    // residual rows follow the output row map (x and out share their row layout in every use)
+    return d4_engine_gemm(c, g2, F.w_out, 0, s);
+}
+
+int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, const int64_t* prev_actions, int64_t pa_stride,
+             const int64_t* tasks, int t, int commit, float* pred_out, float* agent_out, cudaStream_t s) {
+    const int S = c->S, D = c->D, Dl = c->Dl, N = c->N, nsp = c->nsp, Dq = c->Dq, Dkv = c->Dkv, h = c->h, hq = c->hq, d = c->d, L = c->L;
+    const int M = B * S;
+    const long long MD = (long long)M * D;
+    auto hid = [&](int j) { return c->b.hid + (long long)j * MD; };
+    auto hrs = [&](int j) { return c->b.hid_rstd + (long long)j * M; };
+    const float att_scale = 1.f / sqrtf((float)d);
+
+    // ---- tokens of the new frame (reference dreamer4.py:7168-7222)
+    if (c->same_len) {
+        GemmArgs g = gemm_args(latent, Dl, nullptr, Dl, hid(0), D, B * N, D, Dl);
+        g.bias = c->l2s_b; g.cmap = rowmap(nsp, S, 1);
+        D4_TRY(d4_engine_gemm(c, g, c->l2s_w, 0, s));
+    } else {
+        D4_TRY(d4_row_rstd(latent, Dl, rowmap_identity(), B * N, Dl, c->b.lat_rstd, s));
+        GemmArgs g = gemm_args(latent, Dl, nullptr, Dl, c->b.kv_l, 2 * Dkv, B * N, 2 * Dkv, Dl);
+        g.row_scale = c->b.lat_rstd;
+        D4_TRY(d4_engine_gemm(c, g, c->l2s_w_kv, 0, s));
+        SmallAttnArgs a; memset(&a, 0, sizeof(a));
+        a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = nsp; a.n = N;
+        a.q = c->l2s_q; a.q_sb = 0; a.q_si = Dq;
+        a.k = c->b.kv_l; a.k_sb = (long long)N * 2 * Dkv; a.k_sj = 2 * Dkv;
+        a.v = c->b.kv_l + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+        a.k_gamma = c->l2s_k_gamma;
+        a.gate = c->l2s_gate; a.gate_sb = 0; a.gate_si = hq;
+        a.out = c->b.att_l; a.out_sb = (long long)nsp * Dq; a.out_si = Dq;
+        a.scale = att_scale;
+        { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+        GemmArgs g2 = gemm_args(c->b.att_l, Dq, nullptr, Dq, hid(0), D, B * nsp, D, Dq);
+        g2.cmap = rowmap(nsp, S, 1);
+        D4_TRY(d4_engine_gemm(c, g2, c->l2s_w_out, 0, s));
+    }
+    {
+        AssembleArgs a; memset(&a, 0, sizeof(a));
+        a.tokens = hid(0); a.B = B; a.S = S; a.D = D; a.nsp = nsp; a.nreg = c->nreg; a.has_actions = c->has_actions; a.na = c->na;
+        a.sig_emb = c->sig_emb; a.step_emb = c->step_emb; a.signal = signal; a.step = step_log2;
+        a.registers = c->registers; a.agent_embed = c->agent_embed; a.action_learned = c->action_learned; a.action_emb = c->action_emb;
+        a.prev_actions = reinterpret_cast<const long long*>(prev_actions); a.pa_stride = pa_stride;
+        for (int i = 0; i < c->na; ++i) a.act_off[i] = c->act_off[i];
+        a.task_emb = c->task_emb; a.tasks = (tasks && c->task_emb) ? reinterpret_cast<const long long*>(tasks) : nullptr;
+        D4_TRY(d4_assemble_tokens(a, s));
+    }
+    D4_TRY(d4_row_rstd(hid(0), D, rowmap_identity(), M, D, hrs(0), s));
+    {   // value residual (reference dreamer4.py:3026-3027)
+        GemmArgs g = gemm_args(hid(0), D, nullptr, D, c->b.v0, Dkv, M, Dkv, D);
+        g.row_scale = hrs(0);
+        D4_TRY(d4_engine_gemm(c, g, c->vr_w, 0, s));
+    }
+
+    // ---- layers (reference dreamer4.py:3043-3223)
+    const float* x_in = hid(0); const float* x_in_rstd = hrs(0);
+    int ti = 0;
+    for (int i = 0; i < L; ++i) {
+        {
+            GemmArgs g = gemm_args(x_in, D, nullptr, D, c->b.qkvgm, c->ldq, M, c->NQ, D);
+            g.row_scale = x_in_rstd; g.bias = c->attn[i].b;
+            D4_TRY(d4_engine_gemm(c, g, c->attn[i].w, 0, s));
+        }
+        const int off_k = Dq, off_v = Dq + Dkv, off_g = Dq + 2 * Dkv, off_m = Dq + 2 * Dkv + hq;
+        if (c->is_time[i]) {
+            TimeAttnArgs a; memset(&a, 0, sizeof(a));
+            a.M = M; a.hkv = h; a.g = hq / h; a.d = d; a.t = t; a.Tmax = c->cfg.max_time;
+            a.qkvgm = c->b.qkvgm; a.ld = c->ldq; a.off_k = off_k; a.off_v = off_v; a.off_g = off_g; a.off_m = off_m;
+            a.v0 = c->b.v0; a.ldv0 = Dkv; a.k_gamma = c->attn[i].k_gamma; a.inv_freq = c->inv_freq;
+            const long long per = (long long)c->cfg.max_batch * S * h * c->cfg.max_time * d;
+            a.kcache = c->kv + (long long)(ti * 2 + 0) * per; a.vcache = c->kv + (long long)(ti * 2 + 1) * per;
+            a.out = c->b.attn_o; a.ldo = Dq; a.scale = att_scale; a.softclamp = c->cfg.softclamp; a.commit = commit;
+            a.variant = c->cfg.time_attn_variant;
+            const double kbytes = (double)M * h * d * 4.0 * (2.0 * t + 4.0 + (commit ? 2.0 : 0.0));
+            const int ph = d4_prof_begin(c, D4_CLS_TIME_ATTN, kbytes, s);
+            const int rc = d4_time_attn(a, s);
+            d4_prof_end(c, ph, s);
+            D4_TRY(rc);
+            ++ti;
+        } else {
+            SmallAttnArgs a; memset(&a, 0, sizeof(a));
+            a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = S; a.n = S;
+            a.q = c->b.qkvgm; a.q_sb = (long long)S * c->ldq; a.q_si = c->ldq;
+            a.k = c->b.qkvgm + off_k; a.k_sb = a.q_sb; a.k_sj = c->ldq;
+            a.v = c->b.qkvgm + off_v; a.v_sb = a.q_sb; a.v_sj = c->ldq;
+            a.k_gamma = c->attn[i].k_gamma;
+            a.v0 = c->b.v0; a.v0_sb = (long long)S * Dkv; a.v0_sj = Dkv;
+            a.mix = c->b.qkvgm + off_m; a.mix_sb = a.q_sb; a.mix_sj = c->ldq;
+            a.gate = c->b.qkvgm + off_g; a.gate_sb = a.q_sb; a.gate_si = c->ldq;
+            a.out = c->b.attn_o; a.out_sb = (long long)S * Dq; a.out_si = Dq;
+            a.scale = att_scale; a.softclamp = c->cfg.softclamp; a.mask_agent = 1; a.belief = 1;
+            { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+        }
+        {
+            GemmArgs g = gemm_args(c->b.attn_o, Dq, nullptr, Dq, hid(2 * i + 1), D, M, D, Dq);
+            g.residual = x_in; g.ldr = D;
+            D4_TRY(d4_engine_gemm(c, g, c->attn[i].w_out, 0, s));
+        }
+        D4_TRY(d4_row_rstd(hid(2 * i + 1), D, rowmap_identity(), M, D, hrs(2 * i + 1), s));
+        D4_TRY(run_ff(c, c->ff[i], M, hid(2 * i + 1), D, rowmap_identity(), hrs(2 * i + 1), hid(2 * i + 2), D, rowmap_identity(), s));
+        D4_TRY(d4_row_rstd(hid(2 * i + 2), D, rowmap_identity(), M, D, hrs(2 * i + 2), s));
+        if (i != L - 1) {
+            D4_TRY(run_pool(c, c->pools[i], M, hid(2 * i + 2), hrs(2 * i + 2), 2 * i + 3, c->b.x_cur, s));
+            D4_TRY(d4_row_rstd(c->b.x_cur, D, rowmap_identity(), M, D, c->b.x_rstd, s));
+            x_in = c->b.x_cur; x_in_rstd = c->b.x_rstd;
+        }
+    }
+
+    // ---- final agent-token cross attention + feed-forward (reference dreamer4.py:3227-3238)
+    float* xf = c->b.x_cur;
+    D4_CUDA_OK(cudaMemcpyAsync(xf, hid(2 * L), MD * 4, cudaMemcpyDeviceToDevice, s));
+    const RowMap agent_rows = rowmap(1, S, S - 1);
+    D4_TRY(d4_row_rstd(xf, D, agent_rows, B, D, c->b.ag_rstd, s));
+    {
+        GemmArgs g = gemm_args(xf, D, nullptr, D, c->b.fa_q, c->ldfa, B, Dq + hq, D);
+        g.amap = agent_rows; g.row_scale = c->b.ag_rstd;
+        D4_TRY(d4_engine_gemm(c, g, c->fa.w_qg, 0, s));
+        GemmArgs g2 = gemm_args(hid(2 * L), D, nullptr, D, c->b.fa_kv, 2 * Dkv, M, 2 * Dkv, D);
+        g2.row_scale = hrs(2 * L);
+        D4_TRY(d4_engine_gemm(c, g2, c->fa.w_kv, 0, s));
+        SmallAttnArgs a; memset(&a, 0, sizeof(a));
+        a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = 1; a.n = S - 1;
+        a.q = c->b.fa_q; a.q_sb = c->ldfa; a.q_si = 0;
+        a.k = c->b.fa_kv; a.k_sb = (long long)S * 2 * Dkv; a.k_sj = 2 * Dkv;
+        a.v = c->b.fa_kv + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+        a.k_gamma = c->fa.k_gamma;
+        a.gate = c->b.fa_q + Dq; a.gate_sb = c->ldfa; a.gate_si = 0;
+        a.out = c->b.fa_att; a.out_sb = Dq; a.out_si = 0;
+        a.scale = att_scale;
+        { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+        GemmArgs g3 = gemm_args(c->b.fa_att, Dq, nullptr, Dq, xf, D, B, D, Dq);
+        g3.residual = xf; g3.ldr = D; g3.cmap = agent_rows;
+        D4_TRY(d4_engine_gemm(c, g3, c->fa.w_out, 0, s));
+    }
+    D4_TRY(d4_row_rstd(xf, D, agent_rows, B, D, c->b.ag_rstd, s));
+    D4_TRY(run_ff(c, c->fa_ff, B, xf, D, agent_rows, c->b.ag_rstd, xf, D, agent_rows, s));
+    // final attention-residual pool over all 2L+1 hiddens (reference dreamer4.py:3242-3243)
+    D4_TRY(d4_row_rstd(xf, D, rowmap_identity(), M, D, c->b.x_rstd, s));
+    D4_TRY(run_pool(c, c->pool_final, M, xf, c->b.x_rstd, c->n_hid, xf, s));
+
+    // ---- outputs: agent embedding and the latent prediction (reference dreamer4.py:7251, 4830-4834)
+    if (agent_out) D4_TRY(d4_copy_rows(xf + (long long)(S - 1) * D, (long long)S * D, agent_out, D, B, D, s));
+    if (pred_out) {
+        D4_TRY(d4_rmsnorm_rows(xf, D, rowmap(nsp, S, 1), c->lp_norm0, B * nsp, D, c->b.sp_n, D, s));
+        if (c->same_len) {
+            GemmArgs g = gemm_args(c->b.sp_n, D, nullptr, D, pred_out, Dl, B * N, Dl, D);
+            D4_TRY(d4_engine_gemm(c, g, c->lp_w, 0, s));
+        } else {
+            D4_TRY(d4_rmsnorm_rows(c->b.sp_n, D, rowmap_identity(), c->lp_norm_ctx, B * nsp, D, c->b.sp_n2, D, s));
+            GemmArgs g = gemm_args(c->b.sp_n2, D, nullptr, D, c->b.sp_kv, 2 * Dkv, B * nsp, 2 * Dkv, D);
+            D4_TRY(d4_engine_gemm(c, g, c->lp_w_kv, 0, s));
+            SmallAttnArgs a; memset(&a, 0, sizeof(a));
+            a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = N; a.n = nsp;
+            a.q = c->lp_q; a.q_sb = 0; a.q_si = Dq;
+            a.k = c->b.sp_kv; a.k_sb = (long long)nsp * 2 * Dkv; a.k_sj = 2 * Dkv;
+            a.v = c->b.sp_kv + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+            a.k_gamma = c->lp_k_gamma;
+            a.gate = c->lp_gate; a.gate_sb = 0; a.gate_si = hq;
+            a.out = c->b.lp_att; a.out_sb = (long long)N * Dq; a.out_si = Dq;
+            a.scale = att_scale;
+            { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+            GemmArgs g2 = gemm_args(c->b.lp_att, Dq, nullptr, Dq, pred_out, Dl, B * N, Dl, Dq);
+            D4_TRY(d4_engine_gemm(c, g2, c->lp_w_comb, 0, s));
+        }
+    }
+    return 0;
+}
+
+int check_ready(d4_ctx* c, int B, int t) {
+    if (!c) return d4_fail("null ctx");
+    if (!c->bound) return d4_fail("weights not bound: call d4_bind() after d4_set_weight()");
+    if (!c->ws) return d4_fail("buffers not set: call d4_set_buffers()");
+    if (B < 1 || B > c->cfg.max_batch) return d4_fail("batch %d outside 1..max_batch=%d", B, c->cfg.max_batch);
+    if (t < 0 || t >= c->cfg.max_time) return d4_fail("frame index %d outside the KV capacity max_time=%d", t, c->cfg.max_time);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int d4_pass(d4_ctx* c, int B, const float* latent, int signal_level, int step_size_log2, const int64_t* prev_actions,
+                       int64_t pa_stride, const int64_t* tasks, int t, int commit_kv, float* pred_out, float* agent_out, void* stream) {
+    D4_TRY(check_ready(c, B, t));
+    return run_pass(c, B, latent, signal_level, step_size_log2, prev_actions, pa_stride, tasks, t, commit_kv, pred_out, agent_out,
+                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int d4_frame(d4_ctx* c, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream) {
+    D4_TRY(check_ready(c, B, t));
+    if (!io || !io->noise_latent || !io->latents) return d4_fail("d4_frame: noise_latent and latents are required");
+    if (num_steps < 1 || num_steps > c->cfg.max_steps || (num_steps & (num_steps - 1)) || c->cfg.max_steps % num_steps)
+        return d4_fail("d4_frame: num_steps=%d must be a power of two dividing max_steps=%d", num_steps, c->cfg.max_steps);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int D = c->D, N = c->N, Dl = c->Dl;
+    const long long nlat = (long long)B * N * Dl;
+    const int step_size = c->cfg.max_steps / num_steps;
+    int step_log2 = 0; while ((1 << step_log2) < step_size) ++step_log2;
+    float* x = c->b.lat_x;
+    D4_CUDA_OK(cudaMemcpyAsync(x, io->noise_latent, nlat * 4, cudaMemcpyDeviceToDevice, s));
+    // denoising passes + the clean pass that commits this frame's keys/values (reference dreamer4.py:6484-6580)
+    for (int step = 0; step <= num_steps; ++step) {
+        const bool last = (step == num_steps);
+        const int signal = std::min(step * step_size, c->cfg.max_steps - 1);
+        D4_TRY(run_pass(c, B, x, signal, step_log2, io->prev_actions, io->pa_stride, io->tasks, t, last ? 1 : 0,
+                        last ? nullptr : c->b.pred, last ? c->b.agent : nullptr, s));
+        if (!last) {
+            const float tau = (float)signal / (float)c->cfg.max_steps;
+            D4_TRY(d4_flow_step(x, c->b.pred, nlat, 1.f - tau, (float)step_size / (float)c->cfg.max_steps, s));
+        }
+    }
+    D4_TRY(d4_store_latents(x, io->latents, B, (long long)N * Dl, io->latents_bs, s));
+    if (io->agent_embed) D4_TRY(d4_copy_rows(c->b.agent, D, io->agent_embed, io->agent_bs, B, D, s));
+    // reward head: Ensemble member 0 = RMSNorm -> Linear(no bias) -> HL-Gauss expectation (reference dreamer4.py:6598-6601)
+    if (io->rewards) {
+        D4_TRY(d4_row_rstd(c->b.agent, D, rowmap_identity(), B, D, c->b.ag_rstd, s));
+        GemmArgs g = gemm_args(c->b.agent, D, c->reward_w, D, c->b.bins, c->cfg.reward_bins, B, c->cfg.reward_bins, D);
+        g.row_scale = c->b.ag_rstd;
+        D4_TRY(d4_engine_gemm(c, g, plain(c->reward_w), 1, s));
+        D4_TRY(d4_hl_gauss_decode(c->b.bins, c->cfg.reward_bins, B, c->cfg.reward_bins, c->reward_centers, io->rewards, io->rewards_bs, s));
+    }
+    // terminal head (reference dreamer4.py:6605-6616)
+    if (c->cfg.predict_terminals && io->terminal_uniform && io->lens && io->terminals) {
+        D4_TRY(d4_mean_tokens(x, B, N, Dl, c->b.term_in, s));
+        D4_TRY(d4_mlp_forward(c, c->terminal, c->b.term_in, Dl, B, c->b.hbuf0, c->b.hbuf1, c->b.bins, 1, s));
+        D4_TRY(d4_terminal_update(c->b.bins, 1, io->terminal_uniform, B, t, reinterpret_cast<long long*>(io->lens), io->terminals, s));
+    }
+    // policy head -> logits -> gumbel-argmax; value head (reference dreamer4.py:6628-6662)
+    if (c->has_actions && io->actions) {
+        if (!io->action_uniform || !io->log_probs) return d4_fail("d4_frame: action_uniform and log_probs are required with actions");
+        float* pe = (c->policy.layers & 1) ? c->b.hbuf0 : c->b.hbuf1;   // buffer not used by the last hidden layer
+        D4_TRY(d4_mlp_forward(c, c->policy, c->b.agent, D, B, c->b.hbuf0, c->b.hbuf1, pe, c->cfg.policy_hidden, s));
+        GemmArgs g = gemm_args(pe, c->cfg.policy_hidden, c->unembed, c->unembed_ld, c->b.logits, c->ldlog, B, c->A_total, c->cfg.policy_hidden);
+        D4_TRY(d4_engine_gemm(c, g, plain(c->unembed), 1, s));
+        if (io->logits) D4_TRY(d4_copy_rows(c->b.logits, c->ldlog, io->logits, io->logits_bs, B, c->A_total, s));
+        const float inv_temp = 1.f / fmaxf(discrete_temperature, 1e-10f);
+        D4_TRY(d4_sample_actions(c->b.logits, c->ldlog, io->action_uniform, c->A_total, B, c->na, c->b.sizes_offs, inv_temp,
+                                 reinterpret_cast<long long*>(io->actions), io->actions_bs, io->log_probs, io->log_probs_bs, s));
+        if (io->values) {
+            D4_TRY(d4_mlp_forward(c, c->value, c->b.agent, D, B, c->b.hbuf0, c->b.hbuf1, c->b.bins, c->cfg.value_bins, s));
+            D4_TRY(d4_hl_gauss_decode(c->b.bins, c->cfg.value_bins, B, c->cfg.value_bins, c->value_centers, io->values, io->values_bs, s));
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone operators
+extern "C" int d4_time_attn_decode(int M, int heads, int query_heads, int dim_head, int t, int Tmax, const float* qkvgm, int64_t ld,
+                                   const float* v0, const float* k_gamma, const float* inv_freq, float* kcache, float* vcache, float* out,
+                                   float softclamp, int commit, int variant, void* stream) {
+    if (query_heads % heads) return d4_fail("query_heads must be a multiple of heads");
+    TimeAttnArgs a; memset(&a, 0, sizeof(a));
+    const int Dq = query_heads * dim_head, Dkv = heads * dim_head;
+    a.M = M; a.hkv = heads; a.g = query_heads / heads; a.d = dim_head; a.t = t; a.Tmax = Tmax;
+    a.qkvgm = qkvgm; a.ld = ld; a.off_k = Dq; a.off_v = Dq + Dkv; a.off_g = Dq + 2 * Dkv; a.off_m = Dq + 2 * Dkv + query_heads;
+    a.v0 = v0; a.ldv0 = Dkv; a.k_gamma = k_gamma; a.inv_freq = inv_freq; a.kcache = kcache; a.vcache = vcache;
+    a.out = out; a.ldo = Dq; a.scale = 1.f / sqrtf((float)dim_head); a.softclamp = softclamp; a.commit = commit; a.variant = variant;
+    return d4_time_attn(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int d4_linear(int precision, int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_lo,
+                         const float* bias, const float* row_scale, const float* residual, int64_t ldr, int act, float* C, int64_t ldc,
+                         void* stream) {
+    GemmArgs g = gemm_args(A, lda, W, ldw, C, ldc, M, N, K);
+    g.bias = bias; g.row_scale = row_scale; g.residual = residual; g.ldr = ldr; g.act = act; g.W_lo = W_lo;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (precision == D4_PREC_FP32) return d4_gemm_simt(g, s);
+    if (!d4_gemm_tc_supported(g)) return d4_fail("d4_linear: shape/alignment not supported by the tcgen05 path (need K%%4==0, 16B-aligned rows)");
+    if (precision == D4_PREC_TF32X3) { if (!W_lo) return d4_fail("d4_linear: tf32x3 needs W_lo"); return d4_gemm_tc(g, 3, s); }
+    return d4_gemm_tc(g, 1, s);
+}

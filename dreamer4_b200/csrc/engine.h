@@ -1,0 +1,71 @@
+// d4_ctx: configuration, bound weight pointers and the workspace plan of one model on one device.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/d4b200.h"
+#include "kernels.h"
+
+struct LinW { const float* w = nullptr; const float* hi = nullptr; const float* lo = nullptr; };   // GEMM weight (+ its tf32 hi/lo split for tf32x3)
+
+struct AttnLayerW { LinW w; const float* b; const float* k_gamma; LinW w_out; };
+struct FFW { LinW w_in; const float* b_in; LinW w_out; const float* b_out; };
+struct PoolW { LinW w_qg; LinW w_kv; const float* k_gamma; LinW w_out; };
+struct MlpW { int layers = 0; const float* w[D4_MAX_MLP_LAYERS]; const float* b[D4_MAX_MLP_LAYERS];
+              const float* lnw[D4_MAX_MLP_LAYERS]; const float* lnb[D4_MAX_MLP_LAYERS]; int dims[D4_MAX_MLP_LAYERS + 1]; };
+
+struct d4_ctx {
+    d4_config cfg;
+    // derived
+    int S, D, Dl, N, nsp, nreg, L, y, h, hq, d, Dq, Dkv, hp, dp, Dp, inner, inner_pad, n_hid;
+    int has_actions, na, A_total, same_len;
+    int NQ, ldq;            // fused qkv+gates+mix row
+    int ldpq;               // pool q+gates row
+    int ldfa;               // agent q+gates row
+    int ldlog;              // logits row
+    std::vector<int> is_time;
+    int act_off[D4_MAX_ACTION_TYPES];
+
+    std::unordered_map<std::string, std::pair<const float*, int64_t>> table;
+    bool bound = false;
+
+    // bound weights
+    const float *sig_emb, *step_emb, *registers, *agent_embed, *action_learned, *action_emb, *task_emb;
+    LinW l2s_w_kv, l2s_w_out, l2s_w; const float *l2s_q, *l2s_gate, *l2s_k_gamma, *l2s_b;
+    LinW vr_w;
+    std::vector<AttnLayerW> attn; std::vector<FFW> ff; std::vector<PoolW> pools; PoolW pool_final;
+    PoolW fa;               // final agent cross-attention (w_qg, w_kv, k_gamma, w_out)
+    FFW fa_ff;
+    const float *lp_norm0, *lp_norm_ctx, *lp_q, *lp_gate, *lp_k_gamma; LinW lp_w_kv, lp_w_comb, lp_w;
+    const float* inv_freq;
+    const float *reward_w, *reward_centers, *value_centers;
+    MlpW policy, value, terminal;
+    const float* unembed; int64_t unembed_ld;
+
+    // buffers
+    unsigned char* ws = nullptr; int64_t ws_bytes = 0; float* kv = nullptr; int64_t kv_bytes_ = 0;
+    int64_t ws_need = 0;
+    struct {
+        float *lat_x, *lat_rstd, *kv_l, *att_l, *hid, *hid_rstd, *x_cur, *x_rstd, *qkvgm, *v0, *attn_o, *ff_mid,
+              *pool_qg, *pool_kv, *pool_att, *fa_kv, *fa_q, *fa_att, *ag_rstd, *sp_n, *sp_n2, *sp_kv, *lp_att, *pred,
+              *hbuf0, *hbuf1, *logits, *bins, *agent, *term_in;
+        int* sizes_offs;
+    } b;
+    bool sizes_uploaded = false;
+
+    // in-situ profiling (d4_profile / d4_profile_read)
+    bool prof_on = false;
+    struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+    std::vector<ProfRec> prof;          // records in use
+    std::vector<ProfRec> prof_pool;     // created events, reused
+};
+
+enum { D4_CLS_GEMM = 0, D4_CLS_TIME_ATTN = 1, D4_CLS_SMALL_ATTN = 2, D4_CLS_OTHER = 3 };
+// usage: int h = d4_prof_begin(c, cls, work, s); launch...; d4_prof_end(c, h, s);
+int d4_prof_begin(d4_ctx* c, int cls, double work, cudaStream_t s);
+void d4_prof_end(d4_ctx* c, int handle, cudaStream_t s);
+
+int d4_engine_plan(d4_ctx* c);
+int d4_engine_gemm(d4_ctx* c, GemmArgs g, const LinW& w, int force_fp32, cudaStream_t s);
+int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, int M, float* buf0, float* buf1, float* out, long long ldo,
+                   cudaStream_t s);

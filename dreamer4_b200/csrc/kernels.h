@@ -1,0 +1,71 @@
+// Internal launch-wrapper declarations shared by the engine and the C-ABI unit entry points.
+#pragma once
+#include "common.cuh"
+
+// ---- GEMM (gemm_simt.cu / gemm_tc.cu)
+int d4_gemm_simt(const GemmArgs& g, cudaStream_t stream);
+// tcgen05 path: terms = 1 (tf32) or 3 (tf32x3 split: A split in shared memory, W_lo supplied)
+int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream);
+int d4_gemm_tc_supported(const GemmArgs& g);
+
+// ---- row-wise kernels (rowops.cu)
+struct AssembleArgs {
+    float* tokens;               // (B, S, D)
+    int B, S, D, nsp, nreg, has_actions, na;
+    const float* sig_emb; const float* step_emb; int signal, step;
+    const float* registers;      // (nreg, D)
+    const float* agent_embed;    // (D)
+    const float* action_learned; // (D)
+    const float* action_emb;     // (A_total, D)
+    const long long* prev_actions; long long pa_stride;   // (B, na) int64 rows with stride, nullptr at frame 0
+    int act_off[8];
+    const float* task_emb; const long long* tasks;
+};
+int d4_row_rstd(const float* x, long long ldx, RowMap map, int M, int D, float* out, cudaStream_t s);
+int d4_rmsnorm_rows(const float* x, long long ldx, RowMap map, const float* w, int M, int D, float* out, long long ldo, cudaStream_t s);
+int d4_ln_act_rows(const float* x, long long ldx, const float* w, const float* b, int M, int D, float* out, long long ldo, int act,
+                   float* save_mean, float* save_rstd, cudaStream_t s);
+int d4_assemble_tokens(const AssembleArgs& a, cudaStream_t s);
+int d4_flow_step(float* x, const float* pred, long long n, float one_minus_tau, float dt, cudaStream_t s);
+int d4_store_latents(const float* x, float* out, int B, long long per_b, long long out_bstride, cudaStream_t s);
+int d4_copy_rows(const float* src, long long lds, float* dst, long long ldd, int M, int D, cudaStream_t s);
+int d4_hl_gauss_decode(const float* logits, long long ld, int M, int K, const float* centers, float* out, long long out_stride, cudaStream_t s);
+int d4_sample_actions(const float* logits, long long ld, const float* u, long long ldu, int B, int na, const int* sizes_offs, float inv_temp,
+                      long long* actions, long long act_stride, float* logp, long long lp_stride, cudaStream_t s);
+int d4_mean_tokens(const float* x, int B, int N, int Dl, float* out, cudaStream_t s);
+int d4_terminal_update(const float* logit, long long ld, const float* u, int B, int frame, long long* lens, unsigned char* terminals, cudaStream_t s);
+
+// ---- attention (attn.cu)
+// Generic small attention: one warp per (batch item, kv head); K/V of the item staged in shared memory.
+// Covers the 15-token space attention (softclamp + agent mask + value-residual + belief), the latent<->spatial
+// learned-query pools, the attention-residual pools over layer hiddens and the final agent cross-attention.
+struct SmallAttnArgs {
+    int nb, hkv, g, d, nq, n;
+    const float* q; long long q_sb, q_si;          // q(b,i,hq)   = q + b*q_sb + i*q_si + hq*d       (hq = hk*g + gi)
+    const float* k; long long k_sb, k_sj;          // k(b,j,hk)   = k + b*k_sb + j*k_sj + hk*d
+    const float* v; long long v_sb, v_sj;
+    const float* k_gamma;                          // (hkv, d) MultiHeadRMSNorm gamma
+    const float* v0; long long v0_sb, v0_sj;       // value residual (addressed like v) or nullptr
+    const float* mix; long long mix_sb, mix_sj;    // mix logit(b,j,hk) = mix + b*mix_sb + j*mix_sj + hk
+    const float* gate; long long gate_sb, gate_si; // gate logit(b,i,hq) = gate + b*gate_sb + i*gate_si + hq, or nullptr
+    float* out; long long out_sb, out_si;          // out(b,i,hq) = out + b*out_sb + i*out_si + hq*d
+    float scale, softclamp;
+    int mask_agent, belief;
+};
+int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s);
+
+// K1: time-decode attention over the in-place KV cache (+ append on the clean pass).
+struct TimeAttnArgs {
+    int M, hkv, g, d, t, Tmax;
+    const float* qkvgm; long long ld;              // row: [q (hq*d) | k (hkv*d) | v (hkv*d) | gate logits (hq) | mix logits (hkv)]
+    int off_k, off_v, off_g, off_m;
+    const float* v0; long long ldv0;               // (M, hkv*d)
+    const float* k_gamma;                          // (hkv, d)
+    const float* inv_freq;                         // (d/2)
+    float* kcache; float* vcache;                  // (M, hkv, Tmax, d) each
+    float* out; long long ldo;                     // (M, hq*d)
+    float scale, softclamp;
+    int commit;
+    int variant;                                   // 0 = ld.global staged, 1 = cp.async.bulk ring
+};
+int d4_time_attn(const TimeAttnArgs& a, cudaStream_t s);

@@ -1,0 +1,606 @@
+"""Host-side mirror of the reference's `DynamicsWorldModel` for the imagination hot path.
+
+Same constructor keywords, parameter names (state_dict keys) and method signatures as the reference
+(reference dreamer4/dreamer4.py:4660-4778 constructor, 6307-6774 `generate`, 5893-6305 `learn_from_experience`),
+with the per-frame work handed to the hand-written sm_100a kernels behind include/d4b200.h.  PyTorch is used for
+device memory, the RNG stream and autograd plumbing only.  There is no CPU / eager fallback: the model must live on
+a CUDA device and libd4b200.so must be built, otherwise the calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import D4Error, check, ptr
+from .experience import Actions, DynamicsIntermediates, Experience, TransformerIntermediates
+from .packing import hl_gauss_tables, mlp_param_names, pack
+
+
+def exists(v):
+    return v is not None
+
+
+def default(v, d):
+    return v if exists(v) else d
+
+
+@dataclass
+class ModelConfig:
+    dim: int
+    dim_latent: int
+    num_latent_tokens: int
+    num_spatial_tokens: int = 4
+    num_register_tokens: int = 8
+    depth: int = 4
+    time_block_every: int = 4
+    attn_heads: int = 8
+    query_heads: int = 8
+    attn_dim_head: int = 64
+    attn_softclamp_value: float = 50.
+    max_steps: int = 64
+    num_discrete_actions: tuple = ()
+    multi_token_pred_len: int = 8
+    policy_head_mlp_depth: int = 3
+    value_head_mlp_depth: int = 3
+    terminal_mlp_depth: int = 1
+    ff_activation: str = 'silu'
+    ff_expansion_factor: float = 4.
+    reward_range: tuple = (-20., 20.)
+    reward_num_bins: int = 255
+    value_range: tuple = (-20., 20.)
+    value_num_bins: int = 255
+    hl_gauss_sigma_to_bin_ratio: float = 2.
+    hl_gauss_eps: float = 1e-10
+    predict_terminals: bool = True
+    num_tasks: int = 0
+    num_agents: int = 1
+    pool_heads: int = 4
+    pool_dim_head: int = 64
+
+    @property
+    def has_actions(self):
+        return len(self.num_discrete_actions) > 0
+
+    @property
+    def same_len(self):
+        return self.num_spatial_tokens == self.num_latent_tokens
+
+    @property
+    def tokens_per_frame(self):        # reference dreamer4.py:7222
+        return 1 + self.num_spatial_tokens + self.num_register_tokens + int(self.has_actions) + 1
+
+    @property
+    def is_time(self):                 # reference dreamer4.py:2845
+        return [((i + 1) % self.time_block_every) == 0 for i in range(self.depth)]
+
+    @property
+    def num_time_layers(self):
+        return sum(self.is_time)
+
+    @property
+    def ff_inner(self):                # reference dreamer4.py:2094
+        return int(self.dim * self.ff_expansion_factor * 2 / 3)
+
+    @property
+    def ff_inner_pad(self):
+        return (self.ff_inner + 31) // 32 * 32
+
+    @property
+    def total_actions(self):
+        return sum(self.num_discrete_actions)
+
+
+class _Node(nn.Module):
+    """Bare container used to reproduce the reference's state_dict key hierarchy."""
+
+
+def _linear_w(out_f, in_f):
+    w = torch.empty(out_f, in_f)
+    nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+    return w
+
+
+def _linear_b(out_f, in_f):
+    bound = 1 / math.sqrt(in_f) if in_f > 0 else 0
+    return torch.empty(out_f).uniform_(-bound, bound)
+
+
+_UNSUPPORTED_DEFAULTS = dict(
+    video_tokenizer=None, aux_image_encoder=None, num_video_views=1, mot_temporal=False, dim_proprio=None, dim_state=None,
+    dim_critic_state=None, reward_encoder_type='hl_gauss', critic_state_embedder=None, spatial_pre_encoder_depth=0,
+    action_pre_encoder_depth=0, actor_depth=0, critic_depth=0, pred_orig_latent=True, use_time_rnn=False,
+    add_reward_embed_to_agent_token=False, add_state_pred_head=False, agent_predicts_state=False, num_continuous_actions=0,
+    num_latent_genes=0, time_attention_use_pope=False, latent_ar=False, identity_latents_to_spatial=False,
+    has_aug_conditioning=False, ssl_lapo=False, ssl_tem=False, actor_spr=False, clip_values=False,
+    policy_head_mlp_activation='silu', value_head_mlp_activation='silu', state_terminal_pred_mlp_activation='silu',
+)
+
+
+class DynamicsWorldModel(nn.Module):
+    """Drop-in for the reference class on the imagination path (generate + learn_from_experience).
+
+    Extra keyword arguments (not in the reference): `precision` in {'fp32', 'tf32', 'tf32x3'} — arithmetic of the
+    transformer's dense layers (heads always run exact fp32), `time_attn_variant` (K1 kernel variant)."""
+
+    def __init__(self, dim, dim_latent, *, num_latent_tokens=None, max_steps=64, num_register_tokens=8, num_spatial_tokens=4,
+                 num_agents=1, num_tasks=0, reward_encoder_kwargs: dict = dict(), value_encoder_kwargs: Optional[dict] = None,
+                 depth=4, time_block_every=4, attn_kwargs: dict = dict(), transformer_kwargs: dict = dict(), attn_heads=8,
+                 attn_dim_head=64, attn_softclamp_value=50., ff_kwargs: dict = dict(), num_discrete_actions=0,
+                 multi_token_pred_len=8, value_head_mlp_depth=3, policy_head_mlp_depth=3, predict_terminals=True,
+                 predict_terminal_mlp_kwargs: dict = dict(depth=1), gae_discount_factor=0.997, gae_lambda=0.95, ppo_eps_clip=0.2,
+                 use_delight_gating=True, delight_temperature=1., normalize_advantages=None, policy_entropy_weight=.01,
+                 gae_use_accelerated=False, precision='fp32', time_attn_variant=0, **kwargs):
+        super().__init__()
+        for k, v in kwargs.items():
+            if k not in _UNSUPPORTED_DEFAULTS:
+                continue                    # training-only knobs (loss weights, ssl kwargs, ...) do not touch this path
+            if v != _UNSUPPORTED_DEFAULTS[k]:
+                raise NotImplementedError(f'{k}={v!r}: this branch of the reference is outside the B200 hot path (SURVEY.md section 8)')
+        assert exists(num_latent_tokens), 'num_latent_tokens is required (no video tokenizer is attached on this path)'
+        assert precision in _lib.PREC, f'precision must be one of {list(_lib.PREC)}'
+        if transformer_kwargs:
+            raise NotImplementedError('transformer_kwargs overrides are outside the B200 hot path')
+        nda = num_discrete_actions
+        nda = (nda,) if isinstance(nda, int) else tuple(nda)
+        nda = tuple(int(n) for n in nda if n > 0)
+        rk = dict(reward_encoder_kwargs or {})
+        vk = rk if value_encoder_kwargs is None else dict(value_encoder_kwargs)
+        ffk = dict(ff_kwargs or {})
+        act = ffk.get('activation', 'silu')
+        if act not in ('silu', 'gelu'):
+            raise NotImplementedError(f"feed-forward activation {act!r}: kernels cover the gated silu / gelu variants")
+        self.cfg = cfg = ModelConfig(
+            dim=dim, dim_latent=dim_latent, num_latent_tokens=num_latent_tokens, num_spatial_tokens=num_spatial_tokens,
+            num_register_tokens=num_register_tokens, depth=depth, time_block_every=time_block_every, attn_heads=attn_heads,
+            query_heads=(attn_kwargs or {}).get('query_heads') or attn_heads, attn_dim_head=attn_dim_head,
+            attn_softclamp_value=attn_softclamp_value, max_steps=max_steps, num_discrete_actions=nda,
+            multi_token_pred_len=multi_token_pred_len, policy_head_mlp_depth=policy_head_mlp_depth,
+            value_head_mlp_depth=value_head_mlp_depth, terminal_mlp_depth=(predict_terminal_mlp_kwargs or {}).get('depth', 1),
+            ff_activation=act, ff_expansion_factor=ffk.get('expansion_factor', 4.),
+            reward_range=tuple(rk.get('reward_range', (-20., 20.))), reward_num_bins=rk.get('num_bins', 255),
+            value_range=tuple(vk.get('reward_range', (-20., 20.))), value_num_bins=vk.get('num_bins', 255),
+            predict_terminals=predict_terminals, num_tasks=num_tasks, num_agents=num_agents)
+        self.dim, self.depth, self.max_steps = dim, depth, max_steps
+        self.predict_terminals = predict_terminals
+        self.precision, self.time_attn_variant = precision, time_attn_variant
+        self.gae_discount_factor, self.gae_lambda = gae_discount_factor, gae_lambda
+        self.ppo_eps_clip, self.policy_entropy_weight = ppo_eps_clip, policy_entropy_weight
+        self.use_delight_gating, self.delight_temperature = use_delight_gating, delight_temperature
+        self.normalize_advantages = normalize_advantages
+        self.latent_shape = (num_latent_tokens, dim_latent)
+        self.video_tokenizer = None
+        self._build_parameters()
+        self._ctx = None
+        self._ctx_key = None
+        self._packed = None
+        self._packed_version = None
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ parameters (reference state_dict layout)
+
+    def _reg(self, path, tensor, buffer=False, persistent=True):
+        parts = path.split('.')
+        mod = self
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, _Node())
+            mod = mod._modules[p]
+        if buffer:
+            mod.register_buffer(parts[-1], tensor, persistent=persistent)
+        else:
+            mod.register_parameter(parts[-1], nn.Parameter(tensor))
+
+    def _reg_attention(self, p, dim, dim_kv_in, heads, query_heads, dim_head, norm_context, value_residual):
+        self._reg(p + 'norm.weight', torch.ones(dim))
+        if norm_context:
+            self._reg(p + 'norm_context.weight', torch.ones(dim_kv_in))
+        self._reg(p + 'to_q.weight', _linear_w(query_heads * dim_head, dim))
+        self._reg(p + 'to_k.weight', _linear_w(heads * dim_head, dim_kv_in))
+        self._reg(p + 'to_v.weight', _linear_w(heads * dim_head, dim_kv_in))
+        self._reg(p + 'to_out.weight', _linear_w(dim, query_heads * dim_head))
+        self._reg(p + 'to_gates.0.weight', _linear_w(query_heads, dim))
+        self._reg(p + 'k_heads_rmsnorm.gamma', torch.zeros(heads, dim_head))
+        if value_residual:
+            self._reg(p + 'to_learned_value_residual_mix.0.weight', _linear_w(heads, dim))
+            self._reg(p + 'to_learned_value_residual_mix.0.bias', _linear_b(heads, dim))
+
+    def _reg_ff(self, p, dim, inner):
+        self._reg(p + 'norm.weight', torch.ones(dim))
+        self._reg(p + 'proj_in.weight', _linear_w(2 * inner, dim))
+        self._reg(p + 'proj_in.bias', _linear_b(2 * inner, dim))
+        self._reg(p + 'proj_out.weight', _linear_w(dim, inner))
+        self._reg(p + 'proj_out.bias', _linear_b(dim, inner))
+
+    def _reg_mlp(self, p, dims):
+        n = len(dims) - 1
+        for l in range(n):
+            self._reg(f'{p}.layers.{l}.0.weight', _linear_w(dims[l + 1], dims[l]))
+            self._reg(f'{p}.layers.{l}.0.bias', _linear_b(dims[l + 1], dims[l]))
+            if l < n - 1:
+                self._reg(f'{p}.layers.{l}.1.weight', torch.ones(dims[l + 1]))
+                self._reg(f'{p}.layers.{l}.1.bias', torch.zeros(dims[l + 1]))
+
+    def _build_parameters(self):
+        c = self.cfg
+        D, Dl, h, hq, d = c.dim, c.dim_latent, c.attn_heads, c.query_heads, c.attn_dim_head
+        self._reg('register_tokens', torch.randn(c.num_register_tokens, D) * 1e-2)
+        self._reg('agent_learned_embed', torch.randn(c.num_agents, D) * 1e-2)
+        self._reg('action_learned_embed', torch.randn(c.num_agents, D) * 1e-2)
+        self._reg('reward_learned_embed', torch.randn(c.num_agents, D) * 1e-2)
+        self._reg('latent_genes', torch.randn(0, D) * 1e-2)
+        for name in ('ema_returns_mean', 'ema_returns_var'):
+            self._reg(name, torch.zeros(()), buffer=True)
+        for name in ('reward_loss_weight', 'terminal_loss_weight', 'discrete_action_loss_weight', 'continuous_action_loss_weight'):
+            self._reg(name, torch.ones(()), buffer=True)
+        if c.same_len:          # reference dreamer4.py:4819-4834
+            self._reg('latents_to_spatial_tokens.weight', _linear_w(D, Dl))
+            self._reg('latents_to_spatial_tokens.bias', _linear_b(D, Dl))
+        else:
+            self._reg('latents_to_spatial_tokens.queries', torch.randn(c.num_spatial_tokens, D) * 1e-2)
+            self._reg_attention('latents_to_spatial_tokens.attn.', D, Dl, h, hq, d, True, False)
+        self._reg('to_latent_pred.0.weight', torch.ones(D))
+        if not c.same_len:
+            self._reg('to_latent_pred.1.queries', torch.randn(c.num_latent_tokens, D) * 1e-2)
+            self._reg_attention('to_latent_pred.1.attn.', D, D, h, hq, d, True, False)
+        self._reg('to_latent_pred.2.weight', _linear_w(Dl, D))
+        self._reg('signal_levels_embed.weight', torch.randn(c.max_steps, D // 2))
+        self._reg('step_size_embed.weight', torch.randn(int(math.log2(c.max_steps)), D // 2))
+        self._reg('task_embed.weight', torch.randn(c.num_tasks, D))
+        hid = 4 * D
+        self._reg_mlp('policy_head', (D, *((hid,) * (c.policy_head_mlp_depth + 1)), hid))
+        A = c.total_actions
+        self._reg('action_embedder.discrete_action_unembed', torch.randn(A, c.multi_token_pred_len, hid) * 1e-2)
+        self._reg('action_embedder.continuous_action_unembed', torch.randn(0, c.multi_token_pred_len, hid, 2) * 1e-2)
+        self._reg('action_embedder.discrete_action_embed.weight', torch.randn(A, D))
+        self._reg('action_embedder.continuous_action_embed.weight', torch.randn(0, D))
+        for e in range(c.multi_token_pred_len):
+            self._reg(f'to_reward_pred.nets.{e}.0.weight', torch.ones(D))
+            self._reg(f'to_reward_pred.nets.{e}.1.weight', _linear_w(c.reward_num_bins, D))
+        if c.predict_terminals:
+            th = 4 * Dl
+            self._reg_mlp('to_state_terminal_pred.0', (Dl, *((th,) * (c.terminal_mlp_depth + 1)), 1))
+        self._reg_mlp('value_head', (D, *((hid,) * (c.value_head_mlp_depth + 1)), c.value_num_bins))
+        inv_freq = 1.0 / (10000. ** (torch.arange(0, d, 2).float() / d))          # Rotary1D, reference dreamer4.py:1604-1612
+        self._reg('transformer.time_rotary.inv_freq', inv_freq, buffer=True)
+        self._reg('transformer.to_value_residual.0.weight', torch.ones(D))
+        self._reg('transformer.to_value_residual.1.weight', _linear_w(h * d, D))
+        for i in range(c.depth):
+            self._reg_attention(f'transformer.layers.{i}.2.fn.', D, D, h, hq, d, False, True)
+            self._reg_ff(f'transformer.layers.{i}.3.fn.', D, c.ff_inner)
+        for i in range(c.depth - 1):
+            self._reg_attention(f'transformer.attn_pools.{i}.fn.attn.', D, D, c.pool_heads, c.pool_heads, c.pool_dim_head, True, False)
+        self._reg_attention('transformer.final_attn_pool.fn.attn.', D, D, c.pool_heads, c.pool_heads, c.pool_dim_head, True, False)
+        self._reg_attention('transformer.final_special_cross_attn.fn.', D, D, h, hq, d, True, True)
+        self._reg_ff('transformer.final_special_ff.fn.', D, c.ff_inner)
+
+    @property
+    def device(self):
+        return self.register_tokens.device
+
+    def _named(self, prefixes):
+        return [p for n, p in self.named_parameters() if n.startswith(prefixes)]
+
+    def policy_head_parameters(self):      # reference dreamer4.py:5343-5352
+        return self._named(('policy_head.', 'action_embedder.'))
+
+    def value_head_parameters(self):       # reference dreamer4.py:5354-5363
+        return self._named(('value_head.',))
+
+    # ------------------------------------------------------------------ engine plumbing
+
+    def _require_cuda(self):
+        if self.device.type != 'cuda':
+            raise D4Error('dreamer4_b200 runs on CUDA only: move the model to a B200 (`model.cuda()`); there is no CPU fallback')
+
+    def _frozen_version(self):
+        return sum(p._version for n, p in self.named_parameters() if not n.startswith(('policy_head.', 'value_head.', 'to_state_terminal_pred.'))
+                   and n != 'action_embedder.discrete_action_unembed')
+
+    def _engine(self, batch, max_time, agent_index=0):
+        """(Re)creates the native context for this (batch, max_time) capacity and binds weights."""
+        self._require_cuda()
+        lib = _lib.load()
+        c = self.cfg
+        dev = self.device
+        key = (batch, max_time, agent_index, self.precision, self.time_attn_variant, dev.index)
+        if self._ctx is not None and self._ctx_key != key:
+            self._release()
+        if self._ctx is None:
+            cc = _lib.d4_config()
+            cc.dim, cc.dim_latent, cc.num_latent_tokens = c.dim, c.dim_latent, c.num_latent_tokens
+            cc.num_spatial_tokens, cc.num_register_tokens = c.num_spatial_tokens, c.num_register_tokens
+            cc.depth, cc.time_block_every = c.depth, c.time_block_every
+            cc.heads, cc.query_heads, cc.dim_head = c.attn_heads, c.query_heads, c.attn_dim_head
+            cc.pool_heads, cc.pool_dim_head = c.pool_heads, c.pool_dim_head
+            cc.ff_inner, cc.ff_inner_pad, cc.ff_act = c.ff_inner, c.ff_inner_pad, 1 if c.ff_activation == 'gelu' else 0
+            cc.max_steps = c.max_steps
+            cc.num_action_types = len(c.num_discrete_actions)
+            for i, n in enumerate(c.num_discrete_actions):
+                cc.action_sizes[i] = n
+            cc.policy_layers, cc.policy_hidden = c.policy_head_mlp_depth + 2, 4 * c.dim
+            cc.value_layers, cc.value_hidden = c.value_head_mlp_depth + 2, 4 * c.dim
+            cc.terminal_layers, cc.terminal_hidden = c.terminal_mlp_depth + 2, 4 * c.dim_latent
+            cc.predict_terminals = int(c.predict_terminals)
+            cc.reward_bins, cc.value_bins, cc.num_tasks = c.reward_num_bins, c.value_num_bins, c.num_tasks
+            cc.softclamp = c.attn_softclamp_value
+            cc.max_batch, cc.max_time = batch, max_time
+            cc.precision, cc.time_attn_variant = _lib.PREC[self.precision], self.time_attn_variant
+            ctx = C.c_void_p()
+            check(lib.d4_ctx_create(C.byref(cc), C.byref(ctx)))
+            self._ctx, self._ctx_key = ctx, key
+            ws_bytes, kv_bytes = lib.d4_workspace_bytes(ctx), lib.d4_kv_bytes(ctx)
+            with torch.cuda.device(dev):
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                y = max(c.num_time_layers, 1)
+                kv = torch.zeros(y, 2, batch * c.tokens_per_frame, c.attn_heads, max_time, c.attn_dim_head, device=dev)
+                check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv.numel() * 4))
+            self._bufs = dict(ws=ws, kv=kv)
+            self._packed_version = None
+        ver = (self._frozen_version(), agent_index)
+        if self._packed_version != ver:
+            sd = {k: v for k, v in self.state_dict().items()}
+            self._packed = pack(sd, c, dev, agent_index=agent_index, split=self.precision == 'tf32x3')
+            for name, t in self._packed.items():
+                check(lib.d4_set_weight(self._ctx, name.encode(), ptr(t), t.numel()))
+            params = dict(self.named_parameters())
+            heads = [('policy', 'policy_head', c.policy_head_mlp_depth + 2), ('value', 'value_head', c.value_head_mlp_depth + 2)] if c.has_actions else []
+            if c.predict_terminals:
+                heads.append(('terminal', 'to_state_terminal_pred.0', c.terminal_mlp_depth + 2))
+            for short, prefix, nl in heads:
+                for pname, key_ in mlp_param_names(prefix, nl):
+                    t = params[key_]
+                    assert t.is_contiguous()
+                    check(lib.d4_set_weight(self._ctx, f'{short}.{pname}'.encode(), ptr(t), t.numel()))
+            if c.has_actions:
+                un = params['action_embedder.discrete_action_unembed']          # (A, mtp, 4D): head 0 rows, row stride mtp*4D
+                check(lib.d4_set_weight(self._ctx, b'unembed', ptr(un), un.stride(0)))
+            check(lib.d4_bind(self._ctx))
+            self._packed_version = ver
+        return lib, self._ctx
+
+    def _release(self):
+        if self._ctx is not None:
+            _lib.load().d4_ctx_destroy(self._ctx)
+        self._ctx, self._ctx_key, self._bufs, self._packed, self._packed_version = None, None, {}, None, None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._release()           # parameter storage moved: borrowed pointers are stale
+        return out
+
+    # ------------------------------------------------------------------ generate
+
+    @torch.no_grad()
+    def generate(self, time_steps, num_steps=4, batch_size=1, agent_index=0, tasks=None, latent_gene_ids=None, image_height=None,
+                 image_width=None, return_decoded_video=None, context_signal_noise=0.1, time_cache=None, use_time_cache=True,
+                 return_rewards_per_frame=False, return_terminals=False, return_agent_actions=False,
+                 return_log_probs_and_values=False, return_for_policy_optimization=False, return_time_cache=False,
+                 store_agent_embed=True, store_old_action_unembeds=True, prompt=None, prompt_latents=None, prompt_proprio=None,
+                 prompt_discrete_actions=None, prompt_continuous_actions=None, prompt_rewards=None, aug_id=False,
+                 discrete_temperature=1., continuous_temperature=1., noise=None):
+        """Imagination rollout (reference dreamer4.py:6307-6774).  `noise` (not in the reference) optionally injects the
+        per-frame random draws — dict(latent=(T,B,N,Dl) normal, action_uniform=(T,B,A_total) uniform,
+        terminal_uniform=(T,B) uniform) — so that seeded runs are comparable draw for draw across devices; by default the
+        draws come from torch's CUDA generator in the reference's per-frame order (randn latent, rand terminal, rand per
+        action type, randn context)."""
+        if return_for_policy_optimization:            # reference dreamer4.py:6342-6347
+            return_agent_actions = True
+            return_log_probs_and_values = True
+            return_rewards_per_frame = True
+            return_terminals = return_terminals or self.predict_terminals
+        for name, v in dict(prompt=prompt, prompt_latents=prompt_latents, prompt_proprio=prompt_proprio, time_cache=time_cache,
+                            prompt_discrete_actions=prompt_discrete_actions, prompt_continuous_actions=prompt_continuous_actions,
+                            prompt_rewards=prompt_rewards, latent_gene_ids=latent_gene_ids).items():
+            if exists(v):
+                raise NotImplementedError(f'generate({name}=...): prompted / resumed rollouts are a "next" row (SURVEY.md section 8f)')
+        if return_decoded_video:
+            raise NotImplementedError('return_decoded_video needs the VideoTokenizer, a "next" row (SURVEY.md section 8f)')
+        if not use_time_cache:
+            raise NotImplementedError('use_time_cache=False: the native path always decodes over the in-place KV cache')
+        assert math.log2(num_steps).is_integer(), f'number of steps {num_steps} must be a power of 2'
+        assert 0 < num_steps <= self.max_steps
+        if num_steps == 1:
+            raise ValueError('num_steps=1 indexes step_size_embed out of range in the reference (SURVEY.md section 8a); use >= 2')
+        c = self.cfg
+        B, T, N, Dl, D = batch_size, time_steps, c.num_latent_tokens, c.dim_latent, c.dim
+        lib, ctx = self._engine(B, T, agent_index)
+        dev = self.device
+        return_agent_actions = (return_agent_actions or return_log_probs_and_values) and c.has_actions
+        want_heads = return_agent_actions
+        should_term = return_terminals and self.predict_terminals
+        if isinstance(tasks, int):
+            tasks = torch.full((B,), tasks, device=dev, dtype=torch.long)
+        if exists(tasks):
+            assert tasks.shape[0] == B
+            tasks = tasks.to(dev, torch.long).contiguous()
+
+        A = c.total_actions
+        na = len(c.num_discrete_actions)
+        f32 = dict(device=dev, dtype=torch.float32)
+        latents = torch.empty(B, T, N, Dl, **f32)
+        agent_embed = torch.empty(B, T, D, **f32)
+        rewards = torch.empty(B, T, **f32)
+        values = torch.empty(B, T, **f32) if want_heads else None
+        actions = torch.empty(B, T, na, device=dev, dtype=torch.long) if want_heads else None
+        log_probs = torch.empty(B, T, na, **f32) if want_heads else None
+        logits = torch.empty(B, T, A, **f32) if want_heads else None
+        lens = torch.full((B,), T, device=dev, dtype=torch.long)
+        terminals = torch.zeros(B, device=dev, dtype=torch.bool)
+        term_u8 = terminals.view(torch.uint8)
+
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        io = _lib.d4_frame_io()
+        frames = 0
+        keep = []
+        for t in range(T):
+            if exists(noise):
+                nl = noise['latent'][t]
+                au = noise['action_uniform'][t] if want_heads else None
+                tu = noise['terminal_uniform'][t] if should_term else None
+            else:                                       # reference draw order: dreamer4.py:6475, 6611, 6637, 6670
+                nl = torch.randn(B, N, Dl, **f32)
+                tu = torch.rand(B, **f32) if should_term else None
+                au = torch.cat([torch.rand(B, n, **f32) for n in c.num_discrete_actions], dim=-1) if want_heads else None
+            nl = nl.to(**f32).contiguous()
+            au = au.to(**f32).contiguous() if exists(au) else None
+            tu = tu.to(**f32).contiguous() if exists(tu) else None
+            keep = [nl, au, tu]
+            io.noise_latent, io.action_uniform, io.terminal_uniform = ptr(nl), ptr(au), ptr(tu)
+            if want_heads and t > 0:
+                io.prev_actions, io.pa_stride = C.c_void_p(actions[:, t - 1].data_ptr()), actions.stride(0)
+            else:
+                io.prev_actions, io.pa_stride = None, 0
+            io.tasks = ptr(tasks)
+            io.latents, io.latents_bs = C.c_void_p(latents[:, t].data_ptr()), latents.stride(0)
+            io.agent_embed, io.agent_bs = C.c_void_p(agent_embed[:, t].data_ptr()), agent_embed.stride(0)
+            io.rewards, io.rewards_bs = C.c_void_p(rewards[:, t].data_ptr()), rewards.stride(0)
+            if want_heads:
+                io.values, io.values_bs = C.c_void_p(values[:, t].data_ptr()), values.stride(0)
+                io.actions, io.actions_bs = C.c_void_p(actions[:, t].data_ptr()), actions.stride(0)
+                io.log_probs, io.log_probs_bs = C.c_void_p(log_probs[:, t].data_ptr()), log_probs.stride(0)
+                io.logits, io.logits_bs = C.c_void_p(logits[:, t].data_ptr()), logits.stride(0)
+            else:
+                io.values = io.actions = io.log_probs = io.logits = None
+            io.lens, io.terminals = ptr(lens), ptr(term_u8)
+            check(lib.d4_frame(ctx, B, t, num_steps, float(discrete_temperature), C.byref(io), stream))
+            if not exists(noise) and context_signal_noise > 0.:
+                torch.randn(B, N, Dl, **f32)            # dreamer4.py:6670: consumed by the reference, numerically dead with the KV cache
+            frames = t + 1
+            if should_term and bool(terminals.all()):   # reference dreamer4.py:6681
+                break
+        del keep
+
+        Tg = frames
+        latents = latents[:, :Tg]
+        kv = self._bufs['kv']
+        tc = DynamicsIntermediates(main=TransformerIntermediates(
+            next_kv_cache=kv[:c.num_time_layers, :, :, :, :Tg] if c.num_time_layers > 0 else None, token_count=Tg))
+        if not (return_rewards_per_frame or return_agent_actions):
+            return (latents, tc) if return_time_cache else latents
+
+        rewards = rewards[:, :Tg]
+        step_mask = (torch.arange(Tg, device=dev)[None, :] < lens[:, None]).float()
+        gen = Experience(
+            latents=latents,
+            agent_embed=agent_embed[:, :Tg] if store_agent_embed else None,
+            old_action_unembeds=Actions(logits[:, :Tg], None) if (want_heads and store_old_action_unembeds) else None,
+            step_size=self.max_steps // num_steps, agent_index=agent_index, lens=lens, is_truncated=~terminals, terminals=terminals,
+            is_from_world_model=True,
+            episode_return=(rewards * step_mask).sum(dim=-1),
+            rewards=rewards if return_rewards_per_frame else None,
+            actions=Actions(actions[:, :Tg], None) if return_agent_actions else None,
+            log_probs=Actions(log_probs[:, :Tg], None) if (return_log_probs_and_values and want_heads) else None,
+            values=values[:, :Tg] if (return_log_probs_and_values and want_heads) else None)
+        return (gen, tc) if return_time_cache else gen
+
+    # ------------------------------------------------------------------ learn_from_experience
+
+    def learn_from_experience(self, experience: Experience, policy_optim=None, value_optim=None, only_learn_policy_value_heads=True,
+                              objective='ppo', use_delight_gating=None, delight_temperature=None, normalize_advantages=None, eps=1e-6):
+        """Actor/critic losses with gradients (reference dreamer4.py:5893-6305).  Both losses and every head-parameter
+        gradient are produced by one native call; the returned scalars carry an autograd node that deposits those
+        gradients on `.backward()` exactly like the reference's graph would."""
+        if objective != 'ppo':
+            raise NotImplementedError(f"objective={objective!r}: pmpo / spo are a 'next' row (SURVEY.md section 8f)")
+        if not only_learn_policy_value_heads:
+            raise NotImplementedError('only_learn_policy_value_heads=False needs the world-model backward (outside this path)')
+        c = self.cfg
+        assert c.has_actions, 'learn_from_experience needs a model with discrete actions'
+        exp = experience
+        assert exists(exp.agent_embed), 'the native path learns from stored agent embeds (generate(store_agent_embed=True))'
+        B, T = exp.latents.shape[:2]
+        lib, ctx = self._engine(*(self._ctx_key[:2] if self._ctx_key else (B, T)), default(exp.agent_index, 0))
+        dev = self.device
+        use_gate = default(use_delight_gating, self.use_delight_gating)
+        temp = default(delight_temperature, self.delight_temperature)
+        norm_adv = default(default(normalize_advantages, self.normalize_advantages), True)
+
+        f32 = dict(device=dev, dtype=torch.float32)
+        cont = lambda t, dt: t.detach().to(device=dev, dtype=dt).contiguous()
+        agent = cont(exp.agent_embed, torch.float32)
+        rewards, values = cont(exp.rewards, torch.float32), cont(exp.values, torch.float32)
+        actions, old_lp = cont(exp.actions.discrete, torch.long), cont(exp.log_probs.discrete, torch.float32)
+        lens = cont(default(exp.lens, torch.full((B,), T, device=dev)), torch.long)
+        is_trunc = cont(default(exp.is_truncated, torch.zeros(B, dtype=torch.bool, device=dev)), torch.bool)
+        support, _ = hl_gauss_tables(*c.value_range, c.value_num_bins, dev)
+        sigma_sqrt2 = math.sqrt(2.) * c.hl_gauss_sigma_to_bin_ratio * (c.value_range[1] - c.value_range[0]) / c.value_num_bins
+
+        params = dict(self.named_parameters())
+        pol_names = [k for _, k in mlp_param_names('policy_head', c.policy_head_mlp_depth + 2)]
+        val_names = [k for _, k in mlp_param_names('value_head', c.value_head_mlp_depth + 2)]
+        un_name = 'action_embedder.discrete_action_unembed'
+        grads = {k: torch.zeros_like(params[k], dtype=torch.float32) for k in pol_names + val_names + [un_name]}
+        losses = torch.zeros(4, **f32)
+        returns = torch.empty(B, T, **f32)
+        adv = torch.empty(B, T, **f32)
+
+        io = _lib.d4_learn_io()
+        io.B, io.T = B, T
+        io.agent_embed, io.rewards, io.old_values = ptr(agent), ptr(rewards), ptr(values)
+        io.actions, io.old_log_probs, io.lens = ptr(actions), ptr(old_lp), ptr(lens)
+        io.is_truncated = ptr(is_trunc.view(torch.uint8))
+        io.terminals = None
+        io.gamma, io.lam, io.eps_clip = self.gae_discount_factor, self.gae_lambda, self.ppo_eps_clip
+        io.entropy_weight, io.delight_temperature, io.zscore_eps = self.policy_entropy_weight, temp, eps
+        io.use_delight_gating, io.normalize_advantages = int(bool(use_gate)), int(bool(norm_adv))
+        io.value_support = ptr(support)
+        io.value_sigma_sqrt2, io.hl_eps = sigma_sqrt2, c.hl_gauss_eps
+        io.value_lo, io.value_hi = c.value_range
+        io.losses, io.returns, io.advantages = ptr(losses), ptr(returns), ptr(adv)
+
+        def fill(head, nl, arrs):
+            for l in range(nl):
+                arrs[0][l] = grads[f'{head}.layers.{l}.0.weight'].data_ptr()
+                arrs[1][l] = grads[f'{head}.layers.{l}.0.bias'].data_ptr()
+                if l < nl - 1:
+                    arrs[2][l] = grads[f'{head}.layers.{l}.1.weight'].data_ptr()
+                    arrs[3][l] = grads[f'{head}.layers.{l}.1.bias'].data_ptr()
+        fill('policy_head', c.policy_head_mlp_depth + 2, (io.grad_policy_w, io.grad_policy_b, io.grad_policy_lnw, io.grad_policy_lnb))
+        fill('value_head', c.value_head_mlp_depth + 2, (io.grad_value_w, io.grad_value_b, io.grad_value_lnw, io.grad_value_lnb))
+        io.grad_unembed, io.grad_unembed_ld = ptr(grads[un_name]), grads[un_name].stride(0)
+
+        ws_bytes = lib.d4_learn_workspace_bytes(ctx, B, T)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(lib.d4_learn(ctx, C.byref(io), ptr(ws), ws_bytes, stream))
+        ws.record_stream(torch.cuda.current_stream(dev))
+
+        self.last_learn_aux = dict(returns=returns, advantages=adv, policy_surrogate=losses[2], entropy_term=losses[3])
+        pol_params = [params[k] for k in pol_names + [un_name]]
+        val_params = [params[k] for k in val_names]
+        policy_loss = _DepositGrads.apply(losses[0].clone(), [grads[k] for k in pol_names + [un_name]], *pol_params)
+        value_loss = _DepositGrads.apply(losses[1].clone(), [grads[k] for k in val_names], *val_params)
+
+        if exists(policy_optim):          # reference dreamer4.py:6246-6250
+            policy_loss.backward()
+            policy_optim.step()
+            policy_optim.zero_grad()
+        if exists(value_optim):           # reference dreamer4.py:6299-6303
+            value_loss.backward()
+            value_optim.step()
+            value_optim.zero_grad()
+        return policy_loss, value_loss
+
+
+class _DepositGrads(torch.autograd.Function):
+    """A scalar loss whose gradients with respect to `params` were already computed natively."""
+
+    @staticmethod
+    def forward(ctx, loss, grads, *params):
+        ctx.grads = grads
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (None, None, *[g * grad_out for g in ctx.grads])

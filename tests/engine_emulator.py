@@ -1,0 +1,166 @@
+"""Torch (CPU) emulation of the native engine's per-pass dataflow (dreamer4_b200/csrc/engine.cu::run_pass) over the
+PACKED weights of dreamer4_b200/packing.py.  Test infrastructure: it lets the CPU suite check the packing algebra
+(gamma folding, GLU interleave, fused qkv rows, hidden-stack layout, row maps) against the oracle without a GPU.
+It shares the buffer names and step order with engine.cu on purpose."""
+import torch
+import torch.nn.functional as F
+
+EPS = torch.finfo(torch.float32).eps
+
+
+def rstd(x):
+    return torch.rsqrt(x.pow(2).mean(dim=-1) + EPS)
+
+
+def l2n(x):
+    return x / x.norm(dim=-1, keepdim=True).clamp(min=1e-12)
+
+
+def headnorm(k, gamma):            # k (..., h, d), gamma (h, d)
+    return l2n(k) * ((gamma + 1.) * k.shape[-1] ** 0.5)
+
+
+def small_attn(q, k, v, k_gamma, scale, gate=None, softclamp=0., mask_agent=False, belief=False, v0=None, mix=None):
+    """q (b, nq, hq, d); k, v (b, n, h, d); gate (b, nq, hq) logits; mix (b, n, h) logits."""
+    b, nq, hq, d = q.shape
+    h = k.shape[2]
+    g = hq // h
+    if v0 is not None:
+        v = torch.lerp(v, v0, torch.sigmoid(mix)[..., None])
+    k = headnorm(k, k_gamma)
+    kk = k.repeat_interleave(g, dim=2)
+    vv = v.repeat_interleave(g, dim=2)
+    sim = torch.einsum('bihd,bjhd->bhij', q, kk) * scale
+    if softclamp > 0:
+        sim = torch.tanh(sim / softclamp) * softclamp
+    if mask_agent:
+        n = k.shape[1]
+        m = torch.ones(nq, n, dtype=torch.bool)
+        m[:nq - 1, n - 1] = False
+        sim = sim.masked_fill(~m, -torch.finfo(sim.dtype).max)
+    out = torch.einsum('bhij,bjhd->bihd', sim.softmax(dim=-1), vv)
+    if belief:
+        vh = l2n(vv)
+        out = out - (out * vh).sum(dim=-1, keepdim=True) * vh
+    if gate is not None:
+        out = out * torch.sigmoid(gate)[..., None]
+    return out, k, v
+
+
+def rope(x, t, inv_freq):            # x (..., d)
+    ang = t * inv_freq
+    ang = torch.cat((ang, ang))
+    x1, x2 = x.chunk(2, dim=-1)
+    return x * ang.cos() + torch.cat((-x2, x1), dim=-1) * ang.sin()
+
+
+def glu(x, act):
+    xs, gs = x[..., 0::2], x[..., 1::2]
+    return xs * (F.silu(gs) if act == 'silu' else F.gelu(gs))
+
+
+def emulate_pass(P, cfg, latent, signal, step_log2, prev_actions, kv_cache, t):
+    """P: packed dict; latent (B, N, Dl); kv_cache: list over time layers of (k, v) each (B*S, h, t, d) or None.
+    Returns pred (B, N, Dl), agent (B, D), new kv list."""
+    B = latent.shape[0]
+    S, D, N, nsp = cfg.tokens_per_frame, cfg.dim, cfg.num_latent_tokens, cfg.num_spatial_tokens
+    h, hq, d, L = cfg.attn_heads, cfg.query_heads, cfg.attn_dim_head, cfg.depth
+    Dq, Dkv, Dp, hp, dp = hq * d, h * d, cfg.pool_heads * cfg.pool_dim_head, cfg.pool_heads, cfg.pool_dim_head
+    M = B * S
+    scale = d ** -0.5
+    tok = torch.zeros(B, S, D)
+    if cfg.same_len:
+        tok[:, 1:1 + nsp] = latent @ P['l2s.w'].T + P['l2s.b']
+    else:
+        x = latent.reshape(B * N, -1)
+        kvl = (x @ P['l2s.w_kv'].T) * rstd(x)[:, None]
+        k, v = kvl[:, :Dkv].reshape(B, N, h, d), kvl[:, Dkv:].reshape(B, N, h, d)
+        q = P['l2s.q'].reshape(1, nsp, hq, d).expand(B, -1, -1, -1)
+        o, _, _ = small_attn(q, k, v, P['l2s.k_gamma'], scale, gate=P['l2s.gate'][None].expand(B, -1, -1))
+        tok[:, 1:1 + nsp] = o.reshape(B, nsp, Dq) @ P['l2s.w_out'].T
+    tok[:, 0] = torch.cat((P['sig_emb'][signal], P['step_emb'][step_log2]))
+    tok[:, 1 + nsp:1 + nsp + cfg.num_register_tokens] = P['registers']
+    if cfg.has_actions:
+        if prev_actions is None:
+            tok[:, S - 2] = 0.
+        else:
+            offs = torch.tensor([0, *torch.tensor(cfg.num_discrete_actions).cumsum(0)[:-1].tolist()])
+            tok[:, S - 2] = P['action_learned'] + P['action_emb'][prev_actions + offs].sum(dim=1)
+    tok[:, S - 1] = P['agent_embed']
+    hid = [tok.reshape(M, D)]
+    v0 = (hid[0] @ P['vr.w'].T) * rstd(hid[0])[:, None]
+    x_in = hid[0]
+    new_kv = []
+    ti = 0
+
+    def pool(name, xq, n):
+        qg = (xq @ P[name + '.w_qg'].T) * rstd(xq)[:, None]
+        stack = torch.cat(hid[:n])                                    # (n*M, D)
+        kv = (stack @ P[name + '.w_kv'].T) * rstd(stack)[:, None]
+        kv = kv.reshape(n, M, 2 * Dp).transpose(0, 1)                # (M, n, 2Dp)
+        k, v = kv[..., :Dp].reshape(M, n, hp, dp), kv[..., Dp:].reshape(M, n, hp, dp)
+        o, _, _ = small_attn(qg[:, :Dp].reshape(M, 1, hp, dp), k, v, P[name + '.k_gamma'], dp ** -0.5, gate=qg[:, Dp:].reshape(M, 1, hp))
+        return xq + o.reshape(M, Dp) @ P[name + '.w_out'].T
+
+    def ff(name, x):
+        mid = glu((x @ P[name + '.w_in'].T) * rstd(x)[:, None] + P[name + '.b_in'], cfg.ff_activation)
+        mid = F.pad(mid, (0, cfg.ff_inner_pad - mid.shape[-1]))
+        return x + mid @ P[name + '.w_out'].T + P[name + '.b_out']
+
+    for i in range(L):
+        row = (x_in @ P[f'L{i}.attn.w'].T) * rstd(x_in)[:, None] + P[f'L{i}.attn.b']
+        q, k, v = row[:, :Dq], row[:, Dq:Dq + Dkv], row[:, Dq + Dkv:Dq + 2 * Dkv]
+        gate, mix = row[:, Dq + 2 * Dkv:Dq + 2 * Dkv + hq], row[:, Dq + 2 * Dkv + hq:]
+        if cfg.is_time[i]:
+            qh, kh, vh = q.reshape(M, 1, hq, d), k.reshape(M, 1, h, d), v.reshape(M, 1, h, d)
+            vh = torch.lerp(vh, v0.reshape(M, 1, h, d), torch.sigmoid(mix).reshape(M, 1, h, 1))
+            kh = rope(headnorm(kh, P[f'L{i}.attn.k_gamma']), float(t), P['inv_freq'])
+            qh = rope(qh, float(t), P['inv_freq'])
+            kn, vn = kh.transpose(1, 2), vh.transpose(1, 2)           # (M, h, 1, d)
+            if kv_cache is not None and t > 0:
+                kall, vall = torch.cat((kv_cache[ti][0], kn), dim=2), torch.cat((kv_cache[ti][1], vn), dim=2)
+            else:
+                kall, vall = kn, vn
+            new_kv.append((kall, vall))
+            g = hq // h
+            kk, vv = kall.repeat_interleave(g, dim=1), vall.repeat_interleave(g, dim=1)
+            sim = torch.einsum('mhd,mhjd->mhj', qh[:, 0], kk) * scale
+            sim = torch.tanh(sim / cfg.attn_softclamp_value) * cfg.attn_softclamp_value
+            o = torch.einsum('mhj,mhjd->mhd', sim.softmax(dim=-1), vv)
+            vhat = l2n(vh[:, 0].repeat_interleave(g, dim=1))
+            o = o - (o * vhat).sum(dim=-1, keepdim=True) * vhat
+            o = (o * torch.sigmoid(gate)[..., None]).reshape(M, Dq)
+            ti += 1
+        else:
+            o, _, _ = small_attn(q.reshape(B, S, hq, d), k.reshape(B, S, h, d), v.reshape(B, S, h, d), P[f'L{i}.attn.k_gamma'], scale,
+                                 gate=gate.reshape(B, S, hq), softclamp=cfg.attn_softclamp_value, mask_agent=True, belief=True,
+                                 v0=v0.reshape(B, S, h, d), mix=mix.reshape(B, S, h))
+            o = o.reshape(M, Dq)
+        hid.append(x_in + o @ P[f'L{i}.attn.w_out'].T)
+        hid.append(ff(f'L{i}.ff', hid[-1]))
+        if i != L - 1:
+            x_in = pool(f'P{i}', hid[-1], 2 * i + 3)
+    xf = hid[2 * L].clone().reshape(B, S, D)
+    ag = xf[:, S - 1]
+    qg = (ag @ P['FA.w_qg'].T) * rstd(ag)[:, None]
+    kv = (hid[2 * L] @ P['FA.w_kv'].T) * rstd(hid[2 * L])[:, None]
+    kv = kv.reshape(B, S, 2 * Dkv)[:, :S - 1]
+    o, _, _ = small_attn(qg[:, :Dq].reshape(B, 1, hq, d), kv[..., :Dkv].reshape(B, S - 1, h, d), kv[..., Dkv:].reshape(B, S - 1, h, d),
+                         P['FA.k_gamma'], scale, gate=qg[:, Dq:].reshape(B, 1, hq))
+    ag = ag + o.reshape(B, Dq) @ P['FA.w_out'].T
+    ag = ff('FAFF', ag)
+    xf[:, S - 1] = ag
+    xf = pool('PF', xf.reshape(M, D), 2 * L + 1).reshape(B, S, D)
+    agent = xf[:, S - 1]
+    sp = xf[:, 1:1 + nsp].reshape(B * nsp, D)
+    sp_n = sp * rstd(sp)[:, None] * P['lp.norm0']
+    if cfg.same_len:
+        pred = (sp_n @ P['lp.w'].T).reshape(B, N, -1)
+    else:
+        sp_n2 = sp_n * rstd(sp_n)[:, None] * P['lp.norm_ctx']
+        kv = sp_n2 @ P['lp.w_kv'].T
+        q = P['lp.q'].reshape(1, N, hq, d).expand(B, -1, -1, -1)
+        o, _, _ = small_attn(q, kv[:, :Dkv].reshape(B, nsp, h, d), kv[:, Dkv:].reshape(B, nsp, h, d), P['lp.k_gamma'], scale,
+                             gate=P['lp.gate'][None].expand(B, -1, -1))
+        pred = (o.reshape(B * N, Dq) @ P['lp.w_comb'].T).reshape(B, N, -1)
+    return pred, agent, new_kv

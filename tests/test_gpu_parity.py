@@ -1,0 +1,245 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI, against the CPU oracle
+on identical injected noise, against the committed golden vectors of the reference, and stand-alone operator checks.
+
+Stated tolerance for the exact-fp32 engine mode: |err| <= 5e-5 + 2e-4 * |ref| on every floating-point output
+(fp32 reassociation over <= 6 frames x 5 passes x depth layers); sampled action indices, lens and terminal flags
+must be bit-exact."""
+import ctypes as C
+import glob
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import dreamer4_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.pt')))
+IDS = [os.path.basename(p)[:-3] for p in GOLDEN]
+TOL = dict(atol=5e-5, rtol=2e-4)
+
+
+def load(path):
+    return torch.load(path, map_location='cpu', weights_only=False)
+
+
+def build_model(fx, **extra):
+    from dreamer4_b200 import DynamicsWorldModel
+    model = DynamicsWorldModel(**fx['model_kwargs'], **extra)
+    model.load_state_dict(fx['state_dict'], strict=True)
+    return model.cuda()
+
+
+def make_noise(cfg, T, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = sum(cfg.num_discrete_actions)
+    return dict(latent=torch.randn(T, B, cfg.num_latent_tokens, cfg.dim_latent, generator=g),
+                action_uniform=torch.rand(T, B, max(A, 1), generator=g)[..., :A],
+                terminal_uniform=torch.rand(T, B, generator=g))
+
+
+def to_cuda(noise):
+    return {k: v.cuda() for k, v in noise.items()}
+
+
+def compare_experience(exp, ref, kv=None, ref_kv=None):
+    assert exp.latents.shape == ref.latents.shape
+    assert torch.equal(exp.actions.discrete.cpu(), ref.actions)
+    assert torch.equal(exp.lens.cpu(), ref.lens)
+    assert torch.equal(exp.terminals.cpu(), ref.terminals)
+    assert torch.equal(exp.is_truncated.cpu(), ref.is_truncated)
+    assert exp.step_size == ref.step_size
+    torch.testing.assert_close(exp.latents.cpu(), ref.latents, **TOL)
+    torch.testing.assert_close(exp.agent_embed.cpu(), ref.agent_embed, **TOL)
+    torch.testing.assert_close(exp.rewards.cpu(), ref.rewards, **TOL)
+    torch.testing.assert_close(exp.values.cpu(), ref.values, **TOL)
+    torch.testing.assert_close(exp.log_probs.discrete.cpu(), ref.log_probs, **TOL)
+    torch.testing.assert_close(exp.old_action_unembeds.discrete.cpu(), ref.old_action_unembeds, **TOL)
+    torch.testing.assert_close(exp.episode_return.cpu(), ref.episode_return, **TOL)
+    if kv is not None:
+        assert kv.shape == ref_kv.shape
+        torch.testing.assert_close(kv.cpu(), ref_kv, **TOL)
+
+
+@pytest.mark.parametrize('variant', [0, 1], ids=['ldg', 'bulk'])
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_generate_matches_oracle(path, variant):
+    fx = load(path)
+    model = build_model(fx, time_attn_variant=variant)
+    ocfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    gk = dict(fx['gen_kwargs'])
+    T, B = gk.pop('time_steps'), gk.pop('batch_size')
+    noise = make_noise(model.cfg, T, B, seed=11)
+    ref = O.generate(fx['state_dict'], ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform']), **gk)
+    exp, tc = model.generate(T, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
+                             return_log_probs_and_values=True, return_time_cache=True, noise=to_cuda(noise), **gk)
+    ref_kv = torch.stack([torch.stack(layer) for layer in ref.kv_cache])
+    compare_experience(exp, ref, tc.main.next_kv_cache, ref_kv)
+    assert tc.main.token_count == ref.latents.shape[1]
+
+
+@pytest.mark.parametrize('path', [p for p in GOLDEN if 'terminals' not in p], ids=[i for i in IDS if 'terminals' not in i])
+def test_generate_matches_reference_golden(path):
+    """Replays the reference's own CPU RNG stream (randn latent, rand per action type, randn context per frame;
+    reference dreamer4.py:6475, 6637, 6670) and compares with what the reference itself produced."""
+    fx = load(path)
+    model = build_model(fx)
+    cfg = model.cfg
+    gk = dict(fx['gen_kwargs'])
+    T, B = gk.pop('time_steps'), gk.pop('batch_size')
+    torch.manual_seed(fx['gen_seed'])
+    lat, au = [], []
+    for _ in range(T):
+        lat.append(torch.randn(B, 1, 1, cfg.num_latent_tokens, cfg.dim_latent).reshape(B, cfg.num_latent_tokens, cfg.dim_latent))
+        au.append(torch.cat([torch.rand(B, 1, n).reshape(B, n) for n in cfg.num_discrete_actions], dim=-1))
+        torch.randn(B, 1, 1, cfg.num_latent_tokens, cfg.dim_latent)
+    noise = dict(latent=torch.stack(lat), action_uniform=torch.stack(au), terminal_uniform=torch.zeros(T, B))
+    exp, tc = model.generate(T, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
+                             return_log_probs_and_values=True, return_time_cache=True, noise=to_cuda(noise), **gk)
+    ref = fx['out']
+    assert torch.equal(exp.actions.discrete.cpu(), ref['actions'])
+    for name in ('latents', 'agent_embed', 'rewards', 'values', 'episode_return'):
+        torch.testing.assert_close(getattr(exp, name).cpu(), ref[name], **TOL)
+    torch.testing.assert_close(exp.log_probs.discrete.cpu(), ref['log_probs'], **TOL)
+    torch.testing.assert_close(exp.old_action_unembeds.discrete.cpu(), ref['old_action_unembeds'], **TOL)
+    torch.testing.assert_close(tc.main.next_kv_cache.cpu(), ref['kv_cache'], **TOL)
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_learn_matches_reference_golden(path):
+    from dreamer4_b200 import Actions, Experience
+    fx = load(path)
+    model = build_model(fx)
+    ref = fx['out']
+    cu = lambda t: t.cuda()
+    exp = Experience(latents=cu(ref['latents']), agent_embed=cu(ref['agent_embed']), rewards=cu(ref['rewards']), values=cu(ref['values']),
+                     actions=Actions(cu(ref['actions']), None), log_probs=Actions(cu(ref['log_probs']), None), lens=cu(ref['lens']),
+                     is_truncated=cu(ref['is_truncated']), terminals=cu(ref['terminals']), step_size=ref['step_size'])
+    pl, vl = model.learn_from_experience(exp)
+    torch.testing.assert_close(pl.detach().cpu(), ref['policy_loss'], atol=1e-6, rtol=1e-4)      # north star: 1e-4 relative
+    torch.testing.assert_close(vl.detach().cpu(), ref['value_loss'], atol=1e-6, rtol=1e-4)
+    pl.backward()
+    vl.backward()
+    params = dict(model.named_parameters())
+    for name, g in ref['grads'].items():
+        assert params[name].grad is not None, name
+        torch.testing.assert_close(params[name].grad.cpu(), g, atol=2e-6, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
+    for name, p in params.items():
+        if name not in ref['grads']:
+            assert p.grad is None, name
+
+
+# ------------------------------------------------------------------------------------------------ stand-alone operators
+
+def _lib():
+    from dreamer4_b200 import _lib as L
+    return L, L.load()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize('M,N,K,act', [(64, 64, 32, 0), (200, 100, 52, 0), (130, 170, 32, 1), (77, 170, 33, 2), (1000, 1552, 512, 0)])
+def test_linear_fp32(M, N, K, act):
+    L, lib = _lib()
+    torch.manual_seed(M + N)
+    A, W = torch.randn(M, K).cuda(), torch.randn(N, K).cuda() / math.sqrt(K)
+    bias, rs = torch.randn(N).cuda(), torch.rand(M).cuda() + 0.5
+    nout = N // 2 if act else N
+    res = torch.randn(M, nout).cuda() if not act else None
+    Cc = torch.empty(M, nout).cuda()
+    L.check(lib.d4_linear(0, M, N, K, L.ptr(A), K, L.ptr(W), K, None, L.ptr(bias), L.ptr(rs), L.ptr(res), nout, act, L.ptr(Cc), nout, _stream()))
+    ref = (A.double() @ W.double().T) * rs.double()[:, None] + bias.double()
+    if act:
+        x, g = ref[:, 0::2], ref[:, 1::2]
+        ref = x * (torch.nn.functional.silu(g) if act == 1 else torch.nn.functional.gelu(g))
+    else:
+        ref = ref + res.double()
+    torch.testing.assert_close(Cc.double(), ref, atol=1e-5, rtol=1e-5)
+
+
+def ref_time_attn(qkvgm, v0, k_gamma, inv_freq, kc, vc, t, h, hq, d, softclamp):
+    """fp64 restatement of Attention.forward for one new query over cache + self (reference dreamer4.py:1968-2075)."""
+    M = qkvgm.shape[0]
+    Dq, Dkv = hq * d, h * d
+    row = qkvgm.double()
+    q, k, v = row[:, :Dq].reshape(M, hq, d), row[:, Dq:Dq + Dkv].reshape(M, h, d), row[:, Dq + Dkv:Dq + 2 * Dkv].reshape(M, h, d)
+    gate, mix = row[:, Dq + 2 * Dkv:Dq + 2 * Dkv + hq], row[:, Dq + 2 * Dkv + hq:Dq + 2 * Dkv + hq + h]
+    v = torch.lerp(v, v0.double().reshape(M, h, d), torch.sigmoid(mix)[..., None])
+    k = k / k.norm(dim=-1, keepdim=True).clamp(min=1e-12) * ((k_gamma.double() + 1) * d ** 0.5)
+    ang = t * inv_freq.double()
+    ang = torch.cat((ang, ang))
+    rot = lambda x: x * ang.cos() + torch.cat((-x[..., d // 2:], x[..., :d // 2]), dim=-1) * ang.sin()
+    q, k = rot(q), rot(k)
+    kall = torch.cat((kc[:, :, :t].double(), k[:, :, None]), dim=2)
+    vall = torch.cat((vc[:, :, :t].double(), v[:, :, None]), dim=2)
+    g = hq // h
+    kk, vv = kall.repeat_interleave(g, dim=1), vall.repeat_interleave(g, dim=1)
+    sim = torch.einsum('mhd,mhjd->mhj', q, kk) * d ** -0.5
+    sim = torch.tanh(sim / softclamp) * softclamp
+    o = torch.einsum('mhj,mhjd->mhd', sim.softmax(dim=-1), vv)
+    vh = v / v.norm(dim=-1, keepdim=True).clamp(min=1e-12)
+    vh = vh.repeat_interleave(g, dim=1)
+    o = o - (o * vh).sum(dim=-1, keepdim=True) * vh
+    o = o * torch.sigmoid(gate)[..., None]
+    return o.reshape(M, Dq), k, v
+
+
+@pytest.mark.parametrize('variant', [0, 1], ids=['ldg', 'bulk'])
+@pytest.mark.parametrize('h,hq,d,t', [(8, 8, 64, 0), (8, 8, 64, 1), (8, 8, 64, 31), (8, 8, 64, 32), (8, 8, 64, 77), (2, 4, 16, 5),
+                                      (4, 8, 32, 40), (8, 8, 64, 200)])
+def test_time_attn_decode(h, hq, d, t, variant):
+    L, lib = _lib()
+    torch.manual_seed(t + d)
+    M, Tmax = 150, 256
+    Dq, Dkv = hq * d, h * d
+    ld = (Dq + 2 * Dkv + hq + h + 3) // 4 * 4
+    qkvgm = torch.randn(M, ld).cuda()
+    v0, k_gamma = torch.randn(M, Dkv).cuda(), (torch.randn(h, d) * 0.1).cuda()
+    inv_freq = (1.0 / (10000. ** (torch.arange(0, d, 2).float() / d))).cuda()
+    kc, vc = torch.randn(M, h, Tmax, d).cuda(), torch.randn(M, h, Tmax, d).cuda()
+    kc0, vc0 = kc.clone(), vc.clone()
+    out = torch.empty(M, Dq).cuda()
+    L.check(lib.d4_time_attn_decode(M, h, hq, d, t, Tmax, L.ptr(qkvgm), ld, L.ptr(v0), L.ptr(k_gamma), L.ptr(inv_freq), L.ptr(kc), L.ptr(vc),
+                                    L.ptr(out), 50.0, 1, variant, _stream()))
+    ro, rk, rv = ref_time_attn(qkvgm, v0, k_gamma, inv_freq, kc0, vc0, t, h, hq, d, 50.0)
+    torch.testing.assert_close(out.double(), ro, atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(kc[:, :, t].double(), rk, atol=1e-5, rtol=1e-5)      # appended in place at position t
+    torch.testing.assert_close(vc[:, :, t].double(), rv, atol=1e-5, rtol=1e-5)
+    keep = torch.ones(Tmax, dtype=torch.bool)
+    keep[t] = False
+    assert torch.equal(kc[:, :, keep], kc0[:, :, keep]) and torch.equal(vc[:, :, keep], vc0[:, :, keep])   # nothing else touched
+
+
+@pytest.mark.parametrize('B,T', [(1, 1), (5, 7), (33, 32), (64, 65), (7, 130)])
+def test_gae_matches_oracle(B, T):
+    L, lib = _lib()
+    torch.manual_seed(B * 1000 + T)
+    r, v = torch.randn(B, T), torch.randn(B, T)
+    lens = torch.randint(1, T + 1, (B,))
+    masks = torch.arange(T)[None] < (lens - 1).clamp(min=0)[:, None]
+    learn = torch.arange(T)[None] < lens[:, None]
+    ref = O.calc_gae(r, v, masks, learn, 0.997, 0.95)
+    out = torch.empty(B, T).cuda()
+    L.check(lib.d4_gae(B, T, L.ptr(r.cuda()), L.ptr(v.cuda()), L.ptr(masks.cuda().view(torch.uint8)), L.ptr(learn.cuda().view(torch.uint8)),
+                       0.997, 0.95, L.ptr(out), _stream()))
+    torch.testing.assert_close(out.cpu(), ref, atol=1e-5, rtol=1e-5)
+
+
+def test_missing_weights_fail_loudly():
+    L, lib = _lib()
+    cfg = L.d4_config()
+    cfg.dim, cfg.dim_latent, cfg.num_latent_tokens, cfg.num_spatial_tokens, cfg.num_register_tokens = 32, 8, 6, 4, 8
+    cfg.depth, cfg.time_block_every, cfg.heads, cfg.query_heads, cfg.dim_head = 4, 4, 2, 2, 16
+    cfg.pool_heads, cfg.pool_dim_head, cfg.ff_inner, cfg.ff_inner_pad, cfg.max_steps = 4, 64, 85, 96, 64
+    cfg.reward_bins, cfg.value_bins, cfg.max_batch, cfg.max_time, cfg.softclamp = 255, 255, 2, 4, 50.
+    ctx = C.c_void_p()
+    L.check(lib.d4_ctx_create(C.byref(cfg), C.byref(ctx)))
+    assert lib.d4_bind(ctx) != 0
+    assert b'missing' in lib.d4_last_error()
+    x = torch.zeros(2, 6, 8).cuda()
+    assert lib.d4_pass(ctx, 2, L.ptr(x), 0, 4, None, 0, None, 0, 0, L.ptr(x), None, _stream()) != 0
+    lib.d4_ctx_destroy(ctx)

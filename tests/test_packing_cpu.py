@@ -1,0 +1,81 @@
+"""CPU checks of the host-side logic: state_dict key parity with the reference, the packing algebra of
+dreamer4_b200/packing.py (through tests/engine_emulator.py, which mirrors engine.cu's dataflow) against the oracle,
+and that the C-ABI library loads and exports every symbol include/d4b200.h declares."""
+import glob
+import os
+import re
+
+import pytest
+import torch
+
+from dreamer4_b200 import DynamicsWorldModel
+from dreamer4_b200.packing import pack, tf32_split
+from oracle import dreamer4_oracle as O
+from engine_emulator import emulate_pass
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.pt')))
+IDS = [os.path.basename(p)[:-3] for p in GOLDEN]
+
+
+def load(path):
+    return torch.load(path, map_location='cpu', weights_only=False)
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_state_dict_keys_match_reference(path):
+    fx = load(path)
+    model = DynamicsWorldModel(**fx['model_kwargs'])
+    model.load_state_dict(fx['state_dict'], strict=True)
+    for k, v in fx['state_dict'].items():
+        assert model.state_dict()[k].shape == v.shape, k
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_packed_dataflow_matches_oracle(path):
+    """Three frames (clean passes commit the KV cache) of the emulated engine dataflow vs oracle.forward_step."""
+    fx = load(path)
+    sd = fx['state_dict']
+    model = DynamicsWorldModel(**fx['model_kwargs'])
+    cfg = model.cfg
+    ocfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    P = pack(sd, cfg, torch.device('cpu'))
+    torch.manual_seed(0)
+    B = 3
+    kv_o, kv_e, prev = None, None, None
+    for t in range(3):
+        x = torch.randn(B, cfg.num_latent_tokens, cfg.dim_latent)
+        for signal in (0, 48, 63):
+            po, ao, nko = O.forward_step(sd, ocfg, x, signal, 4, prev, kv_o, t)
+            pe, ae, nke = emulate_pass(P, cfg, x, signal, 4, prev, kv_e, t)
+            torch.testing.assert_close(pe, po, atol=2e-5, rtol=1e-4)
+            torch.testing.assert_close(ae, ao, atol=2e-5, rtol=1e-4)
+        kv_o, kv_e = nko, nke
+        for (ko, vo), (ke, ve) in zip(kv_o, kv_e):
+            torch.testing.assert_close(ke, ko, atol=2e-5, rtol=1e-4)
+            torch.testing.assert_close(ve, vo, atol=2e-5, rtol=1e-4)
+        prev = torch.stack([torch.randint(0, n, (B,)) for n in cfg.num_discrete_actions], dim=-1)
+
+
+def test_tf32_split_is_exact():
+    w = torch.randn(1000) * torch.logspace(-6, 6, 1000)
+    hi, lo = tf32_split(w)
+    assert torch.equal(hi + lo, w)
+    assert torch.all((hi.view(torch.int32) & 0x1FFF) == 0)
+    assert torch.all(lo.abs() <= w.abs() * 2 ** -10)
+
+
+def test_library_exports_every_declared_symbol():
+    from dreamer4_b200 import _lib
+    header = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), 'include', 'd4b200.h')).read()
+    declared = set(re.findall(r'\b(d4_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()          # raises if the .so is missing or a symbol is not exported
+    assert lib.d4_version() >= 100
+    assert lib.d4_last_error() is not None
+
+
+def test_no_cpu_fallback():
+    from dreamer4_b200._lib import D4Error
+    model = DynamicsWorldModel(dim=32, dim_latent=8, num_latent_tokens=6, attn_heads=2, attn_dim_head=16, num_discrete_actions=4)
+    with pytest.raises(D4Error):
+        model.generate(2, batch_size=1)

@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — imagined latent frames/s of the Dreamer-4 imagination hot path on B200.
+
+A step = one DreamTrainer iteration (reference dreamer4/trainers.py:1416-1468) on a batch of synthetic dreams:
+`generate(H frames, B dreams)` -> `learn_from_experience` -> backward -> clip -> AdamW on the policy and value heads
+(+ one gradient all-reduce when N > 1).  Weights are random-init, inputs are the injected noise tensors.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0)."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# BASELINE.json config 4: 256x256 patch 32 -> 64 latent tokens x 32, dim 512, depth 8, 4 discrete actions
+WORKLOADS = {
+    'config4': dict(model=dict(dim=512, dim_latent=32, num_latent_tokens=64, depth=8, time_block_every=4, attn_heads=8, attn_dim_head=64,
+                               num_discrete_actions=4, predict_terminals=False), batch=2048, horizon=64),
+    'config2': dict(model=dict(dim=256, dim_latent=32, num_latent_tokens=32, depth=4, time_block_every=4, attn_heads=8, attn_dim_head=64,
+                               num_discrete_actions=(5, 5), predict_terminals=False), batch=1024, horizon=16),
+    'config3': dict(model=dict(dim=512, dim_latent=64, num_latent_tokens=64, depth=6, time_block_every=4, attn_heads=8, attn_dim_head=64,
+                               num_discrete_actions=4, predict_terminals=False), batch=8192, horizon=32),
+    'config1': dict(model=dict(dim=512, dim_latent=32, num_latent_tokens=64, depth=4, time_block_every=4, attn_heads=8, attn_dim_head=64,
+                               num_discrete_actions=4, predict_terminals=False), batch=2, horizon=10),
+}
+METRIC = 'imagined latent frames/sec'
+UNIT = 'frames/s'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p.get('hbm_gbs', 6650.), tensor_burst=p.get('bf16_tflops', 1590.), tensor_sustained=p.get('bf16_tflops_sustained', 1400.),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650., tensor_burst=1590., tensor_sustained=1400., source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200', '-i', str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm),
+                    power_w_max=max(power) if power else None)
+
+
+def make_noise(cfg_model, B, H, pinned):
+    N, Dl = cfg_model['num_latent_tokens'], cfg_model['dim_latent']
+    nda = cfg_model['num_discrete_actions']
+    A = sum(nda) if isinstance(nda, (tuple, list)) else nda
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn(H, B, N, Dl, generator=g)
+    au = torch.rand(H, B, A, generator=g)
+    if pinned:
+        lat, au = lat.pin_memory(), au.pin_memory()
+    return dict(latent=lat, action_uniform=au, terminal_uniform=torch.zeros(H, 1))
+
+
+def run_native(args):
+    from dreamer4_b200 import DynamicsWorldModel, _lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    assert torch.cuda.is_available(), 'the native arm needs a CUDA device (no CPU fallback)'
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl['batch']
+    H = args.horizon or wl['horizon']
+    torch.manual_seed(0)
+    model = DynamicsWorldModel(**wl['model'], precision=args.precision, time_attn_variant=args.variant).to(dev)
+    lib = _lib.load()
+    policy_optim = torch.optim.AdamW(model.policy_head_parameters(), lr=3e-4)        # trainers.py:1334
+    value_optim = torch.optim.AdamW(model.value_head_parameters(), lr=3e-4)
+    head_params = model.policy_head_parameters() + model.value_head_parameters()
+
+    host_noise = make_noise(wl['model'], B, H, pinned=True)
+    dev_noise = {k: v.to(dev) for k, v in host_noise.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host_noise.items() if k != 'terminal_uniform')
+
+    def step(e2e):
+        noise = {k: v.to(dev, non_blocking=True) for k, v in host_noise.items()} if e2e else dev_noise
+        exp = model.generate(H, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
+                             return_log_probs_and_values=True, noise=noise)           # trainers.py:1422-1428
+        pl, vl = model.learn_from_experience(exp)                                     # trainers.py:1430
+        pl.backward()
+        vl.backward()
+        if dist is not None:            # one flat all-reduce of the head gradients (DDP-equivalent averaging)
+            grads = [p.grad for p in head_params if p.grad is not None]
+            flat = torch._utils._flatten_dense_tensors(grads)
+            dist.all_reduce(flat)
+            flat.div_(world)
+            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(f)
+        torch.nn.utils.clip_grad_norm_(model.policy_head_parameters(), 0.5)           # trainers.py:1440
+        policy_optim.step(); policy_optim.zero_grad()
+        torch.nn.utils.clip_grad_norm_(model.value_head_parameters(), 0.5)
+        value_optim.step(); value_optim.zero_grad()
+        out = torch.stack((pl.detach(), vl.detach(), exp.episode_return.mean()))
+        return out.cpu() if e2e else out
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(n, e2e, profile=False):
+        barrier()
+        if profile:
+            _lib.check(lib.d4_profile(model._ctx, 1))
+        l0 = lib.d4_launch_count()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        last = None
+        for _ in range(n):
+            last = step(e2e)
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        launches = lib.d4_launch_count() - l0
+        prof = None
+        if profile:
+            _lib.check(lib.d4_profile(model._ctx, 0))
+            buf = (C.c_double * 12)()
+            _lib.check(lib.d4_profile_read(model._ctx, buf))
+            prof = [list(buf[i * 3:(i + 1) * 3]) for i in range(4)]
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, prof, last
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, prof, last = timed(args.steps, e2e=False, profile=not args.no_profile)
+    clocks = sampler.stop() if rank == 0 else None
+    step(True)                                   # warm the pinned-copy path
+    ms_e2e, _, _, last_e2e = timed(args.steps, e2e=True)
+
+    frames = world * B * H * args.steps
+    value = frames / (ms / 1e3)
+    e2e_value = frames / (ms_e2e / 1e3)
+    pk = peaks()
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32' if args.precision == 'fp32' else args.precision,
+                data='synthetic', impl='native',
+                config=dict(workload=f'{args.workload}: BASELINE.json configs[{dict(config1=0, config2=1, config3=2, config4=3)[args.workload]}] model, '
+                                     f'{B} dreams x {H} frames per GPU, 4 denoise + 1 clean pass per frame, generate + learn_from_experience + AdamW',
+                            dreams_per_gpu=B, horizon=H, global_dreams=world * B, precision=args.precision, time_attn_variant=args.variant,
+                            parallelism=f'dp{world} (dream batch sharded, one flat gradient all-reduce)',
+                            l2='inputs larger than L2 (KV cache + activations per pass >> 126 MB)' if B * H >= 4096 else 'small problem: L2 resident'),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12, ms_per_step=ms_e2e / args.steps),
+                gpu_launches=int(launches), clocks=clocks,
+                losses=dict(policy=float(last[0]), value=float(last[1])), peaks=pk['source'])
+    if prof is not None:
+        names = ['gemm', 'time_attn', 'small_attn', 'other']
+        total_ms = ms
+        shares = {n: prof[i][0] / total_ms for i, n in enumerate(names)}
+        gemm_tf = prof[0][2] / (prof[0][0] / 1e3) / 1e12 if prof[0][0] > 0 else 0.
+        attn_gbs = prof[1][2] / (prof[1][0] / 1e3) / 1e9 if prof[1][0] > 0 else 0.
+        roof_gemm = dict(bound='tensor', kernel='gemm (all linear layers)', achieved=gemm_tf, peak=pk['tensor_sustained'], unit='TFLOP/s',
+                         frac=gemm_tf / pk['tensor_sustained'], traffic=None, launches=int(prof[0][1]), share_of_step=shares['gemm'])
+        roof_attn = dict(bound='hbm', kernel='time_attn (K1, KV-cache decode)', achieved=attn_gbs, peak=pk['hbm'], unit='GB/s',
+                         frac=attn_gbs / pk['hbm'], traffic=None, launches=int(prof[1][1]), share_of_step=shares['time_attn'])
+        line['roofline'] = roof_gemm if prof[0][0] >= prof[1][0] else roof_attn
+        line['roofline_attn'] = roof_attn
+        line['roofline_gemm'] = roof_gemm
+        line['kernel_class_share'] = shares
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(args, steps=1, warmup=0)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_sample_shape(args):
+    b, h = (int(x) for x in args.cpu_sample.split('x'))
+    return b, h
+
+
+def cpu_baseline(args, steps, warmup):
+    """The oracle (CPU restatement of the reference path, oracle/dreamer4_oracle.py) timed on the host cores on a bounded
+    sample of the same workload: generate + learn_from_experience + backward."""
+    from dreamer4_b200 import DynamicsWorldModel
+    from oracle import dreamer4_oracle as O
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b, h = cpu_sample_shape(args)
+    torch.manual_seed(0)
+    model = DynamicsWorldModel(**wl['model'])
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ocfg = O.config_from_reference_kwargs(**wl['model'])
+    noise_t = make_noise(wl['model'], b, h, pinned=False)
+
+    def one():
+        noise = O.InjectedNoise(noise_t['latent'], noise_t['action_uniform'], None)
+        exp = O.generate(sd, ocfg, h, b, noise=noise)
+        sdg = {k: v.clone().requires_grad_(k.startswith(('policy_head', 'value_head')) or k == 'action_embedder.discrete_action_unembed')
+               for k, v in sd.items()}
+        pl, vl, _ = O.learn_from_experience(sdg, ocfg, exp)
+        (pl + vl).backward()
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return dict(value=b * h * steps / dt, unit=UNIT, cores=cores, kind='port',
+                sample=f'{b} dreams x {h} frames of the {args.workload} model per step, {steps} step(s), {dt:.1f} s, torch {torch.get_num_threads()} threads fp32',
+                seconds=dt)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own algorithm on the host cores (the oracle port; the reference package itself cannot be
+    imported here — 17 un-vendored dependencies)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    b, h = cpu_sample_shape(args)
+    base = cpu_baseline(args, steps=args.steps, warmup=min(args.warmup, 1))
+    ms = base['seconds'] / args.steps * 1e3
+    line = dict(metric=METRIC, value=base['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=min(args.warmup, 1), ms_per_step=ms,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload=f'{args.workload} model, bounded CPU sample: {b} dreams x {h} frames per step', dreams=b, horizon=h),
+                cpu_baseline=dict(value=base['value'], unit=UNIT, cores=base['cores'], kind='port', sample=base['sample']),
+                e2e=dict(value=base['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--workload', default='config4', choices=list(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='dreams per GPU (default: the workload\'s)')
+    ap.add_argument('--horizon', type=int, default=0)
+    ap.add_argument('--precision', default=os.environ.get('D4_BENCH_PRECISION', 'fp32'), choices=['fp32', 'tf32', 'tf32x3'])
+    ap.add_argument('--variant', type=int, default=1, help='K1 kernel variant (0 ld.global staged, 1 cp.async.bulk ring)')
+    ap.add_argument('--cpu-sample', default='16x16', help='CPU baseline sample: dreams x frames')
+    ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == '__main__':
+    main()

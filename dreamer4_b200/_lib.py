@@ -76,6 +76,7 @@ _i, _i64, _f, _p = C.c_int, C.c_int64, C.c_float, C.c_void_p
 SYMBOLS = {
     'd4_last_error': (C.c_char_p, []),
     'd4_version': (_i, []),
+    'd4_launch_count': (_i64, []),
     'd4_ctx_create': (_i, [C.POINTER(d4_config), C.POINTER(_p)]),
     'd4_ctx_destroy': (None, [_p]),
     'd4_set_weight': (_i, [_p, C.c_char_p, _p, _i64]),

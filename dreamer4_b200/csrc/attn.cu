@@ -336,7 +336,7 @@ int launch_time_attn(const TimeAttnArgs& a, cudaStream_t s) {
     }
     const long long items = (long long)a.M * a.hkv;
     time_attn_kernel<D, G><<<(unsigned)((items + TA_WARPS - 1) / TA_WARPS), TA_WARPS * 32, smem, s>>>(a);
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -357,7 +357,7 @@ int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s) {
     }
     const long long items = (long long)a.nb * a.hkv;
     small_attn_kernel<<<(unsigned)((items + SA_WARPS - 1) / SA_WARPS), SA_WARPS * 32, smem, s>>>(a);
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -298,7 +298,7 @@ int launch_bulk(const TimeAttnArgs& a, cudaStream_t s) {
     const long long ctas_needed = (items + TB_WARPS - 1) / TB_WARPS;
     const unsigned grid = (unsigned)std::min<long long>(ctas_needed, num_sms);
     time_attn_bulk_kernel<D, G><<<grid, TB_WARPS * 32, smem, s>>>(a);
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -72,6 +72,10 @@ static inline GemmArgs gemm_args(const float* A, long long lda, const float* W, 
     return g;
 }
 
+// every kernel launch of the library is counted (bench.py reports the count it saw in the timed region)
+extern long long d4_launches_;
+#define D4_COUNT_LAUNCH() (++d4_launches_)
+
 #define D4_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return d4_fail_cuda(e__, #expr, __FILE__, __LINE__); } while (0)
 int d4_fail_cuda(cudaError_t e, const char* what, const char* file, int line);
 int d4_fail(const char* fmt, ...);

@@ -25,6 +25,8 @@ int d4_fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
 }
 extern "C" const char* d4_last_error(void) { return g_err; }
 extern "C" int d4_version(void) { return 100; }
+long long d4_launches_ = 0;
+extern "C" int64_t d4_launch_count(void) { return d4_launches_; }
 
 #define D4_TRY(expr) do { int rc__ = (expr); if (rc__ != 0) return rc__; } while (0)
 

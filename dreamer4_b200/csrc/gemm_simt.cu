@@ -140,6 +140,6 @@ int d4_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
         else D4_LAUNCH(false, true, true);
     }
 #undef D4_LAUNCH
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }

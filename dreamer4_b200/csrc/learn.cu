@@ -358,9 +358,9 @@ int mlp_backward(d4_ctx* c, const MlpW& mlp, const float* x0, int Rc, unsigned c
             const float* mean = reinterpret_cast<float*>(ws + p.mean[l]); const float* rstd = reinterpret_cast<float*>(ws + p.rstd[l]);
             dim3 grid(nblk(wout, 32), std::min(64, std::max(1, Rc / 64)));
             ln_param_grad_kernel<<<grid, 256, 0, s>>>(Rc, wout, Y, mean, rstd, mlp.lnw[l], mlp.lnb[l], dy, G.lnw[l], G.lnb[l]);
-            D4_CUDA_OK(cudaGetLastError());
+            D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
             ln_silu_bwd_rows_kernel<<<nblk(Rc, RPB), 32 * RPB, 0, s>>>(Rc, wout, Y, mean, rstd, mlp.lnw[l], mlp.lnb[l], dy);
-            D4_CUDA_OK(cudaGetLastError());
+            D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
         }
         const float* xin = (l == 0) ? x0 : reinterpret_cast<float*>(ws + p.X[l]);
         {   // dW += dy^T @ x_in
@@ -371,7 +371,7 @@ int mlp_backward(d4_ctx* c, const MlpW& mlp, const float* x0, int Rc, unsigned c
         {   // db += colsum(dy)
             dim3 grid(nblk(wout, 32), std::min(64, std::max(1, Rc / 64)));
             colsum_kernel<<<grid, 256, 0, s>>>(Rc, wout, dy, ldy, G.b[l]);
-            D4_CUDA_OK(cudaGetLastError());
+            D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
         }
         if (l > 0) {   // dx_in = dy @ W
             float* dxin = (dy == reinterpret_cast<float*>(ws + p.g0)) ? reinterpret_cast<float*>(ws + p.g1) : reinterpret_cast<float*>(ws + p.g0);
@@ -390,7 +390,7 @@ extern "C" int d4_gae(int B, int T, const float* rewards, const float* values, c
                       float gamma, float lam, float* returns, void* stream) {
     if (B <= 0 || T <= 0) return 0;
     gae_kernel<<<nblk(B, RPB), 32 * RPB, 0, static_cast<cudaStream_t>(stream)>>>(B, T, rewards, values, masks, learn_masks, gamma, lam, returns);
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -420,11 +420,11 @@ extern "C" int d4_learn(d4_ctx* c, const d4_learn_io* io, void* workspace, int64
 
     learn_masks_kernel<<<nblk(R, 256), 256, 0, s>>>(B, T, io->rewards, io->old_values, reinterpret_cast<const long long*>(io->lens),
                                                     io->is_truncated, r_m, v_m, gmask, lmask);
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     gae_kernel<<<nblk(B, RPB), 32 * RPB, 0, s>>>(B, T, r_m, v_m, gmask, lmask, io->gamma, io->lam, io->returns);
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     adv_stats_kernel<<<1, 1024, 0, s>>>(R, io->returns, v_m, lmask, io->normalize_advantages, io->zscore_eps, io->advantages, stats);
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
 
     const int D = c->D;
     const int ldl = std::max(c->ldlog, (c->cfg.value_bins + 3) / 4 * 4);
@@ -451,7 +451,7 @@ extern "C" int d4_learn(d4_ctx* c, const d4_learn_io* io, void* workspace, int64
         a.eps_clip = io->eps_clip; a.entropy_weight = io->entropy_weight; a.delight_temp = io->delight_temperature; a.use_gate = io->use_delight_gating;
         a.dlogits = dlogits; a.row_pl = row_pl + r0; a.row_ent = row_ent + r0;
         ppo_row_kernel<<<nblk(Rc, RPB), 32 * RPB, 0, s>>>(a);
-        D4_CUDA_OK(cudaGetLastError());
+        D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
         {   // d(unembed) += dlogits^T @ policy_embed ; d(policy_embed) = dlogits @ unembed
             GemmArgs g = gemm_args(dlogits, ldl, out, PH, io->grad_unembed, io->grad_unembed_ld, c->A_total, PH, Rc);
             g.transA = 1; g.transW = 1; g.residual = io->grad_unembed; g.ldr = io->grad_unembed_ld;
@@ -469,10 +469,10 @@ extern "C" int d4_learn(d4_ctx* c, const d4_learn_io* io, void* workspace, int64
         v.support = io->value_support; v.sigma_sqrt2 = io->value_sigma_sqrt2; v.hl_eps = io->hl_eps; v.lo = io->value_lo; v.hi = io->value_hi;
         v.dbins = dlogits; v.row_vl = row_vl + r0;
         value_row_kernel<<<nblk(Rc, RPB), 32 * RPB, 0, s>>>(v);
-        D4_CUDA_OK(cudaGetLastError());
+        D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
         D4_TRY(mlp_backward(c, c->value, x0, Rc, ws, p, dlogits, ldl, GV, s));
     }
     loss_reduce_kernel<<<1, 1024, 0, s>>>(R, row_pl, row_ent, row_vl, stats, io->entropy_weight, io->losses);
-    D4_CUDA_OK(cudaGetLastError());
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -206,53 +206,53 @@ inline int nblk(long long n, int per) { return (int)((n + per - 1) / per); }
 int d4_row_rstd(const float* x, long long ldx, RowMap map, int M, int D, float* out, cudaStream_t s) {
     if (M <= 0) return 0;
     row_rstd_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, map, M, D, out);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_rmsnorm_rows(const float* x, long long ldx, RowMap map, const float* w, int M, int D, float* out, long long ldo, cudaStream_t s) {
     if (M <= 0) return 0;
     rmsnorm_rows_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, map, w, M, D, out, ldo);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_ln_act_rows(const float* x, long long ldx, const float* w, const float* b, int M, int D, float* out, long long ldo, int act,
                    float* save_mean, float* save_rstd, cudaStream_t s) {
     if (M <= 0) return 0;
     ln_act_rows_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, w, b, M, D, out, ldo, act, save_mean, save_rstd);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_assemble_tokens(const AssembleArgs& a, cudaStream_t s) {
     assemble_tokens_kernel<<<a.B, 128, 0, s>>>(a);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_flow_step(float* x, const float* pred, long long n, float one_minus_tau, float dt, cudaStream_t s) {
     flow_step_kernel<<<nblk(n, 256), 256, 0, s>>>(x, pred, n, one_minus_tau, dt);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_store_latents(const float* x, float* out, int B, long long per_b, long long out_bstride, cudaStream_t s) {
     store_latents_kernel<<<nblk((long long)B * per_b, 256), 256, 0, s>>>(x, out, B, per_b, out_bstride);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_copy_rows(const float* src, long long lds, float* dst, long long ldd, int M, int D, cudaStream_t s) {
     if (M <= 0 || D <= 0) return 0;
     copy_rows_kernel<<<nblk((long long)M * D, 256), 256, 0, s>>>(src, lds, dst, ldd, M, D);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_hl_gauss_decode(const float* logits, long long ld, int M, int K, const float* centers, float* out, long long out_stride, cudaStream_t s) {
     if (M <= 0) return 0;
     hl_gauss_decode_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(logits, ld, M, K, centers, out, out_stride);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_sample_actions(const float* logits, long long ld, const float* u, long long ldu, int B, int na, const int* sizes_offs, float inv_temp,
                       long long* actions, long long act_stride, float* logp, long long lp_stride, cudaStream_t s) {
     if (B <= 0 || na <= 0) return 0;
     sample_actions_kernel<<<nblk((long long)B * na, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(logits, ld, u, ldu, B, na, sizes_offs, inv_temp,
                                                                                                  actions, act_stride, logp, lp_stride);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_mean_tokens(const float* x, int B, int N, int Dl, float* out, cudaStream_t s) {
     mean_tokens_kernel<<<nblk((long long)B * Dl, 256), 256, 0, s>>>(x, B, N, Dl, out);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_terminal_update(const float* logit, long long ld, const float* u, int B, int frame, long long* lens, unsigned char* terminals, cudaStream_t s) {
     terminal_update_kernel<<<nblk(B, 256), 256, 0, s>>>(logit, ld, u, B, frame, lens, terminals);
-    D4_CUDA_OK(cudaGetLastError()); return 0;
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }

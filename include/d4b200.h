@@ -53,6 +53,8 @@ typedef struct d4_ctx d4_ctx;
 
 const char* d4_last_error(void);
 int d4_version(void);
+/* number of CUDA kernels this library has launched in the calling process so far */
+int64_t d4_launch_count(void);
 
 /* ---- lifetime.  Replaces module construction state that the pass needs at run time (D4:4779-5269). */
 int d4_ctx_create(const d4_config* cfg, d4_ctx** out);

@@ -166,8 +166,9 @@ def test_linear_fp32(M, N, K, act):
                                            (515, 2730, 512, 1, 0), (700, 512, 1376, 0, 0), (4096, 260, 512, 0, 0), (256, 512, 512, 0, 4),
                                            (130, 170, 64, 2, 0), (3840, 1024, 32, 0, 0)])
 def test_linear_tcgen05(M, N, K, act, grp, terms):
-    """tcgen05 TF32 GEMM vs fp64.  Stated tolerance: tf32 (1 term) 2e-3 of the row/col norm product (10-bit mantissa inputs);
-    tf32x3 (3-term split) 2e-6 — fp32-level."""
+    """tcgen05 TF32 GEMM vs fp64.  Stated tolerance relative to max|C|: tf32 (1 term) 4e-3 (10-bit mantissa operands);
+    tf32x3 (3-term split) 1e-5 * max(1, K/256): the operand rounding is gone (2^-22) and what remains is the tensor-core
+    accumulator rounding toward zero, one step per UMMA (3*K/8 accumulations into TMEM)."""
     from dreamer4_b200.packing import tf32_split
     L, lib = _lib()
     torch.manual_seed(M + N + K)
@@ -198,7 +199,7 @@ def test_linear_tcgen05(M, N, K, act, grp, terms):
     else:
         ref = ref + res.double()
     assert not torch.isnan(Cc).any()
-    tol = 4e-3 if terms == 1 else 4e-6
+    tol = 4e-3 if terms == 1 else 1e-5 * max(1.0, K / 256)
     err = (Cc.double() - ref).abs().max().item()
     assert err < tol * max(1.0, ref.abs().max().item()), f'max abs err {err}'
 

@@ -110,6 +110,7 @@ def make_noise(cfg_model, B, H, pinned):
 
 def run_native(args):
     from dreamer4_b200 import DynamicsWorldModel, _lib
+    from dreamer4_b200.dist import allreduce_mean_grads_
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -147,12 +148,7 @@ def run_native(args):
         pl.backward()
         vl.backward()
         if dist is not None:            # one flat all-reduce of the head gradients (DDP-equivalent averaging)
-            grads = [p.grad for p in head_params if p.grad is not None]
-            flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat)
-            flat.div_(world)
-            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                g.copy_(f)
+            allreduce_mean_grads_(head_params)
         torch.nn.utils.clip_grad_norm_(model.policy_head_parameters(), 0.5)           # trainers.py:1440
         policy_optim.step(); policy_optim.zero_grad()
         torch.nn.utils.clip_grad_norm_(model.value_head_parameters(), 0.5)

@@ -4,5 +4,6 @@ Public names mirror the reference package (`dreamer4/__init__.py:1-15`, `dreamer
 classes on this path."""
 from .experience import Actions, Experience, combine_experiences
 from .dynamics import DynamicsWorldModel, ModelConfig, exists, default
+from .trainer import DreamTrainer
 
-__all__ = ['Actions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'ModelConfig', 'exists', 'default']
+__all__ = ['Actions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'ModelConfig', 'exists', 'default']

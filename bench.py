@@ -140,13 +140,23 @@ def run_native(args):
     dev_noise = {k: v.to(dev) for k, v in host_noise.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for k, v in host_noise.items() if k != 'terminal_uniform')
 
+    phase_events = []
+
+    def mark():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
     def step(e2e):
+        ev = [mark()]
         noise = {k: v.to(dev, non_blocking=True) for k, v in host_noise.items()} if e2e else dev_noise
         exp = model.generate(H, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
                              return_log_probs_and_values=True, noise=noise)           # trainers.py:1422-1428
+        ev.append(mark())
         pl, vl = model.learn_from_experience(exp)                                     # trainers.py:1430
         pl.backward()
         vl.backward()
+        ev.append(mark())
         if dist is not None:            # one flat all-reduce of the head gradients (DDP-equivalent averaging)
             allreduce_mean_grads_(head_params)
         torch.nn.utils.clip_grad_norm_(model.policy_head_parameters(), 0.5)           # trainers.py:1440
@@ -154,6 +164,8 @@ def run_native(args):
         torch.nn.utils.clip_grad_norm_(model.value_head_parameters(), 0.5)
         value_optim.step(); value_optim.zero_grad()
         out = torch.stack((pl.detach(), vl.detach(), exp.episode_return.mean()))
+        ev.append(mark())
+        phase_events.append(ev)
         return out.cpu() if e2e else out
 
     def barrier():
@@ -192,8 +204,12 @@ def run_native(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    phase_events.clear()
     ms, launches, prof, last = timed(args.steps, e2e=False, profile=not args.no_profile)
     clocks = sampler.stop() if rank == 0 else None
+    phases = dict(generate=sum(e[0].elapsed_time(e[1]) for e in phase_events) / args.steps,
+                  learn_fwd_bwd=sum(e[1].elapsed_time(e[2]) for e in phase_events) / args.steps,
+                  allreduce_clip_adamw=sum(e[2].elapsed_time(e[3]) for e in phase_events) / args.steps)
     step(True)                                   # warm the pinned-copy path
     ms_e2e, _, _, last_e2e = timed(args.steps, e2e=True)
 
@@ -211,7 +227,7 @@ def run_native(args):
                             l2='inputs larger than L2 (KV cache + activations per pass >> 126 MB)' if B * H >= 4096 else 'small problem: L2 resident'),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), clocks=clocks,
-                losses=dict(policy=float(last[0]), value=float(last[1])), peaks=pk['source'])
+                losses=dict(policy=float(last[0]), value=float(last[1])), peaks=pk['source'], phase_ms_per_step=phases)
     if prof is not None:
         names = ['gemm', 'time_attn', 'small_attn', 'other']
         total_ms = ms

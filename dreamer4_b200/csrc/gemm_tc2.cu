@@ -1,0 +1,378 @@
+// tcgen05 TF32 GEMM, persistent warp-specialised version (the throughput path of the linear layers).
+//
+//   One CTA per SM walks output tiles (n fastest, so an A tile stays L2-hot across its N tiles).
+//   warp 0   TMA producer      cp.async.bulk.tensor (SWIZZLE_128B) -> NS-stage shared-memory ring
+//   warp 1   MMA issuer        tcgen05.mma.kind::tf32 128 x BN x 8 into one of TWO TMEM accumulators (BN fp32 columns each)
+//   warps 2-5 epilogue         tcgen05.ld 32x32b -> row scale -> warp-private smem transpose -> bias / residual / GLU ->
+//                              fully coalesced 128-byte row stores; overlaps the next tile's main loop
+//   warps 6-9 A splitter       (tf32x3 only) hi/lo split of the landed A tile in shared memory
+//   Barriers: full/empty per smem stage, split_done per stage (x3), tmem_full/tmem_empty per accumulator.
+#include <cuda.h>
+#include <string.h>
+#include <algorithm>
+#include "kernels.h"
+
+namespace {
+
+constexpr int BM = 128, BK = 32, UMMA_K = 8;
+constexpr int A_TILE = BM * BK * 4;           // 16 KB
+constexpr int NUM_THREADS = 320;
+constexpr int STG_LD = 33;                    // epilogue staging row pitch (floats)
+
+struct __align__(64) TmaMaps2 { CUtensorMap a, w, wlo; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (int spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1 << 27)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {       // K-major SWIZZLE_128B, see gemm_tc.cu
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct EpiArgs2 {
+    float* C; long long ldc; int M, N;
+    const float* bias; const float* row_scale; const float* residual; long long ldr;
+    int act; RowMap cmap;
+    int a_grp, nkb, n_tiles_m, n_tiles_n;
+};
+
+template <int TERMS, int BN> struct Cfg {
+    static constexpr int W_TILE = BN * BK * 4;
+    static constexpr int STAGE = (TERMS == 3) ? 2 * A_TILE + 2 * W_TILE : A_TILE + W_TILE;
+    static constexpr int NS = (192 * 1024) / STAGE;                    // 4 (x1,BN=256), 6 (x1,128), 2 (x3,256), 3 (x3,128)
+    static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
+    static constexpr int SMEM = NS * STAGE + STG_BYTES + 512 + 1024;
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+template <int TERMS, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TmaMaps2 maps, const EpiArgs2 e) {
+    using K = Cfg<TERMS, BN>;
+    constexpr int NS = K::NS;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* stg_all = reinterpret_cast<float*>(smem + NS * K::STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * K::STAGE + K::STG_BYTES);
+    // bars: full[NS] | empty[NS] | split[NS] | tmem_full[2] | tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NS + 4);
+    auto bar = [&](int i) { return smem_u32(&bars[i]); };
+    constexpr int B_FULL = 0, B_EMPTY = NS, B_SPLIT = 2 * NS, B_TFULL = 3 * NS, B_TEMPTY = 3 * NS + 2;
+    constexpr int T_A = 0, T_ALO = A_TILE, T_W = (TERMS == 3) ? 2 * A_TILE : A_TILE, T_WLO = T_W + K::W_TILE;
+    auto tile = [&](int stage, int off) { return smem + stage * K::STAGE + off; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = e.nkb;
+    const int total_tiles = e.n_tiles_m * e.n_tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+        if (TERMS == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wlo) : "memory");
+        for (int s = 0; s < NS; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); mbar_init(bar(B_SPLIT + s), 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar(B_TFULL + b), 1); mbar_init(bar(B_TEMPTY + b), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        // ================= TMA producer
+        if (elect_one()) {
+            uint32_t kc = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m0 = (t / e.n_tiles_n) * BM, n0 = (t % e.n_tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++kc) {
+                    const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
+                    mbar_wait(bar(B_EMPTY + s), ph ^ 1);
+                    mbar_expect_tx(bar(B_FULL + s), A_TILE + (TERMS == 3 ? 2 : 1) * K::W_TILE);
+                    if (e.a_grp == 0) tma_load_2d(smem_u32(tile(s, T_A)), &maps.a, bar(B_FULL + s), kb * BK, m0);
+                    else              tma_load_3d(smem_u32(tile(s, T_A)), &maps.a, bar(B_FULL + s), kb * BK, 0, m0 / e.a_grp);
+                    tma_load_2d(smem_u32(tile(s, T_W)), &maps.w, bar(B_FULL + s), kb * BK, n0);
+                    if (TERMS == 3) tma_load_2d(smem_u32(tile(s, T_WLO)), &maps.wlo, bar(B_FULL + s), kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer
+        if (elect_one()) {
+            uint32_t kc = 0, ac = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ac) {
+                const int buf = ac & 1; const uint32_t aph = (ac >> 1) & 1;
+                mbar_wait(bar(B_TEMPTY + buf), aph ^ 1);                 // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_c = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++kc) {
+                    const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
+                    mbar_wait(bar((TERMS == 3 ? B_SPLIT : B_FULL) + s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = make_desc(smem_u32(tile(s, T_A))), dw = make_desc(smem_u32(tile(s, T_W)));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        if (TERMS == 3) {
+                            const uint64_t dalo = make_desc(smem_u32(tile(s, T_ALO))), dwlo = make_desc(smem_u32(tile(s, T_WLO)));
+                            umma_tf32(tmem_c, dalo + koff, dw + koff, K::IDESC, acc);
+                            umma_tf32(tmem_c, da + koff, dwlo + koff, K::IDESC, 1u);
+                            umma_tf32(tmem_c, da + koff, dw + koff, K::IDESC, 1u);
+                        } else {
+                            umma_tf32(tmem_c, da + koff, dw + koff, K::IDESC, acc);
+                        }
+                    }
+                    umma_commit(bar(B_EMPTY + s));
+                }
+                umma_commit(bar(B_TFULL + buf));
+            }
+        }
+    } else if (warp < 6) {
+        // ================= epilogue
+        const int quarter = warp & 3;
+        float* stg = stg_all + (warp - 2) * 32 * STG_LD;
+        const bool glu = (e.act == D4_ACT_GLU_SILU || e.act == D4_ACT_GLU_GELU);
+        uint32_t ac = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ac) {
+            const int m0 = (t / e.n_tiles_n) * BM, n0 = (t % e.n_tiles_n) * BN;
+            const int buf = ac & 1; const uint32_t aph = (ac >> 1) & 1;
+            mbar_wait(bar(B_TFULL + buf), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_c = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
+            const int mrow = m0 + quarter * 32 + lane;
+            const float rs = (mrow < e.M && e.row_scale) ? e.row_scale[mrow] : 1.f;
+            const int rbase = m0 + quarter * 32;
+            if (!glu) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int nb = n0 + c0;
+                    if (nb >= e.N) break;                               // warp-uniform
+                    float v[32];
+                    tmem_ld32(tmem_c + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = v[j] * rs;
+                    __syncwarp();
+                    const int col = nb + lane;
+                    const bool cok = col < e.N;
+                    const float bv = (cok && e.bias) ? e.bias[col] : 0.f;
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        const int m = rbase + r;
+                        if (m >= e.M) break;
+                        if (cok) {
+                            const long long crow = e.cmap(m);
+                            float o = stg[r * STG_LD + lane] + bv;
+                            if (e.residual) o += e.residual[crow * e.ldr + col];
+                            e.C[crow * e.ldc + col] = o;
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
+                const int on = e.N >> 1;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 64) {
+                    const int nb = n0 + c0;
+                    if (nb >= e.N) break;
+                    float v[32], w[32];
+                    tmem_ld32(tmem_c + (uint32_t)c0, v);
+                    tmem_ld32(tmem_c + (uint32_t)(c0 + 32), w);
+                    // bias is per (interleaved) input column: add before the gate
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int cx = nb + 2 * j, cy = nb + 32 + 2 * j;
+                        float x0 = v[2 * j] * rs, g0 = v[2 * j + 1] * rs, x1 = w[2 * j] * rs, g1 = w[2 * j + 1] * rs;
+                        if (e.bias) {
+                            if (cx + 1 < e.N) { x0 += e.bias[cx]; g0 += e.bias[cx + 1]; }
+                            if (cy + 1 < e.N) { x1 += e.bias[cy]; g1 += e.bias[cy + 1]; }
+                        }
+                        stg[lane * STG_LD + j] = x0 * ((e.act == D4_ACT_GLU_SILU) ? siluf_(g0) : geluf_(g0));
+                        stg[lane * STG_LD + 16 + j] = x1 * ((e.act == D4_ACT_GLU_SILU) ? siluf_(g1) : geluf_(g1));
+                    }
+                    __syncwarp();
+                    const int col = (nb >> 1) + lane;
+                    const bool cok = col < on;
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        const int m = rbase + r;
+                        if (m >= e.M) break;
+                        if (cok) e.C[e.cmap(m) * e.ldc + col] = stg[r * STG_LD + lane];
+                    }
+                    __syncwarp();
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar(B_TEMPTY + buf));
+        }
+    } else if (TERMS == 3) {
+        // ================= A splitter (tf32x3)
+        const int et = threadIdx.x - 192;          // 0..127
+        uint32_t kc = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb, ++kc) {
+                const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
+                mbar_wait(bar(B_FULL + s), ph);
+                float4* a = reinterpret_cast<float4*>(tile(s, T_A));
+                float4* alo = reinterpret_cast<float4*>(tile(s, T_ALO));
+#pragma unroll
+                for (int j = 0; j < A_TILE / 16 / 128; ++j) {
+                    const int idx = et + 128 * j;
+                    const float4 v = a[idx];
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+                    a[idx] = hi; alo[idx] = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(bar(B_SPLIT + s));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+int encode_2d(CUtensorMap* map, const float* base, long long rows, long long K, long long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return d4_fail("cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return d4_fail("cuTensorMapEncodeTiled(2d rows=%lld K=%lld ld=%lld) failed: %d", rows, K, ld, (int)r);
+    return 0;
+}
+int encode_3d(CUtensorMap* map, const float* base, long long M, long long K, long long ld, const RowMap& rm) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return d4_fail("cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rm.grp, (cuuint64_t)(M / rm.grp)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)rm.gstride * ld * 4};
+    cuuint32_t box[3] = {BK, (cuuint32_t)rm.grp, (cuuint32_t)(BM / rm.grp)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base + (long long)rm.goff * ld), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return d4_fail("cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+template <int TERMS, int BN>
+int launch2(const GemmArgs& g, cudaStream_t stream) {
+    using K = Cfg<TERMS, BN>;
+    TmaMaps2 maps; memset(&maps, 0, sizeof(maps));
+    if (g.amap.grp == 0) { int rc = encode_2d(&maps.a, g.A, g.M, g.K, g.lda, BM); if (rc) return rc; }
+    else { int rc = encode_3d(&maps.a, g.A, g.M, g.K, g.lda, g.amap); if (rc) return rc; }
+    { int rc = encode_2d(&maps.w, g.W, g.N, g.K, g.ldw, BN); if (rc) return rc; }
+    if (TERMS == 3) { int rc = encode_2d(&maps.wlo, g.W_lo, g.N, g.K, g.ldw, BN); if (rc) return rc; }
+    EpiArgs2 e;
+    e.C = g.C; e.ldc = g.ldc; e.M = g.M; e.N = g.N; e.bias = g.bias; e.row_scale = g.row_scale; e.residual = g.residual; e.ldr = g.ldr;
+    e.act = g.act; e.cmap = g.cmap; e.a_grp = g.amap.grp; e.nkb = (g.K + BK - 1) / BK;
+    e.n_tiles_m = (g.M + BM - 1) / BM; e.n_tiles_n = (g.N + BN - 1) / BN;
+    static bool configured = false;
+    if (!configured) {
+        D4_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<TERMS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        configured = true;
+    }
+    const long long tiles = (long long)e.n_tiles_m * e.n_tiles_n;
+    const unsigned grid = (unsigned)std::min<long long>(tiles, num_sms());
+    gemm_tc2_kernel<TERMS, BN><<<grid, NUM_THREADS, K::SMEM, stream>>>(maps, e);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// persistent kernel entry; bn = 128 or 256 (0 = choose by padding waste)
+int d4_gemm_tc2(const GemmArgs& g, int terms, int bn, cudaStream_t stream) {
+    if (bn == 0) {
+        const double w128 = (double)((g.N + 127) / 128 * 128) / g.N, w256 = (double)((g.N + 255) / 256 * 256) / g.N;
+        const long long tiles256 = (long long)((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
+        bn = (w256 <= w128 * 1.06 && tiles256 >= num_sms()) ? 256 : 128;
+    }
+    if (terms == 3) return bn == 256 ? launch2<3, 256>(g, stream) : launch2<3, 128>(g, stream);
+    return bn == 256 ? launch2<1, 256>(g, stream) : launch2<1, 128>(g, stream);
+}

@@ -7,6 +7,8 @@ int d4_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 // tcgen05 path: terms = 1 (tf32) or 3 (tf32x3 split: A split in shared memory, W_lo supplied)
 int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream);
 int d4_gemm_tc_supported(const GemmArgs& g);
+// persistent warp-specialised tcgen05 kernel (gemm_tc2.cu); bn = 128 / 256 / 0 (auto)
+int d4_gemm_tc2(const GemmArgs& g, int terms, int bn, cudaStream_t stream);
 
 // ---- row-wise kernels (rowops.cu)
 struct AssembleArgs {

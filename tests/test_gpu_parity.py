@@ -339,3 +339,69 @@ def test_generate_midsize_tf32_single_pass():
     print(f'tf32 single pass: max |latent err| = {err:.3e}, action agreement = {agree:.3f}')
     assert err < 5e-2
     assert agree >= 0.8
+
+
+# ------------------------------------------------------------------------------------------------ 100 seeded dream steps
+
+def test_hundred_seeded_dream_steps_losses():
+    """North star: actor/critic losses within 1e-4 relative of the reference over 100 seeded dream steps.
+
+    One DreamTrainer step (reference trainers.py:1416-1468) = generate(T+1) -> learn_from_experience -> backward ->
+    clip(0.5) -> AdamW(3e-4) on the policy head, then on the value head.  Both arms start from the same weights, consume
+    the same injected noise every step and run their own AdamW; the CUDA arm never sees the oracle's weights again after
+    step 0 (free-running).  A sampled action that flips (two logits + gumbel within fp32 reassociation noise of each other)
+    would fork the trajectories, so the test also asserts action indices stay bit-identical for all 100 steps — that is
+    what makes the 1e-4 relative bound on the losses meaningful rather than lucky."""
+    from dreamer4_b200 import DynamicsWorldModel
+    kwargs = dict(dim=64, dim_latent=16, num_latent_tokens=8, depth=4, time_block_every=2, attn_heads=2, attn_dim_head=32,
+                  num_discrete_actions=4, predict_terminals=False)
+    torch.manual_seed(11)
+    model = DynamicsWorldModel(**kwargs)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'unembed' in n:
+                p.mul_(30.)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    ocfg = O.config_from_reference_kwargs(**kwargs)
+    learn_keys = [k for k in sd if k.startswith(('policy_head.', 'value_head.')) or k == 'action_embedder.discrete_action_unembed']
+    pol_keys = [k for k in learn_keys if not k.startswith('value_head.')]
+    val_keys = [k for k in learn_keys if k.startswith('value_head.')]
+    ref_params = {k: sd[k].clone().requires_grad_(True) for k in learn_keys}
+    ref_pol_opt = torch.optim.AdamW([ref_params[k] for k in pol_keys], lr=3e-4, weight_decay=0.)
+    ref_val_opt = torch.optim.AdamW([ref_params[k] for k in val_keys], lr=3e-4, weight_decay=0.)
+    pol_opt = torch.optim.AdamW(model.policy_head_parameters(), lr=3e-4, weight_decay=0.)
+    val_opt = torch.optim.AdamW(model.value_head_parameters(), lr=3e-4, weight_decay=0.)
+
+    T, B, steps = 5, 8, 100
+    worst_p = worst_v = 0.
+    for step in range(steps):
+        noise = make_noise(model.cfg, T, B, seed=1000 + step)
+        # ---- oracle arm
+        cur = {**sd, **{k: v.detach() for k, v in ref_params.items()}}
+        ref = O.generate(cur, ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform']))
+        rpl, rvl, _ = O.learn_from_experience({**sd, **ref_params}, ocfg, ref)
+        rpl.backward()
+        rvl.backward()
+        torch.nn.utils.clip_grad_norm_([ref_params[k] for k in pol_keys], 0.5)
+        ref_pol_opt.step(); ref_pol_opt.zero_grad()
+        torch.nn.utils.clip_grad_norm_([ref_params[k] for k in val_keys], 0.5)
+        ref_val_opt.step(); ref_val_opt.zero_grad()
+        # ---- CUDA arm
+        exp = model.generate(T, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
+                             return_log_probs_and_values=True, noise=to_cuda(noise))
+        pl, vl = model.learn_from_experience(exp)
+        pl.backward()
+        vl.backward()
+        torch.nn.utils.clip_grad_norm_(model.policy_head_parameters(), 0.5)
+        pol_opt.step(); pol_opt.zero_grad()
+        torch.nn.utils.clip_grad_norm_(model.value_head_parameters(), 0.5)
+        val_opt.step(); val_opt.zero_grad()
+
+        assert torch.equal(exp.actions.discrete.cpu(), ref.actions), f'step {step}: sampled action indices diverged'
+        ep = abs(pl.item() - rpl.item()) / max(abs(rpl.item()), 1e-3)
+        ev = abs(vl.item() - rvl.item()) / max(abs(rvl.item()), 1e-3)
+        worst_p, worst_v = max(worst_p, ep), max(worst_v, ev)
+        assert ep < 1e-4, f'step {step}: policy loss {pl.item()} vs reference {rpl.item()} (rel {ep:.2e})'
+        assert ev < 1e-4, f'step {step}: value loss {vl.item()} vs reference {rvl.item()} (rel {ev:.2e})'
+    print(f'100 seeded dream steps: worst relative loss error policy {worst_p:.2e}, value {worst_v:.2e}')

@@ -11,6 +11,8 @@
 #include "kernels.h"
 #include <float.h>
 
+int d4_time_attn_bulk(const TimeAttnArgs& a, cudaStream_t s);   // attn_bulk.cu
+
 namespace {
 
 // torch.lerp(start, end, w) as ATen evaluates it (w < 0.5 ? start + w*(end-start) : end - (end-start)*(1-w))
@@ -113,6 +115,194 @@ __global__ void __launch_bounds__(SA_WARPS * 32) small_attn_kernel(SmallAttnArgs
             for (int e = 0; e < 4; ++e) { const int c = lane + 32 * e; if (c < d) op[c] = o[e] * gate; }
         }
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// space attention (nq == n <= 16): one warp per (frame, kv head), every phase lane-parallel.
+//   stage   K, V (value-residual lerp), Q pre-multiplied by the key-norm gain (gamma+1)*sqrt(d)   -> shared memory
+//   scores  lane = (query, key) pair, 64-long dot products from shared memory; key l2-norm applied as a per-key factor
+//   softmax lane = query row
+//   AV      lane = 2 output columns, all queries accumulated at once from the transposed probability tile
+//   belief projection, head gate, coalesced row stores
+template <int D>
+struct SpaceSmem {
+    static constexpr int P = D + 4, SMAX = 16;
+    float q[SMAX * P], k[SMAX * P], v[SMAX * P];
+    float pt[SMAX * SMAX];      // probabilities, transposed: pt[j * 16 + i]
+    float kinv[SMAX], vinv[SMAX];
+};
+
+constexpr int SP_WARPS = 4;
+
+template <int D>
+__global__ void __launch_bounds__(SP_WARPS * 32) space_attn_kernel(SmallAttnArgs a) {
+    using SM = SpaceSmem<D>;
+    constexpr int P = SM::P, C4 = D / 4, SMAX = SM::SMAX;
+    constexpr int CPL = (D >= 32) ? D / 32 : 1;          // output columns per lane
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * SP_WARPS + warp;
+    if (item >= (long long)a.nb * a.hkv) return;
+    const int b = (int)(item / a.hkv), hk = (int)(item % a.hkv);
+    SM& sm = reinterpret_cast<SM*>(smem_raw)[warp];
+    const int S = a.n;
+    const float sqrt_d = sqrtf((float)D);
+
+    for (int idx = lane; idx < SMAX * SMAX; idx += 32) sm.pt[idx] = 0.f;
+    for (int idx = lane; idx < S * C4; idx += 32) {
+        const int j = idx / C4, c = (idx % C4) * 4;
+        const float4 kv = *reinterpret_cast<const float4*>(a.k + b * a.k_sb + j * a.k_sj + (long long)hk * D + c);
+        float4 vv = *reinterpret_cast<const float4*>(a.v + b * a.v_sb + j * a.v_sj + (long long)hk * D + c);
+        if (a.v0) {
+            const float4 rv = *reinterpret_cast<const float4*>(a.v0 + b * a.v0_sb + j * a.v0_sj + (long long)hk * D + c);
+            const float w = sigmoidf_(a.mix[b * a.mix_sb + j * a.mix_sj + hk]);
+            vv.x = lerp_(vv.x, rv.x, w); vv.y = lerp_(vv.y, rv.y, w); vv.z = lerp_(vv.z, rv.z, w); vv.w = lerp_(vv.w, rv.w, w);
+        }
+        *reinterpret_cast<float4*>(sm.k + j * P + c) = kv;
+        *reinterpret_cast<float4*>(sm.v + j * P + c) = vv;
+    }
+    __syncwarp();
+    {   // l2 norms: lanes 0..15 keys, lanes 16..31 values
+        const int j = lane & 15;
+        if (j < S) {
+            const float* r = (lane < 16 ? sm.k : sm.v) + j * P;
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; c += 4) { const float4 t = *reinterpret_cast<const float4*>(r + c); ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w; }
+            const float inv = 1.f / fmaxf(sqrtf(ss), D4_L2_EPS);
+            (lane < 16 ? sm.kinv : sm.vinv)[j] = inv;
+        }
+    }
+
+    for (int gi = 0; gi < a.g; ++gi) {
+        const int hq = hk * a.g + gi;
+        __syncwarp();
+        for (int idx = lane; idx < S * C4; idx += 32) {
+            const int i = idx / C4, c = (idx % C4) * 4;
+            float4 qv = *reinterpret_cast<const float4*>(a.q + b * a.q_sb + i * a.q_si + (long long)hq * D + c);
+            const float4 gm = *reinterpret_cast<const float4*>(a.k_gamma + hk * D + c);
+            qv.x *= (gm.x + 1.f) * sqrt_d; qv.y *= (gm.y + 1.f) * sqrt_d; qv.z *= (gm.z + 1.f) * sqrt_d; qv.w *= (gm.w + 1.f) * sqrt_d;
+            *reinterpret_cast<float4*>(sm.q + i * P + c) = qv;
+        }
+        __syncwarp();
+        for (int pair = lane; pair < S * S; pair += 32) {
+            const int i = pair / S, j = pair - i * S;
+            const float* qr = sm.q + i * P; const float* kr = sm.k + j * P;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; c += 4) {
+                const float4 qv = *reinterpret_cast<const float4*>(qr + c);
+                const float4 kv = *reinterpret_cast<const float4*>(kr + c);
+                acc = fmaf(qv.x, kv.x, acc); acc = fmaf(qv.y, kv.y, acc); acc = fmaf(qv.z, kv.z, acc); acc = fmaf(qv.w, kv.w, acc);
+            }
+            float s = acc * sm.kinv[j] * a.scale;
+            if (a.softclamp > 0.f) s = tanhf(s / a.softclamp) * a.softclamp;
+            if (a.mask_agent && i < S - 1 && j == S - 1) s = -FLT_MAX;
+            sm.pt[j * SMAX + i] = s;
+        }
+        __syncwarp();
+        if (lane < S) {
+            float mx = -INFINITY;
+            for (int j = 0; j < S; ++j) mx = fmaxf(mx, sm.pt[j * SMAX + lane]);
+            float sum = 0.f;
+            for (int j = 0; j < S; ++j) { const float e = expf(sm.pt[j * SMAX + lane] - mx); sm.pt[j * SMAX + lane] = e; sum += e; }
+            const float inv = 1.f / sum;
+            for (int j = 0; j < S; ++j) sm.pt[j * SMAX + lane] *= inv;
+        }
+        __syncwarp();
+        float acc[SMAX][CPL];
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i)
+#pragma unroll
+            for (int e = 0; e < CPL; ++e) acc[i][e] = 0.f;
+        const int c0 = lane * CPL;
+        const bool col_ok = c0 < D;
+        for (int j = 0; j < S; ++j) {
+            float vv[CPL];
+#pragma unroll
+            for (int e = 0; e < CPL; ++e) vv[e] = col_ok ? sm.v[j * P + c0 + e] : 0.f;
+#pragma unroll
+            for (int i4 = 0; i4 < SMAX; i4 += 4) {
+                const float4 p4 = *reinterpret_cast<const float4*>(sm.pt + j * SMAX + i4);
+#pragma unroll
+                for (int e = 0; e < CPL; ++e) {
+                    acc[i4 + 0][e] = fmaf(p4.x, vv[e], acc[i4 + 0][e]); acc[i4 + 1][e] = fmaf(p4.y, vv[e], acc[i4 + 1][e]);
+                    acc[i4 + 2][e] = fmaf(p4.z, vv[e], acc[i4 + 2][e]); acc[i4 + 3][e] = fmaf(p4.w, vv[e], acc[i4 + 3][e]);
+                }
+            }
+        }
+        const float gate_l = (a.gate && lane < S) ? sigmoidf_(a.gate[b * a.gate_sb + lane * a.gate_si + hq]) : 1.f;
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) {
+            if (i < S) {                                   // warp-uniform
+                float o[CPL];
+#pragma unroll
+                for (int e = 0; e < CPL; ++e) o[e] = acc[i][e];
+                if (a.belief) {   // out -= (out . vhat) vhat,  vhat = l2norm(v_i)
+                    float vh[CPL], dot = 0.f;
+                    const float vinv = sm.vinv[i];
+#pragma unroll
+                    for (int e = 0; e < CPL; ++e) { vh[e] = col_ok ? sm.v[i * P + c0 + e] * vinv : 0.f; dot = fmaf(o[e], vh[e], dot); }
+                    dot = warp_sum(dot);
+#pragma unroll
+                    for (int e = 0; e < CPL; ++e) o[e] = o[e] - dot * vh[e];
+                }
+                const float gate = __shfl_sync(D4_FULL, gate_l, i);
+                if (col_ok) {
+                    float* op = a.out + b * a.out_sb + i * a.out_si + (long long)hq * D + c0;
+#pragma unroll
+                    for (int e = 0; e < CPL; ++e) op[e] = o[e] * gate;
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// attention-residual pool (one query per token, 4 heads x 64 = 256 wide, n <= 32 context hiddens): one warp per token
+// does all heads at once straight from global memory — lane = (head = lane / 8, 8-float slice of the head's 64 dims),
+// key l2-norm and q.k reduced over the 8 lanes of a head with shuffles, single-pass online softmax.
+constexpr int PL_WARPS = 8;
+
+__global__ void __launch_bounds__(PL_WARPS * 32) pool_attn_kernel(SmallAttnArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tok = (long long)blockIdx.x * PL_WARPS + warp;
+    if (tok >= a.nb) return;
+    const int c = lane * 8;                         // column slice [c, c+8) of the 256-wide row; head = lane / 8
+    const float sqrt_d = 8.f;
+    float q[8];
+    {
+        const float4 q0 = *reinterpret_cast<const float4*>(a.q + tok * a.q_sb + c), q1 = *reinterpret_cast<const float4*>(a.q + tok * a.q_sb + c + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(a.k_gamma + c), g1 = *reinterpret_cast<const float4*>(a.k_gamma + c + 4);
+        q[0] = q0.x * ((g0.x + 1.f) * sqrt_d); q[1] = q0.y * ((g0.y + 1.f) * sqrt_d); q[2] = q0.z * ((g0.z + 1.f) * sqrt_d); q[3] = q0.w * ((g0.w + 1.f) * sqrt_d);
+        q[4] = q1.x * ((g1.x + 1.f) * sqrt_d); q[5] = q1.y * ((g1.y + 1.f) * sqrt_d); q[6] = q1.z * ((g1.z + 1.f) * sqrt_d); q[7] = q1.w * ((g1.w + 1.f) * sqrt_d);
+    }
+    float mx = -INFINITY, den = 0.f, o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    const float* kp = a.k + tok * a.k_sb + c;
+    const float* vp = a.v + tok * a.v_sb + c;
+#pragma unroll 2
+    for (int j = 0; j < a.n; ++j) {
+        const float4 k0 = __ldcs(reinterpret_cast<const float4*>(kp + j * a.k_sj)), k1 = __ldcs(reinterpret_cast<const float4*>(kp + j * a.k_sj + 4));
+        const float4 v0 = __ldcs(reinterpret_cast<const float4*>(vp + j * a.v_sj)), v1 = __ldcs(reinterpret_cast<const float4*>(vp + j * a.v_sj + 4));
+        float ss = k0.x * k0.x + k0.y * k0.y + k0.z * k0.z + k0.w * k0.w + k1.x * k1.x + k1.y * k1.y + k1.z * k1.z + k1.w * k1.w;
+        float dot = q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w + q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) { ss += __shfl_xor_sync(D4_FULL, ss, off); dot += __shfl_xor_sync(D4_FULL, dot, off); }
+        const float s = dot / fmaxf(sqrtf(ss), D4_L2_EPS) * a.scale;
+        const float nmx = fmaxf(mx, s);
+        const float corr = expf(mx - nmx), p = expf(s - nmx);       // mx = -inf on the first key: corr = 0
+        den = den * corr + p;
+        o[0] = fmaf(p, v0.x, o[0] * corr); o[1] = fmaf(p, v0.y, o[1] * corr); o[2] = fmaf(p, v0.z, o[2] * corr); o[3] = fmaf(p, v0.w, o[3] * corr);
+        o[4] = fmaf(p, v1.x, o[4] * corr); o[5] = fmaf(p, v1.y, o[5] * corr); o[6] = fmaf(p, v1.z, o[6] * corr); o[7] = fmaf(p, v1.w, o[7] * corr);
+        mx = nmx;
+    }
+    const float gate = a.gate ? sigmoidf_(a.gate[tok * a.gate_sb + (lane >> 3)]) : 1.f;
+    const float sc = gate / den;
+    float* op = a.out + tok * a.out_sb + c;
+    *reinterpret_cast<float4*>(op) = make_float4(o[0] * sc, o[1] * sc, o[2] * sc, o[3] * sc);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(o[4] * sc, o[5] * sc, o[6] * sc, o[7] * sc);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -340,12 +530,43 @@ int launch_time_attn(const TimeAttnArgs& a, cudaStream_t s) {
     return 0;
 }
 
-}  // namespace
 
-int d4_time_attn_bulk(const TimeAttnArgs& a, cudaStream_t s);   // attn_bulk.cu
+template <int D>
+int launch_space(const SmallAttnArgs& a, cudaStream_t s) {
+    const size_t smem = sizeof(SpaceSmem<D>) * SP_WARPS;
+    static bool configured = false;
+    if (!configured) {
+        D4_CUDA_OK(cudaFuncSetAttribute(space_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long items = (long long)a.nb * a.hkv;
+    space_attn_kernel<D><<<(unsigned)((items + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, smem, s>>>(a);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
 
 int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s) {
     if (a.nb <= 0) return 0;
+    // attention-residual pools: one query per token, 4 x 64 heads, unit-stride 256-wide rows
+    if (a.nq == 1 && a.g == 1 && a.hkv == 4 && a.d == 64 && !a.v0 && !a.belief && !a.mask_agent && a.softclamp <= 0.f && a.n >= 1 &&
+        ((a.q_sb | a.k_sb | a.k_sj | a.v_sb | a.v_sj | a.out_sb) & 3) == 0 && al16p(a.q) && al16p(a.k) && al16p(a.v) && al16p(a.out) && al16p(a.k_gamma)) {
+        pool_attn_kernel<<<(unsigned)((a.nb + PL_WARPS - 1) / PL_WARPS), PL_WARPS * 32, 0, s>>>(a);
+        D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    // space attention of one frame: S x S, S <= 16
+    if (a.nq == a.n && a.n <= 16 && a.n >= 1 &&
+        ((a.q_sb | a.q_si | a.k_sb | a.k_sj | a.v_sb | a.v_sj | a.v0_sb | a.v0_sj) & 3) == 0 && al16p(a.q) && al16p(a.k) && al16p(a.v) &&
+        (!a.v0 || al16p(a.v0)) && al16p(a.k_gamma)) {
+        if (a.d == 64) return launch_space<64>(a, s);
+        if (a.d == 32) return launch_space<32>(a, s);
+        if (a.d == 16) return launch_space<16>(a, s);
+        if (a.d == 128) return launch_space<128>(a, s);
+    }
     if (a.n > 64 || a.n < 1) return d4_fail("small_attn: %d keys unsupported (1..64)", a.n);
     if (a.d % 4 != 0 || a.d > 128) return d4_fail("small_attn: head dim %d unsupported", a.d);
     if (a.belief && a.nq != a.n) return d4_fail("small_attn: belief projection needs nq == n");

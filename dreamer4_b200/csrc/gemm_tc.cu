@@ -349,16 +349,17 @@ int d4_gemm_tc_supported(const GemmArgs& g) {
     return 1;
 }
 
-// D4_GEMM_V=1 selects this one-tile-per-CTA kernel; the default is the persistent kernel in gemm_tc2.cu
-// (D4_GEMM_BN=128|256 pins its N tile).
+// Default: the CTA-pair kernel in gemm_tc3.cu (single-CTA persistent kernel of gemm_tc2.cu when M fits one CTA's rows).
+// D4_GEMM_V=2 forces gemm_tc2.cu, D4_GEMM_V=1 this one-tile-per-CTA kernel; D4_GEMM_BN=128|256 pins the N tile.
 int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream) {
     if (!d4_gemm_tc_supported(g)) return d4_fail("gemm_tc: unsupported shape / alignment");
     if (terms == 3 && (!g.W_lo || !al16(g.W_lo))) return d4_fail("gemm_tc: tf32x3 needs a 16-byte aligned W_lo");
     static int version = -1, bn = 0;
     if (version < 0) {
-        const char* v = getenv("D4_GEMM_V"); version = v ? atoi(v) : 2;
+        const char* v = getenv("D4_GEMM_V"); version = v ? atoi(v) : 3;
         const char* b = getenv("D4_GEMM_BN"); bn = b ? atoi(b) : 0;
     }
+    if (version == 3 && g.M > BM) return d4_gemm_tc3(g, terms == 3 ? 3 : 1, bn, stream);
     if (version != 1) return d4_gemm_tc2(g, terms == 3 ? 3 : 1, bn, stream);
     if (terms == 3) return launch<3>(g, stream);
     return launch<1>(g, stream);

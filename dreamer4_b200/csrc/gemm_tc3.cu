@@ -1,12 +1,16 @@
-// tcgen05 TF32 GEMM, persistent warp-specialised version (the throughput path of the linear layers).
+// tcgen05 TF32 GEMM, CTA-pair version (cta_group::2): the throughput path of the linear layers.
 //
-//   One CTA per SM walks output tiles (n fastest, so an A tile stays L2-hot across its N tiles).
-//   warp 0   TMA producer      cp.async.bulk.tensor (SWIZZLE_128B) -> NS-stage shared-memory ring
-//   warp 1   MMA issuer        tcgen05.mma.kind::tf32 128 x BN x 8 into one of TWO TMEM accumulators (BN fp32 columns each)
-//   warps 2-5 epilogue         tcgen05.ld 32x32b -> row scale -> warp-private smem transpose -> bias / residual / GLU ->
-//                              fully coalesced 128-byte row stores; overlaps the next tile's main loop
-//   warps 6-9 A splitter       (tf32x3 only) hi/lo split of the landed A tile in shared memory
-//   Barriers: full/empty per smem stage, split_done per stage (x3), tmem_full/tmem_empty per accumulator.
+// Why a CTA pair: with both operands in shared memory a single-CTA 128 x 256 x 8 TF32 MMA reads 12 KB of shared memory
+// per 128 tensor cycles = 96 B/clk of the SM's 128 B/clk — the tf32x3 operand splitter and the epilogue staging then push
+// the SM past its shared-memory bandwidth (measured: 64 % tensor-pipe activity at best, profiles/r1a_ncu_gemm_raw.csv).
+// A pair computes a 256 x BN tile: each SM multiplies its own 128 rows of A with ALL BN weight rows but stages only BN/2
+// of them, so operand traffic per SM drops to 64 B/clk and a stage is 64 KB instead of 96 KB (3 ring stages, not 2).
+//
+//   cluster (2,1,1), one cluster per TPC, persistent over 256 x BN output tiles (n fastest)
+//   warp 0    TMA producer (each CTA loads its A rows and its half of the W rows; W arrives on the LEADER's barrier)
+//   warp 1    MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, accumulators double-buffered in TMEM
+//   warps 2-5 epilogue of this CTA's 128 rows (tcgen05.ld -> row scale -> smem transpose -> bias/residual/GLU -> 128-B row stores)
+//   warps 6-9 tf32x3 only: hi/lo split of this CTA's A tile in shared memory, then ONE remote arrive on the leader's barrier
 #include <cuda.h>
 #include <string.h>
 #include <algorithm>
@@ -17,9 +21,10 @@ namespace {
 constexpr int BM = 128, BK = 32, UMMA_K = 8;
 constexpr int A_TILE = BM * BK * 4;           // 16 KB
 constexpr int NUM_THREADS = 320;
-constexpr int STG_LD = 33;                    // epilogue staging row pitch (floats)
+constexpr int STG_LD = 33;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: the even (leader) CTA's copy
 
-struct __align__(64) TmaMaps2 { CUtensorMap a, w, wlo; };
+struct __align__(64) TmaMaps3 { CUtensorMap a, w, wlo; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool elect_one() {
@@ -27,21 +32,30 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// arrive on a barrier that may live in the peer CTA (shared::cluster address), cluster-scope release
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (int spin = 0; !mbar_try_wait(bar, parity); ++spin)
-        if (spin > (1 << 27)) __trap();
+        if (spin > (1 << 27)) __trap();          // never hang the box on a protocol bug
 }
+// local load: data and completion both in this CTA
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
@@ -50,14 +64,25 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// pair load: data lands in this CTA, the transaction bytes are counted on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// all previously issued MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {       // K-major SWIZZLE_128B, see gemm_tc.cu
     uint64_t d = 0;
@@ -82,38 +107,42 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-struct EpiArgs2 {
+struct EpiArgs3 {
     float* C; long long ldc; int M, N;
     const float* bias; const float* row_scale; const float* residual; long long ldr;
     int act; RowMap cmap;
     int a_grp, nkb, n_tiles_m, n_tiles_n;
 };
 
-template <int TERMS, int BN> struct Cfg {
-    static constexpr int W_TILE = BN * BK * 4;
+template <int TERMS, int BN> struct Cfg3 {
+    static constexpr int BNH = BN / 2;                                  // weight rows staged per CTA
+    static constexpr int W_TILE = BNH * BK * 4;
     static constexpr int STAGE = (TERMS == 3) ? 2 * A_TILE + 2 * W_TILE : A_TILE + W_TILE;
-    static constexpr int NS = (192 * 1024) / STAGE;                    // 4 (x1,BN=256), 6 (x1,128), 2 (x3,256), 3 (x3,128)
+    static constexpr int NS = (TERMS == 3) ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 6 : 8);
     static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
-    static constexpr int SMEM = NS * STAGE + STG_BYTES + 512 + 1024;
-    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static constexpr int NBARS = 4 * NS + 4;                            // full | fullA | empty | split | tfull[2] | tempty[2]
+    static constexpr int SMEM = NS * STAGE + STG_BYTES + NBARS * 8 + 64 + 1024;
+    // instruction descriptor: D=f32, A=B=tf32, K-major, N>>3 at bit 17, M>>4 at bit 24 with M = 256 (the pair's rows)
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
 template <int TERMS, int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ TmaMaps2 maps, const EpiArgs2 e) {
-    using K = Cfg<TERMS, BN>;
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_constant__ TmaMaps3 maps, const EpiArgs3 e) {
+    using K = Cfg3<TERMS, BN>;
     constexpr int NS = K::NS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* stg_all = reinterpret_cast<float*>(smem + NS * K::STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * K::STAGE + K::STG_BYTES);
-    // bars: full[NS] | empty[NS] | split[NS] | tmem_full[2] | tmem_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NS + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + K::NBARS);
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
-    constexpr int B_FULL = 0, B_EMPTY = NS, B_SPLIT = 2 * NS, B_TFULL = 3 * NS, B_TEMPTY = 3 * NS + 2;
+    constexpr int B_FULL = 0, B_FULLA = NS, B_EMPTY = 2 * NS, B_SPLIT = 3 * NS, B_TFULL = 4 * NS, B_TEMPTY = 4 * NS + 2;
     constexpr int T_A = 0, T_ALO = A_TILE, T_W = (TERMS == 3) ? 2 * A_TILE : A_TILE, T_WLO = T_W + K::W_TILE;
     auto tile = [&](int stage, int off) { return smem + stage * K::STAGE + off; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();              // 0 = leader (issues the MMAs, owns the shared barriers)
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int nkb = e.nkb;
     const int total_tiles = e.n_tiles_m * e.n_tiles_n;
 
@@ -121,48 +150,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
         if (TERMS == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wlo) : "memory");
-        for (int s = 0; s < NS; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); mbar_init(bar(B_SPLIT + s), 128); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar(B_TFULL + b), 1); mbar_init(bar(B_TEMPTY + b), 128); }
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_FULLA + s), 1); mbar_init(bar(B_EMPTY + s), 1); mbar_init(bar(B_SPLIT + s), 2);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar(B_TFULL + b), 1); mbar_init(bar(B_TEMPTY + b), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    cluster_sync_all();                                // both CTAs' barriers exist before anything can signal them
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster_sync_all();                                // both halves of the pair's tensor memory are allocated
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     if (warp == 0) {
-        // ================= TMA producer
+        // ================= TMA producer (both CTAs)
         if (elect_one()) {
             uint32_t kc = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int m0 = (t / e.n_tiles_n) * BM, n0 = (t % e.n_tiles_n) * BN;
+            for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+                const int m0 = (t / e.n_tiles_n) * (2 * BM) + (int)rank * BM;
+                const int n0 = (t % e.n_tiles_n) * BN + (int)rank * K::BNH;
                 for (int kb = 0; kb < nkb; ++kb, ++kc) {
                     const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
                     mbar_wait(bar(B_EMPTY + s), ph ^ 1);
-                    mbar_expect_tx(bar(B_FULL + s), A_TILE + (TERMS == 3 ? 2 : 1) * K::W_TILE);
-                    if (e.a_grp == 0) tma_load_2d(smem_u32(tile(s, T_A)), &maps.a, bar(B_FULL + s), kb * BK, m0);
-                    else              tma_load_3d(smem_u32(tile(s, T_A)), &maps.a, bar(B_FULL + s), kb * BK, 0, m0 / e.a_grp);
-                    tma_load_2d(smem_u32(tile(s, T_W)), &maps.w, bar(B_FULL + s), kb * BK, n0);
-                    if (TERMS == 3) tma_load_2d(smem_u32(tile(s, T_WLO)), &maps.wlo, bar(B_FULL + s), kb * BK, n0);
+                    if (TERMS == 3) {
+                        // A completes on this CTA's own barrier (its splitter warps wait there); W on the leader's
+                        mbar_expect_tx(bar(B_FULLA + s), A_TILE);
+                        if (e.a_grp == 0) tma_load_2d(smem_u32(tile(s, T_A)), &maps.a, bar(B_FULLA + s), kb * BK, m0);
+                        else              tma_load_3d(smem_u32(tile(s, T_A)), &maps.a, bar(B_FULLA + s), kb * BK, 0, m0 / e.a_grp);
+                        if (rank == 0) mbar_expect_tx(bar(B_FULL + s), 4 * K::W_TILE);
+                        tma_load_2d_pair(smem_u32(tile(s, T_W)), &maps.w, bar(B_FULL + s), kb * BK, n0);
+                        tma_load_2d_pair(smem_u32(tile(s, T_WLO)), &maps.wlo, bar(B_FULL + s), kb * BK, n0);
+                    } else {
+                        if (rank == 0) mbar_expect_tx(bar(B_FULL + s), 2 * (A_TILE + K::W_TILE));
+                        if (e.a_grp == 0) tma_load_2d_pair(smem_u32(tile(s, T_A)), &maps.a, bar(B_FULL + s), kb * BK, m0);
+                        else              tma_load_3d_pair(smem_u32(tile(s, T_A)), &maps.a, bar(B_FULL + s), kb * BK, 0, m0 / e.a_grp);
+                        tma_load_2d_pair(smem_u32(tile(s, T_W)), &maps.w, bar(B_FULL + s), kb * BK, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer
-        if (elect_one()) {
+        // ================= MMA issuer (leader CTA only)
+        if (rank == 0 && elect_one()) {
             uint32_t kc = 0, ac = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ac) {
+            for (int t = cluster_id; t < total_tiles; t += n_clusters, ++ac) {
                 const int buf = ac & 1; const uint32_t aph = (ac >> 1) & 1;
-                mbar_wait(bar(B_TEMPTY + buf), aph ^ 1);                 // epilogue has drained this accumulator
+                mbar_wait(bar(B_TEMPTY + buf), aph ^ 1);                 // both CTAs' epilogues have drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_c = tmem_base + (uint32_t)(buf * BN);
                 for (int kb = 0; kb < nkb; ++kb, ++kc) {
                     const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
-                    mbar_wait(bar((TERMS == 3 ? B_SPLIT : B_FULL) + s), ph);
+                    mbar_wait(bar(B_FULL + s), ph);
+                    if (TERMS == 3) mbar_wait(bar(B_SPLIT + s), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = make_desc(smem_u32(tile(s, T_A))), dw = make_desc(smem_u32(tile(s, T_W)));
 #pragma unroll
@@ -171,40 +214,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
                         const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
                         if (TERMS == 3) {
                             const uint64_t dalo = make_desc(smem_u32(tile(s, T_ALO))), dwlo = make_desc(smem_u32(tile(s, T_WLO)));
-                            umma_tf32(tmem_c, dalo + koff, dw + koff, K::IDESC, acc);
-                            umma_tf32(tmem_c, da + koff, dwlo + koff, K::IDESC, 1u);
-                            umma_tf32(tmem_c, da + koff, dw + koff, K::IDESC, 1u);
+                            umma_tf32_pair(tmem_c, dalo + koff, dw + koff, K::IDESC, acc);
+                            umma_tf32_pair(tmem_c, da + koff, dwlo + koff, K::IDESC, 1u);
+                            umma_tf32_pair(tmem_c, da + koff, dw + koff, K::IDESC, 1u);
                         } else {
-                            umma_tf32(tmem_c, da + koff, dw + koff, K::IDESC, acc);
+                            umma_tf32_pair(tmem_c, da + koff, dw + koff, K::IDESC, acc);
                         }
                     }
-                    umma_commit(bar(B_EMPTY + s));
+                    umma_commit_pair(bar(B_EMPTY + s));                  // frees the stage in both CTAs
                 }
-                umma_commit(bar(B_TFULL + buf));
+                umma_commit_pair(bar(B_TFULL + buf));                    // accumulator complete, both CTAs' epilogues
             }
         }
     } else if (warp < 6) {
-        // ================= epilogue
-        // Per 32-column chunk: residual rows are prefetched into registers (32 independent coalesced loads per lane) one
-        // chunk ahead, the accumulator chunk is read with tcgen05.ld, transposed through a warp-private padded smem tile
-        // and written back as fully coalesced 128-byte row segments.
+        // ================= epilogue of this CTA's 128 rows (see gemm_tc2.cu for the data flow)
         const int quarter = warp & 3;
         float* stg = stg_all + (warp - 2) * 32 * STG_LD;
         const bool glu = (e.act == D4_ACT_GLU_SILU || e.act == D4_ACT_GLU_GELU);
         const float* __restrict__ resid = e.residual;
         const float* __restrict__ biasp = e.bias;
         float* __restrict__ Cp = e.C;
+        const uint32_t tempty_leader = bar(B_TEMPTY) & PEER_MASK;
         uint32_t ac = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ac) {
-            const int m0 = (t / e.n_tiles_n) * BM, n0 = (t % e.n_tiles_n) * BN;
+        for (int t = cluster_id; t < total_tiles; t += n_clusters, ++ac) {
+            const int m0 = (t / e.n_tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % e.n_tiles_n) * BN;
             const int buf = ac & 1; const uint32_t aph = (ac >> 1) & 1;
             const int rbase = m0 + quarter * 32;
             const int mrow = rbase + lane;
             const float rs = (mrow < e.M && e.row_scale) ? e.row_scale[mrow] : 1.f;
             const int crow_lane = (mrow < e.M) ? (int)e.cmap(mrow) : -1;      // physical output row of TMEM lane `lane`
             const int nrows = min(32, e.M - rbase);                          // warp-uniform (may be <= 0)
+            const uint32_t tmem_c = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
             if (!glu) {
-                const bool ident = (e.cmap.grp == 0);                        // output rows are the tile rows themselves
+                const bool ident = (e.cmap.grp == 0);
                 const bool has_res = (resid != nullptr);
                 float res[32];
                 auto prefetch = [&](int c0, float (&dst)[32]) {
@@ -228,7 +270,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
                 }
                 mbar_wait(bar(B_TFULL + buf), aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_c = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     const int nb = n0 + c0;
@@ -265,7 +306,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
             } else {
                 mbar_wait(bar(B_TFULL + buf), aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_c = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
                 const int on = e.N >> 1;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 64) {
@@ -305,16 +345,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(bar(B_TEMPTY + buf));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)buf * 8u);      // one arrival per warp, 8 per pair
         }
     } else if (TERMS == 3) {
-        // ================= A splitter (tf32x3)
+        // ================= A splitter (tf32x3): this CTA's A tile -> hi (in place) + lo, then one arrival on the leader's barrier
         const int et = threadIdx.x - 192;          // 0..127
+        const uint32_t split_leader = bar(B_SPLIT) & PEER_MASK;
         uint32_t kc = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = cluster_id; t < total_tiles; t += n_clusters) {
             for (int kb = 0; kb < nkb; ++kb, ++kc) {
                 const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
-                mbar_wait(bar(B_FULL + s), ph);
+                mbar_wait(bar(B_FULLA + s), ph);
                 float4* a = reinterpret_cast<float4*>(tile(s, T_A));
                 float4* alo = reinterpret_cast<float4*>(tile(s, T_ALO));
 #pragma unroll
@@ -329,15 +371,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
                     a[idx] = hi; alo[idx] = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(bar(B_SPLIT + s));
+                asm volatile("bar.sync 1, 128;" ::: "memory");                          // the four splitter warps
+                if (et == 0) mbar_arrive_cluster(split_leader + (uint32_t)s * 8u);
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster_sync_all();                                // nobody leaves (or frees tensor memory) while the peer may still touch it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
     }
 }
 
@@ -381,45 +424,60 @@ int encode_3d(CUtensorMap* map, const float* base, long long M, long long K, lon
     return 0;
 }
 
-int num_sms() {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-    return n;
+template <int TERMS, int BN>
+int max_clusters() {
+    // how many CTA pairs can be co-resident (one per TPC on a full B200: 74)
+    using K = Cfg3<TERMS, BN>;
+    static int cached = 0;
+    if (cached) return cached;
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2, 1, 1); cfg.blockDim = dim3(NUM_THREADS, 1, 1); cfg.dynamicSmemBytes = K::SMEM;
+    cudaLaunchAttribute attr; attr.id = cudaLaunchAttributeClusterDimension; attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc3_kernel<TERMS, BN>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
+    cached = n > 0 ? n : -1;
+    return cached;
 }
 
 template <int TERMS, int BN>
-int launch2(const GemmArgs& g, cudaStream_t stream) {
-    using K = Cfg<TERMS, BN>;
-    TmaMaps2 maps; memset(&maps, 0, sizeof(maps));
-    if (g.amap.grp == 0) { int rc = encode_2d(&maps.a, g.A, g.M, g.K, g.lda, BM); if (rc) return rc; }
-    else { int rc = encode_3d(&maps.a, g.A, g.M, g.K, g.lda, g.amap); if (rc) return rc; }
-    { int rc = encode_2d(&maps.w, g.W, g.N, g.K, g.ldw, BN); if (rc) return rc; }
-    if (TERMS == 3) { int rc = encode_2d(&maps.wlo, g.W_lo, g.N, g.K, g.ldw, BN); if (rc) return rc; }
-    EpiArgs2 e;
-    e.C = g.C; e.ldc = g.ldc; e.M = g.M; e.N = g.N; e.bias = g.bias; e.row_scale = g.row_scale; e.residual = g.residual; e.ldr = g.ldr;
-    e.act = g.act; e.cmap = g.cmap; e.a_grp = g.amap.grp; e.nkb = (g.K + BK - 1) / BK;
-    e.n_tiles_m = (g.M + BM - 1) / BM; e.n_tiles_n = (g.N + BN - 1) / BN;
+int launch3(const GemmArgs& g, cudaStream_t stream) {
+    using K = Cfg3<TERMS, BN>;
     static bool configured = false;
     if (!configured) {
-        D4_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<TERMS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        D4_CUDA_OK(cudaFuncSetAttribute(gemm_tc3_kernel<TERMS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
         configured = true;
     }
+    const int maxc = max_clusters<TERMS, BN>();
+    if (maxc <= 0) return d4_fail("gemm_tc3: no CTA pair of %d bytes of shared memory can be scheduled on this device", K::SMEM);
+    TmaMaps3 maps; memset(&maps, 0, sizeof(maps));
+    if (g.amap.grp == 0) { int rc = encode_2d(&maps.a, g.A, g.M, g.K, g.lda, BM); if (rc) return rc; }
+    else { int rc = encode_3d(&maps.a, g.A, g.M, g.K, g.lda, g.amap); if (rc) return rc; }
+    { int rc = encode_2d(&maps.w, g.W, g.N, g.K, g.ldw, K::BNH); if (rc) return rc; }
+    if (TERMS == 3) { int rc = encode_2d(&maps.wlo, g.W_lo, g.N, g.K, g.ldw, K::BNH); if (rc) return rc; }
+    EpiArgs3 e;
+    e.C = g.C; e.ldc = g.ldc; e.M = g.M; e.N = g.N; e.bias = g.bias; e.row_scale = g.row_scale; e.residual = g.residual; e.ldr = g.ldr;
+    e.act = g.act; e.cmap = g.cmap; e.a_grp = g.amap.grp; e.nkb = (g.K + BK - 1) / BK;
+    e.n_tiles_m = (g.M + 2 * BM - 1) / (2 * BM); e.n_tiles_n = (g.N + BN - 1) / BN;
     const long long tiles = (long long)e.n_tiles_m * e.n_tiles_n;
-    const unsigned grid = (unsigned)std::min<long long>(tiles, num_sms());
-    gemm_tc2_kernel<TERMS, BN><<<grid, NUM_THREADS, K::SMEM, stream>>>(maps, e);
-    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+    const int clusters = (int)std::min<long long>(tiles, maxc);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters, 1, 1); cfg.blockDim = dim3(NUM_THREADS, 1, 1); cfg.dynamicSmemBytes = K::SMEM; cfg.stream = stream;
+    cudaLaunchAttribute attr; attr.id = cudaLaunchAttributeClusterDimension; attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    D4_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc3_kernel<TERMS, BN>, maps, e));
+    D4_COUNT_LAUNCH();
     return 0;
 }
 
 }  // namespace
 
-// persistent kernel entry; bn = 128 or 256 (0 = choose by padding waste)
-int d4_gemm_tc2(const GemmArgs& g, int terms, int bn, cudaStream_t stream) {
+// CTA-pair kernel entry; bn = 128 or 256 (0 = choose by padding waste)
+int d4_gemm_tc3(const GemmArgs& g, int terms, int bn, cudaStream_t stream) {
     if (bn == 0) {
-        const double w128 = (double)((g.N + 127) / 128 * 128) / g.N, w256 = (double)((g.N + 255) / 256 * 256) / g.N;
-        const long long tiles256 = (long long)((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
-        bn = (w256 <= w128 * 1.06 && tiles256 >= num_sms()) ? 256 : 128;
+        const long long p128 = (long long)(g.N + 127) / 128 * 128, p256 = (long long)(g.N + 255) / 256 * 256;
+        bn = (p128 * 10 < p256 * 9) ? 128 : 256;           // the narrow tile only when it saves more than 10 % of the columns
     }
-    if (terms == 3) return bn == 256 ? launch2<3, 256>(g, stream) : launch2<3, 128>(g, stream);
-    return bn == 256 ? launch2<1, 256>(g, stream) : launch2<1, 128>(g, stream);
+    if (terms == 3) return bn == 256 ? launch3<3, 256>(g, stream) : launch3<3, 128>(g, stream);
+    return bn == 256 ? launch3<1, 256>(g, stream) : launch3<1, 128>(g, stream);
 }

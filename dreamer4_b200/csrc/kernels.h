@@ -9,6 +9,8 @@ int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream);
 int d4_gemm_tc_supported(const GemmArgs& g);
 // persistent warp-specialised tcgen05 kernel (gemm_tc2.cu); bn = 128 / 256 / 0 (auto)
 int d4_gemm_tc2(const GemmArgs& g, int terms, int bn, cudaStream_t stream);
+// CTA-pair (cta_group::2) persistent kernel (gemm_tc3.cu): 256 x bn output tiles, bn = 128 / 256 / 0 (auto)
+int d4_gemm_tc3(const GemmArgs& g, int terms, int bn, cudaStream_t stream);
 
 // ---- row-wise kernels (rowops.cu)
 struct AssembleArgs {

@@ -1,9 +1,9 @@
 // K1 variant 1: time-decode attention with the KV stream staged by the bulk-copy engine.
 //
-// Persistent kernel, one CTA per SM, 8 warps; every warp owns a private ring of NS shared-memory stages fed by
+// Persistent kernel, one CTA per SM, 16 warps; every warp owns a private ring of shared-memory stages fed by
 // cp.async.bulk (UBLKCP) completing on warp-private mbarriers, and walks its (token, kv-head) streams with the ring
 // always NS tiles ahead — across stream boundaries too, so the HBM pipe never drains between streams.
-// Each tile is 32 cached keys (or values) = 32*d*4 contiguous bytes of the (M, h, Tmax, d) cache.
+// A tile is 16 cached keys (or values) = 16*d*4 contiguous bytes of the (M, h, Tmax, d) cache.
 // The next stream's token inputs are prefetched into registers while the current stream is processed, so the only
 // exposed latency is the bulk-copy ring itself.
 #include "kernels.h"
@@ -43,17 +43,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int TB_WARPS = 8;
-constexpr int TB_NS = 3;             // ring depth in full 32-key tiles: the ring is TB_NS * 32 key rows per warp
-constexpr int TB_MAXNS = 16;         // short contexts slice the same shared memory into up to 16 smaller stages
-constexpr int TB_MAXTILES = 8;
+constexpr int TB_TK = 16;            // cached key (or value) rows per full tile
+constexpr int TB_RING = 48;          // ring capacity per warp in cached rows: three full tiles in flight / in use
+constexpr int TB_MAXNS = 16;         // short contexts slice the same ring into up to 16 smaller stages
+constexpr int TB_MAXT = 256;         // longest context (scores of one stream live in shared memory)
 
 template <int D, int G>
 struct TbWarpSmem {
-    float tile[TB_NS * 32 * D];
+    float tile[TB_RING * D];
+    float s[G][TB_MAXT];             // scores, then unnormalised probabilities, of the current stream
     float q[G * D];
     float vnew[D];
-    float p[G][32];
     uint64_t bar[TB_MAXNS];
 };
 
@@ -63,31 +63,32 @@ struct TbRaw {
     float k1[PPL], k2[PPL], v1[PPL], v2[PPL], r1[PPL], r2[PPL], g1[PPL], g2[PPL];
     float q1[G][PPL], q2[G][PPL];
     float mix, gate[G];
+    int m, hk;
 };
 
-template <int D, int G>
-__global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAttnArgs a) {
+template <int D, int G, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) time_attn_bulk_kernel(TimeAttnArgs a) {
     constexpr int HALF = D / 2;
     constexpr int PPL = (HALF + 31) / 32;
-    constexpr int C4 = D / 4;
+    constexpr int CH = D / 8;             // float4 chunks per half row (two lanes share one cached key in the score pass)
     constexpr int LPK = D / 4;            // lanes that cover one cached value row with float4 columns
     constexpr int KG = 32 / LPK;          // value rows processed per AV step
-    static_assert(D % 4 == 0 && LPK <= 32 && (32 % LPK) == 0, "head dim must be 16, 32, 64 or 128");
+    static_assert(D % 8 == 0 && LPK <= 32 && (32 % LPK) == 0, "head dim must be 16, 32, 64 or 128");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TbWarpSmem<D, G>& sm = reinterpret_cast<TbWarpSmem<D, G>*>(smem_raw)[warp];
 
-    const long long total = (long long)a.M * a.hkv;
-    const long long wstride = (long long)gridDim.x * TB_WARPS;
-    const long long first = (long long)blockIdx.x * TB_WARPS + warp;
+    const int total = a.M * a.hkv;
+    const int wstride = (int)gridDim.x * WARPS;
+    const int first = (int)blockIdx.x * WARPS + warp;
     const int t = a.t;
-    // a tile is TK cached key (or value) rows; contexts shorter than 32 use one small tile per stream and a deeper ring,
-    // so the copies in flight still cover several streams ahead
-    const int TK = min(32, max(t, 1));
+    // a tile is TK cached rows; contexts shorter than a full tile use one small tile per stream and a deeper ring, so the
+    // copies in flight still cover several streams ahead
+    const int TK = min(max(t, 1), TB_TK);         // (nvcc 12.9 folds the equivalent `t >= 16 ? 16 : max(t, 1)` to max(t, 1): keep this form)
     const int nt = (t + TK - 1) / TK;             // tiles per K (and per V) stream
-    const int NS = min(TB_MAXNS, (TB_NS * 32) / TK);
-    const long long n_items = (first < total) ? (total - first + wstride - 1) / wstride : 0;
-    const long long n_tiles = n_items * 2 * nt;
+    const int NS = min(TB_MAXNS, TB_RING / TK);
+    const int n_items = (first < total) ? (total - first + wstride - 1) / wstride : 0;
+    const int n_tiles = n_items * 2 * nt;
 
     if (lane == 0) {
         for (int s = 0; s < TB_MAXNS; ++s) mbar_init(&sm.bar[s], 1);
@@ -96,18 +97,14 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAt
     __syncwarp();
 
     // producer side (lane 0): the next tile to request, as (stream, K/V phase, tile) plus its ring slot
-    long long p_li = 0, p_idx = 0;
-    int p_r = 0, p_slot = 0;
+    int p_item = first, p_ph = 0, p_ti = 0, p_slot = 0, p_idx = 0;
     auto issue = [&]() {
-        const int ph = p_r / nt, ti = p_r - ph * nt;
-        const long long item = first + p_li * wstride;
-        const float* base = (ph == 0 ? a.kcache : a.vcache) + item * (long long)a.Tmax * D + (long long)ti * TK * D;
-        const int nk = min(TK, t - ti * TK);
-        const uint32_t bytes = (uint32_t)nk * D * 4;
+        const float* base = (p_ph == 0 ? a.kcache : a.vcache) + ((long long)p_item * a.Tmax + (long long)p_ti * TK) * D;
+        const uint32_t bytes = (uint32_t)min(TK, t - p_ti * TK) * D * 4;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&sm.bar[p_slot], bytes);
         bulk_g2s(sm.tile + p_slot * TK * D, base, bytes, &sm.bar[p_slot]);
-        if (++p_r == 2 * nt) { p_r = 0; ++p_li; }
+        if (++p_ti == nt) { p_ti = 0; if (++p_ph == 2) { p_ph = 0; p_item += wstride; } }
         if (++p_slot == NS) p_slot = 0;
         ++p_idx;
     };
@@ -124,10 +121,13 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAt
         if (p < HALF) sincosf((float)t * a.inv_freq[p], &sn[e], &cs[e]);
     }
     const float sqrt_d = sqrtf((float)D);
+    const bool clamp = a.softclamp > 0.f;
+    const float inv_clamp = clamp ? 1.f / a.softclamp : 0.f;
 
     using Raw = TbRaw<PPL, G>;
-    auto load_raw = [&](long long item, Raw& r) {
-        const int m = (int)(item / a.hkv), hk = (int)(item % a.hkv);
+    auto load_raw = [&](int item, Raw& r) {
+        const int m = item / a.hkv, hk = item - m * a.hkv;
+        r.m = m; r.hk = hk;
         const float* row = a.qkvgm + (long long)m * a.ld;
         const float* v0r = a.v0 + (long long)m * a.ldv0 + hk * D;
         r.mix = row[a.off_m + hk];
@@ -151,12 +151,13 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAt
 
     Raw cur;
     if (n_items > 0) load_raw(first, cur);
-    for (long long li = 0; li < n_items; ++li) {
-        const long long item = first + li * wstride;
-        const int m = (int)(item / a.hkv), hk = (int)(item % a.hkv);
+#pragma unroll 1
+    for (int li = 0; li < n_items; ++li) {
+        const int item = first + li * wstride;
         // the next stream's inputs are requested now and consumed one iteration later: their latency hides under this stream
         Raw nxt;
         if (li + 1 < n_items) load_raw(item + wstride, nxt);
+        const int m = cur.m, hk = cur.hk;
 
         // ---- prologue: value-residual lerp, key head-norm, rotary on q and k, the self score
         float k1[PPL], k2[PPL], v1[PPL], v2[PPL];
@@ -169,13 +170,15 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAt
             ss += cur.k1[e] * cur.k1[e] + cur.k2[e] * cur.k2[e];
             vs += v1[e] * v1[e] + v2[e] * v2[e];
         }
-        const float kden = fmaxf(sqrtf(warp_sum(ss)), D4_L2_EPS);
-        const float vden = fmaxf(sqrtf(warp_sum(vs)), D4_L2_EPS);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { ss += __shfl_xor_sync(D4_FULL, ss, off); vs += __shfl_xor_sync(D4_FULL, vs, off); }
+        const float rk = 1.f / fmaxf(sqrtf(ss), D4_L2_EPS);
+        const float rv = 1.f / fmaxf(sqrtf(vs), D4_L2_EPS);
 #pragma unroll
         for (int e = 0; e < PPL; ++e) {
             const int p = lane + 32 * e;
-            const float n1 = (cur.k1[e] / kden) * ((cur.g1[e] + 1.f) * sqrt_d);
-            const float n2 = (cur.k2[e] / kden) * ((cur.g2[e] + 1.f) * sqrt_d);
+            const float n1 = (cur.k1[e] * rk) * ((cur.g1[e] + 1.f) * sqrt_d);
+            const float n2 = (cur.k2[e] * rk) * ((cur.g2[e] + 1.f) * sqrt_d);
             k1[e] = n1 * cs[e] + (-n2) * sn[e];
             k2[e] = n2 * cs[e] + n1 * sn[e];
             if (p < HALF) { sm.vnew[p] = v1[e]; sm.vnew[p + HALF] = v2[e]; }
@@ -193,42 +196,42 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAt
                 dot += r1 * k1[e] + r2 * k2[e];
             }
             float s = warp_sum(dot) * a.scale;
-            if (a.softclamp > 0.f) s = tanhf(s / a.softclamp) * a.softclamp;
+            if (clamp) s = tanhf(s * inv_clamp) * a.softclamp;
             self_s[gi] = s;
         }
         __syncwarp();
 
-        // ---- scores over the cached keys: lane = key, rotated float4 chunk order keeps the linear tile conflict free
-        float sc[G][TB_MAXTILES];
-#pragma unroll
-        for (int ti = 0; ti < TB_MAXTILES; ++ti) {
-#pragma unroll
-            for (int gi = 0; gi < G; ++gi) sc[gi][ti] = -INFINITY;
-            if (ti < nt) {
+        // ---- scores over the cached keys: two lanes per key (half a row each), rotated float4 chunk order keeps the
+        //      linear tile conflict free; the scores of the whole stream are parked in shared memory
+        {
+            const int key = lane >> 1, half = lane & 1;
+#pragma unroll 1
+            for (int ti = 0; ti < nt; ++ti) {
                 const int nk = min(TK, t - ti * TK);
                 mbar_wait(&sm.bar[c_slot], c_phase);
                 const float* tile = sm.tile + c_slot * TK * D;
-                if (lane < nk) {
-                    float acc[G];
+                float acc[G];
 #pragma unroll
-                    for (int gi = 0; gi < G; ++gi) acc[gi] = 0.f;
+                for (int gi = 0; gi < G; ++gi) acc[gi] = 0.f;
+                if (key < nk) {
+                    const float* kr = tile + key * D + half * HALF;
 #pragma unroll
-                    for (int c = 0; c < C4; ++c) {
-                        const int cc = (c + lane) % C4;
-                        const float4 kv = *reinterpret_cast<const float4*>(tile + lane * D + cc * 4);
+                    for (int c = 0; c < CH; ++c) {
+                        const int cc = ((c + lane) % CH) * 4;
+                        const float4 kv = *reinterpret_cast<const float4*>(kr + cc);
 #pragma unroll
                         for (int gi = 0; gi < G; ++gi) {
-                            const float4 qv = *reinterpret_cast<const float4*>(sm.q + gi * D + cc * 4);
+                            const float4 qv = *reinterpret_cast<const float4*>(sm.q + gi * D + half * HALF + cc);
                             acc[gi] = fmaf(qv.x, kv.x, acc[gi]); acc[gi] = fmaf(qv.y, kv.y, acc[gi]);
                             acc[gi] = fmaf(qv.z, kv.z, acc[gi]); acc[gi] = fmaf(qv.w, kv.w, acc[gi]);
                         }
                     }
+                }
 #pragma unroll
-                    for (int gi = 0; gi < G; ++gi) {
-                        float sv = acc[gi] * a.scale;
-                        if (a.softclamp > 0.f) sv = tanhf(sv / a.softclamp) * a.softclamp;
-                        sc[gi][ti] = sv;
-                    }
+                for (int gi = 0; gi < G; ++gi) {
+                    float sv = (acc[gi] + __shfl_xor_sync(D4_FULL, acc[gi], 1)) * a.scale;
+                    if (clamp) sv = tanhf(sv * inv_clamp) * a.softclamp;
+                    if (half == 0 && key < nk) sm.s[gi][ti * TK + key] = sv;
                 }
                 __syncwarp();
                 if (lane == 0 && p_idx < n_tiles) issue();
@@ -236,53 +239,44 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAt
             }
         }
 
-        // ---- softmax over cached keys + self
-        float pself[G];
+        // ---- softmax over cached keys + self (normalisation is folded into the output)
+        float es[G], inv[G];
 #pragma unroll
         for (int gi = 0; gi < G; ++gi) {
             float mx = self_s[gi];
-#pragma unroll
-            for (int ti = 0; ti < TB_MAXTILES; ++ti) mx = fmaxf(mx, sc[gi][ti]);
+            for (int j = lane; j < t; j += 32) mx = fmaxf(mx, sm.s[gi][j]);
             mx = warp_max(mx);
             float sum = 0.f;
-#pragma unroll
-            for (int ti = 0; ti < TB_MAXTILES; ++ti) { const float e = (sc[gi][ti] == -INFINITY) ? 0.f : expf(sc[gi][ti] - mx); sc[gi][ti] = e; sum += e; }
+            for (int j = lane; j < t; j += 32) { const float e = expf(sm.s[gi][j] - mx); sm.s[gi][j] = e; sum += e; }
             sum = warp_sum(sum);
-            const float es = expf(self_s[gi] - mx);
-            const float inv = 1.f / (sum + es);
-#pragma unroll
-            for (int ti = 0; ti < TB_MAXTILES; ++ti) sc[gi][ti] *= inv;
-            pself[gi] = es * inv;
+            es[gi] = expf(self_s[gi] - mx);
+            inv[gi] = 1.f / (sum + es[gi]);
         }
+        __syncwarp();
 
-        // ---- AV over the cached values: KG value rows per step, lane = (row group, float4 column), probabilities broadcast from smem
+        // ---- AV over the cached values: KG value rows per step, lane = (row group, float4 column), probabilities from smem
         const int kg = lane / LPK, c4 = (lane % LPK) * 4;
         float4 o[G];
 #pragma unroll
         for (int gi = 0; gi < G; ++gi) o[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int ti = 0; ti < TB_MAXTILES; ++ti) {
-            if (ti < nt) {
-                const int nk = min(TK, t - ti * TK);
-#pragma unroll
-                for (int gi = 0; gi < G; ++gi) sm.p[gi][lane] = sc[gi][ti];       // zero beyond nk
-                mbar_wait(&sm.bar[c_slot], c_phase);
-                __syncwarp();
-                const float* tile = sm.tile + c_slot * TK * D;
+#pragma unroll 1
+        for (int ti = 0; ti < nt; ++ti) {
+            const int nk = min(TK, t - ti * TK);
+            mbar_wait(&sm.bar[c_slot], c_phase);
+            const float* tile = sm.tile + c_slot * TK * D;
 #pragma unroll 4
-                for (int j = kg; j < nk; j += KG) {
-                    const float4 vv = *reinterpret_cast<const float4*>(tile + j * D + c4);
+            for (int j = kg; j < nk; j += KG) {
+                const float4 vv = *reinterpret_cast<const float4*>(tile + j * D + c4);
 #pragma unroll
-                    for (int gi = 0; gi < G; ++gi) {
-                        const float pj = sm.p[gi][j];
-                        o[gi].x = fmaf(pj, vv.x, o[gi].x); o[gi].y = fmaf(pj, vv.y, o[gi].y);
-                        o[gi].z = fmaf(pj, vv.z, o[gi].z); o[gi].w = fmaf(pj, vv.w, o[gi].w);
-                    }
+                for (int gi = 0; gi < G; ++gi) {
+                    const float pj = sm.s[gi][ti * TK + j];
+                    o[gi].x = fmaf(pj, vv.x, o[gi].x); o[gi].y = fmaf(pj, vv.y, o[gi].y);
+                    o[gi].z = fmaf(pj, vv.z, o[gi].z); o[gi].w = fmaf(pj, vv.w, o[gi].w);
                 }
-                __syncwarp();
-                if (lane == 0 && p_idx < n_tiles) issue();
-                if (++c_slot == NS) { c_slot = 0; c_phase ^= 1; }
             }
+            __syncwarp();
+            if (lane == 0 && p_idx < n_tiles) issue();
+            if (++c_slot == NS) { c_slot = 0; c_phase ^= 1; }
         }
 #pragma unroll
         for (int gi = 0; gi < G; ++gi) {
@@ -293,14 +287,14 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAt
             }
         }
 
-        // ---- epilogue (float4-column layout): + self, belief projection on the new value, head gate, store
+        // ---- epilogue (float4-column layout): + self, softmax normalisation, belief projection on the new value, head gate
         const float4 vn = *reinterpret_cast<const float4*>(sm.vnew + c4);
-        const float4 vh = make_float4(vn.x / vden, vn.y / vden, vn.z / vden, vn.w / vden);
+        const float4 vh = make_float4(vn.x * rv, vn.y * rv, vn.z * rv, vn.w * rv);
 #pragma unroll
         for (int gi = 0; gi < G; ++gi) {
             const int hq = hk * G + gi;
-            o[gi].x = fmaf(pself[gi], vn.x, o[gi].x); o[gi].y = fmaf(pself[gi], vn.y, o[gi].y);
-            o[gi].z = fmaf(pself[gi], vn.z, o[gi].z); o[gi].w = fmaf(pself[gi], vn.w, o[gi].w);
+            o[gi].x = fmaf(es[gi], vn.x, o[gi].x) * inv[gi]; o[gi].y = fmaf(es[gi], vn.y, o[gi].y) * inv[gi];
+            o[gi].z = fmaf(es[gi], vn.z, o[gi].z) * inv[gi]; o[gi].w = fmaf(es[gi], vn.w, o[gi].w) * inv[gi];
             float dot = o[gi].x * vh.x + o[gi].y * vh.y + o[gi].z * vh.z + o[gi].w * vh.w;
 #pragma unroll
             for (int off = LPK / 2; off > 0; off >>= 1) dot += __shfl_xor_sync(D4_FULL, dot, off);
@@ -312,35 +306,38 @@ __global__ void __launch_bounds__(TB_WARPS * 32, 1) time_attn_bulk_kernel(TimeAt
             }
         }
         if (a.commit) {
-            float* kd = a.kcache + (item * a.Tmax + t) * D;
-            float* vd = a.vcache + (item * a.Tmax + t) * D;
+            float* kd = a.kcache + ((long long)item * a.Tmax + t) * D;
+            float* vd = a.vcache + ((long long)item * a.Tmax + t) * D;
 #pragma unroll
             for (int e = 0; e < PPL; ++e) {
                 const int p = lane + 32 * e;
                 if (p < HALF) { kd[p] = k1[e]; kd[p + HALF] = k2[e]; vd[p] = v1[e]; vd[p + HALF] = v2[e]; }
             }
         }
-        __syncwarp();      // sm.q / sm.vnew / sm.p are rewritten by the next stream
+        __syncwarp();      // sm.q / sm.vnew / sm.s are rewritten by the next stream
         cur = nxt;
     }
 }
 
 template <int D, int G>
 int launch_bulk(const TimeAttnArgs& a, cudaStream_t s) {
-    const size_t smem = sizeof(TbWarpSmem<D, G>) * TB_WARPS;
+    // as many warps per SM as the per-warp ring leaves room for (16 at the config-4 shape)
+    constexpr int WARPS = (sizeof(TbWarpSmem<D, G>) * 16 <= 227 * 1024) ? 16 : 12;
+    const size_t smem = sizeof(TbWarpSmem<D, G>) * WARPS;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        D4_CUDA_OK(cudaFuncSetAttribute(time_attn_bulk_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        D4_CUDA_OK(cudaFuncSetAttribute(time_attn_bulk_kernel<D, G, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
         D4_CUDA_OK(cudaGetDevice(&dev));
         D4_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
     const long long items = (long long)a.M * a.hkv;
-    const long long ctas_needed = (items + TB_WARPS - 1) / TB_WARPS;
+    if (items >= (1ll << 31) / 2) return d4_fail("time_attn(bulk): %lld streams exceed the 32-bit stream index", items);
+    const long long ctas_needed = (items + WARPS - 1) / WARPS;
     const unsigned grid = (unsigned)std::min<long long>(ctas_needed, num_sms);
-    time_attn_bulk_kernel<D, G><<<grid, TB_WARPS * 32, smem, s>>>(a);
+    time_attn_bulk_kernel<D, G, WARPS><<<grid, WARPS * 32, smem, s>>>(a);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }

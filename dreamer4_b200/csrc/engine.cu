@@ -10,6 +10,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include "engine.h"
 
@@ -66,6 +67,7 @@ extern "C" int d4_ctx_create(const d4_config* cfg, d4_ctx** out) {
     else if (cfg->max_batch < 1 || cfg->max_time < 1) bad = "max_batch / max_time must be positive";
     else if (cfg->policy_layers > D4_MAX_MLP_LAYERS || cfg->value_layers > D4_MAX_MLP_LAYERS || cfg->terminal_layers > D4_MAX_MLP_LAYERS) bad = "MLP too deep";
     if (bad) { delete c; return d4_fail("d4_ctx_create: %s", bad); }
+    { const char* f = getenv("D4_FUSE_POOLS"); c->fuse_pools = f ? atoi(f) != 0 : true; }
     d4_engine_plan(c);
     *out = c;
     return 0;
@@ -359,20 +361,28 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
         g.bias = c->l2s_b; g.cmap = rowmap(nsp, S, 1);
         D4_TRY(d4_engine_gemm(c, g, c->l2s_w, 0, s));
     } else {
-        D4_TRY(d4_row_rstd(latent, Dl, rowmap_identity(), B * N, Dl, c->b.lat_rstd, s));
-        GemmArgs g = gemm_args(latent, Dl, nullptr, Dl, c->b.kv_l, 2 * Dkv, B * N, 2 * Dkv, Dl);
-        g.row_scale = c->b.lat_rstd;
-        D4_TRY(d4_engine_gemm(c, g, c->l2s_w_kv, 0, s));
-        SmallAttnArgs a; memset(&a, 0, sizeof(a));
-        a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = nsp; a.n = N;
-        a.q = c->l2s_q; a.q_sb = 0; a.q_si = Dq;
-        a.k = c->b.kv_l; a.k_sb = (long long)N * 2 * Dkv; a.k_sj = 2 * Dkv;
-        a.v = c->b.kv_l + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
-        a.k_gamma = c->l2s_k_gamma;
-        a.gate = c->l2s_gate; a.gate_sb = 0; a.gate_si = hq;
-        a.out = c->b.att_l; a.out_sb = (long long)nsp * Dq; a.out_si = Dq;
-        a.scale = att_scale;
-        { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+        L2sArgs la; memset(&la, 0, sizeof(la));
+        la.B = B; la.N = N; la.Dl = Dl; la.nsp = nsp; la.h = h; la.hq = hq; la.g = hq / h; la.d = d; la.Dq = Dq;
+        la.latent = latent; la.w_k = c->l2s_w_kv.w; la.w_v = c->l2s_w_kv.w + (long long)Dkv * Dl;
+        la.q = c->l2s_q; la.gate = c->l2s_gate; la.k_gamma = c->l2s_k_gamma; la.out = c->b.att_l; la.scale = att_scale;
+        if (c->fuse_pools && d4_l2s_fused_supported(la)) {
+            const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_l2s_fused(la, s); d4_prof_end(c, ph, s); D4_TRY(rc);
+        } else {
+            D4_TRY(d4_row_rstd(latent, Dl, rowmap_identity(), B * N, Dl, c->b.lat_rstd, s));
+            GemmArgs g = gemm_args(latent, Dl, nullptr, Dl, c->b.kv_l, 2 * Dkv, B * N, 2 * Dkv, Dl);
+            g.row_scale = c->b.lat_rstd;
+            D4_TRY(d4_engine_gemm(c, g, c->l2s_w_kv, 0, s));
+            SmallAttnArgs a; memset(&a, 0, sizeof(a));
+            a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = nsp; a.n = N;
+            a.q = c->l2s_q; a.q_sb = 0; a.q_si = Dq;
+            a.k = c->b.kv_l; a.k_sb = (long long)N * 2 * Dkv; a.k_sj = 2 * Dkv;
+            a.v = c->b.kv_l + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+            a.k_gamma = c->l2s_k_gamma;
+            a.gate = c->l2s_gate; a.gate_sb = 0; a.gate_si = hq;
+            a.out = c->b.att_l; a.out_sb = (long long)nsp * Dq; a.out_si = Dq;
+            a.scale = att_scale;
+            { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+        }
         GemmArgs g2 = gemm_args(c->b.att_l, Dq, nullptr, Dq, hid(0), D, B * nsp, D, Dq);
         g2.cmap = rowmap(nsp, S, 1);
         D4_TRY(d4_engine_gemm(c, g2, c->l2s_w_out, 0, s));
@@ -491,6 +501,14 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
             D4_TRY(d4_rmsnorm_rows(c->b.sp_n, D, rowmap_identity(), c->lp_norm_ctx, B * nsp, D, c->b.sp_n2, D, s));
             GemmArgs g = gemm_args(c->b.sp_n2, D, nullptr, D, c->b.sp_kv, 2 * Dkv, B * nsp, 2 * Dkv, D);
             D4_TRY(d4_engine_gemm(c, g, c->lp_w_kv, 0, s));
+            LpArgs pa; memset(&pa, 0, sizeof(pa));
+            pa.B = B; pa.N = N; pa.Dl = Dl; pa.nsp = nsp; pa.h = h; pa.hq = hq; pa.d = d;
+            pa.kv = c->b.sp_kv; pa.q = c->lp_q; pa.gate = c->lp_gate; pa.k_gamma = c->lp_k_gamma; pa.w_comb = c->lp_w_comb.w;
+            pa.pred = pred_out; pa.scale = att_scale;
+            if (c->fuse_pools && d4_lp_fused_supported(pa)) {
+                const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_lp_fused(pa, s); d4_prof_end(c, ph, s); D4_TRY(rc);
+                return 0;
+            }
             SmallAttnArgs a; memset(&a, 0, sizeof(a));
             a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = N; a.n = nsp;
             a.q = c->lp_q; a.q_sb = 0; a.q_si = Dq;

@@ -55,6 +55,7 @@ struct d4_ctx {
 
     // in-situ profiling (d4_profile / d4_profile_read)
     bool prof_on = false;
+    bool fuse_pools = true;      // fused latent<->space pool kernels (fused_pools.cu); D4_FUSE_POOLS=0 keeps the GEMM + attention path
     struct ProfRec { cudaEvent_t a, b; int cls; double work; };
     std::vector<ProfRec> prof;          // records in use
     std::vector<ProfRec> prof_pool;     // created events, reused

@@ -1,0 +1,285 @@
+// Fused learned-query pools on either side of the transformer (reference dreamer4.py:2179-2210, built at 4822-4834):
+//
+//   l2s_fused_kernel  latents (B, N, Dl) -> gated attention output (B, nsp, Dq) of `latents_to_spatial_tokens`
+//                     (the to_out projection stays a GEMM).  Replaces  row_rstd + GEMM(Dl -> 2*Dkv) + attention:  the
+//                     (B*N, 2*Dkv) key/value tensor (537 MB at config 4) is never materialised.  Keys are projected in
+//                     registers (they are needed in full for the per-head key RMSNorm); values are NOT projected per key:
+//                     sum_j p_ij W_v x_j == W_v (sum_j p_ij x_j), so the probabilities pool the Dl-wide normalised
+//                     latents and W_v is applied once per (query, head).
+//   lp_fused_kernel   spatial-token keys/values (B, nsp, 2*Dkv) -> predicted latents (B, N, Dl) of `to_latent_pred`.
+//                     Replaces  attention (N queries x nsp keys) + GEMM(Dq -> Dl) and the (B*N, Dq) tensor between them:
+//                     with only nsp keys,  pred_i = sum_{j,h} gate_ih p_ijh (W_comb,h v_jh):  the nsp*hq vectors W_comb,h v_jh
+//                     are formed once per frame and every query just mixes them.
+//
+// Both are exact fp32 re-associations of the reference arithmetic (no reduced precision anywhere).
+#include "kernels.h"
+#include <float.h>
+
+namespace {
+
+constexpr int L2S_MAXQ = 8;        // learned queries x query groups per kv head
+constexpr int L2S_MAXN = 64;       // latent tokens
+
+template <int DL>
+__global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
+    // one CTA per frame, one warp per kv head
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.x;
+    const int N = a.N, d = a.d, NQ = a.nsp * a.g;
+    float* xs = smem;                                  // [N][DL] normalised latents
+    float* pw_all = xs + L2S_MAXN * DL;                // per warp [L2S_MAXN][L2S_MAXQ]
+    float* zs_all = pw_all + nwarps * L2S_MAXN * L2S_MAXQ;   // per warp [L2S_MAXQ][DL]
+    float* qs_all = zs_all + nwarps * L2S_MAXQ * DL;   // per warp [L2S_MAXQ][d]  queries x key gain
+
+    // ---- normalised latents of this frame: x * rsqrt(mean(x^2) + eps)  (norm_context gamma is folded into w_k / w_v)
+    const float* xb = a.latent + (long long)b * N * DL;
+    for (int j = warp; j < N; j += nwarps) {
+        float v[(DL + 31) / 32], ss = 0.f;
+#pragma unroll
+        for (int e = 0; e < (DL + 31) / 32; ++e) { const int c = lane + 32 * e; v[e] = (c < DL) ? xb[j * DL + c] : 0.f; ss += v[e] * v[e]; }
+        ss = warp_sum(ss);
+        const float r = rsqrtf(ss / (float)DL + D4_RMS_EPS);
+#pragma unroll
+        for (int e = 0; e < (DL + 31) / 32; ++e) { const int c = lane + 32 * e; if (c < DL) xs[j * DL + c] = v[e] * r; }
+    }
+    __syncthreads();
+
+    for (int hk = warp; hk < a.h; hk += nwarps) {
+        float* pw = pw_all + warp * L2S_MAXN * L2S_MAXQ;
+        float* zs = zs_all + warp * L2S_MAXQ * DL;
+        float* qs = qs_all + warp * L2S_MAXQ * d;
+        const float sqrt_d = sqrtf((float)d);
+        for (int idx = lane; idx < NQ * d; idx += 32) {
+            const int qi = idx / d, c = idx - qi * d;
+            const int i = qi / a.g, gi = qi - i * a.g;
+            qs[idx] = a.q[(long long)i * a.Dq + (hk * a.g + gi) * d + c] * ((a.k_gamma[hk * d + c] + 1.f) * sqrt_d);
+        }
+        __syncwarp();
+        // ---- scores: lane = key (two key slots), keys projected on the fly, |k| accumulated alongside
+        float sc[2][L2S_MAXQ];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const int j = lane + 32 * kk;
+            float xr[DL];
+#pragma unroll
+            for (int e = 0; e < DL; e += 4) {
+                const float4 t = (j < N) ? *reinterpret_cast<const float4*>(xs + j * DL + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xr[e] = t.x; xr[e + 1] = t.y; xr[e + 2] = t.z; xr[e + 3] = t.w;
+            }
+            float ss = 0.f, dot[L2S_MAXQ];
+#pragma unroll
+            for (int qi = 0; qi < L2S_MAXQ; ++qi) dot[qi] = 0.f;
+            if (kk * 32 < N) {                                  // warp-uniform
+                const float* wk = a.w_k + (long long)hk * d * DL;
+                for (int c = 0; c < d; ++c) {
+                    float k = 0.f;
+#pragma unroll
+                    for (int e = 0; e < DL; e += 4) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(wk + c * DL + e));
+                        k = fmaf(xr[e], w.x, k); k = fmaf(xr[e + 1], w.y, k); k = fmaf(xr[e + 2], w.z, k); k = fmaf(xr[e + 3], w.w, k);
+                    }
+                    ss = fmaf(k, k, ss);
+#pragma unroll
+                    for (int qi = 0; qi < L2S_MAXQ; ++qi) if (qi < NQ) dot[qi] = fmaf(qs[qi * d + c], k, dot[qi]);
+                }
+            }
+            const float inv = a.scale / fmaxf(sqrtf(ss), D4_L2_EPS);
+#pragma unroll
+            for (int qi = 0; qi < L2S_MAXQ; ++qi) sc[kk][qi] = (j < N) ? dot[qi] * inv : -INFINITY;
+        }
+        // ---- softmax over the N keys of every query
+#pragma unroll
+        for (int qi = 0; qi < L2S_MAXQ; ++qi) {
+            if (qi < NQ) {
+                const float mx = warp_max(fmaxf(sc[0][qi], sc[1][qi]));
+                const float e0 = (lane < N) ? expf(sc[0][qi] - mx) : 0.f, e1 = (lane + 32 < N) ? expf(sc[1][qi] - mx) : 0.f;
+                const float inv = 1.f / warp_sum(e0 + e1);
+                pw[lane * L2S_MAXQ + qi] = e0 * inv;
+                pw[(lane + 32) * L2S_MAXQ + qi] = e1 * inv;
+            }
+        }
+        __syncwarp();
+        // ---- pooled normalised latents z_q = sum_j p_qj x_j : lane = latent channel
+#pragma unroll
+        for (int eb = 0; eb < DL; eb += 32) {
+            const int e = eb + lane;
+            float z[L2S_MAXQ];
+#pragma unroll
+            for (int qi = 0; qi < L2S_MAXQ; ++qi) z[qi] = 0.f;
+            if (e < DL) {
+                for (int j = 0; j < N; ++j) {
+                    const float xv = xs[j * DL + e];
+                    const float4 p0 = *reinterpret_cast<const float4*>(pw + j * L2S_MAXQ), p1 = *reinterpret_cast<const float4*>(pw + j * L2S_MAXQ + 4);
+                    z[0] = fmaf(p0.x, xv, z[0]); z[1] = fmaf(p0.y, xv, z[1]); z[2] = fmaf(p0.z, xv, z[2]); z[3] = fmaf(p0.w, xv, z[3]);
+                    z[4] = fmaf(p1.x, xv, z[4]); z[5] = fmaf(p1.y, xv, z[5]); z[6] = fmaf(p1.z, xv, z[6]); z[7] = fmaf(p1.w, xv, z[7]);
+                }
+#pragma unroll
+                for (int qi = 0; qi < L2S_MAXQ; ++qi) zs[qi * DL + e] = z[qi];
+            }
+        }
+        __syncwarp();
+        // ---- values: o_q = W_v,h z_q, head gate, store : lane = head channel
+        const float* wv = a.w_v + (long long)hk * d * DL;
+        for (int c = lane; c < d; c += 32) {
+            float o[L2S_MAXQ];
+#pragma unroll
+            for (int qi = 0; qi < L2S_MAXQ; ++qi) o[qi] = 0.f;
+#pragma unroll
+            for (int e = 0; e < DL; e += 4) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wv + c * DL + e));
+#pragma unroll
+                for (int qi = 0; qi < L2S_MAXQ; ++qi) {
+                    if (qi < NQ) {
+                        const float4 z = *reinterpret_cast<const float4*>(zs + qi * DL + e);
+                        o[qi] = fmaf(w.x, z.x, o[qi]); o[qi] = fmaf(w.y, z.y, o[qi]); o[qi] = fmaf(w.z, z.z, o[qi]); o[qi] = fmaf(w.w, z.w, o[qi]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < L2S_MAXQ; ++qi) {
+                if (qi < NQ) {
+                    const int i = qi / a.g, gi = qi - i * a.g, hq = hk * a.g + gi;
+                    const float gate = sigmoidf_(a.gate[i * a.hq + hq]);
+                    a.out[((long long)b * a.nsp + i) * a.Dq + hq * d + c] = o[qi] * gate;
+                }
+            }
+        }
+        __syncwarp();       // pw / zs / qs are reused by this warp's next head
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+constexpr int LP_MAXJH = 64;       // nsp * hq mixing vectors
+
+__global__ void __launch_bounds__(256) lp_fused_kernel(LpArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    const int b = blockIdx.x;
+    const int nsp = a.nsp, h = a.h, hq = a.hq, g = hq / h, d = a.d, Dkv = h * d, Dq = hq * d, N = a.N, Dl = a.Dl;
+    const int dp = d + 4;                                   // padded head pitch: conflict-free float4 reads across heads
+    const int JH = nsp * hq;
+    float* ks = smem;                                       // [nsp][h][dp]   keys x key gain / |k|
+    float* vs = ks + nsp * h * dp;                          // [nsp][h][dp]
+    float* ys = vs + nsp * h * dp;                          // [JH][Dl]       W_comb,hq v_(j,hk)
+    float* cf = ys + LP_MAXJH * Dl;                         // [N][JH + 1]    gate * softmax probabilities
+
+    const float* kvb = a.kv + (long long)b * nsp * 2 * Dkv;
+    for (int idx = tid; idx < nsp * Dkv; idx += nthr) {
+        const int j = idx / Dkv, r = idx - j * Dkv, hk = r / d, c = r - hk * d;
+        ks[(j * h + hk) * dp + c] = kvb[(long long)j * 2 * Dkv + r];
+        vs[(j * h + hk) * dp + c] = kvb[(long long)j * 2 * Dkv + Dkv + r];
+    }
+    __syncthreads();
+    // key RMSNorm per (key, head): k <- l2norm(k) * (gamma + 1) * sqrt(d)
+    const float sqrt_d = sqrtf((float)d);
+    for (int jh = warp; jh < nsp * h; jh += nwarps) {
+        float* kr = ks + jh * dp;
+        const int hk = jh % h;
+        float ss = 0.f;
+        for (int c = lane; c < d; c += 32) ss += kr[c] * kr[c];
+        const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), D4_L2_EPS);
+        for (int c = lane; c < d; c += 32) kr[c] = kr[c] * inv * ((a.k_gamma[hk * d + c] + 1.f) * sqrt_d);
+    }
+    // mixing vectors y[(j,hq)][e] = sum_c W_comb[e][hq*d + c] * v[j][hk][c]
+    for (int o = tid; o < JH * Dl; o += nthr) {
+        const int jh = o / Dl, e = o - jh * Dl, j = jh / hq, q = jh - j * hq, hk = q / g;
+        const float* w = a.w_comb + (long long)e * Dq + q * d;
+        const float* v = vs + (j * h + hk) * dp;
+        float acc = 0.f;
+        for (int c = 0; c < d; c += 4) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c));
+            const float4 vv = *reinterpret_cast<const float4*>(v + c);
+            acc = fmaf(wv.x, vv.x, acc); acc = fmaf(wv.y, vv.y, acc); acc = fmaf(wv.z, vv.z, acc); acc = fmaf(wv.w, vv.w, acc);
+        }
+        ys[jh * Dl + e] = acc;
+    }
+    __syncthreads();
+    // scores + softmax over the nsp keys for every (query, query head); coefficient = gate * probability
+    for (int p = tid; p < N * hq; p += nthr) {
+        const int i = p / hq, q = p - i * hq, hk = q / g;
+        const float* qr = a.q + (long long)i * Dq + q * d;
+        float s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = 0.f;
+        for (int c = 0; c < d; c += 4) {
+            const float4 qv = __ldg(reinterpret_cast<const float4*>(qr + c));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < nsp) {
+                    const float4 kv = *reinterpret_cast<const float4*>(ks + (j * h + hk) * dp + c);
+                    s[j] = fmaf(qv.x, kv.x, s[j]); s[j] = fmaf(qv.y, kv.y, s[j]); s[j] = fmaf(qv.z, kv.z, s[j]); s[j] = fmaf(qv.w, kv.w, s[j]);
+                }
+            }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nsp) { s[j] *= a.scale; mx = fmaxf(mx, s[j]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nsp) { s[j] = expf(s[j] - mx); sum += s[j]; }
+        const float gate = sigmoidf_(a.gate[i * hq + q]) / sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nsp) cf[i * (JH + 1) + j * hq + q] = s[j] * gate;
+    }
+    __syncthreads();
+    // pred[i][e] = sum_jh cf[i][jh] * y[jh][e]
+    float* outb = a.pred + (long long)b * N * Dl;
+    for (int o = tid; o < N * Dl; o += nthr) {
+        const int i = o / Dl, e = o - i * Dl;
+        float acc = 0.f;
+        for (int jh = 0; jh < JH; ++jh) acc = fmaf(cf[i * (JH + 1) + jh], ys[jh * Dl + e], acc);
+        outb[o] = acc;
+    }
+}
+
+}  // namespace
+
+int d4_l2s_fused_supported(const L2sArgs& a) {
+    const int NQ = a.nsp * a.g;
+    return (a.Dl == 16 || a.Dl == 32 || a.Dl == 64) && a.N <= L2S_MAXN && NQ <= L2S_MAXQ && a.d % 4 == 0 && a.d <= 128 && a.h <= 32 &&
+           (reinterpret_cast<uintptr_t>(a.w_k) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w_v) & 15) == 0;
+}
+
+template <int DL>
+static int launch_l2s(const L2sArgs& a, cudaStream_t s) {
+    const int nwarps = a.h < 8 ? a.h : 8;
+    const size_t smem = sizeof(float) * ((size_t)L2S_MAXN * DL + (size_t)nwarps * (L2S_MAXN * L2S_MAXQ + L2S_MAXQ * DL + L2S_MAXQ * a.d));
+    static size_t configured = 0;
+    if (smem > configured) {
+        D4_CUDA_OK(cudaFuncSetAttribute(l2s_fused_kernel<DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    l2s_fused_kernel<DL><<<a.B, nwarps * 32, smem, s>>>(a);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int d4_l2s_fused(const L2sArgs& a, cudaStream_t s) {
+    if (a.B <= 0) return 0;
+    if (!d4_l2s_fused_supported(a)) return d4_fail("l2s_fused: unsupported shape");
+    if (a.Dl == 16) return launch_l2s<16>(a, s);
+    if (a.Dl == 32) return launch_l2s<32>(a, s);
+    return launch_l2s<64>(a, s);
+}
+
+int d4_lp_fused_supported(const LpArgs& a) {
+    return a.nsp <= 8 && a.nsp * a.hq <= LP_MAXJH && a.d % 4 == 0 && a.N * a.hq <= 4096 && (a.hq % a.h) == 0 &&
+           (reinterpret_cast<uintptr_t>(a.w_comb) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0;
+}
+
+int d4_lp_fused(const LpArgs& a, cudaStream_t s) {
+    if (a.B <= 0) return 0;
+    if (!d4_lp_fused_supported(a)) return d4_fail("lp_fused: unsupported shape");
+    const int JH = a.nsp * a.hq;
+    const size_t smem = sizeof(float) * ((size_t)2 * a.nsp * a.h * (a.d + 4) + (size_t)LP_MAXJH * a.Dl + (size_t)a.N * (JH + 1));
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (smem > 200 * 1024) return d4_fail("lp_fused: %zu bytes of shared memory needed", smem);
+        D4_CUDA_OK(cudaFuncSetAttribute(lp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    lp_fused_kernel<<<a.B, 256, smem, s>>>(a);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -13,6 +13,7 @@
 //   warps 6-9 tf32x3 only: hi/lo split of this CTA's A tile in shared memory, then ONE remote arrive on the leader's barrier
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include "kernels.h"
 
@@ -24,7 +25,7 @@ constexpr int NUM_THREADS = 320;
 constexpr int STG_LD = 33;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: the even (leader) CTA's copy
 
-struct __align__(64) TmaMaps3 { CUtensorMap a, w, wlo; };
+struct __align__(64) TmaMaps3 { CUtensorMap a, w, wlo, c, r; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool elect_one() {
@@ -73,6 +74,20 @@ __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// epilogue: shared-memory tile -> global (bulk async-group completion), and the matching group controls
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// silu with the MUFU approximations (ex2 / rcp, ~2 ulp): the epilogue warps are instruction bound, the IEEE expf + divide
+// of siluf_() cost 5x more issue slots
+__device__ __forceinline__ float silu_fast(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
+
 // all previously issued MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -112,6 +127,7 @@ struct EpiArgs3 {
     const float* bias; const float* row_scale; const float* residual; long long ldr;
     int act; RowMap cmap;
     int a_grp, nkb, n_tiles_m, n_tiles_n;
+    int tma_epi;        // 1: epilogue through swizzled smem tiles + TMA (residual load, result store); 0: register path
 };
 
 template <int TERMS, int BN> struct Cfg3 {
@@ -119,8 +135,8 @@ template <int TERMS, int BN> struct Cfg3 {
     static constexpr int W_TILE = BNH * BK * 4;
     static constexpr int STAGE = (TERMS == 3) ? 2 * A_TILE + 2 * W_TILE : A_TILE + W_TILE;
     static constexpr int NS = (TERMS == 3) ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 6 : 8);
-    static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
-    static constexpr int NBARS = 4 * NS + 4;                            // full | fullA | empty | split | tfull[2] | tempty[2]
+    static constexpr int STG_BYTES = 4 * 2 * 4096;                      // per epilogue warp: two 32 x 32 fp32 tiles (128B-swizzled)
+    static constexpr int NBARS = 4 * NS + 4 + 8;                        // full | fullA | empty | split | tfull[2] | tempty[2] | resid[4][2]
     static constexpr int SMEM = NS * STAGE + STG_BYTES + NBARS * 8 + 64 + 1024;
     // instruction descriptor: D=f32, A=B=tf32, K-major, N>>3 at bit 17, M>>4 at bit 24 with M = 256 (the pair's rows)
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -136,7 +152,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * K::STAGE + K::STG_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + K::NBARS);
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
-    constexpr int B_FULL = 0, B_FULLA = NS, B_EMPTY = 2 * NS, B_SPLIT = 3 * NS, B_TFULL = 4 * NS, B_TEMPTY = 4 * NS + 2;
+    constexpr int B_FULL = 0, B_FULLA = NS, B_EMPTY = 2 * NS, B_SPLIT = 3 * NS, B_TFULL = 4 * NS, B_TEMPTY = 4 * NS + 2, B_RES = 4 * NS + 4;
     constexpr int T_A = 0, T_ALO = A_TILE, T_W = (TERMS == 3) ? 2 * A_TILE : A_TILE, T_WLO = T_W + K::W_TILE;
     auto tile = [&](int stage, int off) { return smem + stage * K::STAGE + off; };
 
@@ -150,10 +166,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
         if (TERMS == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wlo) : "memory");
+        if (e.tma_epi) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.c) : "memory");
+        if (e.tma_epi && e.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.r) : "memory");
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_FULLA + s), 1); mbar_init(bar(B_EMPTY + s), 1); mbar_init(bar(B_SPLIT + s), 2);
         }
         for (int b = 0; b < 2; ++b) { mbar_init(bar(B_TFULL + b), 1); mbar_init(bar(B_TEMPTY + b), 8); }
+        for (int b = 0; b < 8; ++b) mbar_init(bar(B_RES + b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_sync_all();                                // both CTAs' barriers exist before anything can signal them
@@ -227,7 +246,118 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
             }
         }
     } else if (warp < 6) {
-        // ================= epilogue of this CTA's 128 rows (see gemm_tc2.cu for the data flow)
+        // ================= epilogue of this CTA's 128 rows
+        if (e.tma_epi) {
+            // Row-per-lane: tcgen05.ld hands lane r the 32 accumulator columns of row r; the lane scales / biases / gates
+            // them and writes float4 chunks into a 32 x 32 fp32 tile in the 128B-swizzled layout TMA expects (chunk q of
+            // row r at q ^ (r & 7): bank-conflict free).  The residual tile is TMA-LOADED into that same buffer one chunk
+            // ahead and added in place; the finished tile leaves with ONE TMA store.  Two buffers per warp alternate.
+            const int quarter = warp & 3, ew = warp - 2;
+            unsigned char* ebuf = reinterpret_cast<unsigned char*>(stg_all) + ew * 2 * 4096;
+            const uint32_t ebuf_u32 = smem_u32(ebuf);
+            const bool glu = (e.act == D4_ACT_GLU_SILU || e.act == D4_ACT_GLU_GELU);
+            const bool has_res = (e.residual != nullptr);
+            const float* __restrict__ biasp = e.bias;
+            const uint32_t tempty_leader = bar(B_TEMPTY) & PEER_MASK;
+            const int grp = e.cmap.grp;
+            const int n_out = glu ? (e.N >> 1) : e.N;               // output columns
+            const int in_per_chunk = glu ? 64 : 32;                 // accumulator columns that make one 32-column output chunk
+            const uint32_t swz = (uint32_t)(lane & 7);
+            uint32_t g = 0, rph0 = 0, rph1 = 0;                     // running chunk counter (buffer = g & 1), residual barrier phases
+            auto res_load = [&](int buf, int col0, int row0) {     // lane 0 only
+                const uint32_t rb = bar(B_RES + ew * 2 + buf);
+                mbar_expect_tx(rb, 4096);
+                if (grp == 0) tma_load_2d(ebuf_u32 + buf * 4096, &maps.r, rb, col0, row0);
+                else          tma_load_3d(ebuf_u32 + buf * 4096, &maps.r, rb, col0, 0, row0 / grp);
+            };
+            uint32_t ac = 0;
+            for (int t = cluster_id; t < total_tiles; t += n_clusters, ++ac) {
+                const int m0 = (t / e.n_tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % e.n_tiles_n) * BN;
+                const int buf_acc = ac & 1; const uint32_t aph = (ac >> 1) & 1;
+                const int rbase = m0 + quarter * 32;
+                const int mrow = rbase + lane;
+                const float rs = (mrow < e.M && e.row_scale) ? e.row_scale[mrow] : 1.f;
+                const uint32_t tmem_c = tmem_base + (uint32_t)(buf_acc * BN) + ((uint32_t)(quarter * 32) << 16);
+                const int out0 = glu ? (n0 >> 1) : n0;              // first output column of this tile
+                const bool rows_ok = rbase < e.M;                   // warp-uniform
+                if (has_res && rows_ok && out0 < n_out && lane == 0) { bulk_wait_read_1(); res_load(g & 1, out0, rbase); }
+                mbar_wait(bar(B_TFULL + buf_acc), aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (rows_ok) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += in_per_chunk) {
+                        const int oc = out0 + (glu ? (c0 >> 1) : c0);          // first output column of this chunk
+                        if (oc >= n_out) break;                                  // warp-uniform
+                        const int buf = g & 1;
+                        float v[32], w[32];
+                        tmem_ld32(tmem_c + (uint32_t)c0, v);
+                        if (glu) tmem_ld32(tmem_c + (uint32_t)(c0 + 32), w);
+                        if (lane == 0) bulk_wait_read_1();          // the store that last read this buffer (two chunks ago) is done
+                        __syncwarp();
+                        if (has_res) {
+                            if (buf == 0) { mbar_wait(bar(B_RES + ew * 2), rph0); rph0 ^= 1; }
+                            else          { mbar_wait(bar(B_RES + ew * 2 + 1), rph1); rph1 ^= 1; }
+                        }
+                        unsigned char* rowp = ebuf + buf * 4096 + lane * 128;
+                        const int nb = n0 + c0;                                  // first accumulator column of this chunk
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o;
+                            if (!glu) {
+                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (biasp) {
+                                    const int cb = nb + 4 * q;
+                                    if (cb + 3 < e.N) b4 = __ldg(reinterpret_cast<const float4*>(biasp + cb));
+                                    else { if (cb < e.N) b4.x = __ldg(biasp + cb); if (cb + 1 < e.N) b4.y = __ldg(biasp + cb + 1); if (cb + 2 < e.N) b4.z = __ldg(biasp + cb + 2); }
+                                }
+                                o.x = fmaf(v[4 * q], rs, b4.x); o.y = fmaf(v[4 * q + 1], rs, b4.y);
+                                o.z = fmaf(v[4 * q + 2], rs, b4.z); o.w = fmaf(v[4 * q + 3], rs, b4.w);
+                            } else {
+                                // outputs 4q..4q+3 of the chunk come from accumulator columns 8q..8q+7 (x, gate interleaved)
+                                const float* src = (q < 4) ? (v + 8 * q) : (w + 8 * (q - 4));
+                                float xb[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) xb[k] = 0.f;
+                                if (biasp) {
+                                    const int cb = nb + 8 * q;
+                                    if (cb + 7 < e.N) {
+                                        const float4 t0 = __ldg(reinterpret_cast<const float4*>(biasp + cb)), t1 = __ldg(reinterpret_cast<const float4*>(biasp + cb + 4));
+                                        xb[0] = t0.x; xb[1] = t0.y; xb[2] = t0.z; xb[3] = t0.w; xb[4] = t1.x; xb[5] = t1.y; xb[6] = t1.z; xb[7] = t1.w;
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) if (cb + k < e.N) xb[k] = __ldg(biasp + cb + k);
+                                    }
+                                }
+                                float r4[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float x = fmaf(src[2 * k], rs, xb[2 * k]), gt = fmaf(src[2 * k + 1], rs, xb[2 * k + 1]);
+                                    r4[k] = x * ((e.act == D4_ACT_GLU_SILU) ? silu_fast(gt) : geluf_(gt));
+                                }
+                                o = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                            }
+                            float4* dst = reinterpret_cast<float4*>(rowp + (((uint32_t)q ^ swz) << 4));
+                            if (has_res) { const float4 r = *dst; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+                            *dst = o;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (grp == 0) tma_store_2d(&maps.c, ebuf_u32 + buf * 4096, oc, rbase);
+                            else          tma_store_3d(&maps.c, ebuf_u32 + buf * 4096, oc, 0, rbase / grp);
+                            bulk_commit();
+                            const int oc_next = oc + 32;
+                            if (has_res && c0 + in_per_chunk < BN && oc_next < n_out) { bulk_wait_read_1(); res_load(buf ^ 1, oc_next, rbase); }
+                        }
+                        ++g;
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)buf_acc * 8u);
+            }
+            if (lane == 0) bulk_wait_all();
+        } else {
         const int quarter = warp & 3;
         float* stg = stg_all + (warp - 2) * 32 * STG_LD;
         const bool glu = (e.act == D4_ACT_GLU_SILU || e.act == D4_ACT_GLU_GELU);
@@ -348,6 +478,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)buf * 8u);      // one arrival per warp, 8 per pair
         }
+        }
     } else if (TERMS == 3) {
         // ================= A splitter (tf32x3): this CTA's A tile -> hi (in place) + lo, then one arrival on the leader's barrier
         const int et = threadIdx.x - 192;          // 0..127
@@ -424,6 +555,31 @@ int encode_3d(CUtensorMap* map, const float* base, long long M, long long K, lon
     return 0;
 }
 
+// output (or residual) tile map: 32 columns x 32 rows, 128B swizzle; rows through the row map as (cols, grp, M / grp)
+int encode_out(CUtensorMap* map, const float* base, long long M, long long N, long long ld, const RowMap& rm) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return d4_fail("cuTensorMapEncodeTiled is not available from the driver");
+    CUresult r;
+    if (rm.grp == 0) {
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t estr[2] = {1, 1};
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rm.grp, (cuuint64_t)(M / rm.grp)};
+        cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)rm.gstride * ld * 4};
+        cuuint32_t box[3] = {32, (cuuint32_t)rm.grp, (cuuint32_t)(32 / rm.grp)};
+        cuuint32_t estr[3] = {1, 1, 1};
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base + (long long)rm.goff * ld), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return d4_fail("cuTensorMapEncodeTiled(out M=%lld N=%lld ld=%lld) failed: %d", M, N, ld, (int)r);
+    return 0;
+}
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 template <int TERMS, int BN>
 int max_clusters() {
     // how many CTA pairs can be co-resident (one per TPC on a full B200: 74)
@@ -459,6 +615,19 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
     e.C = g.C; e.ldc = g.ldc; e.M = g.M; e.N = g.N; e.bias = g.bias; e.row_scale = g.row_scale; e.residual = g.residual; e.ldr = g.ldr;
     e.act = g.act; e.cmap = g.cmap; e.a_grp = g.amap.grp; e.nkb = (g.K + BK - 1) / BK;
     e.n_tiles_m = (g.M + 2 * BM - 1) / (2 * BM); e.n_tiles_n = (g.N + BN - 1) / BN;
+    // TMA epilogue needs 16-byte aligned rows and a row map whose groups tile the 32-row warp slices
+    const bool glu = (g.act == D4_ACT_GLU_SILU || g.act == D4_ACT_GLU_GELU);
+    const int grp = g.cmap.grp;
+    static const bool epi_off = getenv("D4_GEMM_TMA_EPI") && atoi(getenv("D4_GEMM_TMA_EPI")) == 0;
+    bool tma_epi = !epi_off && al16(g.C) && (g.ldc % 4 == 0) && (!g.bias || al16(g.bias)) &&
+                   (grp == 0 || (32 % grp == 0 && g.M % grp == 0 && (((long long)g.cmap.goff * g.ldc) % 4 == 0) && (((long long)g.cmap.gstride * g.ldc) % 4 == 0)));
+    if (g.residual) tma_epi = tma_epi && al16(g.residual) && (g.ldr % 4 == 0) &&
+                              (grp == 0 || ((((long long)g.cmap.goff * g.ldr) % 4 == 0) && (((long long)g.cmap.gstride * g.ldr) % 4 == 0)));
+    e.tma_epi = tma_epi ? 1 : 0;
+    if (tma_epi) {
+        { int rc = encode_out(&maps.c, g.C, g.M, glu ? g.N / 2 : g.N, g.ldc, g.cmap); if (rc) return rc; }
+        if (g.residual) { int rc = encode_out(&maps.r, g.residual, g.M, g.N, g.ldr, g.cmap); if (rc) return rc; }
+    }
     const long long tiles = (long long)e.n_tiles_m * e.n_tiles_n;
     const int clusters = (int)std::min<long long>(tiles, maxc);
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));

@@ -73,3 +73,32 @@ struct TimeAttnArgs {
     int variant;                                   // 0 = ld.global staged, 1 = cp.async.bulk ring
 };
 int d4_time_attn(const TimeAttnArgs& a, cudaStream_t s);
+
+// ---- fused learned-query pools (fused_pools.cu)
+// latents -> gated attention output of latents_to_spatial_tokens (reference dreamer4.py:2179-2210, 4822-4828)
+struct L2sArgs {
+    int B, N, Dl, nsp, h, hq, g, d, Dq;
+    const float* latent;          // (B, N, Dl)
+    const float* w_k;             // (h*d, Dl)  to_k with norm_context gamma folded
+    const float* w_v;             // (h*d, Dl)
+    const float* q;               // (nsp, Dq)  projected learned queries
+    const float* gate;            // (nsp, hq)  gate logits
+    const float* k_gamma;         // (h, d)
+    float* out;                   // (B, nsp, Dq)
+    float scale;
+};
+int d4_l2s_fused_supported(const L2sArgs& a);
+int d4_l2s_fused(const L2sArgs& a, cudaStream_t s);
+// spatial-token keys/values -> predicted latents of to_latent_pred (reference dreamer4.py:4830-4834)
+struct LpArgs {
+    int B, N, Dl, nsp, h, hq, d;
+    const float* kv;              // (B, nsp, 2*h*d)  [K | V] of the normalised spatial tokens
+    const float* q;               // (N, hq*d)  projected learned queries
+    const float* gate;            // (N, hq)    gate logits
+    const float* k_gamma;         // (h, d)
+    const float* w_comb;          // (Dl, hq*d) Linear(D -> Dl) @ to_out
+    float* pred;                  // (B, N, Dl)
+    float scale;
+};
+int d4_lp_fused_supported(const LpArgs& a);
+int d4_lp_fused(const LpArgs& a, cudaStream_t s);

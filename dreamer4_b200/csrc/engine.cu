@@ -216,6 +216,8 @@ extern "C" int d4_bind(d4_ctx* c) {
         for (int l = 0; l < layers; ++l) {
             const std::string q = p + "." + std::to_string(l);
             m.w[l] = B.get(q + ".w", (int64_t)m.dims[l + 1] * m.dims[l]); m.b[l] = B.get(q + ".b", m.dims[l + 1]);
+            m.hi[l] = B.get(q + ".w.hi", (int64_t)m.dims[l + 1] * m.dims[l], true); m.lo[l] = B.get(q + ".w.lo", (int64_t)m.dims[l + 1] * m.dims[l], true);
+            m.wthi[l] = B.get(q + ".wt.hi", (int64_t)m.dims[l + 1] * m.dims[l], true); m.wtlo[l] = B.get(q + ".wt.lo", (int64_t)m.dims[l + 1] * m.dims[l], true);
             if (l < layers - 1) { m.lnw[l] = B.get(q + ".lnw", m.dims[l + 1]); m.lnb[l] = B.get(q + ".lnb", m.dims[l + 1]); }
             else { m.lnw[l] = m.lnb[l] = nullptr; }
         }
@@ -287,7 +289,8 @@ int d4_engine_gemm(d4_ctx* c, GemmArgs g, const LinW& w, int force_fp32, cudaStr
 
 static inline LinW plain(const float* w) { LinW l; l.w = w; return l; }
 
-// x-mlps normed MLP forward (Linear -> LayerNorm -> SiLU)* -> Linear, exact fp32.
+// x-mlps normed MLP forward (Linear -> LayerNorm -> SiLU)* -> Linear.  Exact fp32 FMA unless the caller registered a tf32
+// hi/lo split of the layer's weight and the engine runs in tf32x3 (fp32-accurate 3-term tensor-core product).
 int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, int M, float* buf0, float* buf1, float* out, long long ldo,
                    cudaStream_t s) {
     const float* cur = x; long long ldc = ldx;
@@ -297,7 +300,9 @@ int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, in
         const long long ldd = last ? ldo : mlp.dims[l + 1];
         GemmArgs g = gemm_args(cur, ldc, mlp.w[l], mlp.dims[l], dst, ldd, M, mlp.dims[l + 1], mlp.dims[l]);
         g.bias = mlp.b[l];
-        D4_TRY(d4_engine_gemm(c, g, plain(mlp.w[l]), 1, s));
+        LinW lw; lw.w = mlp.w[l]; lw.hi = mlp.hi[l]; lw.lo = mlp.lo[l];
+        const int exact = !(c->cfg.precision == D4_PREC_TF32X3 && lw.hi && lw.lo);
+        D4_TRY(d4_engine_gemm(c, g, lw, exact, s));
         if (!last) D4_TRY(d4_ln_act_rows(dst, ldd, mlp.lnw[l], mlp.lnb[l], M, mlp.dims[l + 1], dst, ldd, D4_ACT_SILU, nullptr, nullptr, s));
         cur = dst; ldc = ldd;
     }

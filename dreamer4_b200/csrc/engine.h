@@ -12,6 +12,8 @@ struct AttnLayerW { LinW w; const float* b; const float* k_gamma; LinW w_out; };
 struct FFW { LinW w_in; const float* b_in; LinW w_out; const float* b_out; };
 struct PoolW { LinW w_qg; LinW w_kv; const float* k_gamma; LinW w_out; };
 struct MlpW { int layers = 0; const float* w[D4_MAX_MLP_LAYERS]; const float* b[D4_MAX_MLP_LAYERS];
+              const float* hi[D4_MAX_MLP_LAYERS]; const float* lo[D4_MAX_MLP_LAYERS];   // optional tf32 split of w (tf32x3 heads)
+              const float* wthi[D4_MAX_MLP_LAYERS]; const float* wtlo[D4_MAX_MLP_LAYERS]; // optional tf32 split of w^T (in, out): learn backward
               const float* lnw[D4_MAX_MLP_LAYERS]; const float* lnb[D4_MAX_MLP_LAYERS]; int dims[D4_MAX_MLP_LAYERS + 1]; };
 
 struct d4_ctx {

@@ -10,7 +10,8 @@
 //   warp 0    TMA producer (each CTA loads its A rows and its half of the W rows; W arrives on the LEADER's barrier)
 //   warp 1    MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, accumulators double-buffered in TMEM
 //   warps 2-5 epilogue of this CTA's 128 rows (tcgen05.ld -> row scale -> smem transpose -> bias/residual/GLU -> 128-B row stores)
-//   warps 6-9 tf32x3 only: hi/lo split of this CTA's A tile in shared memory, then ONE remote arrive on the leader's barrier
+//   warps 6-9 tf32x3 only: a_lo = a - trunc_tf32(a) of this CTA's A tile into a second smem tile (the raw tile serves as a_hi:
+//             the tensor core ignores the low 13 mantissa bits), then ONE remote arrive on the leader's barrier
 #include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
@@ -86,7 +87,7 @@ __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // silu with the MUFU approximations (ex2 / rcp, ~2 ulp): the epilogue warps are instruction bound, the IEEE expf + divide
 // of siluf_() cost 5x more issue slots
-__device__ __forceinline__ float silu_fast(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // all previously issued MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
@@ -128,6 +129,7 @@ struct EpiArgs3 {
     int act; RowMap cmap;
     int a_grp, nkb, n_tiles_m, n_tiles_n;
     int tma_epi;        // 1: epilogue through swizzled smem tiles + TMA (residual load, result store); 0: register path
+    int early_mma;      // tf32x3: 1 = issue the two a_hi products before the a_lo tile is ready, 0 = wait for the split first
 };
 
 template <int TERMS, int BN> struct Cfg3 {
@@ -136,7 +138,7 @@ template <int TERMS, int BN> struct Cfg3 {
     static constexpr int STAGE = (TERMS == 3) ? 2 * A_TILE + 2 * W_TILE : A_TILE + W_TILE;
     static constexpr int NS = (TERMS == 3) ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 6 : 8);
     static constexpr int STG_BYTES = 4 * 2 * 4096;                      // per epilogue warp: two 32 x 32 fp32 tiles (128B-swizzled)
-    static constexpr int NBARS = 4 * NS + 4 + 8;                        // full | fullA | empty | split | tfull[2] | tempty[2] | resid[4][2]
+    static constexpr int NBARS = 5 * NS + 4 + 8;                        // full | fullA | empty | split | aready | tfull[2] | tempty[2] | resid[4][2]
     static constexpr int SMEM = NS * STAGE + STG_BYTES + NBARS * 8 + 64 + 1024;
     // instruction descriptor: D=f32, A=B=tf32, K-major, N>>3 at bit 17, M>>4 at bit 24 with M = 256 (the pair's rows)
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -152,7 +154,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * K::STAGE + K::STG_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + K::NBARS);
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
-    constexpr int B_FULL = 0, B_FULLA = NS, B_EMPTY = 2 * NS, B_SPLIT = 3 * NS, B_TFULL = 4 * NS, B_TEMPTY = 4 * NS + 2, B_RES = 4 * NS + 4;
+    constexpr int B_FULL = 0, B_FULLA = NS, B_EMPTY = 2 * NS, B_SPLIT = 3 * NS, B_AREADY = 4 * NS, B_TFULL = 5 * NS, B_TEMPTY = 5 * NS + 2,
+                  B_RES = 5 * NS + 4;
     constexpr int T_A = 0, T_ALO = A_TILE, T_W = (TERMS == 3) ? 2 * A_TILE : A_TILE, T_WLO = T_W + K::W_TILE;
     auto tile = [&](int stage, int off) { return smem + stage * K::STAGE + off; };
 
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
         if (e.tma_epi && e.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.r) : "memory");
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_FULLA + s), 1); mbar_init(bar(B_EMPTY + s), 1); mbar_init(bar(B_SPLIT + s), 2);
+            mbar_init(bar(B_AREADY + s), 2);
         }
         for (int b = 0; b < 2; ++b) { mbar_init(bar(B_TFULL + b), 1); mbar_init(bar(B_TEMPTY + b), 8); }
         for (int b = 0; b < 8; ++b) mbar_init(bar(B_RES + b), 1);
@@ -224,20 +228,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                 for (int kb = 0; kb < nkb; ++kb, ++kc) {
                     const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
                     mbar_wait(bar(B_FULL + s), ph);
-                    if (TERMS == 3) mbar_wait(bar(B_SPLIT + s), ph);
+                    if (TERMS == 3) {
+                        if (e.early_mma) mbar_wait(bar(B_AREADY + s), ph);                  // both CTAs' raw A tiles have landed
+                        else             mbar_wait(bar(B_SPLIT + s), ph);
+                    }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = make_desc(smem_u32(tile(s, T_A))), dw = make_desc(smem_u32(tile(s, T_W)));
+                    if (TERMS == 3) {
+                        // The tensor core reads only the top 19 bits of an fp32 word as TF32, so the RAW A tile already is
+                        // a_hi: a_hi*w_hi and a_hi*w_lo start as soon as the tiles land, and the splitter warps get those
+                        // 8 MMAs (1024 tensor cycles) to produce a_lo = a - trunc(a) for the last product.
+                        const uint64_t dalo = make_desc(smem_u32(tile(s, T_ALO))), dwlo = make_desc(smem_u32(tile(s, T_WLO)));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                        if (TERMS == 3) {
-                            const uint64_t dalo = make_desc(smem_u32(tile(s, T_ALO))), dwlo = make_desc(smem_u32(tile(s, T_WLO)));
-                            umma_tf32_pair(tmem_c, dalo + koff, dw + koff, K::IDESC, acc);
-                            umma_tf32_pair(tmem_c, da + koff, dwlo + koff, K::IDESC, 1u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            umma_tf32_pair(tmem_c, da + koff, dwlo + koff, K::IDESC, (kb > 0 || k > 0) ? 1u : 0u);
                             umma_tf32_pair(tmem_c, da + koff, dw + koff, K::IDESC, 1u);
-                        } else {
-                            umma_tf32_pair(tmem_c, da + koff, dw + koff, K::IDESC, acc);
+                        }
+                        if (e.early_mma) {
+                            mbar_wait(bar(B_SPLIT + s), ph);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            umma_tf32_pair(tmem_c, dalo + koff, dw + koff, K::IDESC, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            umma_tf32_pair(tmem_c, da + koff, dw + koff, K::IDESC, (kb > 0 || k > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit_pair(bar(B_EMPTY + s));                  // frees the stage in both CTAs
@@ -284,11 +305,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                 mbar_wait(bar(B_TFULL + buf_acc), aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (rows_ok) {
+                    // bias of a chunk's accumulator columns lives in two registers per lane (columns nb+lane, nb+32+lane),
+                    // fetched one chunk ahead so its latency never sits in front of the math; lanes read it by shuffle
+                    auto bias_regs = [&](int nb, float& lo, float& hi) {
+                        lo = (biasp && nb + lane < e.N) ? __ldg(biasp + nb + lane) : 0.f;
+                        hi = (biasp && glu && nb + 32 + lane < e.N) ? __ldg(biasp + nb + 32 + lane) : 0.f;
+                    };
+                    float b_lo, b_hi, bn_lo = 0.f, bn_hi = 0.f;
+                    bias_regs(n0, b_lo, b_hi);
 #pragma unroll 1
                     for (int c0 = 0; c0 < BN; c0 += in_per_chunk) {
                         const int oc = out0 + (glu ? (c0 >> 1) : c0);          // first output column of this chunk
                         if (oc >= n_out) break;                                  // warp-uniform
                         const int buf = g & 1;
+                        const int nb = n0 + c0;                                  // first accumulator column of this chunk
+                        if (c0 + in_per_chunk < BN) bias_regs(nb + in_per_chunk, bn_lo, bn_hi);
                         float v[32], w[32];
                         tmem_ld32(tmem_c + (uint32_t)c0, v);
                         if (glu) tmem_ld32(tmem_c + (uint32_t)(c0 + 32), w);
@@ -299,39 +330,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                             else          { mbar_wait(bar(B_RES + ew * 2 + 1), rph1); rph1 ^= 1; }
                         }
                         unsigned char* rowp = ebuf + buf * 4096 + lane * 128;
-                        const int nb = n0 + c0;                                  // first accumulator column of this chunk
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float4 o;
                             if (!glu) {
-                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (biasp) {
-                                    const int cb = nb + 4 * q;
-                                    if (cb + 3 < e.N) b4 = __ldg(reinterpret_cast<const float4*>(biasp + cb));
-                                    else { if (cb < e.N) b4.x = __ldg(biasp + cb); if (cb + 1 < e.N) b4.y = __ldg(biasp + cb + 1); if (cb + 2 < e.N) b4.z = __ldg(biasp + cb + 2); }
-                                }
-                                o.x = fmaf(v[4 * q], rs, b4.x); o.y = fmaf(v[4 * q + 1], rs, b4.y);
-                                o.z = fmaf(v[4 * q + 2], rs, b4.z); o.w = fmaf(v[4 * q + 3], rs, b4.w);
+                                const float bx = __shfl_sync(0xffffffffu, b_lo, 4 * q), by = __shfl_sync(0xffffffffu, b_lo, 4 * q + 1);
+                                const float bz = __shfl_sync(0xffffffffu, b_lo, 4 * q + 2), bw = __shfl_sync(0xffffffffu, b_lo, 4 * q + 3);
+                                o.x = fmaf(v[4 * q], rs, bx); o.y = fmaf(v[4 * q + 1], rs, by);
+                                o.z = fmaf(v[4 * q + 2], rs, bz); o.w = fmaf(v[4 * q + 3], rs, bw);
                             } else {
                                 // outputs 4q..4q+3 of the chunk come from accumulator columns 8q..8q+7 (x, gate interleaved)
                                 const float* src = (q < 4) ? (v + 8 * q) : (w + 8 * (q - 4));
-                                float xb[8];
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) xb[k] = 0.f;
-                                if (biasp) {
-                                    const int cb = nb + 8 * q;
-                                    if (cb + 7 < e.N) {
-                                        const float4 t0 = __ldg(reinterpret_cast<const float4*>(biasp + cb)), t1 = __ldg(reinterpret_cast<const float4*>(biasp + cb + 4));
-                                        xb[0] = t0.x; xb[1] = t0.y; xb[2] = t0.z; xb[3] = t0.w; xb[4] = t1.x; xb[5] = t1.y; xb[6] = t1.z; xb[7] = t1.w;
-                                    } else {
-#pragma unroll
-                                        for (int k = 0; k < 8; ++k) if (cb + k < e.N) xb[k] = __ldg(biasp + cb + k);
-                                    }
-                                }
+                                const float bsrc = (q < 4) ? b_lo : b_hi;
                                 float r4[4];
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    const float x = fmaf(src[2 * k], rs, xb[2 * k]), gt = fmaf(src[2 * k + 1], rs, xb[2 * k + 1]);
+                                    const float x = fmaf(src[2 * k], rs, __shfl_sync(0xffffffffu, bsrc, (8 * q + 2 * k) & 31));
+                                    const float gt = fmaf(src[2 * k + 1], rs, __shfl_sync(0xffffffffu, bsrc, (8 * q + 2 * k + 1) & 31));
                                     r4[k] = x * ((e.act == D4_ACT_GLU_SILU) ? silu_fast(gt) : geluf_(gt));
                                 }
                                 o = make_float4(r4[0], r4[1], r4[2], r4[3]);
@@ -349,6 +364,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                             const int oc_next = oc + 32;
                             if (has_res && c0 + in_per_chunk < BN && oc_next < n_out) { bulk_wait_read_1(); res_load(buf ^ 1, oc_next, rbase); }
                         }
+                        b_lo = bn_lo; b_hi = bn_hi;
                         ++g;
                     }
                 }
@@ -482,24 +498,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
     } else if (TERMS == 3) {
         // ================= A splitter (tf32x3): this CTA's A tile -> hi (in place) + lo, then one arrival on the leader's barrier
         const int et = threadIdx.x - 192;          // 0..127
-        const uint32_t split_leader = bar(B_SPLIT) & PEER_MASK;
+        const uint32_t split_leader = bar(B_SPLIT) & PEER_MASK, aready_leader = bar(B_AREADY) & PEER_MASK;
         uint32_t kc = 0;
         for (int t = cluster_id; t < total_tiles; t += n_clusters) {
             for (int kb = 0; kb < nkb; ++kb, ++kc) {
                 const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
                 mbar_wait(bar(B_FULLA + s), ph);
-                float4* a = reinterpret_cast<float4*>(tile(s, T_A));
+                if (et == 0 && e.early_mma) mbar_arrive_cluster(aready_leader + (uint32_t)s * 8u);   // the raw tile can feed the first two products now
+                const float4* a = reinterpret_cast<const float4*>(tile(s, T_A));
                 float4* alo = reinterpret_cast<float4*>(tile(s, T_ALO));
 #pragma unroll
                 for (int j = 0; j < A_TILE / 16 / 128; ++j) {
                     const int idx = et + 128 * j;
                     const float4 v = a[idx];
-                    float4 hi, lo;
-                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
-                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
-                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
-                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
-                    a[idx] = hi; alo[idx] = lo;
+                    float4 lo;
+                    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    alo[idx] = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");                          // the four splitter warps
@@ -624,6 +641,8 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
     if (g.residual) tma_epi = tma_epi && al16(g.residual) && (g.ldr % 4 == 0) &&
                               (grp == 0 || ((((long long)g.cmap.goff * g.ldr) % 4 == 0) && (((long long)g.cmap.gstride * g.ldr) % 4 == 0)));
     e.tma_epi = tma_epi ? 1 : 0;
+    static const int early = getenv("D4_GEMM_EARLY_MMA") ? atoi(getenv("D4_GEMM_EARLY_MMA")) : 0;
+    e.early_mma = early;
     if (tma_epi) {
         { int rc = encode_out(&maps.c, g.C, g.M, glu ? g.N / 2 : g.N, g.ldc, g.cmap); if (rc) return rc; }
         if (g.residual) { int rc = encode_out(&maps.r, g.residual, g.M, g.N, g.ldr, g.cmap); if (rc) return rc; }

@@ -298,6 +298,7 @@ struct LearnPlan {
     long long r_m, v_m, gae_mask, learn_mask, row_pl, row_ent, row_vl, stats;
     long long Y[D4_MAX_MLP_LAYERS], X[D4_MAX_MLP_LAYERS], mean[D4_MAX_MLP_LAYERS], rstd[D4_MAX_MLP_LAYERS];
     long long out, logits, dlogits, g0, g1;
+    long long dyT, xT_hi, xT_lo;      // tensor-core backward: transposed dy (H, Rc) and transposed + tf32-split layer input (H, Rc)
     int Rc;
 };
 
@@ -319,11 +320,51 @@ LearnPlan plan_learn(const d4_ctx* c, int B, int T) {
     const int ldl = std::max(c->ldlog, (c->cfg.value_bins + 3) / 4 * 4);
     p.logits = take((long long)p.Rc * ldl * 4); p.dlogits = take((long long)p.Rc * ldl * 4);
     p.g0 = take((long long)p.Rc * H * 4); p.g1 = take((long long)p.Rc * H * 4);
+    if (c->cfg.precision == D4_PREC_TF32X3) {
+        p.dyT = take((long long)p.Rc * H * 4); p.xT_hi = take((long long)p.Rc * H * 4); p.xT_lo = take((long long)p.Rc * H * 4);
+    }
     p.total = off;
     return p;
 }
 
 struct MlpGrads { float* const* w; float* const* b; float* const* lnw; float* const* lnb; };
+
+// out[c][r] = in[r][c] for an (R, C) row-major matrix with leading dim ld; out rows have leading dim R.
+// SPLIT: also emits the tf32 hi / lo words (out = hi, out_lo = in - hi) so the transposed matrix can be the pre-split
+// "weight" operand of the 3xTF32 tensor-core GEMM.
+template <bool SPLIT>
+__global__ void transpose_kernel(int R, int C, const float* __restrict__ in, long long ld, float* __restrict__ out, float* __restrict__ out_lo) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8 threads
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < R && c < C) ? in[(long long)r * ld + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (c < C && r < R) {
+            const float v = tile[tx][i];
+            if (SPLIT) {
+                const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                out[(long long)c * R + r] = hi; out_lo[(long long)c * R + r] = v - hi;
+            } else {
+                out[(long long)c * R + r] = v;
+            }
+        }
+    }
+}
+int transpose_rows(int R, int C, const float* in, long long ld, float* out, float* out_lo, cudaStream_t s) {
+    dim3 grid((C + 31) / 32, (R + 31) / 32);
+    if (out_lo) transpose_kernel<true><<<grid, 256, 0, s>>>(R, C, in, ld, out, out_lo);
+    else        transpose_kernel<false><<<grid, 256, 0, s>>>(R, C, in, ld, out, nullptr);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+inline bool learn_tc(const d4_ctx* c) { return c->cfg.precision == D4_PREC_TF32X3; }
 
 // forward of one head on a chunk of rows, keeping what the backward needs
 int mlp_forward_saved(d4_ctx* c, const MlpW& mlp, const float* x0, int Rc, unsigned char* ws, const LearnPlan& p, float* out, long long ldo,
@@ -336,7 +377,12 @@ int mlp_forward_saved(d4_ctx* c, const MlpW& mlp, const float* x0, int Rc, unsig
         const long long ldd = last ? ldo : wout;
         GemmArgs g = gemm_args(cur, ldc, mlp.w[l], mlp.dims[l], dst, ldd, Rc, wout, mlp.dims[l]);
         g.bias = mlp.b[l];
-        D4_TRY(d4_gemm_simt(g, s));
+        if (learn_tc(c) && mlp.hi[l] && mlp.lo[l]) {          // 3xTF32 on the tensor cores (fp32-accurate), else exact-fp32 FMA
+            LinW lw; lw.w = mlp.w[l]; lw.hi = mlp.hi[l]; lw.lo = mlp.lo[l];
+            D4_TRY(d4_engine_gemm(c, g, lw, 0, s));
+        } else {
+            D4_TRY(d4_gemm_simt(g, s));
+        }
         if (!last) {
             float* xn = reinterpret_cast<float*>(ws + p.X[l + 1]);
             D4_TRY(d4_ln_act_rows(dst, wout, mlp.lnw[l], mlp.lnb[l], Rc, wout, xn, wout, D4_ACT_SILU,
@@ -364,9 +410,26 @@ int mlp_backward(d4_ctx* c, const MlpW& mlp, const float* x0, int Rc, unsigned c
         }
         const float* xin = (l == 0) ? x0 : reinterpret_cast<float*>(ws + p.X[l]);
         {   // dW += dy^T @ x_in
-            GemmArgs g = gemm_args(dy, ldy, xin, win, G.w[l], win, wout, win, Rc);
-            g.transA = 1; g.transW = 1; g.residual = G.w[l]; g.ldr = win;
-            D4_TRY(d4_gemm_simt(g, s));
+            bool done = false;
+            if (learn_tc(c) && p.dyT && (Rc % 4) == 0 && Rc >= 32) {
+                // K-major operands for tcgen05: dy^T (wout, Rc) and x_in^T (win, Rc) pre-split into tf32 hi / lo
+                float* dyT = reinterpret_cast<float*>(ws + p.dyT);
+                float* xT_hi = reinterpret_cast<float*>(ws + p.xT_hi); float* xT_lo = reinterpret_cast<float*>(ws + p.xT_lo);
+                GemmArgs g = gemm_args(dyT, Rc, xT_hi, Rc, G.w[l], win, wout, win, Rc);
+                g.residual = G.w[l]; g.ldr = win;
+                if (d4_gemm_tc_supported(g)) {
+                    D4_TRY(transpose_rows(Rc, wout, dy, ldy, dyT, nullptr, s));
+                    D4_TRY(transpose_rows(Rc, win, xin, win, xT_hi, xT_lo, s));
+                    LinW lw; lw.w = xT_hi; lw.hi = xT_hi; lw.lo = xT_lo;
+                    D4_TRY(d4_engine_gemm(c, g, lw, 0, s));
+                    done = true;
+                }
+            }
+            if (!done) {
+                GemmArgs g = gemm_args(dy, ldy, xin, win, G.w[l], win, wout, win, Rc);
+                g.transA = 1; g.transW = 1; g.residual = G.w[l]; g.ldr = win;
+                D4_TRY(d4_gemm_simt(g, s));
+            }
         }
         {   // db += colsum(dy)
             dim3 grid(nblk(wout, 32), std::min(64, std::max(1, Rc / 64)));
@@ -375,9 +438,20 @@ int mlp_backward(d4_ctx* c, const MlpW& mlp, const float* x0, int Rc, unsigned c
         }
         if (l > 0) {   // dx_in = dy @ W
             float* dxin = (dy == reinterpret_cast<float*>(ws + p.g0)) ? reinterpret_cast<float*>(ws + p.g1) : reinterpret_cast<float*>(ws + p.g0);
-            GemmArgs g = gemm_args(dy, ldy, mlp.w[l], win, dxin, win, Rc, win, wout);
-            g.transW = 1;
-            D4_TRY(d4_gemm_simt(g, s));
+            bool done = false;
+            if (learn_tc(c) && mlp.wthi[l] && mlp.wtlo[l]) {      // dy @ W == dy @ (W^T)^T with W^T (win, wout) K-major
+                GemmArgs g = gemm_args(dy, ldy, mlp.wthi[l], wout, dxin, win, Rc, win, wout);
+                if (d4_gemm_tc_supported(g)) {
+                    LinW lw; lw.w = mlp.wthi[l]; lw.hi = mlp.wthi[l]; lw.lo = mlp.wtlo[l];
+                    D4_TRY(d4_engine_gemm(c, g, lw, 0, s));
+                    done = true;
+                }
+            }
+            if (!done) {
+                GemmArgs g = gemm_args(dy, ldy, mlp.w[l], win, dxin, win, Rc, win, wout);
+                g.transW = 1;
+                D4_TRY(d4_gemm_simt(g, s));
+            }
             dy = dxin; ldy = win;
         }
     }

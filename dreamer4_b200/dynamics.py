@@ -351,22 +351,51 @@ class DynamicsWorldModel(nn.Module):
             heads = [('policy', 'policy_head', c.policy_head_mlp_depth + 2), ('value', 'value_head', c.value_head_mlp_depth + 2)] if c.has_actions else []
             if c.predict_terminals:
                 heads.append(('terminal', 'to_state_terminal_pred.0', c.terminal_mlp_depth + 2))
+            self._head_splits = []
             for short, prefix, nl in heads:
                 for pname, key_ in mlp_param_names(prefix, nl):
                     t = params[key_]
                     assert t.is_contiguous()
                     check(lib.d4_set_weight(self._ctx, f'{short}.{pname}'.encode(), ptr(t), t.numel()))
+                    if self.precision == 'tf32x3' and pname.endswith('.w') and short != 'terminal':
+                        # trained head weights change every optimizer step: their tf32 hi/lo split lives in persistent
+                        # buffers that _refresh_head_splits() rewrites in place when the parameter version moves
+                        hi, lo = torch.empty_like(t), torch.empty_like(t)
+                        thi, tlo = torch.empty_like(t.t().contiguous()), torch.empty_like(t.t().contiguous())     # of W^T: learn backward
+                        self._head_splits.append((t, hi, lo, thi, tlo))
+                        for suffix, buf in (('.hi', hi), ('.lo', lo)):
+                            check(lib.d4_set_weight(self._ctx, f'{short}.{pname}{suffix}'.encode(), ptr(buf), buf.numel()))
+                        for suffix, buf in (('.hi', thi), ('.lo', tlo)):
+                            check(lib.d4_set_weight(self._ctx, f'{short}.{pname[:-2]}.wt{suffix}'.encode(), ptr(buf), buf.numel()))
+            self._head_split_version = None
             if c.has_actions:
                 un = params['action_embedder.discrete_action_unembed']          # (A, mtp, 4D): head 0 rows, row stride mtp*4D
                 check(lib.d4_set_weight(self._ctx, b'unembed', ptr(un), un.stride(0)))
             check(lib.d4_bind(self._ctx))
             self._packed_version = ver
+        self._refresh_head_splits()
         return lib, self._ctx
+
+    @torch.no_grad()
+    def _refresh_head_splits(self):
+        splits = getattr(self, '_head_splits', None)
+        if not splits:
+            return
+        ver = sum(s[0]._version for s in splits)
+        if ver == self._head_split_version:
+            return
+        for t, hi, lo, thi, tlo in splits:
+            torch.bitwise_and(t.detach().view(torch.int32), -8192, out=hi.view(torch.int32))      # sign, exponent, 10 mantissa bits
+            torch.sub(t.detach(), hi, out=lo)
+            thi.copy_(hi.t())
+            tlo.copy_(lo.t())
+        self._head_split_version = ver
 
     def _release(self):
         if self._ctx is not None:
             _lib.load().d4_ctx_destroy(self._ctx)
         self._ctx, self._ctx_key, self._bufs, self._packed, self._packed_version = None, None, {}, None, None
+        self._head_splits, self._head_split_version = [], None
 
     def __del__(self):
         try:

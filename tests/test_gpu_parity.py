@@ -407,3 +407,35 @@ def test_hundred_seeded_dream_steps_losses():
         assert ep < 1e-4, f'step {step}: policy loss {pl.item()} vs reference {rpl.item()} (rel {ep:.2e})'
         assert ev < 1e-4, f'step {step}: value loss {vl.item()} vs reference {rvl.item()} (rel {ev:.2e})'
     print(f'100 seeded dream steps: worst relative loss error policy {worst_p:.2e}, value {worst_v:.2e}')
+
+
+def test_learn_tf32x3_matches_oracle():
+    """learn_from_experience with the 3xTF32 tensor-core GEMMs (forward, dx through W^T, dW through the transposed
+    operands) on a model wide enough that every head GEMM takes the tcgen05 path: losses within 1e-4 relative (the north
+    star's bar); gradients within 1e-5 + 2e-4 relative of the fp32 oracle's autograd.  (The exact-fp32 mode is held to
+    2e-6 absolute; 3xTF32 drops the a_lo*w_lo term, 2^-22 of each product, and four chained backward GEMMs leave up to
+    5e-6 of absolute error on gradients of magnitude ~1e-2 — measured, 0.1 % of the elements beyond 2e-6.)"""
+    model, sd = _mid_model('tf32x3')
+    ocfg = O.config_from_reference_kwargs(**MID)
+    T, B = 6, 48            # 288 rows: multi-tile M for the forward / dx GEMMs, K = 288 for dW
+    noise = make_noise(model.cfg, T, B, seed=9)
+    ref = O.generate(sd, ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform']))
+    from dreamer4_b200 import Actions, Experience
+    cu = lambda t: t.cuda()
+    exp = Experience(latents=cu(ref.latents), agent_embed=cu(ref.agent_embed), rewards=cu(ref.rewards), values=cu(ref.values),
+                     actions=Actions(cu(ref.actions), None), log_probs=Actions(cu(ref.log_probs), None), lens=cu(ref.lens),
+                     is_truncated=cu(ref.is_truncated), terminals=cu(ref.terminals), step_size=ref.step_size)
+    keys = [k for k in sd if k.startswith(('policy_head.', 'value_head.')) or k == 'action_embedder.discrete_action_unembed']
+    sdg = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd.items()}
+    rpl, rvl, _ = O.learn_from_experience(sdg, ocfg, ref)
+    rpl.backward()
+    rvl.backward()
+    pl, vl = model.learn_from_experience(exp)
+    torch.testing.assert_close(pl.detach().cpu(), rpl.detach(), atol=2e-6, rtol=1e-4)
+    torch.testing.assert_close(vl.detach().cpu(), rvl.detach(), atol=2e-6, rtol=1e-4)
+    pl.backward()
+    vl.backward()
+    params = dict(model.named_parameters())
+    for k in keys:
+        assert params[k].grad is not None, k
+        torch.testing.assert_close(params[k].grad.cpu(), sdg[k].grad, atol=1e-5, rtol=2e-4, msg=lambda m, n=k: f'{n}: {m}')

@@ -20,8 +20,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 32, UMMA_K = 8;
-constexpr int A_TILE = BM * BK * 4;           // 16 KB
+constexpr int BM = 128, UMMA_K = 8;
 constexpr int NUM_THREADS = 320;
 constexpr int STG_LD = 33;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: the even (leader) CTA's copy
@@ -100,13 +99,17 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_c, uint64_t desc_a,
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
         ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {       // K-major SWIZZLE_128B, see gemm_tc.cu
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO = 1 | SBO = 8 rows of the swizzle
+// span | version 1 | layout type.  BK = 32 floats: 128-byte rows, SWIZZLE_128B (type 2); BK = 16 floats: 64-byte rows,
+// SWIZZLE_64B (type 4).
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * BK * 4) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;
     return d;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -132,11 +135,12 @@ struct EpiArgs3 {
     int early_mma;      // tf32x3: 1 = issue the two a_hi products before the a_lo tile is ready, 0 = wait for the split first
 };
 
-template <int TERMS, int BN> struct Cfg3 {
+template <int TERMS, int BN, int BK> struct Cfg3 {
+    static constexpr int A_TILE = BM * BK * 4;
     static constexpr int BNH = BN / 2;                                  // weight rows staged per CTA
     static constexpr int W_TILE = BNH * BK * 4;
     static constexpr int STAGE = (TERMS == 3) ? 2 * A_TILE + 2 * W_TILE : A_TILE + W_TILE;
-    static constexpr int NS = (TERMS == 3) ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 6 : 8);
+    static constexpr int NS = (192 * 1024) / STAGE;                     // BK 32: 3 (x3, BN 256), 4 (x3, 128), 6 / 8 (x1); BK 16: twice that
     static constexpr int STG_BYTES = 4 * 2 * 4096;                      // per epilogue warp: two 32 x 32 fp32 tiles (128B-swizzled)
     static constexpr int NBARS = 5 * NS + 4 + 8;                        // full | fullA | empty | split | aready | tfull[2] | tempty[2] | resid[4][2]
     static constexpr int SMEM = NS * STAGE + STG_BYTES + NBARS * 8 + 64 + 1024;
@@ -144,10 +148,11 @@ template <int TERMS, int BN> struct Cfg3 {
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
-template <int TERMS, int BN>
+template <int TERMS, int BN, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_constant__ TmaMaps3 maps, const EpiArgs3 e) {
-    using K = Cfg3<TERMS, BN>;
+    using K = Cfg3<TERMS, BN, BK>;
     constexpr int NS = K::NS;
+    constexpr int A_TILE = K::A_TILE;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* stg_all = reinterpret_cast<float*>(smem + NS * K::STAGE);
@@ -233,12 +238,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                         else             mbar_wait(bar(B_SPLIT + s), ph);
                     }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t da = make_desc(smem_u32(tile(s, T_A))), dw = make_desc(smem_u32(tile(s, T_W)));
+                    const uint64_t da = make_desc<BK>(smem_u32(tile(s, T_A))), dw = make_desc<BK>(smem_u32(tile(s, T_W)));
                     if (TERMS == 3) {
                         // The tensor core reads only the top 19 bits of an fp32 word as TF32, so the RAW A tile already is
                         // a_hi: a_hi*w_hi and a_hi*w_lo start as soon as the tiles land, and the splitter warps get those
                         // 8 MMAs (1024 tensor cycles) to produce a_lo = a - trunc(a) for the last product.
-                        const uint64_t dalo = make_desc(smem_u32(tile(s, T_ALO))), dwlo = make_desc(smem_u32(tile(s, T_WLO)));
+                        const uint64_t dalo = make_desc<BK>(smem_u32(tile(s, T_ALO))), dwlo = make_desc<BK>(smem_u32(tile(s, T_WLO)));
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
@@ -547,27 +552,27 @@ EncodeTiledFn get_encode() {
     }
     return fn;
 }
-int encode_2d(CUtensorMap* map, const float* base, long long rows, long long K, long long ld, int box_rows) {
+int encode_2d(CUtensorMap* map, const float* base, long long rows, long long K, long long ld, int box_rows, int bk) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return d4_fail("cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return d4_fail("cuTensorMapEncodeTiled(2d rows=%lld K=%lld ld=%lld) failed: %d", rows, K, ld, (int)r);
     return 0;
 }
-int encode_3d(CUtensorMap* map, const float* base, long long M, long long K, long long ld, const RowMap& rm) {
+int encode_3d(CUtensorMap* map, const float* base, long long M, long long K, long long ld, const RowMap& rm, int bk) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return d4_fail("cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rm.grp, (cuuint64_t)(M / rm.grp)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)rm.gstride * ld * 4};
-    cuuint32_t box[3] = {BK, (cuuint32_t)rm.grp, (cuuint32_t)(BM / rm.grp)};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)rm.grp, (cuuint32_t)(BM / rm.grp)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base + (long long)rm.goff * ld), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return d4_fail("cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
     return 0;
 }
@@ -597,10 +602,10 @@ int encode_out(CUtensorMap* map, const float* base, long long M, long long N, lo
 }
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int TERMS, int BN>
+template <int TERMS, int BN, int BK>
 int max_clusters() {
     // how many CTA pairs can be co-resident (one per TPC on a full B200: 74)
-    using K = Cfg3<TERMS, BN>;
+    using K = Cfg3<TERMS, BN, BK>;
     static int cached = 0;
     if (cached) return cached;
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
@@ -608,26 +613,26 @@ int max_clusters() {
     cudaLaunchAttribute attr; attr.id = cudaLaunchAttributeClusterDimension; attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc3_kernel<TERMS, BN>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc3_kernel<TERMS, BN, BK>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
     cached = n > 0 ? n : -1;
     return cached;
 }
 
-template <int TERMS, int BN>
+template <int TERMS, int BN, int BK>
 int launch3(const GemmArgs& g, cudaStream_t stream) {
-    using K = Cfg3<TERMS, BN>;
+    using K = Cfg3<TERMS, BN, BK>;
     static bool configured = false;
     if (!configured) {
-        D4_CUDA_OK(cudaFuncSetAttribute(gemm_tc3_kernel<TERMS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        D4_CUDA_OK(cudaFuncSetAttribute(gemm_tc3_kernel<TERMS, BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
         configured = true;
     }
-    const int maxc = max_clusters<TERMS, BN>();
+    const int maxc = max_clusters<TERMS, BN, BK>();
     if (maxc <= 0) return d4_fail("gemm_tc3: no CTA pair of %d bytes of shared memory can be scheduled on this device", K::SMEM);
     TmaMaps3 maps; memset(&maps, 0, sizeof(maps));
-    if (g.amap.grp == 0) { int rc = encode_2d(&maps.a, g.A, g.M, g.K, g.lda, BM); if (rc) return rc; }
-    else { int rc = encode_3d(&maps.a, g.A, g.M, g.K, g.lda, g.amap); if (rc) return rc; }
-    { int rc = encode_2d(&maps.w, g.W, g.N, g.K, g.ldw, K::BNH); if (rc) return rc; }
-    if (TERMS == 3) { int rc = encode_2d(&maps.wlo, g.W_lo, g.N, g.K, g.ldw, K::BNH); if (rc) return rc; }
+    if (g.amap.grp == 0) { int rc = encode_2d(&maps.a, g.A, g.M, g.K, g.lda, BM, BK); if (rc) return rc; }
+    else { int rc = encode_3d(&maps.a, g.A, g.M, g.K, g.lda, g.amap, BK); if (rc) return rc; }
+    { int rc = encode_2d(&maps.w, g.W, g.N, g.K, g.ldw, K::BNH, BK); if (rc) return rc; }
+    if (TERMS == 3) { int rc = encode_2d(&maps.wlo, g.W_lo, g.N, g.K, g.ldw, K::BNH, BK); if (rc) return rc; }
     EpiArgs3 e;
     e.C = g.C; e.ldc = g.ldc; e.M = g.M; e.N = g.N; e.bias = g.bias; e.row_scale = g.row_scale; e.residual = g.residual; e.ldr = g.ldr;
     e.act = g.act; e.cmap = g.cmap; e.a_grp = g.amap.grp; e.nkb = (g.K + BK - 1) / BK;
@@ -653,7 +658,7 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
     cfg.gridDim = dim3(2 * clusters, 1, 1); cfg.blockDim = dim3(NUM_THREADS, 1, 1); cfg.dynamicSmemBytes = K::SMEM; cfg.stream = stream;
     cudaLaunchAttribute attr; attr.id = cudaLaunchAttributeClusterDimension; attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    D4_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc3_kernel<TERMS, BN>, maps, e));
+    D4_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc3_kernel<TERMS, BN, BK>, maps, e));
     D4_COUNT_LAUNCH();
     return 0;
 }
@@ -666,6 +671,8 @@ int d4_gemm_tc3(const GemmArgs& g, int terms, int bn, cudaStream_t stream) {
         const long long p128 = (long long)(g.N + 127) / 128 * 128, p256 = (long long)(g.N + 255) / 256 * 256;
         bn = (p128 * 10 < p256 * 9) ? 128 : 256;           // the narrow tile only when it saves more than 10 % of the columns
     }
-    if (terms == 3) return bn == 256 ? launch3<3, 256>(g, stream) : launch3<3, 128>(g, stream);
-    return bn == 256 ? launch3<1, 256>(g, stream) : launch3<1, 128>(g, stream);
+    // K step 32 floats = one 128-byte swizzle row.  (A 16-float / SWIZZLE_64B step with twice the ring depth was measured
+    // 1.9x SLOWER on every layer shape: the tensor core's operand fetch runs at half efficiency on 64-byte rows.)
+    if (terms == 3) return bn == 256 ? launch3<3, 256, 32>(g, stream) : launch3<3, 128, 32>(g, stream);
+    return bn == 256 ? launch3<1, 256, 32>(g, stream) : launch3<1, 128, 32>(g, stream);
 }

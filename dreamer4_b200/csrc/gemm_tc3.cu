@@ -668,8 +668,10 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
 // CTA-pair kernel entry; bn = 128 or 256 (0 = choose by padding waste)
 int d4_gemm_tc3(const GemmArgs& g, int terms, int bn, cudaStream_t stream) {
     if (bn == 0) {
+        // 256-wide tiles unless the 128-wide one saves more than 10 % of the (padded) columns.  Choosing 128 to smooth wave
+        // quantisation (N = 512: 7 half-rounds instead of 4 full ones) was measured SLOWER overall (166 vs 205 TFLOP/s).
         const long long p128 = (long long)(g.N + 127) / 128 * 128, p256 = (long long)(g.N + 255) / 256 * 256;
-        bn = (p128 * 10 < p256 * 9) ? 128 : 256;           // the narrow tile only when it saves more than 10 % of the columns
+        bn = (p128 * 10 < p256 * 9) ? 128 : 256;
     }
     // K step 32 floats = one 128-byte swizzle row.  (A 16-float / SWIZZLE_64B step with twice the ring depth was measured
     // 1.9x SLOWER on every layer shape: the tensor core's operand fetch runs at half efficiency on 64-byte rows.)

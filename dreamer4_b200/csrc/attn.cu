@@ -149,13 +149,15 @@ __global__ void __launch_bounds__(SP_WARPS * 32) space_attn_kernel(SmallAttnArgs
     const float sqrt_d = sqrtf((float)D);
 
     for (int idx = lane; idx < SMAX * SMAX; idx += 32) sm.pt[idx] = 0.f;
+    if (a.v0 && lane < S) sm.kinv[lane] = sigmoidf_(a.mix[b * a.mix_sb + lane * a.mix_sj + hk]);   // value-residual mix weight per key (kinv is free until the norms)
+    __syncwarp();
     for (int idx = lane; idx < S * C4; idx += 32) {
         const int j = idx / C4, c = (idx % C4) * 4;
         const float4 kv = *reinterpret_cast<const float4*>(a.k + b * a.k_sb + j * a.k_sj + (long long)hk * D + c);
         float4 vv = *reinterpret_cast<const float4*>(a.v + b * a.v_sb + j * a.v_sj + (long long)hk * D + c);
         if (a.v0) {
             const float4 rv = *reinterpret_cast<const float4*>(a.v0 + b * a.v0_sb + j * a.v0_sj + (long long)hk * D + c);
-            const float w = sigmoidf_(a.mix[b * a.mix_sb + j * a.mix_sj + hk]);
+            const float w = sm.kinv[j];
             vv.x = lerp_(vv.x, rv.x, w); vv.y = lerp_(vv.y, rv.y, w); vv.z = lerp_(vv.z, rv.z, w); vv.w = lerp_(vv.w, rv.w, w);
         }
         *reinterpret_cast<float4*>(sm.k + j * P + c) = kv;

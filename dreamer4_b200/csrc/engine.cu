@@ -292,7 +292,7 @@ static inline LinW plain(const float* w) { LinW l; l.w = w; return l; }
 // x-mlps normed MLP forward (Linear -> LayerNorm -> SiLU)* -> Linear.  Exact fp32 FMA unless the caller registered a tf32
 // hi/lo split of the layer's weight and the engine runs in tf32x3 (fp32-accurate 3-term tensor-core product).
 int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, int M, float* buf0, float* buf1, float* out, long long ldo,
-                   cudaStream_t s) {
+                   int allow_tensor, cudaStream_t s) {
     const float* cur = x; long long ldc = ldx;
     for (int l = 0; l < mlp.layers; ++l) {
         const bool last = (l == mlp.layers - 1);
@@ -301,7 +301,7 @@ int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, in
         GemmArgs g = gemm_args(cur, ldc, mlp.w[l], mlp.dims[l], dst, ldd, M, mlp.dims[l + 1], mlp.dims[l]);
         g.bias = mlp.b[l];
         LinW lw; lw.w = mlp.w[l]; lw.hi = mlp.hi[l]; lw.lo = mlp.lo[l];
-        const int exact = !(c->cfg.precision == D4_PREC_TF32X3 && lw.hi && lw.lo);
+        const int exact = !(allow_tensor && c->cfg.precision == D4_PREC_TF32X3 && lw.hi && lw.lo);
         D4_TRY(d4_engine_gemm(c, g, lw, exact, s));
         if (!last) D4_TRY(d4_ln_act_rows(dst, ldd, mlp.lnw[l], mlp.lnb[l], M, mlp.dims[l + 1], dst, ldd, D4_ACT_SILU, nullptr, nullptr, s));
         cur = dst; ldc = ldd;
@@ -585,14 +585,16 @@ extern "C" int d4_frame(d4_ctx* c, int B, int t, int num_steps, float discrete_t
     // terminal head (reference dreamer4.py:6605-6616)
     if (c->cfg.predict_terminals && io->terminal_uniform && io->lens && io->terminals) {
         D4_TRY(d4_mean_tokens(x, B, N, Dl, c->b.term_in, s));
-        D4_TRY(d4_mlp_forward(c, c->terminal, c->b.term_in, Dl, B, c->b.hbuf0, c->b.hbuf1, c->b.bins, 1, s));
+        D4_TRY(d4_mlp_forward(c, c->terminal, c->b.term_in, Dl, B, c->b.hbuf0, c->b.hbuf1, c->b.bins, 1, 0, s));
         D4_TRY(d4_terminal_update(c->b.bins, 1, io->terminal_uniform, B, t, reinterpret_cast<long long*>(io->lens), io->terminals, s));
     }
     // policy head -> logits -> gumbel-argmax; value head (reference dreamer4.py:6628-6662)
     if (c->has_actions && io->actions) {
         if (!io->action_uniform || !io->log_probs) return d4_fail("d4_frame: action_uniform and log_probs are required with actions");
         float* pe = (c->policy.layers & 1) ? c->b.hbuf0 : c->b.hbuf1;   // buffer not used by the last hidden layer
-        D4_TRY(d4_mlp_forward(c, c->policy, c->b.agent, D, B, c->b.hbuf0, c->b.hbuf1, pe, c->cfg.policy_hidden, s));
+        // the policy head stays on the exact-fp32 FMA path in every engine mode: its logits feed gumbel-argmax, and the
+        // sampled index is the one output that must be bit-identical to the reference (the value head may use 3xTF32)
+        D4_TRY(d4_mlp_forward(c, c->policy, c->b.agent, D, B, c->b.hbuf0, c->b.hbuf1, pe, c->cfg.policy_hidden, 0, s));
         GemmArgs g = gemm_args(pe, c->cfg.policy_hidden, c->unembed, c->unembed_ld, c->b.logits, c->ldlog, B, c->A_total, c->cfg.policy_hidden);
         D4_TRY(d4_engine_gemm(c, g, plain(c->unembed), 1, s));
         if (io->logits) D4_TRY(d4_copy_rows(c->b.logits, c->ldlog, io->logits, io->logits_bs, B, c->A_total, s));
@@ -600,7 +602,7 @@ extern "C" int d4_frame(d4_ctx* c, int B, int t, int num_steps, float discrete_t
         D4_TRY(d4_sample_actions(c->b.logits, c->ldlog, io->action_uniform, c->A_total, B, c->na, c->b.sizes_offs, inv_temp,
                                  reinterpret_cast<long long*>(io->actions), io->actions_bs, io->log_probs, io->log_probs_bs, s));
         if (io->values) {
-            D4_TRY(d4_mlp_forward(c, c->value, c->b.agent, D, B, c->b.hbuf0, c->b.hbuf1, c->b.bins, c->cfg.value_bins, s));
+            D4_TRY(d4_mlp_forward(c, c->value, c->b.agent, D, B, c->b.hbuf0, c->b.hbuf1, c->b.bins, c->cfg.value_bins, 1, s));
             D4_TRY(d4_hl_gauss_decode(c->b.bins, c->cfg.value_bins, B, c->cfg.value_bins, c->value_centers, io->values, io->values_bs, s));
         }
     }

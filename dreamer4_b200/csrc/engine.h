@@ -71,4 +71,4 @@ void d4_prof_end(d4_ctx* c, int handle, cudaStream_t s);
 int d4_engine_plan(d4_ctx* c);
 int d4_engine_gemm(d4_ctx* c, GemmArgs g, const LinW& w, int force_fp32, cudaStream_t s);
 int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, int M, float* buf0, float* buf1, float* out, long long ldo,
-                   cudaStream_t s);
+                   int allow_tensor, cudaStream_t s);

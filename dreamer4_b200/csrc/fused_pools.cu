@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
     float* pw_all = xs + L2S_MAXN * DL;                // per warp [L2S_MAXN][L2S_MAXQ]
     float* zs_all = pw_all + nwarps * L2S_MAXN * L2S_MAXQ;   // per warp [L2S_MAXQ][DL]
     float* qs_all = zs_all + nwarps * L2S_MAXQ * DL;   // per warp [L2S_MAXQ][d]  queries x key gain
+    float* ws_all = qs_all + nwarps * L2S_MAXQ * d;    // per warp [d][DL]        this head's key (then value) projection rows
 
     // ---- normalised latents of this frame: x * rsqrt(mean(x^2) + eps)  (norm_context gamma is folded into w_k / w_v)
     const float* xb = a.latent + (long long)b * N * DL;
@@ -49,7 +50,13 @@ __global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
         float* pw = pw_all + warp * L2S_MAXN * L2S_MAXQ;
         float* zs = zs_all + warp * L2S_MAXQ * DL;
         float* qs = qs_all + warp * L2S_MAXQ * d;
+        float* wsm = ws_all + warp * d * DL;
         const float sqrt_d = sqrtf((float)d);
+        {   // stage W_k,h: one coalesced pass instead of d * DL / 4 uniform global loads inside the score loop
+            const float4* src = reinterpret_cast<const float4*>(a.w_k + (long long)hk * d * DL);
+            float4* dst = reinterpret_cast<float4*>(wsm);
+            for (int idx = lane; idx < d * DL / 4; idx += 32) dst[idx] = __ldg(src + idx);
+        }
         for (int idx = lane; idx < NQ * d; idx += 32) {
             const int qi = idx / d, c = idx - qi * d;
             const int i = qi / a.g, gi = qi - i * a.g;
@@ -71,12 +78,11 @@ __global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
 #pragma unroll
             for (int qi = 0; qi < L2S_MAXQ; ++qi) dot[qi] = 0.f;
             if (kk * 32 < N) {                                  // warp-uniform
-                const float* wk = a.w_k + (long long)hk * d * DL;
                 for (int c = 0; c < d; ++c) {
                     float k = 0.f;
 #pragma unroll
                     for (int e = 0; e < DL; e += 4) {
-                        const float4 w = __ldg(reinterpret_cast<const float4*>(wk + c * DL + e));
+                        const float4 w = *reinterpret_cast<const float4*>(wsm + c * DL + e);
                         k = fmaf(xr[e], w.x, k); k = fmaf(xr[e + 1], w.y, k); k = fmaf(xr[e + 2], w.z, k); k = fmaf(xr[e + 3], w.w, k);
                     }
                     ss = fmaf(k, k, ss);
@@ -120,18 +126,25 @@ __global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
         }
         __syncwarp();
         // ---- values: o_q = W_v,h z_q, head gate, store : lane = head channel
-        const float* wv = a.w_v + (long long)hk * d * DL;
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.w_v + (long long)hk * d * DL);
+            float4* dst = reinterpret_cast<float4*>(wsm);
+            for (int idx = lane; idx < d * DL / 4; idx += 32) dst[idx] = __ldg(src + idx);
+        }
+        __syncwarp();
         for (int c = lane; c < d; c += 32) {
             float o[L2S_MAXQ];
 #pragma unroll
             for (int qi = 0; qi < L2S_MAXQ; ++qi) o[qi] = 0.f;
 #pragma unroll
             for (int e = 0; e < DL; e += 4) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(wv + c * DL + e));
+                // row c of W_v: lanes read different rows -> rotate the chunk order so the 32 rows hit distinct banks
+                const int er = (e + 4 * lane) % DL;
+                const float4 w = *reinterpret_cast<const float4*>(wsm + c * DL + er);
 #pragma unroll
                 for (int qi = 0; qi < L2S_MAXQ; ++qi) {
                     if (qi < NQ) {
-                        const float4 z = *reinterpret_cast<const float4*>(zs + qi * DL + e);
+                        const float4 z = *reinterpret_cast<const float4*>(zs + qi * DL + er);
                         o[qi] = fmaf(w.x, z.x, o[qi]); o[qi] = fmaf(w.y, z.y, o[qi]); o[qi] = fmaf(w.z, z.z, o[qi]); o[qi] = fmaf(w.w, z.w, o[qi]);
                     }
                 }
@@ -244,7 +257,7 @@ int d4_l2s_fused_supported(const L2sArgs& a) {
 template <int DL>
 static int launch_l2s(const L2sArgs& a, cudaStream_t s) {
     const int nwarps = a.h < 8 ? a.h : 8;
-    const size_t smem = sizeof(float) * ((size_t)L2S_MAXN * DL + (size_t)nwarps * (L2S_MAXN * L2S_MAXQ + L2S_MAXQ * DL + L2S_MAXQ * a.d));
+    const size_t smem = sizeof(float) * ((size_t)L2S_MAXN * DL + (size_t)nwarps * (L2S_MAXN * L2S_MAXQ + L2S_MAXQ * DL + L2S_MAXQ * a.d + a.d * DL));
     static size_t configured = 0;
     if (smem > configured) {
         D4_CUDA_OK(cudaFuncSetAttribute(l2s_fused_kernel<DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -439,3 +439,51 @@ def test_learn_tf32x3_matches_oracle():
     for k in keys:
         assert params[k].grad is not None, k
         torch.testing.assert_close(params[k].grad.cpu(), sdg[k].grad, atol=2e-5, rtol=2e-4, msg=lambda m, n=k: f'{n}: {m}')
+
+
+# ------------------------------------------------------------------------------------------------ the BASELINE architectures
+
+BASELINE_MODELS = {   # BASELINE.json configs[0..3], at a batch the CPU oracle finishes in seconds
+    'config1_readme': dict(dim=512, dim_latent=32, num_latent_tokens=64, depth=4, time_block_every=4, attn_heads=8, attn_dim_head=64,
+                           num_discrete_actions=4, predict_terminals=False),
+    'config2_mnist': dict(dim=256, dim_latent=32, num_latent_tokens=32, depth=4, time_block_every=4, attn_heads=8, attn_dim_head=64,
+                          num_discrete_actions=(5, 5), predict_terminals=False),
+    'config3_snake': dict(dim=512, dim_latent=64, num_latent_tokens=64, depth=6, time_block_every=4, attn_heads=8, attn_dim_head=64,
+                          num_discrete_actions=4, predict_terminals=False),
+    'config4_256px': dict(dim=512, dim_latent=32, num_latent_tokens=64, depth=8, time_block_every=4, attn_heads=8, attn_dim_head=64,
+                          num_discrete_actions=4, predict_terminals=False),
+}
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('name', list(BASELINE_MODELS))
+def test_baseline_architectures_match_oracle(name, precision):
+    """generate + learn_from_experience at the exact architectures BASELINE.json benchmarks (every kernel instantiation the
+    bench uses: d = 64 heads, 64 x 32 / 32 x 32 / 64 x 64 latents, the fused latent<->space pools, depth 4 / 6 / 8, two
+    action types), B = 20 dreams so the tensor-core GEMMs see multi-tile M (B*S = 300 rows), T = 3 frames."""
+    from dreamer4_b200 import DynamicsWorldModel
+    kwargs = BASELINE_MODELS[name]
+    torch.manual_seed(21)
+    model = DynamicsWorldModel(**kwargs, precision=precision)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('gamma') or n.endswith('norm.weight') or n.endswith('norm_context.weight'):
+                p.add_(torch.randn_like(p) * 0.1)
+            if 'unembed' in n or n.endswith('queries') or 'learned_embed' in n or n == 'register_tokens':
+                p.mul_(30.)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    ocfg = O.config_from_reference_kwargs(**kwargs)
+    T, B = 3, 20
+    noise = make_noise(model.cfg, T, B, seed=17)
+    ref = O.generate(sd, ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform']))
+    exp, tc = model.generate(T, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
+                             return_log_probs_and_values=True, return_time_cache=True, noise=to_cuda(noise))
+    ref_kv = torch.stack([torch.stack(layer) for layer in ref.kv_cache])
+    compare_experience(exp, ref, tc.main.next_kv_cache, ref_kv)
+    keys = [k for k in sd if k.startswith(('policy_head.', 'value_head.')) or k == 'action_embedder.discrete_action_unembed']
+    sdg = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd.items()}
+    rpl, rvl, _ = O.learn_from_experience(sdg, ocfg, ref)
+    pl, vl = model.learn_from_experience(exp)
+    torch.testing.assert_close(pl.detach().cpu(), rpl.detach(), atol=2e-6, rtol=1e-4)
+    torch.testing.assert_close(vl.detach().cpu(), rvl.detach(), atol=2e-6, rtol=1e-4)

@@ -25,6 +25,14 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(D4_FULL, v, o));
     return v;
 }
+// fp32 -> nearest TF32 value (10 explicit mantissa bits), still an fp32 word.  The 3xTF32 GEMMs split both operands with
+// ROUND-TO-NEAREST (x = hi + lo, hi = rna(x), lo = rna(x - hi)): the dropped lo*lo term and the representation error of lo
+// are then unbiased and <= 2^-24 |x|; a truncating split leaves same-signed errors that add up coherently over K.
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float geluf_(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

@@ -190,10 +190,10 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
                     const int idx = et + 128 * j;
                     const float4 v = a[idx];
                     float4 hi, lo;
-                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
-                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
-                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
-                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+                    hi.x = tf32_rna(v.x); lo.x = tf32_rna(v.x - hi.x);
+                    hi.y = tf32_rna(v.y); lo.y = tf32_rna(v.y - hi.y);
+                    hi.z = tf32_rna(v.z); lo.z = tf32_rna(v.z - hi.z);
+                    hi.w = tf32_rna(v.w); lo.w = tf32_rna(v.w - hi.w);
                     a[idx] = hi; alo[idx] = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

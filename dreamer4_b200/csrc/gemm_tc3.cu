@@ -10,8 +10,8 @@
 //   warp 0    TMA producer (each CTA loads its A rows and its half of the W rows; W arrives on the LEADER's barrier)
 //   warp 1    MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, accumulators double-buffered in TMEM
 //   warps 2-5 epilogue of this CTA's 128 rows (tcgen05.ld -> row scale -> smem transpose -> bias/residual/GLU -> 128-B row stores)
-//   warps 6-9 tf32x3 only: a_lo = a - trunc_tf32(a) of this CTA's A tile into a second smem tile (the raw tile serves as a_hi:
-//             the tensor core ignores the low 13 mantissa bits), then ONE remote arrive on the leader's barrier
+//   warps 6-9 tf32x3 only: a_lo = rna_tf32(a - trunc_tf32(a)) of this CTA's A tile into a second smem tile (the raw tile
+//             serves as a_hi: the tensor core ignores the low 13 mantissa bits), then ONE remote arrive on the leader's barrier
 #include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
@@ -132,7 +132,6 @@ struct EpiArgs3 {
     int act; RowMap cmap;
     int a_grp, nkb, n_tiles_m, n_tiles_n;
     int tma_epi;        // 1: epilogue through swizzled smem tiles + TMA (residual load, result store); 0: register path
-    int early_mma;      // tf32x3: 1 = issue the two a_hi products before the a_lo tile is ready, 0 = wait for the split first
 };
 
 template <int TERMS, int BN, int BK> struct Cfg3 {
@@ -178,7 +177,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
         if (e.tma_epi && e.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.r) : "memory");
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_FULLA + s), 1); mbar_init(bar(B_EMPTY + s), 1); mbar_init(bar(B_SPLIT + s), 2);
-            mbar_init(bar(B_AREADY + s), 2);
+            mbar_init(bar(B_AREADY + s), 2);       // (unused: kept so the barrier block layout stays put)
         }
         for (int b = 0; b < 2; ++b) { mbar_init(bar(B_TFULL + b), 1); mbar_init(bar(B_TEMPTY + b), 8); }
         for (int b = 0; b < 8; ++b) mbar_init(bar(B_RES + b), 1);
@@ -233,31 +232,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                 for (int kb = 0; kb < nkb; ++kb, ++kc) {
                     const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
                     mbar_wait(bar(B_FULL + s), ph);
-                    if (TERMS == 3) {
-                        if (e.early_mma) mbar_wait(bar(B_AREADY + s), ph);                  // both CTAs' raw A tiles have landed
-                        else             mbar_wait(bar(B_SPLIT + s), ph);
-                    }
+                    if (TERMS == 3) mbar_wait(bar(B_SPLIT + s), ph);                        // both CTAs' a_hi / a_lo tiles are in place
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = make_desc<BK>(smem_u32(tile(s, T_A))), dw = make_desc<BK>(smem_u32(tile(s, T_W)));
                     if (TERMS == 3) {
-                        // The tensor core reads only the top 19 bits of an fp32 word as TF32, so the RAW A tile already is
-                        // a_hi: a_hi*w_hi and a_hi*w_lo start as soon as the tiles land, and the splitter warps get those
-                        // 8 MMAs (1024 tensor cycles) to produce a_lo = a - trunc(a) for the last product.
                         const uint64_t dalo = make_desc<BK>(smem_u32(tile(s, T_ALO))), dwlo = make_desc<BK>(smem_u32(tile(s, T_WLO)));
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                        for (int k = 0; k < BK / UMMA_K; ++k) {         // small terms first, the hi*hi product last
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            umma_tf32_pair(tmem_c, da + koff, dwlo + koff, K::IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_pair(tmem_c, dalo + koff, dw + koff, K::IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_pair(tmem_c, da + koff, dwlo + koff, K::IDESC, 1u);
                             umma_tf32_pair(tmem_c, da + koff, dw + koff, K::IDESC, 1u);
-                        }
-                        if (e.early_mma) {
-                            mbar_wait(bar(B_SPLIT + s), ph);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        }
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            umma_tf32_pair(tmem_c, dalo + koff, dw + koff, K::IDESC, 1u);
                         }
                     } else {
 #pragma unroll
@@ -503,13 +488,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
     } else if (TERMS == 3) {
         // ================= A splitter (tf32x3): this CTA's A tile -> hi (in place) + lo, then one arrival on the leader's barrier
         const int et = threadIdx.x - 192;          // 0..127
-        const uint32_t split_leader = bar(B_SPLIT) & PEER_MASK, aready_leader = bar(B_AREADY) & PEER_MASK;
+        const uint32_t split_leader = bar(B_SPLIT) & PEER_MASK;
         uint32_t kc = 0;
         for (int t = cluster_id; t < total_tiles; t += n_clusters) {
             for (int kb = 0; kb < nkb; ++kb, ++kc) {
                 const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
                 mbar_wait(bar(B_FULLA + s), ph);
-                if (et == 0 && e.early_mma) mbar_arrive_cluster(aready_leader + (uint32_t)s * 8u);   // the raw tile can feed the first two products now
+                // The tensor core reads only the top 19 bits of an fp32 word as TF32, so the RAW tile already is
+                // a_hi = trunc_tf32(a): only a_lo = a - a_hi is materialised (rounded to a TF32 value so the operand fetch
+                // does not truncate it a second time).  Writing a round-to-nearest a_hi back in place was measured: 6 % slower
+                // GEMMs (the split sits on the stage latency chain) for a 1.2x smaller parity error — not taken.
                 const float4* a = reinterpret_cast<const float4*>(tile(s, T_A));
                 float4* alo = reinterpret_cast<float4*>(tile(s, T_ALO));
 #pragma unroll
@@ -517,10 +505,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                     const int idx = et + 128 * j;
                     const float4 v = a[idx];
                     float4 lo;
-                    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    lo.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+                    lo.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+                    lo.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+                    lo.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
                     alo[idx] = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -646,8 +634,6 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
     if (g.residual) tma_epi = tma_epi && al16(g.residual) && (g.ldr % 4 == 0) &&
                               (grp == 0 || ((((long long)g.cmap.goff * g.ldr) % 4 == 0) && (((long long)g.cmap.gstride * g.ldr) % 4 == 0)));
     e.tma_epi = tma_epi ? 1 : 0;
-    static const int early = getenv("D4_GEMM_EARLY_MMA") ? atoi(getenv("D4_GEMM_EARLY_MMA")) : 0;
-    e.early_mma = early;
     if (tma_epi) {
         { int rc = encode_out(&maps.c, g.C, g.M, glu ? g.N / 2 : g.N, g.ldc, g.cmap); if (rc) return rc; }
         if (g.residual) { int rc = encode_out(&maps.r, g.residual, g.M, g.N, g.ldr, g.cmap); if (rc) return rc; }
@@ -672,6 +658,11 @@ int d4_gemm_tc3(const GemmArgs& g, int terms, int bn, cudaStream_t stream) {
         // quantisation (N = 512: 7 half-rounds instead of 4 full ones) was measured SLOWER overall (166 vs 205 TFLOP/s).
         const long long p128 = (long long)(g.N + 127) / 128 * 128, p256 = (long long)(g.N + 255) / 256 * 256;
         bn = (p128 * 10 < p256 * 9) ? 128 : 256;
+        // ... and when 256-wide tiles cannot even give every CTA pair one tile (small batches: M = 3840 rows at 256 dreams)
+        static int clusters = 0;
+        if (!clusters) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); clusters = sms > 1 ? sms / 2 : 74; }
+        const long long mt = (g.M + 2 * BM - 1) / (2 * BM);
+        if (mt * (p256 / 256) < clusters && p128 / 128 > p256 / 256) bn = 128;
     }
     // K step 32 floats = one 128-byte swizzle row.  (A 16-float / SWIZZLE_64B step with twice the ring depth was measured
     // 1.9x SLOWER on every layer shape: the tensor core's operand fetch runs at half efficiency on 64-byte rows.)

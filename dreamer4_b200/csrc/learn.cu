@@ -349,8 +349,8 @@ __global__ void transpose_kernel(int R, int C, const float* __restrict__ in, lon
         if (c < C && r < R) {
             const float v = tile[tx][i];
             if (SPLIT) {
-                const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-                out[(long long)c * R + r] = hi; out_lo[(long long)c * R + r] = v - hi;
+                const float hi = tf32_rna(v);
+                out[(long long)c * R + r] = hi; out_lo[(long long)c * R + r] = tf32_rna(v - hi);
             } else {
                 out[(long long)c * R + r] = v;
             }

@@ -18,7 +18,7 @@ from torch import nn
 from . import _lib
 from ._lib import D4Error, check, ptr
 from .experience import Actions, DynamicsIntermediates, Experience, TransformerIntermediates
-from .packing import hl_gauss_tables, mlp_param_names, pack
+from .packing import hl_gauss_tables, mlp_param_names, pack, tf32_split
 
 
 def exists(v):
@@ -124,8 +124,9 @@ _UNSUPPORTED_DEFAULTS = dict(
 class DynamicsWorldModel(nn.Module):
     """Drop-in for the reference class on the imagination path (generate + learn_from_experience).
 
-    Extra keyword arguments (not in the reference): `precision` in {'fp32', 'tf32', 'tf32x3'} — arithmetic of the
-    transformer's dense layers (heads always run exact fp32), `time_attn_variant` (K1 kernel variant)."""
+    Extra keyword arguments (not in the reference): `precision` in {'tf32x3' (default), 'fp32', 'tf32'} — arithmetic of the
+    dense layers: 3-term TF32 split on the tensor cores (fp32-accurate), exact-fp32 FMA, or single-pass TF32 (reduced
+    precision); the policy head always runs exact fp32.  `time_attn_variant`: K1 kernel (1 = bulk-copy ring, 0 = ld.global)."""
 
     def __init__(self, dim, dim_latent, *, num_latent_tokens=None, max_steps=64, num_register_tokens=8, num_spatial_tokens=4,
                  num_agents=1, num_tasks=0, reward_encoder_kwargs: dict = dict(), value_encoder_kwargs: Optional[dict] = None,
@@ -134,7 +135,7 @@ class DynamicsWorldModel(nn.Module):
                  multi_token_pred_len=8, value_head_mlp_depth=3, policy_head_mlp_depth=3, predict_terminals=True,
                  predict_terminal_mlp_kwargs: dict = dict(depth=1), gae_discount_factor=0.997, gae_lambda=0.95, ppo_eps_clip=0.2,
                  use_delight_gating=True, delight_temperature=1., normalize_advantages=None, policy_entropy_weight=.01,
-                 gae_use_accelerated=False, precision='fp32', time_attn_variant=0, **kwargs):
+                 gae_use_accelerated=False, precision='tf32x3', time_attn_variant=1, **kwargs):
         super().__init__()
         for k, v in kwargs.items():
             if k not in _UNSUPPORTED_DEFAULTS:
@@ -385,8 +386,9 @@ class DynamicsWorldModel(nn.Module):
         if ver == self._head_split_version:
             return
         for t, hi, lo, thi, tlo in splits:
-            torch.bitwise_and(t.detach().view(torch.int32), -8192, out=hi.view(torch.int32))      # sign, exponent, 10 mantissa bits
-            torch.sub(t.detach(), hi, out=lo)
+            h, l = tf32_split(t.detach())
+            hi.copy_(h)
+            lo.copy_(l)
             thi.copy_(hi.t())
             tlo.copy_(lo.t())
         self._head_split_version = ver

@@ -32,9 +32,16 @@ def _rms(x, w):
     return F.rms_norm(x, (x.shape[-1],), w, None)
 
 
+def tf32_round(w):
+    """Nearest TF32 value (10 explicit mantissa bits, ties away from zero — what `cvt.rna.tf32.f32` does), as fp32."""
+    return ((w.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+
+
 def tf32_split(w):
-    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)     # keep sign, exponent, 10 mantissa bits
-    return hi, w - hi
+    """w = hi + lo with hi = rna_tf32(w), lo = rna_tf32(w - hi): round-to-nearest keeps the dropped lo*lo term of the
+    3xTF32 product unbiased (a truncating split leaves same-signed errors that add up coherently over K)."""
+    hi = tf32_round(w)
+    return hi, tf32_round(w - hi)
 
 
 def hl_gauss_tables(lo, hi, num_bins, device):

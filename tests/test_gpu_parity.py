@@ -27,6 +27,7 @@ def load(path):
 
 def build_model(fx, **extra):
     from dreamer4_b200 import DynamicsWorldModel
+    extra.setdefault('precision', 'fp32')        # the golden vectors are held against the exact-fp32 engine mode
     model = DynamicsWorldModel(**fx['model_kwargs'], **extra)
     model.load_state_dict(fx['state_dict'], strict=True)
     return model.cuda()
@@ -44,7 +45,8 @@ def to_cuda(noise):
     return {k: v.cuda() for k, v in noise.items()}
 
 
-def compare_experience(exp, ref, kv=None, ref_kv=None):
+def compare_experience(exp, ref, kv=None, ref_kv=None, TOL=TOL, LOGIT_TOL=None):
+    LOGIT_TOL = LOGIT_TOL or TOL
     assert exp.latents.shape == ref.latents.shape
     assert torch.equal(exp.actions.discrete.cpu(), ref.actions)
     assert torch.equal(exp.lens.cpu(), ref.lens)
@@ -56,7 +58,7 @@ def compare_experience(exp, ref, kv=None, ref_kv=None):
     torch.testing.assert_close(exp.rewards.cpu(), ref.rewards, **TOL)
     torch.testing.assert_close(exp.values.cpu(), ref.values, **TOL)
     torch.testing.assert_close(exp.log_probs.discrete.cpu(), ref.log_probs, **TOL)
-    torch.testing.assert_close(exp.old_action_unembeds.discrete.cpu(), ref.old_action_unembeds, **TOL)
+    torch.testing.assert_close(exp.old_action_unembeds.discrete.cpu(), ref.old_action_unembeds, **LOGIT_TOL)
     torch.testing.assert_close(exp.episode_return.cpu(), ref.episode_return, **TOL)
     if kv is not None:
         assert kv.shape == ref_kv.shape
@@ -343,7 +345,8 @@ def test_generate_midsize_tf32_single_pass():
 
 # ------------------------------------------------------------------------------------------------ 100 seeded dream steps
 
-def test_hundred_seeded_dream_steps_losses():
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+def test_hundred_seeded_dream_steps_losses(precision):
     """North star: actor/critic losses within 1e-4 relative of the reference over 100 seeded dream steps.
 
     One DreamTrainer step (reference trainers.py:1416-1468) = generate(T+1) -> learn_from_experience -> backward ->
@@ -356,7 +359,7 @@ def test_hundred_seeded_dream_steps_losses():
     kwargs = dict(dim=64, dim_latent=16, num_latent_tokens=8, depth=4, time_block_every=2, attn_heads=2, attn_dim_head=32,
                   num_discrete_actions=4, predict_terminals=False)
     torch.manual_seed(11)
-    model = DynamicsWorldModel(**kwargs)
+    model = DynamicsWorldModel(**kwargs, precision=precision)
     with torch.no_grad():
         for n, p in model.named_parameters():
             if 'unembed' in n:
@@ -460,7 +463,12 @@ BASELINE_MODELS = {   # BASELINE.json configs[0..3],
 def test_baseline_architectures_match_oracle(name, precision):
     """generate + learn_from_experience at the exact architectures BASELINE.json benchmarks (every kernel instantiation the
     bench uses: d = 64 heads, 64 x 32 / 32 x 32 / 64 x 64 latents, the fused latent<->space pools, depth 4 / 6 / 8, two
-    action types), B = 20 dreams so the tensor-core GEMMs see multi-tile M (B*S = 300 rows), T = 3 frames."""
+    action types), B = 20 dreams so the tensor-core GEMMs see multi-tile M (B*S = 300 rows), T = 3 frames.
+
+    Sampled action indices are bit-exact in both engine modes.  Floats: exact-fp32 mode 5e-5 + 2e-4 rel; tf32x3 mode
+    1e-4 + 2e-4 rel, action logits 3e-4 (this test scales the unembedding x30, logits reach +-10).  Measured worst cases in
+    tf32x3 at these widths: 7e-5 on a KV-cache element, 2.3e-4 on a logit — the residue of 3xTF32 is the tensor core's own
+    fp32 accumulation (a round-to-nearest operand split changed it by only 1.2x), K up to 1376 over 8 layers."""
     from dreamer4_b200 import DynamicsWorldModel
     kwargs = BASELINE_MODELS[name]
     torch.manual_seed(21)
@@ -480,7 +488,10 @@ def test_baseline_architectures_match_oracle(name, precision):
     exp, tc = model.generate(T, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
                              return_log_probs_and_values=True, return_time_cache=True, noise=to_cuda(noise))
     ref_kv = torch.stack([torch.stack(layer) for layer in ref.kv_cache])
-    compare_experience(exp, ref, tc.main.next_kv_cache, ref_kv)
+    if precision == 'fp32':
+        compare_experience(exp, ref, tc.main.next_kv_cache, ref_kv)
+    else:
+        compare_experience(exp, ref, tc.main.next_kv_cache, ref_kv, TOL=dict(atol=1e-4, rtol=2e-4), LOGIT_TOL=dict(atol=3e-4, rtol=2e-4))
     keys = [k for k in sd if k.startswith(('policy_head.', 'value_head.')) or k == 'action_embedder.discrete_action_unembed']
     sdg = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd.items()}
     rpl, rvl, _ = O.learn_from_experience(sdg, ocfg, ref)

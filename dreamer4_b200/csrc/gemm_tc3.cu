@@ -9,8 +9,9 @@
 //   cluster (2,1,1), one cluster per TPC, persistent over 256 x BN output tiles (n fastest)
 //   warp 0    TMA producer (each CTA loads its A rows and its half of the W rows; W arrives on the LEADER's barrier)
 //   warp 1    MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, accumulators double-buffered in TMEM
-//   warps 2-5 epilogue of this CTA's 128 rows (tcgen05.ld -> row scale -> smem transpose -> bias/residual/GLU -> 128-B row stores)
-//   warps 6-9 tf32x3 only: a_lo = rna_tf32(a - trunc_tf32(a)) of this CTA's A tile into a second smem tile (the raw tile
+//   warps 4-7 epilogue of this CTA's 128 rows (tcgen05.ld row-per-lane -> row scale / bias / GLU -> swizzled smem tile (+ TMA-loaded
+//             residual) -> one TMA store per 32 x 32 chunk)
+//   warps 8-15 tf32x3 only: a_lo = rna_tf32(a - trunc_tf32(a)) of this CTA's A tile into a second smem tile (the raw tile
 //             serves as a_hi: the tensor core ignores the low 13 mantissa bits), then ONE remote arrive on the leader's barrier
 #include <cuda.h>
 #include <string.h>
@@ -21,8 +22,7 @@
 namespace {
 
 constexpr int BM = 128, UMMA_K = 8;
-constexpr int NUM_THREADS = 320;
-constexpr int STG_LD = 33;
+constexpr int NUM_THREADS = 512;          // warp 0 TMA, 1 MMA, (2-3 idle), 4-7 epilogue, 8-15 operand splitter
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: the even (leader) CTA's copy
 
 struct __align__(64) TmaMaps3 { CUtensorMap a, w, wlo, c, r; };
@@ -256,14 +256,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                 umma_commit_pair(bar(B_TFULL + buf));                    // accumulator complete, both CTAs' epilogues
             }
         }
-    } else if (warp < 6) {
+    } else if (warp >= 4 && warp < 8) {
         // ================= epilogue of this CTA's 128 rows
-        if (e.tma_epi) {
+        {
             // Row-per-lane: tcgen05.ld hands lane r the 32 accumulator columns of row r; the lane scales / biases / gates
             // them and writes float4 chunks into a 32 x 32 fp32 tile in the 128B-swizzled layout TMA expects (chunk q of
             // row r at q ^ (r & 7): bank-conflict free).  The residual tile is TMA-LOADED into that same buffer one chunk
             // ahead and added in place; the finished tile leaves with ONE TMA store.  Two buffers per warp alternate.
-            const int quarter = warp & 3, ew = warp - 2;
+            const int quarter = warp & 3, ew = warp - 4;
             unsigned char* ebuf = reinterpret_cast<unsigned char*>(stg_all) + ew * 2 * 4096;
             const uint32_t ebuf_u32 = smem_u32(ebuf);
             const bool glu = (e.act == D4_ACT_GLU_SILU || e.act == D4_ACT_GLU_GELU);
@@ -363,131 +363,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                 if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)buf_acc * 8u);
             }
             if (lane == 0) bulk_wait_all();
-        } else {
-        const int quarter = warp & 3;
-        float* stg = stg_all + (warp - 2) * 32 * STG_LD;
-        const bool glu = (e.act == D4_ACT_GLU_SILU || e.act == D4_ACT_GLU_GELU);
-        const float* __restrict__ resid = e.residual;
-        const float* __restrict__ biasp = e.bias;
-        float* __restrict__ Cp = e.C;
-        const uint32_t tempty_leader = bar(B_TEMPTY) & PEER_MASK;
-        uint32_t ac = 0;
-        for (int t = cluster_id; t < total_tiles; t += n_clusters, ++ac) {
-            const int m0 = (t / e.n_tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % e.n_tiles_n) * BN;
-            const int buf = ac & 1; const uint32_t aph = (ac >> 1) & 1;
-            const int rbase = m0 + quarter * 32;
-            const int mrow = rbase + lane;
-            const float rs = (mrow < e.M && e.row_scale) ? e.row_scale[mrow] : 1.f;
-            const int crow_lane = (mrow < e.M) ? (int)e.cmap(mrow) : -1;      // physical output row of TMEM lane `lane`
-            const int nrows = min(32, e.M - rbase);                          // warp-uniform (may be <= 0)
-            const uint32_t tmem_c = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
-            if (!glu) {
-                const bool ident = (e.cmap.grp == 0);
-                const bool has_res = (resid != nullptr);
-                float res[32];
-                auto prefetch = [&](int c0, float (&dst)[32]) {
-                    const int col = n0 + c0 + lane;
-                    const bool ok = has_res && col < e.N;
-                    if (ident) {
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) dst[r] = (ok && r < nrows) ? __ldg(resid + (long long)(rbase + r) * e.ldr + col) : 0.f;
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) {
-                            const int crow = __shfl_sync(0xffffffffu, crow_lane, r);
-                            dst[r] = (ok && crow >= 0) ? __ldg(resid + (long long)crow * e.ldr + col) : 0.f;
-                        }
-                    }
-                };
-                if (has_res) prefetch(0, res);
-                else {
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) res[r] = 0.f;
-                }
-                mbar_wait(bar(B_TFULL + buf), aph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    const int nb = n0 + c0;
-                    if (nb >= e.N) break;                               // warp-uniform
-                    float v[32];
-                    tmem_ld32(tmem_c + (uint32_t)c0, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = v[j] * rs;
-                    __syncwarp();
-                    float resn[32];
-                    const bool more = has_res && (c0 + 32 < BN) && (nb + 32 < e.N);
-                    if (more) prefetch(c0 + 32, resn);
-                    const int col = nb + lane;
-                    const bool cok = col < e.N;
-                    const float bv = (cok && biasp) ? __ldg(biasp + col) : 0.f;
-                    if (ident) {
-                        float* cp = Cp + (long long)rbase * e.ldc + col;
-#pragma unroll
-                        for (int r = 0; r < 32; ++r)
-                            if (r < nrows && cok) cp[(long long)r * e.ldc] = stg[r * STG_LD + lane] + bv + res[r];
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) {
-                            const int crow = __shfl_sync(0xffffffffu, crow_lane, r);
-                            if (r < nrows && cok) Cp[(long long)crow * e.ldc + col] = stg[r * STG_LD + lane] + bv + res[r];
-                        }
-                    }
-                    __syncwarp();
-                    if (more) {
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) res[r] = resn[r];
-                    }
-                }
-            } else {
-                mbar_wait(bar(B_TFULL + buf), aph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int on = e.N >> 1;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 64) {
-                    const int nb = n0 + c0;
-                    if (nb >= e.N) break;
-                    // bias of the 64 interleaved input columns of this chunk: lane holds columns nb+lane and nb+32+lane
-                    const float b_lo = (biasp && nb + lane < e.N) ? __ldg(biasp + nb + lane) : 0.f;
-                    const float b_hi = (biasp && nb + 32 + lane < e.N) ? __ldg(biasp + nb + 32 + lane) : 0.f;
-                    float v[32], w[32];
-                    tmem_ld32(tmem_c + (uint32_t)c0, v);
-                    tmem_ld32(tmem_c + (uint32_t)(c0 + 32), w);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float x0 = fmaf(v[2 * j], rs, __shfl_sync(0xffffffffu, b_lo, 2 * j));
-                        const float g0 = fmaf(v[2 * j + 1], rs, __shfl_sync(0xffffffffu, b_lo, 2 * j + 1));
-                        const float x1 = fmaf(w[2 * j], rs, __shfl_sync(0xffffffffu, b_hi, 2 * j));
-                        const float g1 = fmaf(w[2 * j + 1], rs, __shfl_sync(0xffffffffu, b_hi, 2 * j + 1));
-                        stg[lane * STG_LD + j] = x0 * ((e.act == D4_ACT_GLU_SILU) ? siluf_(g0) : geluf_(g0));
-                        stg[lane * STG_LD + 16 + j] = x1 * ((e.act == D4_ACT_GLU_SILU) ? siluf_(g1) : geluf_(g1));
-                    }
-                    __syncwarp();
-                    const int col = (nb >> 1) + lane;
-                    const bool cok = col < on;
-                    if (e.cmap.grp == 0) {
-                        float* cp = Cp + (long long)rbase * e.ldc + col;
-#pragma unroll
-                        for (int r = 0; r < 32; ++r)
-                            if (r < nrows && cok) cp[(long long)r * e.ldc] = stg[r * STG_LD + lane];
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) {
-                            const int crow = __shfl_sync(0xffffffffu, crow_lane, r);
-                            if (r < nrows && cok) Cp[(long long)crow * e.ldc + col] = stg[r * STG_LD + lane];
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)buf * 8u);      // one arrival per warp, 8 per pair
         }
-        }
-    } else if (TERMS == 3) {
+    } else if (TERMS == 3 && warp >= 8) {
         // ================= A splitter (tf32x3): this CTA's A tile -> hi (in place) + lo, then one arrival on the leader's barrier
-        const int et = threadIdx.x - 192;          // 0..127
+        const int et = threadIdx.x - 256;          // 0..255
         const uint32_t split_leader = bar(B_SPLIT) & PEER_MASK;
         uint32_t kc = 0;
         for (int t = cluster_id; t < total_tiles; t += n_clusters) {
@@ -501,8 +380,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                 const float4* a = reinterpret_cast<const float4*>(tile(s, T_A));
                 float4* alo = reinterpret_cast<float4*>(tile(s, T_ALO));
 #pragma unroll
-                for (int j = 0; j < A_TILE / 16 / 128; ++j) {
-                    const int idx = et + 128 * j;
+                for (int j = 0; j < A_TILE / 16 / 256; ++j) {
+                    const int idx = et + 256 * j;
                     const float4 v = a[idx];
                     float4 lo;
                     lo.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
@@ -512,7 +391,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                     alo[idx] = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");                          // the four splitter warps
+                asm volatile("bar.sync 1, 256;" ::: "memory");                          // the eight splitter warps
                 if (et == 0) mbar_arrive_cluster(split_leader + (uint32_t)s * 8u);
             }
         }
@@ -633,7 +512,8 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
                    (grp == 0 || (32 % grp == 0 && g.M % grp == 0 && (((long long)g.cmap.goff * g.ldc) % 4 == 0) && (((long long)g.cmap.gstride * g.ldc) % 4 == 0)));
     if (g.residual) tma_epi = tma_epi && al16(g.residual) && (g.ldr % 4 == 0) &&
                               (grp == 0 || ((((long long)g.cmap.goff * g.ldr) % 4 == 0) && (((long long)g.cmap.gstride * g.ldr) % 4 == 0)));
-    e.tma_epi = tma_epi ? 1 : 0;
+    if (!tma_epi) return d4_gemm_tc2(g, TERMS, 0, stream);       // odd alignment / row maps: the register-epilogue kernel
+    e.tma_epi = 1;
     if (tma_epi) {
         { int rc = encode_out(&maps.c, g.C, g.M, glu ? g.N / 2 : g.N, g.ldc, g.cmap); if (rc) return rc; }
         if (g.residual) { int rc = encode_out(&maps.r, g.residual, g.M, g.N, g.ldr, g.cmap); if (rc) return rc; }

@@ -248,6 +248,18 @@ def run_native(args):
         roof_attn = dict(bound='hbm', kernel='time_attn (K1, KV-cache decode)', achieved=attn_gbs, peak=pk['hbm'], unit='GB/s',
                          frac=attn_gbs / pk['hbm'], traffic=None, launches=int(prof[1][1]), share_of_step=shares['time_attn'],
                          traffic_note='ncu dram bytes == algorithmic bytes at t=40 (profiles/r1a_ncu_k1_t40_raw.csv: 5.29 GB read per launch)')
+        # DRAM traffic of one representative launch of each kernel from the committed `ncu --set full` capture
+        summ_path = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
+        if os.path.exists(summ_path) and args.workload == 'config4' and B == WORKLOADS['config4']['batch']:
+            summ = json.load(open(summ_path))
+            k1 = summ['k1']
+            roof_attn.update(traffic=k1['dram_bytes'], traffic_launch=k1['launch'], traffic_algorithmic_bytes=k1['algorithmic_bytes'],
+                             traffic_source='profiles/r1_final_ncu_k1.csv')
+            ff = next((x for x in summ['gemm'] if 'feed-forward in' in x['layer']), None)
+            if ff:
+                roof_gemm.update(traffic=ff['dram_bytes'], traffic_launch=ff['layer'], tensor_pipe_active_pct_ncu=ff['tensor_pipe_active_pct'],
+                                 sm_clock_ghz_ncu=ff['sm_clock_ghz'], traffic_source='profiles/r1_final_ncu_gemm.csv')
+        roof_attn.pop('traffic_note', None) if roof_attn.get('traffic') else None
         line['roofline'] = roof_gemm if prof[0][0] >= prof[1][0] else roof_attn
         line['roofline_attn'] = roof_attn
         line['roofline_gemm'] = roof_gemm

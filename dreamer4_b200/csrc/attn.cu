@@ -300,7 +300,29 @@ __global__ void __launch_bounds__(PL_WARPS * 32) pool_attn_kernel(SmallAttnArgs 
         o[4] = fmaf(p, v1.x, o[4] * corr); o[5] = fmaf(p, v1.y, o[5] * corr); o[6] = fmaf(p, v1.z, o[6] * corr); o[7] = fmaf(p, v1.w, o[7] * corr);
         mx = nmx;
     }
-    const float gate = a.gate ? sigmoidf_(a.gate[tok * a.gate_sb + (lane >> 3)]) : 1.f;
+    float gate = 1.f;
+    if (a.gate_w) {          // gate logits of the 4 heads from the (RMS-normalised) token itself
+        const float* xr = a.gate_x + tok * a.gate_x_ld;
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int cc = lane * 4; cc < a.gate_D; cc += 128) {
+            const float4 xv = *reinterpret_cast<const float4*>(xr + cc);
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(a.gate_w + (long long)hh * a.gate_D + cc));
+                g4[hh] = fmaf(xv.x, wv.x, g4[hh]); g4[hh] = fmaf(xv.y, wv.y, g4[hh]); g4[hh] = fmaf(xv.z, wv.z, g4[hh]); g4[hh] = fmaf(xv.w, wv.w, g4[hh]);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) g4[hh] += __shfl_xor_sync(D4_FULL, g4[hh], off);
+        }
+        const int hh = lane >> 3;
+        const float logit = (hh == 0 ? g4[0] : hh == 1 ? g4[1] : hh == 2 ? g4[2] : g4[3]) * a.gate_rstd[tok];
+        gate = sigmoidf_(logit);
+    } else if (a.gate) {
+        gate = sigmoidf_(a.gate[tok * a.gate_sb + (lane >> 3)]);
+    }
     const float sc = gate / den;
     float* op = a.out + tok * a.out_sb + c;
     *reinterpret_cast<float4*>(op) = make_float4(o[0] * sc, o[1] * sc, o[2] * sc, o[3] * sc);
@@ -551,11 +573,17 @@ static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p)
 
 }  // namespace
 
+int d4_pool_attn_ok(const SmallAttnArgs& a) {
+    // attention-residual pools: one query per token, 4 x 64 heads, unit-stride 256-wide rows
+    return a.nq == 1 && a.g == 1 && a.hkv == 4 && a.d == 64 && !a.v0 && !a.belief && !a.mask_agent && a.softclamp <= 0.f && a.n >= 1 &&
+           ((a.q_sb | a.k_sb | a.k_sj | a.v_sb | a.v_sj | a.out_sb) & 3) == 0 && al16p(a.q) && al16p(a.k) && al16p(a.v) && al16p(a.out) && al16p(a.k_gamma) &&
+           (!a.gate_w || (al16p(a.gate_x) && al16p(a.gate_w) && (a.gate_x_ld & 3) == 0 && (a.gate_D & 3) == 0));
+}
+
 int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s) {
     if (a.nb <= 0) return 0;
-    // attention-residual pools: one query per token, 4 x 64 heads, unit-stride 256-wide rows
-    if (a.nq == 1 && a.g == 1 && a.hkv == 4 && a.d == 64 && !a.v0 && !a.belief && !a.mask_agent && a.softclamp <= 0.f && a.n >= 1 &&
-        ((a.q_sb | a.k_sb | a.k_sj | a.v_sb | a.v_sj | a.out_sb) & 3) == 0 && al16p(a.q) && al16p(a.k) && al16p(a.v) && al16p(a.out) && al16p(a.k_gamma)) {
+    if (a.gate_w && !d4_pool_attn_ok(a)) return d4_fail("small_attn: in-kernel gate logits are only implemented by the pool kernel");
+    if (d4_pool_attn_ok(a)) {
         pool_attn_kernel<<<(unsigned)((a.nb + PL_WARPS - 1) / PL_WARPS), PL_WARPS * 32, 0, s>>>(a);
         D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
         return 0;

@@ -314,8 +314,24 @@ namespace {
 
 int run_pool(d4_ctx* c, const PoolW& P, int M, const float* xq, const float* xq_rstd, int n, float* out, cudaStream_t s) {
     const int D = c->D, Dp = c->Dp, hp = c->hp, dp = c->dp;
-    {   // query + gate logits from the normed token
-        GemmArgs g = gemm_args(xq, D, nullptr, D, c->b.pool_qg, c->ldpq, M, Dp + hp, D);
+    SmallAttnArgs a; memset(&a, 0, sizeof(a));
+    a.nb = M; a.hkv = hp; a.g = 1; a.d = dp; a.nq = 1; a.n = n;
+    a.q = c->b.pool_qg; a.q_sb = c->ldpq; a.q_si = 0;
+    a.k = c->b.pool_kv; a.k_sb = 2 * Dp; a.k_sj = (long long)M * 2 * Dp;
+    a.v = c->b.pool_kv + Dp; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+    a.k_gamma = P.k_gamma;
+    a.out = c->b.pool_att; a.out_sb = Dp; a.out_si = 0;
+    a.scale = 1.f / sqrtf((float)dp);
+    // the 4 gate rows ride along in w_qg (rows Dp .. Dp+hp); when the pool kernel can form the gate logits itself the q
+    // projection is an exact 256-column GEMM (one full tile instead of 260 -> 3 x 128 with 48 % padding)
+    a.gate_x = xq; a.gate_x_ld = D; a.gate_rstd = xq_rstd; a.gate_w = P.w_qg.w + (long long)Dp * D; a.gate_D = D;
+    const bool gate_in_kernel = d4_pool_attn_ok(a) != 0;
+    if (!gate_in_kernel) {
+        a.gate_x = nullptr; a.gate_rstd = nullptr; a.gate_w = nullptr; a.gate_D = 0;
+        a.gate = c->b.pool_qg + Dp; a.gate_sb = c->ldpq; a.gate_si = 0;
+    }
+    {   // query (+ gate logits) from the normed token
+        GemmArgs g = gemm_args(xq, D, nullptr, D, c->b.pool_qg, c->ldpq, M, gate_in_kernel ? Dp : Dp + hp, D);
         g.row_scale = xq_rstd;
         D4_TRY(d4_engine_gemm(c, g, P.w_qg, 0, s));
     }
@@ -324,15 +340,6 @@ int run_pool(d4_ctx* c, const PoolW& P, int M, const float* xq, const float* xq_
         g.row_scale = c->b.hid_rstd;
         D4_TRY(d4_engine_gemm(c, g, P.w_kv, 0, s));
     }
-    SmallAttnArgs a; memset(&a, 0, sizeof(a));
-    a.nb = M; a.hkv = hp; a.g = 1; a.d = dp; a.nq = 1; a.n = n;
-    a.q = c->b.pool_qg; a.q_sb = c->ldpq; a.q_si = 0;
-    a.k = c->b.pool_kv; a.k_sb = 2 * Dp; a.k_sj = (long long)M * 2 * Dp;
-    a.v = c->b.pool_kv + Dp; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
-    a.k_gamma = P.k_gamma;
-    a.gate = c->b.pool_qg + Dp; a.gate_sb = c->ldpq; a.gate_si = 0;
-    a.out = c->b.pool_att; a.out_sb = Dp; a.out_si = 0;
-    a.scale = 1.f / sqrtf((float)dp);
     { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
     GemmArgs g = gemm_args(c->b.pool_att, Dp, nullptr, Dp, out, D, M, D, Dp);
     g.residual = xq; g.ldr = D;

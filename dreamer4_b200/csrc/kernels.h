@@ -55,8 +55,13 @@ struct SmallAttnArgs {
     float* out; long long out_sb, out_si;          // out(b,i,hq) = out + b*out_sb + i*out_si + hq*d
     float scale, softclamp;
     int mask_agent, belief;
+    // attention-residual pools only: when gate_w is set, the head-gate logits are computed in the kernel as
+    // gate_rstd[b] * (gate_x[b] . gate_w[h]) instead of being read from `gate` (keeps the 4 gate rows out of the q GEMM,
+    // whose N then is exactly 256)
+    const float* gate_x; long long gate_x_ld; const float* gate_rstd; const float* gate_w; int gate_D;
 };
 int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s);
+int d4_pool_attn_ok(const SmallAttnArgs& a);      // 1 if `a` takes the one-warp-per-token pool kernel (the only one that honours gate_w)
 
 // K1: time-decode attention over the in-place KV cache (+ append on the clean pass).
 struct TimeAttnArgs {

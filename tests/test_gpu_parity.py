@@ -404,8 +404,11 @@ def test_hundred_seeded_dream_steps_losses(precision):
         assert torch.equal(exp.actions.discrete.cpu(), ref.actions), f'step {step}: sampled action indices diverged'
         # the policy loss is a masked mean of O(1) terms (z-scored advantages x ratio) that nearly cancel, so its fp32
         # evaluation carries an absolute error of a few 1e-7 whatever its own magnitude: tolerance 1e-4 relative + 2e-6
-        ep = abs(pl.item() - rpl.item()) / (abs(rpl.item()) + 2e-2)
-        ev = abs(vl.item() - rvl.item()) / (abs(rvl.item()) + 2e-2)
+        # (tf32x3: the heads' backward runs on 3xTF32 too, so the two free-running AdamW trajectories separate a little faster:
+        #  1e-4 relative + 1e-5; measured worst case 4.4e-6 absolute on a policy loss of -0.009 at step 19)
+        floor = 2e-2 if precision == 'fp32' else 1e-1
+        ep = abs(pl.item() - rpl.item()) / (abs(rpl.item()) + floor)
+        ev = abs(vl.item() - rvl.item()) / (abs(rvl.item()) + floor)
         worst_p, worst_v = max(worst_p, ep), max(worst_v, ev)
         assert ep < 1e-4, f'step {step}: policy loss {pl.item()} vs reference {rpl.item()} (rel {ep:.2e})'
         assert ev < 1e-4, f'step {step}: value loss {vl.item()} vs reference {rvl.item()} (rel {ev:.2e})'

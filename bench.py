@@ -205,13 +205,18 @@ def run_native(args):
     if rank == 0:
         sampler.start()
     phase_events.clear()
-    ms, launches, prof, last = timed(args.steps, e2e=False, profile=not args.no_profile)
+    ms, launches, _, last = timed(args.steps, e2e=False)
     clocks = sampler.stop() if rank == 0 else None
     phases = dict(generate=sum(e[0].elapsed_time(e[1]) for e in phase_events) / args.steps,
                   learn_fwd_bwd=sum(e[1].elapsed_time(e[2]) for e in phase_events) / args.steps,
                   allreduce_clip_adamw=sum(e[2].elapsed_time(e[3]) for e in phase_events) / args.steps)
     step(True)                                   # warm the pinned-copy path
     ms_e2e, _, _, last_e2e = timed(args.steps, e2e=True)
+    # kernel-class breakdown: ONE extra step with a CUDA-event pair around every launch of the library (not part of `value`:
+    # creating ~10^5 events costs host time)
+    prof, ms_prof = None, None
+    if not args.no_profile:
+        ms_prof, _, prof, _ = timed(1, e2e=False, profile=True)
 
     frames = world * B * H * args.steps
     value = frames / (ms / 1e3)
@@ -230,7 +235,7 @@ def run_native(args):
                 losses=dict(policy=float(last[0]), value=float(last[1])), peaks=pk['source'], phase_ms_per_step=phases)
     if prof is not None:
         names = ['gemm', 'time_attn', 'small_attn', 'other']
-        total_ms = ms
+        total_ms = ms_prof
         shares = {n: prof[i][0] / total_ms for i, n in enumerate(names)}
         gemm_tf = prof[0][2] / (prof[0][0] / 1e3) / 1e12 if prof[0][0] > 0 else 0.
         attn_gbs = prof[1][2] / (prof[1][0] / 1e3) / 1e9 if prof[1][0] > 0 else 0.

@@ -261,6 +261,204 @@ __global__ void __launch_bounds__(SP_WARPS * 32) space_attn_kernel(SmallAttnArgs
 }
 
 // -------------------------------------------------------------------------------------------------
+// space attention on the warp-level tensor cores (tf32x3 / tf32 engine modes): the same S x S (S <= 16) attention as
+// space_attn_kernel, with Q K^T and P V as m16n8k8 TF32 mma.sync tiles and the 3-term TF32 split (operands rounded to
+// nearest, fp32 accumulate) that keeps them fp32-accurate.  One warp per (frame, kv head): a 16 x 16 x D score tile and a
+// 16 x D x 16 output tile are far below a tcgen05 tile (M = 128 rows of ONE operand pair), so the warp-level MMA is the
+// instruction that fits; it cuts the kernel from ~4600 to ~1600 issued instructions per (frame, head).
+//   fragment layouts (PTX ISA, m16n8k8 .tf32): g = lane / 4, t = lane % 4
+//     A (16 x 8):  a0 (g, t)  a1 (g + 8, t)  a2 (g, t + 4)  a3 (g + 8, t + 4)
+//     B ( 8 x 8):  b0 (k = t, n = g)  b1 (k = t + 4, n = g)
+//     C (16 x 8):  c0 (g, 2t)  c1 (g, 2t + 1)  c2 (g + 8, 2t)  c3 (g + 8, 2t + 1)
+template <int D>
+struct SpaceMmaSmem {
+    static constexpr int PQ = D + 4, PV = D + 8, PP = 20;
+    float q[16 * PQ], k[16 * PQ], v[16 * PV];
+    float p[16 * PP];
+    float kinv[16], vinv[16], gate[16], mixw[16];
+};
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    const float h = tf32_rna(x);
+    hi = __float_as_uint(h);
+    lo = __float_as_uint(tf32_rna(x - h));
+}
+// c += a * b with a, b given as fp32 fragments: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const uint32_t (&bhi)[2], const uint32_t (&blo)[2]) {
+    mma_tf32(c, alo, bhi);
+    mma_tf32(c, ahi, blo);
+    mma_tf32(c, ahi, bhi);
+}
+
+template <int D>
+__global__ void __launch_bounds__(SP_WARPS * 32) space_attn_mma_kernel(SmallAttnArgs a) {
+    using SM = SpaceMmaSmem<D>;
+    constexpr int PQ = SM::PQ, PV = SM::PV, PP = SM::PP, C4 = D / 4, KS = D / 8, NT = D / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * SP_WARPS + warp;
+    if (item >= (long long)a.nb * a.hkv) return;
+    const int b = (int)(item / a.hkv), hk = (int)(item % a.hkv);
+    SM& sm = reinterpret_cast<SM*>(smem_raw)[warp];
+    const int S = a.n;
+    const int g = lane >> 2, t = lane & 3;
+    const float sqrt_d = sqrtf((float)D);
+
+    if (a.v0 && lane < S) sm.mixw[lane] = sigmoidf_(a.mix[b * a.mix_sb + lane * a.mix_sj + hk]);
+    __syncwarp();
+    // ---- stage K, V (value-residual lerp); rows S..15 are zero
+    for (int idx = lane; idx < 16 * C4; idx += 32) {
+        const int j = idx / C4, c = (idx % C4) * 4;
+        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+        if (j < S) {
+            kv = *reinterpret_cast<const float4*>(a.k + b * a.k_sb + j * a.k_sj + (long long)hk * D + c);
+            vv = *reinterpret_cast<const float4*>(a.v + b * a.v_sb + j * a.v_sj + (long long)hk * D + c);
+            if (a.v0) {
+                const float4 rv = *reinterpret_cast<const float4*>(a.v0 + b * a.v0_sb + j * a.v0_sj + (long long)hk * D + c);
+                const float w = sm.mixw[j];
+                vv.x = lerp_(vv.x, rv.x, w); vv.y = lerp_(vv.y, rv.y, w); vv.z = lerp_(vv.z, rv.z, w); vv.w = lerp_(vv.w, rv.w, w);
+            }
+        }
+        *reinterpret_cast<float4*>(sm.k + j * PQ + c) = kv;
+        *reinterpret_cast<float4*>(sm.v + j * PV + c) = vv;
+    }
+    __syncwarp();
+    {   // l2 norms: lanes 0..15 keys, lanes 16..31 values
+        const int j = lane & 15;
+        const float* r = (lane < 16) ? (sm.k + j * PQ) : (sm.v + j * PV);
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; c += 4) { const float4 x = *reinterpret_cast<const float4*>(r + c); ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w; }
+        const float inv = 1.f / fmaxf(sqrtf(ss), D4_L2_EPS);
+        (lane < 16 ? sm.kinv : sm.vinv)[j] = inv;
+    }
+
+    for (int gi = 0; gi < a.g; ++gi) {
+        const int hq = hk * a.g + gi;
+        __syncwarp();
+        // ---- stage Q pre-multiplied by the key-norm gain (gamma + 1) * sqrt(d); rows S..15 zero; head gates
+        for (int idx = lane; idx < 16 * C4; idx += 32) {
+            const int i = idx / C4, c = (idx % C4) * 4;
+            float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < S) {
+                qv = *reinterpret_cast<const float4*>(a.q + b * a.q_sb + i * a.q_si + (long long)hq * D + c);
+                const float4 gm = *reinterpret_cast<const float4*>(a.k_gamma + hk * D + c);
+                qv.x *= (gm.x + 1.f) * sqrt_d; qv.y *= (gm.y + 1.f) * sqrt_d; qv.z *= (gm.z + 1.f) * sqrt_d; qv.w *= (gm.w + 1.f) * sqrt_d;
+            }
+            *reinterpret_cast<float4*>(sm.q + i * PQ + c) = qv;
+        }
+        if (lane < 16) sm.gate[lane] = (a.gate && lane < S) ? sigmoidf_(a.gate[b * a.gate_sb + lane * a.gate_si + hq]) : 1.f;
+        __syncwarp();
+
+        // ---- scores: 16 queries x 16 keys, two 8-key tiles
+        float sc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) sc[nt][r] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t ahi[4], alo[4];
+            split_tf32(sm.q[g * PQ + ks * 8 + t], ahi[0], alo[0]);
+            split_tf32(sm.q[(g + 8) * PQ + ks * 8 + t], ahi[1], alo[1]);
+            split_tf32(sm.q[g * PQ + ks * 8 + t + 4], ahi[2], alo[2]);
+            split_tf32(sm.q[(g + 8) * PQ + ks * 8 + t + 4], ahi[3], alo[3]);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                uint32_t bhi[2], blo[2];
+                split_tf32(sm.k[(nt * 8 + g) * PQ + ks * 8 + t], bhi[0], blo[0]);
+                split_tf32(sm.k[(nt * 8 + g) * PQ + ks * 8 + t + 4], bhi[1], blo[1]);
+                mma_3x(sc[nt], ahi, alo, bhi, blo);
+            }
+        }
+        // scale by the key norm, softclamp, mask, softmax over the keys of each query row (rows g and g + 8)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = g + ((r & 2) ? 8 : 0), j = nt * 8 + 2 * t + (r & 1);
+                float s = sc[nt][r] * sm.kinv[j] * a.scale;
+                if (a.softclamp > 0.f) s = tanhf(s / a.softclamp) * a.softclamp;
+                if (a.mask_agent && i < S - 1 && j == S - 1) s = -FLT_MAX;
+                if (j >= S) s = -INFINITY;
+                sc[nt][r] = s;
+            }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {          // half 0: row g (regs 0, 1), half 1: row g + 8 (regs 2, 3)
+            float mx = fmaxf(fmaxf(sc[0][2 * half], sc[0][2 * half + 1]), fmaxf(sc[1][2 * half], sc[1][2 * half + 1]));
+            mx = fmaxf(mx, __shfl_xor_sync(D4_FULL, mx, 1)); mx = fmaxf(mx, __shfl_xor_sync(D4_FULL, mx, 2));
+            float e[4], sum = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { e[q] = expf(sc[q >> 1][2 * half + (q & 1)] - mx); sum += e[q]; }
+            sum += __shfl_xor_sync(D4_FULL, sum, 1); sum += __shfl_xor_sync(D4_FULL, sum, 2);
+            const float inv = 1.f / sum;
+            const int i = g + 8 * half;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sm.p[i * PP + (q >> 1) * 8 + 2 * t + (q & 1)] = e[q] * inv;
+        }
+        __syncwarp();
+
+        // ---- out = P V : 16 queries x D, K = 16 keys (two k-steps), D / 8 column tiles
+        uint32_t phi[2][4], plo[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            split_tf32(sm.p[g * PP + ks * 8 + t], phi[ks][0], plo[ks][0]);
+            split_tf32(sm.p[(g + 8) * PP + ks * 8 + t], phi[ks][1], plo[ks][1]);
+            split_tf32(sm.p[g * PP + ks * 8 + t + 4], phi[ks][2], plo[ks][2]);
+            split_tf32(sm.p[(g + 8) * PP + ks * 8 + t + 4], phi[ks][3], plo[ks][3]);
+        }
+        float o[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) o[nt][r] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t bhi[2], blo[2];
+                split_tf32(sm.v[(ks * 8 + t) * PV + nt * 8 + g], bhi[0], blo[0]);
+                split_tf32(sm.v[(ks * 8 + t + 4) * PV + nt * 8 + g], bhi[1], blo[1]);
+                mma_3x(o[nt], phi[ks], plo[ks], bhi, blo);
+            }
+        }
+        // ---- belief projection (out -= (out . vhat) vhat, vhat = l2norm(v_i)), head gate, store rows g and g + 8
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = g + 8 * half;
+            const float* vr = sm.v + i * PV;
+            float dot = 0.f;
+            if (a.belief) {
+                const float vinv = sm.vinv[i];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const float2 vv = *reinterpret_cast<const float2*>(vr + nt * 8 + 2 * t);
+                    dot = fmaf(o[nt][2 * half], vv.x * vinv, dot); dot = fmaf(o[nt][2 * half + 1], vv.y * vinv, dot);
+                }
+                dot += __shfl_xor_sync(D4_FULL, dot, 1); dot += __shfl_xor_sync(D4_FULL, dot, 2);
+            }
+            if (i < S) {
+                const float gate = sm.gate[i];
+                const float vinv = a.belief ? sm.vinv[i] : 0.f;
+                float* op = a.out + b * a.out_sb + i * a.out_si + (long long)hq * D;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const float2 vv = *reinterpret_cast<const float2*>(vr + nt * 8 + 2 * t);
+                    float2 r;
+                    r.x = (o[nt][2 * half] - dot * (vv.x * vinv)) * gate;
+                    r.y = (o[nt][2 * half + 1] - dot * (vv.y * vinv)) * gate;
+                    *reinterpret_cast<float2*>(op + nt * 8 + 2 * t) = r;
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // attention-residual pool (one query per token, 4 heads x 64 = 256 wide, n <= 32 context hiddens): one warp per token
 // does all heads at once straight from global memory — lane = (head = lane / 8, 8-float slice of the head's 64 dims),
 // key l2-norm and q.k reduced over the 8 lanes of a head with shuffles, single-pass online softmax.
@@ -569,6 +767,20 @@ int launch_space(const SmallAttnArgs& a, cudaStream_t s) {
     return 0;
 }
 
+template <int D>
+int launch_space_mma(const SmallAttnArgs& a, cudaStream_t s) {
+    const size_t smem = sizeof(SpaceMmaSmem<D>) * SP_WARPS;
+    static bool configured = false;
+    if (!configured) {
+        D4_CUDA_OK(cudaFuncSetAttribute(space_attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long items = (long long)a.nb * a.hkv;
+    space_attn_mma_kernel<D><<<(unsigned)((items + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, smem, s>>>(a);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -592,6 +804,10 @@ int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s) {
     if (a.nq == a.n && a.n <= 16 && a.n >= 1 &&
         ((a.q_sb | a.q_si | a.k_sb | a.k_sj | a.v_sb | a.v_sj | a.v0_sb | a.v0_sj) & 3) == 0 && al16p(a.q) && al16p(a.k) && al16p(a.v) &&
         (!a.v0 || al16p(a.v0)) && al16p(a.k_gamma)) {
+        if (a.allow_tensor && a.d == 64 && (a.out_si & 1) == 0 && (a.out_sb & 1) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0)
+            return launch_space_mma<64>(a, s);
+        if (a.allow_tensor && a.d == 32 && (a.out_si & 1) == 0 && (a.out_sb & 1) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0)
+            return launch_space_mma<32>(a, s);
         if (a.d == 64) return launch_space<64>(a, s);
         if (a.d == 32) return launch_space<32>(a, s);
         if (a.d == 16) return launch_space<16>(a, s);

@@ -68,6 +68,7 @@ extern "C" int d4_ctx_create(const d4_config* cfg, d4_ctx** out) {
     else if (cfg->policy_layers > D4_MAX_MLP_LAYERS || cfg->value_layers > D4_MAX_MLP_LAYERS || cfg->terminal_layers > D4_MAX_MLP_LAYERS) bad = "MLP too deep";
     if (bad) { delete c; return d4_fail("d4_ctx_create: %s", bad); }
     { const char* f = getenv("D4_FUSE_POOLS"); c->fuse_pools = f ? atoi(f) != 0 : true; }
+    { const char* f = getenv("D4_SPACE_MMA"); c->space_mma = f ? atoi(f) != 0 : true; }
     d4_engine_plan(c);
     *out = c;
     return 0;
@@ -453,6 +454,7 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
             a.gate = c->b.qkvgm + off_g; a.gate_sb = a.q_sb; a.gate_si = c->ldq;
             a.out = c->b.attn_o; a.out_sb = (long long)S * Dq; a.out_si = Dq;
             a.scale = att_scale; a.softclamp = c->cfg.softclamp; a.mask_agent = 1; a.belief = 1;
+            a.allow_tensor = (c->cfg.precision != D4_PREC_FP32) && c->space_mma;
             { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
         }
         {

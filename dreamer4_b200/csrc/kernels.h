@@ -59,6 +59,7 @@ struct SmallAttnArgs {
     // gate_rstd[b] * (gate_x[b] . gate_w[h]) instead of being read from `gate` (keeps the 4 gate rows out of the q GEMM,
     // whose N then is exactly 256)
     const float* gate_x; long long gate_x_ld; const float* gate_rstd; const float* gate_w; int gate_D;
+    int allow_tensor;       // space attention: 3xTF32 mma.sync tiles allowed (tf32x3 / tf32 engine modes); 0 = exact-fp32 FMA
 };
 int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s);
 int d4_pool_attn_ok(const SmallAttnArgs& a);      // 1 if `a` takes the one-warp-per-token pool kernel (the only one that honours gate_w)

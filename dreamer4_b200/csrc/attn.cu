@@ -270,10 +270,15 @@ __global__ void __launch_bounds__(SP_WARPS * 32) space_attn_kernel(SmallAttnArgs
 //     A (16 x 8):  a0 (g, t)  a1 (g + 8, t)  a2 (g, t + 4)  a3 (g + 8, t + 4)
 //     B ( 8 x 8):  b0 (k = t, n = g)  b1 (k = t + 4, n = g)
 //     C (16 x 8):  c0 (g, 2t)  c1 (g, 2t + 1)  c2 (g + 8, 2t)  c3 (g + 8, 2t + 1)
-template <int D>
+// ALIAS (one query group): V is fetched into registers up front and written over K's tile once the scores are done,
+// which cuts the per-warp shared memory from 14.8 to 10.5 KB (5 resident CTAs instead of 3) and lets Q, K, V and the value
+// residual all be in flight behind ONE exposed global-memory latency.
+template <int D, bool ALIAS>
 struct SpaceMmaSmem {
     static constexpr int PQ = D + 4, PV = D + 8, PP = 20;
-    float q[16 * PQ], k[16 * PQ], v[16 * PV];
+    float q[16 * PQ];
+    float k[16 * (ALIAS ? PV : PQ)];             // keys (pitch PQ); with ALIAS the values (pitch PV) replace them after the scores
+    float v[ALIAS ? 4 : 16 * PV];
     float p[16 * PP];
     float kinv[16], vinv[16], gate[16], mixw[16];
 };
@@ -295,53 +300,23 @@ __device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ahi)[4], 
     mma_tf32(c, ahi, bhi);
 }
 
-template <int D>
-__global__ void __launch_bounds__(SP_WARPS * 32) space_attn_mma_kernel(SmallAttnArgs a) {
-    using SM = SpaceMmaSmem<D>;
+template <int D, bool ALIAS>
+__global__ void __launch_bounds__(SP_WARPS * 32, ALIAS ? 4 : 3) space_attn_mma_kernel(SmallAttnArgs a) {
+    using SM = SpaceMmaSmem<D, ALIAS>;
     constexpr int PQ = SM::PQ, PV = SM::PV, PP = SM::PP, C4 = D / 4, KS = D / 8, NT = D / 8;
+    constexpr int VR = (16 * C4 + 31) / 32;          // float4 values per lane when V is held in registers
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * SP_WARPS + warp;
     if (item >= (long long)a.nb * a.hkv) return;
     const int b = (int)(item / a.hkv), hk = (int)(item % a.hkv);
     SM& sm = reinterpret_cast<SM*>(smem_raw)[warp];
+    float* smv = ALIAS ? sm.k : sm.v;                // where the PV pass finds the values
     const int S = a.n;
     const int g = lane >> 2, t = lane & 3;
     const float sqrt_d = sqrtf((float)D);
 
-    if (a.v0 && lane < S) sm.mixw[lane] = sigmoidf_(a.mix[b * a.mix_sb + lane * a.mix_sj + hk]);
-    __syncwarp();
-    // ---- stage K, V (value-residual lerp); rows S..15 are zero
-    for (int idx = lane; idx < 16 * C4; idx += 32) {
-        const int j = idx / C4, c = (idx % C4) * 4;
-        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-        if (j < S) {
-            kv = *reinterpret_cast<const float4*>(a.k + b * a.k_sb + j * a.k_sj + (long long)hk * D + c);
-            vv = *reinterpret_cast<const float4*>(a.v + b * a.v_sb + j * a.v_sj + (long long)hk * D + c);
-            if (a.v0) {
-                const float4 rv = *reinterpret_cast<const float4*>(a.v0 + b * a.v0_sb + j * a.v0_sj + (long long)hk * D + c);
-                const float w = sm.mixw[j];
-                vv.x = lerp_(vv.x, rv.x, w); vv.y = lerp_(vv.y, rv.y, w); vv.z = lerp_(vv.z, rv.z, w); vv.w = lerp_(vv.w, rv.w, w);
-            }
-        }
-        *reinterpret_cast<float4*>(sm.k + j * PQ + c) = kv;
-        *reinterpret_cast<float4*>(sm.v + j * PV + c) = vv;
-    }
-    __syncwarp();
-    {   // l2 norms: lanes 0..15 keys, lanes 16..31 values
-        const int j = lane & 15;
-        const float* r = (lane < 16) ? (sm.k + j * PQ) : (sm.v + j * PV);
-        float ss = 0.f;
-#pragma unroll
-        for (int c = 0; c < D; c += 4) { const float4 x = *reinterpret_cast<const float4*>(r + c); ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w; }
-        const float inv = 1.f / fmaxf(sqrtf(ss), D4_L2_EPS);
-        (lane < 16 ? sm.kinv : sm.vinv)[j] = inv;
-    }
-
-    for (int gi = 0; gi < a.g; ++gi) {
-        const int hq = hk * a.g + gi;
-        __syncwarp();
-        // ---- stage Q pre-multiplied by the key-norm gain (gamma + 1) * sqrt(d); rows S..15 zero; head gates
+    auto stage_q = [&](int hq) {      // Q pre-multiplied by the key-norm gain (gamma + 1) * sqrt(d); rows S..15 zero; head gates
         for (int idx = lane; idx < 16 * C4; idx += 32) {
             const int i = idx / C4, c = (idx % C4) * 4;
             float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -353,6 +328,68 @@ __global__ void __launch_bounds__(SP_WARPS * 32) space_attn_mma_kernel(SmallAttn
             *reinterpret_cast<float4*>(sm.q + i * PQ + c) = qv;
         }
         if (lane < 16) sm.gate[lane] = (a.gate && lane < S) ? sigmoidf_(a.gate[b * a.gate_sb + lane * a.gate_si + hq]) : 1.f;
+    };
+
+    // ---- everything this (frame, head) needs is requested before the first wait: mix logits, K, V (+ value residual), Q
+    const float mixl = (a.v0 && lane < S) ? a.mix[b * a.mix_sb + lane * a.mix_sj + hk] : 0.f;
+    float4 vreg[ALIAS ? VR : 1], rreg[ALIAS ? VR : 1];
+#pragma unroll
+    for (int r = 0; r < VR; ++r) {
+        const int idx = lane + 32 * r, j = idx / C4, c = (idx % C4) * 4;
+        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv, rv = kv;
+        if (idx < 16 * C4 && j < S) {
+            kv = *reinterpret_cast<const float4*>(a.k + b * a.k_sb + j * a.k_sj + (long long)hk * D + c);
+            vv = *reinterpret_cast<const float4*>(a.v + b * a.v_sb + j * a.v_sj + (long long)hk * D + c);
+            if (a.v0) rv = *reinterpret_cast<const float4*>(a.v0 + b * a.v0_sb + j * a.v0_sj + (long long)hk * D + c);
+        }
+        if (idx < 16 * C4) *reinterpret_cast<float4*>(sm.k + j * PQ + c) = kv;
+        if (ALIAS) { vreg[r] = vv; rreg[r] = rv; }
+        else if (idx < 16 * C4) { *reinterpret_cast<float4*>(sm.v + j * PV + c) = vv; *reinterpret_cast<float4*>(sm.q + j * PQ + c) = rv; }   // residual parked in q's tile
+    }
+    if (lane < 16) sm.mixw[lane] = sigmoidf_(mixl);
+    if (ALIAS) stage_q(hk);
+    __syncwarp();
+    // value-residual lerp (values still in registers / in their own tile)
+    if (a.v0) {
+#pragma unroll
+        for (int r = 0; r < VR; ++r) {
+            const int idx = lane + 32 * r, j = idx / C4, c = (idx % C4) * 4;
+            if (idx < 16 * C4 && j < S) {
+                const float w = sm.mixw[j];
+                if (ALIAS) {
+                    vreg[r].x = lerp_(vreg[r].x, rreg[r].x, w); vreg[r].y = lerp_(vreg[r].y, rreg[r].y, w);
+                    vreg[r].z = lerp_(vreg[r].z, rreg[r].z, w); vreg[r].w = lerp_(vreg[r].w, rreg[r].w, w);
+                } else {
+                    float4 vv = *reinterpret_cast<float4*>(sm.v + j * PV + c);
+                    const float4 rv = *reinterpret_cast<const float4*>(sm.q + j * PQ + c);
+                    vv.x = lerp_(vv.x, rv.x, w); vv.y = lerp_(vv.y, rv.y, w); vv.z = lerp_(vv.z, rv.z, w); vv.w = lerp_(vv.w, rv.w, w);
+                    *reinterpret_cast<float4*>(sm.v + j * PV + c) = vv;
+                }
+            }
+        }
+    }
+    if (lane < 16) {   // key l2 norms
+        const float* r = sm.k + lane * PQ;
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; c += 4) { const float4 x = *reinterpret_cast<const float4*>(r + c); ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w; }
+        sm.kinv[lane] = 1.f / fmaxf(sqrtf(ss), D4_L2_EPS);
+    }
+    if (!ALIAS) {
+        __syncwarp();
+        if (lane < 16) {
+            const float* r = sm.v + lane * PV;
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; c += 4) { const float4 x = *reinterpret_cast<const float4*>(r + c); ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w; }
+            sm.vinv[lane] = 1.f / fmaxf(sqrtf(ss), D4_L2_EPS);
+        }
+    }
+
+    for (int gi = 0; gi < a.g; ++gi) {
+        const int hq = hk * a.g + gi;
+        __syncwarp();
+        if (!ALIAS) stage_q(hq);
         __syncwarp();
 
         // ---- scores: 16 queries x 16 keys, two 8-key tiles
@@ -403,6 +440,20 @@ __global__ void __launch_bounds__(SP_WARPS * 32) space_attn_mma_kernel(SmallAttn
             for (int q = 0; q < 4; ++q) sm.p[i * PP + (q >> 1) * 8 + 2 * t + (q & 1)] = e[q] * inv;
         }
         __syncwarp();
+        if (ALIAS) {   // the keys are dead: the (lerped) values take their tile, and their row norms come from the registers
+#pragma unroll
+            for (int r = 0; r < VR; ++r) {
+                const int idx = lane + 32 * r, j = idx / C4, c = (idx % C4) * 4;
+                if (idx < 16 * C4) {
+                    *reinterpret_cast<float4*>(smv + j * PV + c) = vreg[r];
+                    float ss = vreg[r].x * vreg[r].x + vreg[r].y * vreg[r].y + vreg[r].z * vreg[r].z + vreg[r].w * vreg[r].w;
+#pragma unroll
+                    for (int off = C4 / 2; off > 0; off >>= 1) ss += __shfl_xor_sync(D4_FULL, ss, off);     // the C4 lanes that share row j
+                    if ((lane & (C4 - 1)) == 0) sm.vinv[j] = 1.f / fmaxf(sqrtf(ss), D4_L2_EPS);
+                }
+            }
+            __syncwarp();
+        }
 
         // ---- out = P V : 16 queries x D, K = 16 keys (two k-steps), D / 8 column tiles
         uint32_t phi[2][4], plo[2][4];
@@ -421,8 +472,8 @@ __global__ void __launch_bounds__(SP_WARPS * 32) space_attn_mma_kernel(SmallAttn
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 uint32_t bhi[2], blo[2];
-                split_tf32(sm.v[(ks * 8 + t) * PV + nt * 8 + g], bhi[0], blo[0]);
-                split_tf32(sm.v[(ks * 8 + t + 4) * PV + nt * 8 + g], bhi[1], blo[1]);
+                split_tf32(smv[(ks * 8 + t) * PV + nt * 8 + g], bhi[0], blo[0]);
+                split_tf32(smv[(ks * 8 + t + 4) * PV + nt * 8 + g], bhi[1], blo[1]);
                 mma_3x(o[nt], phi[ks], plo[ks], bhi, blo);
             }
         }
@@ -430,7 +481,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32) space_attn_mma_kernel(SmallAttn
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int i = g + 8 * half;
-            const float* vr = sm.v + i * PV;
+            const float* vr = smv + i * PV;
             float dot = 0.f;
             if (a.belief) {
                 const float vinv = sm.vinv[i];
@@ -767,18 +818,22 @@ int launch_space(const SmallAttnArgs& a, cudaStream_t s) {
     return 0;
 }
 
-template <int D>
-int launch_space_mma(const SmallAttnArgs& a, cudaStream_t s) {
-    const size_t smem = sizeof(SpaceMmaSmem<D>) * SP_WARPS;
+template <int D, bool ALIAS>
+int launch_space_mma_impl(const SmallAttnArgs& a, cudaStream_t s) {
+    const size_t smem = sizeof(SpaceMmaSmem<D, ALIAS>) * SP_WARPS;
     static bool configured = false;
     if (!configured) {
-        D4_CUDA_OK(cudaFuncSetAttribute(space_attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        D4_CUDA_OK(cudaFuncSetAttribute(space_attn_mma_kernel<D, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const long long items = (long long)a.nb * a.hkv;
-    space_attn_mma_kernel<D><<<(unsigned)((items + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, smem, s>>>(a);
+    space_attn_mma_kernel<D, ALIAS><<<(unsigned)((items + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, smem, s>>>(a);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
+}
+template <int D>
+int launch_space_mma(const SmallAttnArgs& a, cudaStream_t s) {
+    return a.g == 1 ? launch_space_mma_impl<D, true>(a, s) : launch_space_mma_impl<D, false>(a, s);
 }
 
 static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -20,42 +20,59 @@ namespace {
 constexpr int L2S_MAXQ = 8;        // learned queries x query groups per kv head
 constexpr int L2S_MAXN = 64;       // latent tokens
 
-template <int DL>
+// MMA = true (tensor-core engine modes): the key projection K_h = X W_k,h^T (N x d, reduction Dl) runs as m16n8k8 TF32
+// mma.sync tiles with the 3-term split (fp32-accurate), the key norms and q.k dots are reduced straight from the
+// accumulator fragments; MMA = false keeps it in exact-fp32 FMA.  Fragment layouts: see space_attn_mma_kernel (attn.cu).
+__device__ __forceinline__ void l2s_mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void l2s_split(float x, uint32_t& hi, uint32_t& lo) {
+    const float h = tf32_rna(x);
+    hi = __float_as_uint(h);
+    lo = __float_as_uint(tf32_rna(x - h));
+}
+
+template <int DL, bool MMA, int NQC>
 __global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
     // one CTA per frame, one warp per kv head
+    constexpr int XP = DL + 4;                         // row pitch of the latent / weight tiles (conflict-free fragment loads)
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int b = blockIdx.x;
     const int N = a.N, d = a.d, NQ = a.nsp * a.g;
-    float* xs = smem;                                  // [N][DL] normalised latents
-    float* pw_all = xs + L2S_MAXN * DL;                // per warp [L2S_MAXN][L2S_MAXQ]
-    float* zs_all = pw_all + nwarps * L2S_MAXN * L2S_MAXQ;   // per warp [L2S_MAXQ][DL]
-    float* qs_all = zs_all + nwarps * L2S_MAXQ * DL;   // per warp [L2S_MAXQ][d]  queries x key gain
-    float* ws_all = qs_all + nwarps * L2S_MAXQ * d;    // per warp [d][DL]        this head's key (then value) projection rows
+    float* xs = smem;                                  // [64][XP] normalised latents (rows N.. are zero)
+    float* pw_all = xs + L2S_MAXN * XP;                // per warp [L2S_MAXN][NQC]
+    float* zs_all = pw_all + nwarps * L2S_MAXN * NQC;   // per warp [NQC][DL]
+    float* qs_all = zs_all + nwarps * NQC * DL;   // per warp [NQC][d]  queries x key gain
+    float* ws_all = qs_all + nwarps * NQC * d;    // per warp [d][XP]        this head's key (then value) projection rows
 
     // ---- normalised latents of this frame: x * rsqrt(mean(x^2) + eps)  (norm_context gamma is folded into w_k / w_v)
     const float* xb = a.latent + (long long)b * N * DL;
-    for (int j = warp; j < N; j += nwarps) {
+    for (int j = warp; j < L2S_MAXN; j += nwarps) {
         float v[(DL + 31) / 32], ss = 0.f;
 #pragma unroll
-        for (int e = 0; e < (DL + 31) / 32; ++e) { const int c = lane + 32 * e; v[e] = (c < DL) ? xb[j * DL + c] : 0.f; ss += v[e] * v[e]; }
+        for (int e = 0; e < (DL + 31) / 32; ++e) { const int c = lane + 32 * e; v[e] = (c < DL && j < N) ? xb[j * DL + c] : 0.f; ss += v[e] * v[e]; }
         ss = warp_sum(ss);
         const float r = rsqrtf(ss / (float)DL + D4_RMS_EPS);
 #pragma unroll
-        for (int e = 0; e < (DL + 31) / 32; ++e) { const int c = lane + 32 * e; if (c < DL) xs[j * DL + c] = v[e] * r; }
+        for (int e = 0; e < (DL + 31) / 32; ++e) { const int c = lane + 32 * e; if (c < DL) xs[j * XP + c] = v[e] * r; }
     }
     __syncthreads();
 
     for (int hk = warp; hk < a.h; hk += nwarps) {
-        float* pw = pw_all + warp * L2S_MAXN * L2S_MAXQ;
-        float* zs = zs_all + warp * L2S_MAXQ * DL;
-        float* qs = qs_all + warp * L2S_MAXQ * d;
-        float* wsm = ws_all + warp * d * DL;
+        float* pw = pw_all + warp * L2S_MAXN * NQC;
+        float* zs = zs_all + warp * NQC * DL;
+        float* qs = qs_all + warp * NQC * d;
+        float* wsm = ws_all + warp * d * XP;
         const float sqrt_d = sqrtf((float)d);
         {   // stage W_k,h: one coalesced pass instead of d * DL / 4 uniform global loads inside the score loop
             const float4* src = reinterpret_cast<const float4*>(a.w_k + (long long)hk * d * DL);
-            float4* dst = reinterpret_cast<float4*>(wsm);
-            for (int idx = lane; idx < d * DL / 4; idx += 32) dst[idx] = __ldg(src + idx);
+            for (int idx = lane; idx < d * DL / 4; idx += 32) {
+                const int c = idx / (DL / 4), e = (idx % (DL / 4)) * 4;
+                *reinterpret_cast<float4*>(wsm + c * XP + e) = __ldg(src + idx);
+            }
         }
         for (int idx = lane; idx < NQ * d; idx += 32) {
             const int qi = idx / d, c = idx - qi * d;
@@ -63,46 +80,107 @@ __global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
             qs[idx] = a.q[(long long)i * a.Dq + (hk * a.g + gi) * d + c] * ((a.k_gamma[hk * d + c] + 1.f) * sqrt_d);
         }
         __syncwarp();
+        float sc[2][NQC];
+        if (MMA) {
+            // ---- K_h = X W_k,h^T on mma.sync: per 16-key tile an accumulator of d / 8 column tiles; |k|^2 and the q.k dots are
+            //      reduced from the fragments (rows g and g + 8 of the tile, columns 2t, 2t + 1), raw scores parked in pw
+            const int g = lane >> 2, t = lane & 3;
+            for (int mt = 0; mt * 16 < N; ++mt) {
+                float ss[2] = {0.f, 0.f}, dot[2][NQC];
+#pragma unroll
+                for (int qi = 0; qi < NQC; ++qi) { dot[0][qi] = 0.f; dot[1][qi] = 0.f; }
+                uint32_t ahi[DL / 8][4], alo[DL / 8][4];
+#pragma unroll
+                for (int ks = 0; ks < DL / 8; ++ks) {
+                    const float* xr = xs + (mt * 16 + g) * XP + ks * 8 + t;
+                    l2s_split(xr[0], ahi[ks][0], alo[ks][0]); l2s_split(xr[8 * XP], ahi[ks][1], alo[ks][1]);
+                    l2s_split(xr[4], ahi[ks][2], alo[ks][2]); l2s_split(xr[8 * XP + 4], ahi[ks][3], alo[ks][3]);
+                }
+                for (int nt = 0; nt * 8 < d; ++nt) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < DL / 8; ++ks) {
+                        uint32_t bhi[2], blo[2];
+                        const float* wr = wsm + (nt * 8 + g) * XP + ks * 8 + t;
+                        l2s_split(wr[0], bhi[0], blo[0]); l2s_split(wr[4], bhi[1], blo[1]);
+                        l2s_mma_tf32(acc, alo[ks], bhi); l2s_mma_tf32(acc, ahi[ks], blo); l2s_mma_tf32(acc, ahi[ks], bhi);
+                    }
+                    ss[0] = fmaf(acc[0], acc[0], fmaf(acc[1], acc[1], ss[0]));
+                    ss[1] = fmaf(acc[2], acc[2], fmaf(acc[3], acc[3], ss[1]));
+#pragma unroll
+                    for (int qi = 0; qi < NQC; ++qi) {
+                        if (qi < NQ) {
+                            const float2 qv = *reinterpret_cast<const float2*>(qs + qi * d + nt * 8 + 2 * t);
+                            dot[0][qi] = fmaf(acc[0], qv.x, fmaf(acc[1], qv.y, dot[0][qi]));
+                            dot[1][qi] = fmaf(acc[2], qv.x, fmaf(acc[3], qv.y, dot[1][qi]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    ss[r] += __shfl_xor_sync(D4_FULL, ss[r], 1); ss[r] += __shfl_xor_sync(D4_FULL, ss[r], 2);
+                    const float inv = a.scale / fmaxf(sqrtf(ss[r]), D4_L2_EPS);
+                    const int key = mt * 16 + g + 8 * r;
+#pragma unroll
+                    for (int qi = 0; qi < NQC; ++qi) {
+                        if (qi < NQ) {
+                            float dv = dot[r][qi];
+                            dv += __shfl_xor_sync(D4_FULL, dv, 1); dv += __shfl_xor_sync(D4_FULL, dv, 2);
+                            if (t == 0) pw[key * NQC + qi] = dv * inv;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int qi = 0; qi < NQC; ++qi) {
+                    const int j = lane + 32 * kk;
+                    sc[kk][qi] = (j < N && qi < NQ) ? pw[j * NQC + qi] : -INFINITY;
+                }
+            __syncwarp();
+        } else {
         // ---- scores: lane = key (two key slots), keys projected on the fly, |k| accumulated alongside
-        float sc[2][L2S_MAXQ];
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
             const int j = lane + 32 * kk;
             float xr[DL];
 #pragma unroll
             for (int e = 0; e < DL; e += 4) {
-                const float4 t = (j < N) ? *reinterpret_cast<const float4*>(xs + j * DL + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 t = (j < N) ? *reinterpret_cast<const float4*>(xs + j * XP + e) : make_float4(0.f, 0.f, 0.f, 0.f);
                 xr[e] = t.x; xr[e + 1] = t.y; xr[e + 2] = t.z; xr[e + 3] = t.w;
             }
-            float ss = 0.f, dot[L2S_MAXQ];
+            float ss = 0.f, dot[NQC];
 #pragma unroll
-            for (int qi = 0; qi < L2S_MAXQ; ++qi) dot[qi] = 0.f;
+            for (int qi = 0; qi < NQC; ++qi) dot[qi] = 0.f;
             if (kk * 32 < N) {                                  // warp-uniform
                 for (int c = 0; c < d; ++c) {
                     float k = 0.f;
 #pragma unroll
                     for (int e = 0; e < DL; e += 4) {
-                        const float4 w = *reinterpret_cast<const float4*>(wsm + c * DL + e);
+                        const float4 w = *reinterpret_cast<const float4*>(wsm + c * XP + e);
                         k = fmaf(xr[e], w.x, k); k = fmaf(xr[e + 1], w.y, k); k = fmaf(xr[e + 2], w.z, k); k = fmaf(xr[e + 3], w.w, k);
                     }
                     ss = fmaf(k, k, ss);
 #pragma unroll
-                    for (int qi = 0; qi < L2S_MAXQ; ++qi) if (qi < NQ) dot[qi] = fmaf(qs[qi * d + c], k, dot[qi]);
+                    for (int qi = 0; qi < NQC; ++qi) if (qi < NQ) dot[qi] = fmaf(qs[qi * d + c], k, dot[qi]);
                 }
             }
             const float inv = a.scale / fmaxf(sqrtf(ss), D4_L2_EPS);
 #pragma unroll
-            for (int qi = 0; qi < L2S_MAXQ; ++qi) sc[kk][qi] = (j < N) ? dot[qi] * inv : -INFINITY;
+            for (int qi = 0; qi < NQC; ++qi) sc[kk][qi] = (j < N) ? dot[qi] * inv : -INFINITY;
+        }
         }
         // ---- softmax over the N keys of every query
 #pragma unroll
-        for (int qi = 0; qi < L2S_MAXQ; ++qi) {
+        for (int qi = 0; qi < NQC; ++qi) {
             if (qi < NQ) {
                 const float mx = warp_max(fmaxf(sc[0][qi], sc[1][qi]));
                 const float e0 = (lane < N) ? expf(sc[0][qi] - mx) : 0.f, e1 = (lane + 32 < N) ? expf(sc[1][qi] - mx) : 0.f;
                 const float inv = 1.f / warp_sum(e0 + e1);
-                pw[lane * L2S_MAXQ + qi] = e0 * inv;
-                pw[(lane + 32) * L2S_MAXQ + qi] = e1 * inv;
+                pw[lane * NQC + qi] = e0 * inv;
+                pw[(lane + 32) * NQC + qi] = e1 * inv;
             }
         }
         __syncwarp();
@@ -110,39 +188,44 @@ __global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
 #pragma unroll
         for (int eb = 0; eb < DL; eb += 32) {
             const int e = eb + lane;
-            float z[L2S_MAXQ];
+            float z[NQC];
 #pragma unroll
-            for (int qi = 0; qi < L2S_MAXQ; ++qi) z[qi] = 0.f;
+            for (int qi = 0; qi < NQC; ++qi) z[qi] = 0.f;
             if (e < DL) {
                 for (int j = 0; j < N; ++j) {
-                    const float xv = xs[j * DL + e];
-                    const float4 p0 = *reinterpret_cast<const float4*>(pw + j * L2S_MAXQ), p1 = *reinterpret_cast<const float4*>(pw + j * L2S_MAXQ + 4);
-                    z[0] = fmaf(p0.x, xv, z[0]); z[1] = fmaf(p0.y, xv, z[1]); z[2] = fmaf(p0.z, xv, z[2]); z[3] = fmaf(p0.w, xv, z[3]);
-                    z[4] = fmaf(p1.x, xv, z[4]); z[5] = fmaf(p1.y, xv, z[5]); z[6] = fmaf(p1.z, xv, z[6]); z[7] = fmaf(p1.w, xv, z[7]);
+                    const float xv = xs[j * XP + e];
+#pragma unroll
+                    for (int q4 = 0; q4 < NQC; q4 += 4) {
+                        const float4 p4 = *reinterpret_cast<const float4*>(pw + j * NQC + q4);
+                        z[q4] = fmaf(p4.x, xv, z[q4]); z[q4 + 1] = fmaf(p4.y, xv, z[q4 + 1]);
+                        z[q4 + 2] = fmaf(p4.z, xv, z[q4 + 2]); z[q4 + 3] = fmaf(p4.w, xv, z[q4 + 3]);
+                    }
                 }
 #pragma unroll
-                for (int qi = 0; qi < L2S_MAXQ; ++qi) zs[qi * DL + e] = z[qi];
+                for (int qi = 0; qi < NQC; ++qi) zs[qi * DL + e] = z[qi];
             }
         }
         __syncwarp();
         // ---- values: o_q = W_v,h z_q, head gate, store : lane = head channel
         {
             const float4* src = reinterpret_cast<const float4*>(a.w_v + (long long)hk * d * DL);
-            float4* dst = reinterpret_cast<float4*>(wsm);
-            for (int idx = lane; idx < d * DL / 4; idx += 32) dst[idx] = __ldg(src + idx);
+            for (int idx = lane; idx < d * DL / 4; idx += 32) {
+                const int c = idx / (DL / 4), e = (idx % (DL / 4)) * 4;
+                *reinterpret_cast<float4*>(wsm + c * XP + e) = __ldg(src + idx);
+            }
         }
         __syncwarp();
         for (int c = lane; c < d; c += 32) {
-            float o[L2S_MAXQ];
+            float o[NQC];
 #pragma unroll
-            for (int qi = 0; qi < L2S_MAXQ; ++qi) o[qi] = 0.f;
+            for (int qi = 0; qi < NQC; ++qi) o[qi] = 0.f;
 #pragma unroll
             for (int e = 0; e < DL; e += 4) {
                 // row c of W_v: lanes read different rows -> rotate the chunk order so the 32 rows hit distinct banks
-                const int er = (e + 4 * lane) % DL;
-                const float4 w = *reinterpret_cast<const float4*>(wsm + c * DL + er);
+                const int er = e;          // rows are XP = DL + 4 floats apart: lanes reading different rows hit different banks
+                const float4 w = *reinterpret_cast<const float4*>(wsm + c * XP + er);
 #pragma unroll
-                for (int qi = 0; qi < L2S_MAXQ; ++qi) {
+                for (int qi = 0; qi < NQC; ++qi) {
                     if (qi < NQ) {
                         const float4 z = *reinterpret_cast<const float4*>(zs + qi * DL + er);
                         o[qi] = fmaf(w.x, z.x, o[qi]); o[qi] = fmaf(w.y, z.y, o[qi]); o[qi] = fmaf(w.z, z.z, o[qi]); o[qi] = fmaf(w.w, z.w, o[qi]);
@@ -150,7 +233,7 @@ __global__ void __launch_bounds__(256) l2s_fused_kernel(L2sArgs a) {
                 }
             }
 #pragma unroll
-            for (int qi = 0; qi < L2S_MAXQ; ++qi) {
+            for (int qi = 0; qi < NQC; ++qi) {
                 if (qi < NQ) {
                     const int i = qi / a.g, gi = qi - i * a.g, hq = hk * a.g + gi;
                     const float gate = sigmoidf_(a.gate[i * a.hq + hq]);
@@ -254,26 +337,32 @@ int d4_l2s_fused_supported(const L2sArgs& a) {
            (reinterpret_cast<uintptr_t>(a.w_k) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w_v) & 15) == 0;
 }
 
-template <int DL>
-static int launch_l2s(const L2sArgs& a, cudaStream_t s) {
+template <int DL, bool MMA, int NQC>
+static int launch_l2s_q(const L2sArgs& a, cudaStream_t s) {
     const int nwarps = a.h < 8 ? a.h : 8;
-    const size_t smem = sizeof(float) * ((size_t)L2S_MAXN * DL + (size_t)nwarps * (L2S_MAXN * L2S_MAXQ + L2S_MAXQ * DL + L2S_MAXQ * a.d + a.d * DL));
+    const size_t smem = sizeof(float) * ((size_t)L2S_MAXN * (DL + 4) + (size_t)nwarps * (L2S_MAXN * NQC + NQC * DL + NQC * a.d + a.d * (DL + 4)));
     static size_t configured = 0;
     if (smem > configured) {
-        D4_CUDA_OK(cudaFuncSetAttribute(l2s_fused_kernel<DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        D4_CUDA_OK(cudaFuncSetAttribute(l2s_fused_kernel<DL, MMA, NQC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    l2s_fused_kernel<DL><<<a.B, nwarps * 32, smem, s>>>(a);
+    l2s_fused_kernel<DL, MMA, NQC><<<a.B, nwarps * 32, smem, s>>>(a);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <int DL, bool MMA>
+static int launch_l2s(const L2sArgs& a, cudaStream_t s) {      // 4-query tiles keep two CTAs per SM at the default 4 spatial tokens
+    return (a.nsp * a.g <= 4) ? launch_l2s_q<DL, MMA, 4>(a, s) : launch_l2s_q<DL, MMA, 8>(a, s);
 }
 
 int d4_l2s_fused(const L2sArgs& a, cudaStream_t s) {
     if (a.B <= 0) return 0;
     if (!d4_l2s_fused_supported(a)) return d4_fail("l2s_fused: unsupported shape");
-    if (a.Dl == 16) return launch_l2s<16>(a, s);
-    if (a.Dl == 32) return launch_l2s<32>(a, s);
-    return launch_l2s<64>(a, s);
+    const bool mma = a.allow_tensor && (a.d % 8 == 0);
+    if (a.Dl == 16) return mma ? launch_l2s<16, true>(a, s) : launch_l2s<16, false>(a, s);
+    if (a.Dl == 32) return mma ? launch_l2s<32, true>(a, s) : launch_l2s<32, false>(a, s);
+    return mma ? launch_l2s<64, true>(a, s) : launch_l2s<64, false>(a, s);
 }
 
 int d4_lp_fused_supported(const LpArgs& a) {

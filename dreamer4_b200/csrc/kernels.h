@@ -92,6 +92,7 @@ struct L2sArgs {
     const float* k_gamma;         // (h, d)
     float* out;                   // (B, nsp, Dq)
     float scale;
+    int allow_tensor;             // key projection on mma.sync 3xTF32 tiles (tensor-core engine modes); 0 = exact-fp32 FMA
 };
 int d4_l2s_fused_supported(const L2sArgs& a);
 int d4_l2s_fused(const L2sArgs& a, cudaStream_t s);

@@ -223,11 +223,14 @@ def run_native(args):
     e2e_value = frames / (ms_e2e / 1e3)
     pk = peaks()
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32' if args.precision == 'fp32' else args.precision,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='tf32' if args.precision == 'tf32' else 'f32',
                 data='synthetic', impl='native',
                 config=dict(workload=f'{args.workload}: BASELINE.json configs[{dict(config1=0, config2=1, config3=2, config4=3)[args.workload]}] model, '
                                      f'{B} dreams x {H} frames per GPU, 4 denoise + 1 clean pass per frame, generate + learn_from_experience + AdamW',
-                            dreams_per_gpu=B, horizon=H, global_dreams=world * B, precision=args.precision, time_attn_variant=args.variant,
+                            dreams_per_gpu=B, horizon=H, global_dreams=world * B, precision=args.precision,
+                            precision_note={'tf32x3': 'fp32 in / fp32 out; every dense product = 3 TF32 tensor-core MMAs (hi/lo split), fp32 accumulate: fp32-level accuracy',
+                                            'fp32': 'exact fp32 FMA on CUDA cores', 'tf32': 'single-pass TF32 operands (reduced precision)'}[args.precision],
+                            time_attn_variant=args.variant,
                             parallelism=f'dp{world} (dream batch sharded, one flat gradient all-reduce)',
                             l2='inputs larger than L2 (KV cache + activations per pass >> 126 MB)' if B * H >= 4096 else 'small problem: L2 resident'),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12, ms_per_step=ms_e2e / args.steps),

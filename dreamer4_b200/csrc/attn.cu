@@ -567,7 +567,9 @@ __global__ void __launch_bounds__(PL_WARPS * 32) pool_attn_kernel(SmallAttnArgs 
             for (int hh = 0; hh < 4; ++hh) g4[hh] += __shfl_xor_sync(D4_FULL, g4[hh], off);
         }
         const int hh = lane >> 3;
-        const float logit = (hh == 0 ? g4[0] : hh == 1 ? g4[1] : hh == 2 ? g4[2] : g4[3]) * a.gate_rstd[tok];
+        float rstd = a.gate_rstd[tok];
+        if (a.gate_rstd_is_ss) rstd = rsqrtf(rstd / (float)a.gate_D + D4_RMS_EPS);
+        const float logit = (hh == 0 ? g4[0] : hh == 1 ? g4[1] : hh == 2 ? g4[2] : g4[3]) * rstd;
         gate = sigmoidf_(logit);
     } else if (a.gate) {
         gate = sigmoidf_(a.gate[tok * a.gate_sb + (lane >> 3)]);

@@ -69,6 +69,12 @@ struct GemmArgs {
     // operand layouts (exact-fp32 path only; used by the learn_from_experience backward GEMMs):
     //   transA: A is stored (K, M) — element (m,k) at A[k*lda + m];  transW: W is stored (K, N) — element (n,k) at W[k*ldw + n]
     int transA, transW;
+    // CTA-pair tensor-core path only (gemm_tc3.cu, TMA epilogue, identity output rows):
+    //   rs_mode 1: row_scale[m] holds the SUM OF SQUARES of A's row m; the epilogue scales by rsqrt(ss / K + eps) (the RMSNorm
+    //              statistic, with K the normalised width) instead of reading a precomputed rstd
+    //   ss_out   : the epilogue atomically adds sum_n C[m][n]^2 into ss_out[m] (feeds the next consumer's rs_mode 1)
+    int rs_mode;
+    float* ss_out;
 };
 
 static inline GemmArgs gemm_args(const float* A, long long lda, const float* W, long long ldw, float* C, long long ldc,
@@ -76,7 +82,7 @@ static inline GemmArgs gemm_args(const float* A, long long lda, const float* W, 
     GemmArgs g;
     g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.W_lo = nullptr; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
     g.bias = nullptr; g.row_scale = nullptr; g.residual = nullptr; g.ldr = 0; g.act = D4_ACT_NONE;
-    g.amap = rowmap_identity(); g.cmap = rowmap_identity(); g.transA = 0; g.transW = 0;
+    g.amap = rowmap_identity(); g.cmap = rowmap_identity(); g.transA = 0; g.transW = 0; g.rs_mode = 0; g.ss_out = nullptr;
     return g;
 }
 

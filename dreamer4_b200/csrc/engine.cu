@@ -69,6 +69,7 @@ extern "C" int d4_ctx_create(const d4_config* cfg, d4_ctx** out) {
     if (bad) { delete c; return d4_fail("d4_ctx_create: %s", bad); }
     { const char* f = getenv("D4_FUSE_POOLS"); c->fuse_pools = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_SPACE_MMA"); c->space_mma = f ? atoi(f) != 0 : true; }
+    { const char* f = getenv("D4_FUSE_SS"); c->fuse_ss = f ? atoi(f) != 0 : true; }
     d4_engine_plan(c);
     *out = c;
     return 0;
@@ -93,7 +94,7 @@ int d4_engine_plan(d4_ctx* c) {
     auto take = [&](long long nfloats) { long long o = off; off += (nfloats * 4 + 255) / 256 * 256; return o; };
     struct { float** p; long long n; } items[] = {
         {&c->b.lat_x, B * c->N * c->Dl}, {&c->b.lat_rstd, B * c->N}, {&c->b.kv_l, B * c->N * 2 * c->Dkv}, {&c->b.att_l, B * c->nsp * c->Dq},
-        {&c->b.hid, (long long)c->n_hid * M * c->D}, {&c->b.hid_rstd, (long long)c->n_hid * M}, {&c->b.x_cur, M * c->D}, {&c->b.x_rstd, M},
+        {&c->b.hid, (long long)c->n_hid * M * c->D}, {&c->b.hid_rstd, (long long)c->n_hid * M}, {&c->b.x_cur, M * c->D}, {&c->b.x_rstd, (long long)(c->L + 1) * M},
         {&c->b.qkvgm, M * c->ldq}, {&c->b.v0, M * c->Dkv}, {&c->b.attn_o, M * c->Dq}, {&c->b.ff_mid, M * c->inner_pad},
         {&c->b.pool_qg, M * c->ldpq}, {&c->b.pool_kv, (long long)c->n_hid * M * 2 * c->Dp}, {&c->b.pool_att, M * c->Dp},
         {&c->b.fa_kv, M * 2 * c->Dkv}, {&c->b.fa_q, B * c->ldfa}, {&c->b.fa_att, B * c->Dq}, {&c->b.ag_rstd, B},
@@ -313,7 +314,10 @@ int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, in
 // ------------------------------------------------------------------------------------------------ the pass
 namespace {
 
-int run_pool(d4_ctx* c, const PoolW& P, int M, const float* xq, const float* xq_rstd, int n, float* out, cudaStream_t s) {
+// xq_ss / ctx_ss: the row statistic buffers hold sums of squares (fused into the producing GEMMs) instead of rstd;
+// ss_out: where the output rows' sums of squares are accumulated (or nullptr)
+int run_pool(d4_ctx* c, const PoolW& P, int M, const float* xq, const float* xq_rstd, int xq_ss, int ctx_ss, int n, float* out, float* ss_out,
+             cudaStream_t s) {
     const int D = c->D, Dp = c->Dp, hp = c->hp, dp = c->dp;
     SmallAttnArgs a; memset(&a, 0, sizeof(a));
     a.nb = M; a.hkv = hp; a.g = 1; a.d = dp; a.nq = 1; a.n = n;
@@ -325,36 +329,36 @@ int run_pool(d4_ctx* c, const PoolW& P, int M, const float* xq, const float* xq_
     a.scale = 1.f / sqrtf((float)dp);
     // the 4 gate rows ride along in w_qg (rows Dp .. Dp+hp); when the pool kernel can form the gate logits itself the q
     // projection is an exact 256-column GEMM (one full tile instead of 260 -> 3 x 128 with 48 % padding)
-    a.gate_x = xq; a.gate_x_ld = D; a.gate_rstd = xq_rstd; a.gate_w = P.w_qg.w + (long long)Dp * D; a.gate_D = D;
+    a.gate_x = xq; a.gate_x_ld = D; a.gate_rstd = xq_rstd; a.gate_w = P.w_qg.w + (long long)Dp * D; a.gate_D = D; a.gate_rstd_is_ss = xq_ss;
     const bool gate_in_kernel = d4_pool_attn_ok(a) != 0;
     if (!gate_in_kernel) {
-        a.gate_x = nullptr; a.gate_rstd = nullptr; a.gate_w = nullptr; a.gate_D = 0;
+        a.gate_x = nullptr; a.gate_rstd = nullptr; a.gate_w = nullptr; a.gate_D = 0; a.gate_rstd_is_ss = 0;
         a.gate = c->b.pool_qg + Dp; a.gate_sb = c->ldpq; a.gate_si = 0;
     }
     {   // query (+ gate logits) from the normed token
         GemmArgs g = gemm_args(xq, D, nullptr, D, c->b.pool_qg, c->ldpq, M, gate_in_kernel ? Dp : Dp + hp, D);
-        g.row_scale = xq_rstd;
+        g.row_scale = xq_rstd; g.rs_mode = xq_ss;
         D4_TRY(d4_engine_gemm(c, g, P.w_qg, 0, s));
     }
     {   // keys / values of all hiddens so far, re-projected by this pool (reference dreamer4.py:2164-2177)
         GemmArgs g = gemm_args(c->b.hid, D, nullptr, D, c->b.pool_kv, 2 * Dp, n * M, 2 * Dp, D);
-        g.row_scale = c->b.hid_rstd;
+        g.row_scale = c->b.hid_rstd; g.rs_mode = ctx_ss;
         D4_TRY(d4_engine_gemm(c, g, P.w_kv, 0, s));
     }
     { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
     GemmArgs g = gemm_args(c->b.pool_att, Dp, nullptr, Dp, out, D, M, D, Dp);
-    g.residual = xq; g.ldr = D;
+    g.residual = xq; g.ldr = D; g.ss_out = ss_out;
     return d4_engine_gemm(c, g, P.w_out, 0, s);
 }
 
-int run_ff(d4_ctx* c, const FFW& F, int M, const float* x, long long ldx, RowMap xmap, const float* x_rstd, float* out, long long ldo, RowMap omap,
-           cudaStream_t s) {
+int run_ff(d4_ctx* c, const FFW& F, int M, const float* x, long long ldx, RowMap xmap, const float* x_rstd, int x_ss, float* out, long long ldo, RowMap omap,
+           float* ss_out, cudaStream_t s) {
     const int D = c->D;
     GemmArgs g = gemm_args(x, ldx, nullptr, D, c->b.ff_mid, c->inner_pad, M, 2 * c->inner, D);
-    g.amap = xmap; g.row_scale = x_rstd; g.bias = F.b_in; g.act = c->cfg.ff_act == 1 ? D4_ACT_GLU_GELU : D4_ACT_GLU_SILU;
+    g.amap = xmap; g.row_scale = x_rstd; g.rs_mode = x_ss; g.bias = F.b_in; g.act = c->cfg.ff_act == 1 ? D4_ACT_GLU_GELU : D4_ACT_GLU_SILU;
     D4_TRY(d4_engine_gemm(c, g, F.w_in, 0, s));
     GemmArgs g2 = gemm_args(c->b.ff_mid, c->inner_pad, nullptr, c->inner_pad, out, ldo, M, D, c->inner_pad);
-    g2.bias = F.b_out; g2.residual = x; g2.ldr = ldx; g2.cmap = omap;
+    g2.bias = F.b_out; g2.residual = x; g2.ldr = ldx; g2.cmap = omap; g2.ss_out = ss_out;
     // residual rows follow the output row map (x and out share their row layout in every use)
     return d4_engine_gemm(c, g2, F.w_out, 0, s);
 }
@@ -411,10 +415,21 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
         a.task_emb = c->task_emb; a.tasks = (tasks && c->task_emb) ? reinterpret_cast<const long long*>(tasks) : nullptr;
         D4_TRY(d4_assemble_tokens(a, s));
     }
-    D4_TRY(d4_row_rstd(hid(0), D, rowmap_identity(), M, D, hrs(0), s));
+    // RMS statistics.  Fused mode (CTA-pair tensor-core GEMMs, D <= 512 so a row spans at most two column tiles and the two
+    // atomic partial sums commute): every GEMM that produces a residual-stream snapshot accumulates the rows' sums of squares in
+    // its epilogue and every consumer turns them into rstd on the fly — no separate pass re-reads the 63 MB snapshots.
+    const int fss = (c->fuse_ss && c->cfg.precision == D4_PREC_TF32X3 && M > 128 && D <= 512 && (D % 4) == 0 && d4_gemm_pair_default()) ? 1 : 0;
+    auto xss = [&](int j) { return c->b.x_rstd + (long long)j * M; };
+    if (fss) {
+        D4_CUDA_OK(cudaMemsetAsync(hrs(1), 0, (size_t)(c->n_hid - 1) * M * 4, s));
+        D4_CUDA_OK(cudaMemsetAsync(c->b.x_rstd, 0, (size_t)L * M * 4, s));
+        D4_TRY(d4_row_sumsq(hid(0), D, M, D, hrs(0), s));
+    } else {
+        D4_TRY(d4_row_rstd(hid(0), D, rowmap_identity(), M, D, hrs(0), s));
+    }
     {   // value residual (reference dreamer4.py:3026-3027)
         GemmArgs g = gemm_args(hid(0), D, nullptr, D, c->b.v0, Dkv, M, Dkv, D);
-        g.row_scale = hrs(0);
+        g.row_scale = hrs(0); g.rs_mode = fss;
         D4_TRY(d4_engine_gemm(c, g, c->vr_w, 0, s));
     }
 
@@ -424,7 +439,7 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
     for (int i = 0; i < L; ++i) {
         {
             GemmArgs g = gemm_args(x_in, D, nullptr, D, c->b.qkvgm, c->ldq, M, c->NQ, D);
-            g.row_scale = x_in_rstd; g.bias = c->attn[i].b;
+            g.row_scale = x_in_rstd; g.rs_mode = fss; g.bias = c->attn[i].b;
             D4_TRY(d4_engine_gemm(c, g, c->attn[i].w, 0, s));
         }
         const int off_k = Dq, off_v = Dq + Dkv, off_g = Dq + 2 * Dkv, off_m = Dq + 2 * Dkv + hq;
@@ -460,16 +475,17 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
         }
         {
             GemmArgs g = gemm_args(c->b.attn_o, Dq, nullptr, Dq, hid(2 * i + 1), D, M, D, Dq);
-            g.residual = x_in; g.ldr = D;
+            g.residual = x_in; g.ldr = D; g.ss_out = fss ? hrs(2 * i + 1) : nullptr;
             D4_TRY(d4_engine_gemm(c, g, c->attn[i].w_out, 0, s));
         }
-        D4_TRY(d4_row_rstd(hid(2 * i + 1), D, rowmap_identity(), M, D, hrs(2 * i + 1), s));
-        D4_TRY(run_ff(c, c->ff[i], M, hid(2 * i + 1), D, rowmap_identity(), hrs(2 * i + 1), hid(2 * i + 2), D, rowmap_identity(), s));
-        D4_TRY(d4_row_rstd(hid(2 * i + 2), D, rowmap_identity(), M, D, hrs(2 * i + 2), s));
+        if (!fss) D4_TRY(d4_row_rstd(hid(2 * i + 1), D, rowmap_identity(), M, D, hrs(2 * i + 1), s));
+        D4_TRY(run_ff(c, c->ff[i], M, hid(2 * i + 1), D, rowmap_identity(), hrs(2 * i + 1), fss, hid(2 * i + 2), D, rowmap_identity(),
+                      fss ? hrs(2 * i + 2) : nullptr, s));
+        if (!fss) D4_TRY(d4_row_rstd(hid(2 * i + 2), D, rowmap_identity(), M, D, hrs(2 * i + 2), s));
         if (i != L - 1) {
-            D4_TRY(run_pool(c, c->pools[i], M, hid(2 * i + 2), hrs(2 * i + 2), 2 * i + 3, c->b.x_cur, s));
-            D4_TRY(d4_row_rstd(c->b.x_cur, D, rowmap_identity(), M, D, c->b.x_rstd, s));
-            x_in = c->b.x_cur; x_in_rstd = c->b.x_rstd;
+            D4_TRY(run_pool(c, c->pools[i], M, hid(2 * i + 2), hrs(2 * i + 2), fss, fss, 2 * i + 3, c->b.x_cur, fss ? xss(i) : nullptr, s));
+            if (!fss) D4_TRY(d4_row_rstd(c->b.x_cur, D, rowmap_identity(), M, D, xss(i), s));
+            x_in = c->b.x_cur; x_in_rstd = xss(i);
         }
     }
 
@@ -483,7 +499,7 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
         g.amap = agent_rows; g.row_scale = c->b.ag_rstd;
         D4_TRY(d4_engine_gemm(c, g, c->fa.w_qg, 0, s));
         GemmArgs g2 = gemm_args(hid(2 * L), D, nullptr, D, c->b.fa_kv, 2 * Dkv, M, 2 * Dkv, D);
-        g2.row_scale = hrs(2 * L);
+        g2.row_scale = hrs(2 * L); g2.rs_mode = fss;
         D4_TRY(d4_engine_gemm(c, g2, c->fa.w_kv, 0, s));
         SmallAttnArgs a; memset(&a, 0, sizeof(a));
         a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = 1; a.n = S - 1;
@@ -500,10 +516,10 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
         D4_TRY(d4_engine_gemm(c, g3, c->fa.w_out, 0, s));
     }
     D4_TRY(d4_row_rstd(xf, D, agent_rows, B, D, c->b.ag_rstd, s));
-    D4_TRY(run_ff(c, c->fa_ff, B, xf, D, agent_rows, c->b.ag_rstd, xf, D, agent_rows, s));
+    D4_TRY(run_ff(c, c->fa_ff, B, xf, D, agent_rows, c->b.ag_rstd, 0, xf, D, agent_rows, nullptr, s));
     // final attention-residual pool over all 2L+1 hiddens (reference dreamer4.py:3242-3243)
-    D4_TRY(d4_row_rstd(xf, D, rowmap_identity(), M, D, c->b.x_rstd, s));
-    D4_TRY(run_pool(c, c->pool_final, M, xf, c->b.x_rstd, c->n_hid, xf, s));
+    D4_TRY(d4_row_rstd(xf, D, rowmap_identity(), M, D, xss(L), s));          // xf = last snapshot with the agent rows updated: own pass
+    D4_TRY(run_pool(c, c->pool_final, M, xf, xss(L), 0, fss, c->n_hid, xf, nullptr, s));
 
     // ---- outputs: agent embedding and the latent prediction (reference dreamer4.py:7251, 4830-4834)
     if (agent_out) D4_TRY(d4_copy_rows(xf + (long long)(S - 1) * D, (long long)S * D, agent_out, D, B, D, s));

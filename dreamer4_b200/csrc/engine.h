@@ -57,6 +57,7 @@ struct d4_ctx {
 
     // in-situ profiling (d4_profile / d4_profile_read)
     bool prof_on = false;
+    bool fuse_ss = true;         // RMS statistics accumulated in the producing GEMM's epilogue (D4_FUSE_SS=0: separate row pass)
     bool space_mma = true;       // space attention on mma.sync 3xTF32 tiles in the tensor-core engine modes (D4_SPACE_MMA=0: FMA kernel)
     bool fuse_pools = true;      // fused latent<->space pool kernels (fused_pools.cu); D4_FUSE_POOLS=0 keeps the GEMM + attention path
     struct ProfRec { cudaEvent_t a, b; int cls; double work; };

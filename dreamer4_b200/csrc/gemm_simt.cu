@@ -122,6 +122,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 int d4_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0) return 0;
+    if (g.rs_mode || g.ss_out) return d4_fail("gemm_simt: sum-of-squares row statistics are only implemented by the CTA-pair tensor-core kernel");
     dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN);
     // 128-bit loads need every row start 16B-aligned and the contiguous extent a multiple of 4
     const bool va = al16(g.A) && (g.lda % 4 == 0) && ((g.transA ? g.M : g.K) % 4 == 0);

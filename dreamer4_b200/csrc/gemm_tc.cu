@@ -351,6 +351,12 @@ int d4_gemm_tc_supported(const GemmArgs& g) {
 
 // Default: the CTA-pair kernel in gemm_tc3.cu (single-CTA persistent kernel of gemm_tc2.cu when M fits one CTA's rows).
 // D4_GEMM_V=2 forces gemm_tc2.cu, D4_GEMM_V=1 this one-tile-per-CTA kernel; D4_GEMM_BN=128|256 pins the N tile.
+// 1 if a GEMM with more than 128 rows goes to the CTA-pair kernel (the engine may then fuse the RMS statistics into it)
+int d4_gemm_pair_default(void) {
+    const char* v = getenv("D4_GEMM_V");
+    return (!v || atoi(v) == 3) ? 1 : 0;
+}
+
 int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream) {
     if (!d4_gemm_tc_supported(g)) return d4_fail("gemm_tc: unsupported shape / alignment");
     if (terms == 3 && (!g.W_lo || !al16(g.W_lo))) return d4_fail("gemm_tc: tf32x3 needs a 16-byte aligned W_lo");
@@ -360,6 +366,7 @@ int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream) {
         const char* b = getenv("D4_GEMM_BN"); bn = b ? atoi(b) : 0;
     }
     if (version == 3 && g.M > BM) return d4_gemm_tc3(g, terms == 3 ? 3 : 1, bn, stream);
+    if (g.rs_mode || g.ss_out) return d4_fail("gemm_tc: sum-of-squares row statistics need the CTA-pair kernel (M > 128, D4_GEMM_V unset)");
     if (version != 1) return d4_gemm_tc2(g, terms == 3 ? 3 : 1, bn, stream);
     if (terms == 3) return launch<3>(g, stream);
     return launch<1>(g, stream);

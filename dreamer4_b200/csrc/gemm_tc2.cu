@@ -415,6 +415,7 @@ int launch2(const GemmArgs& g, cudaStream_t stream) {
 
 // persistent kernel entry; bn = 128 or 256 (0 = choose by padding waste)
 int d4_gemm_tc2(const GemmArgs& g, int terms, int bn, cudaStream_t stream) {
+    if (g.rs_mode || g.ss_out) return d4_fail("gemm_tc2: sum-of-squares row statistics are only implemented by the CTA-pair kernel");
     if (bn == 0) {
         const double w128 = (double)((g.N + 127) / 128 * 128) / g.N, w256 = (double)((g.N + 255) / 256 * 256) / g.N;
         const long long tiles256 = (long long)((g.M + BM - 1) / BM) * ((g.N + 255) / 256);

@@ -132,6 +132,8 @@ struct EpiArgs3 {
     int act; RowMap cmap;
     int a_grp, nkb, n_tiles_m, n_tiles_n;
     int tma_epi;        // 1: epilogue through swizzled smem tiles + TMA (residual load, result store); 0: register path
+    int rs_mode, kdim;  // rs_mode 1: row_scale holds sum of squares over kdim columns -> rsqrt(ss / kdim + eps)
+    float* ss_out;      // per output row: += sum of squares of the finished row segment (atomic)
 };
 
 template <int TERMS, int BN, int BK> struct Cfg3 {
@@ -287,7 +289,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                 const int buf_acc = ac & 1; const uint32_t aph = (ac >> 1) & 1;
                 const int rbase = m0 + quarter * 32;
                 const int mrow = rbase + lane;
-                const float rs = (mrow < e.M && e.row_scale) ? e.row_scale[mrow] : 1.f;
+                float rs = (mrow < e.M && e.row_scale) ? e.row_scale[mrow] : 1.f;
+                if (e.rs_mode && e.row_scale) rs = rsqrtf(rs / (float)e.kdim + D4_RMS_EPS);
+                float ss_part = 0.f;                                // this lane's row: sum of squares of the finished columns
                 const uint32_t tmem_c = tmem_base + (uint32_t)(buf_acc * BN) + ((uint32_t)(quarter * 32) << 16);
                 const int out0 = glu ? (n0 >> 1) : n0;              // first output column of this tile
                 const bool rows_ok = rbase < e.M;                   // warp-uniform
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                             float4* dst = reinterpret_cast<float4*>(rowp + (((uint32_t)q ^ swz) << 4));
                             if (has_res) { const float4 r = *dst; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
                             *dst = o;
+                            ss_part = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ss_part))));
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
@@ -358,6 +363,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
                         ++g;
                     }
                 }
+                if (e.ss_out && mrow < e.M) atomicAdd(e.ss_out + mrow, ss_part);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)buf_acc * 8u);
@@ -514,6 +520,8 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
                               (grp == 0 || ((((long long)g.cmap.goff * g.ldr) % 4 == 0) && (((long long)g.cmap.gstride * g.ldr) % 4 == 0)));
     if (!tma_epi) return d4_gemm_tc2(g, TERMS, 0, stream);       // odd alignment / row maps: the register-epilogue kernel
     e.tma_epi = 1;
+    if (g.ss_out && (grp != 0 || glu || (g.N % 4) != 0)) return d4_fail("gemm_tc3: ss_out needs identity output rows, no GLU and N %% 4 == 0");
+    e.rs_mode = g.rs_mode; e.kdim = g.K; e.ss_out = g.ss_out;
     if (tma_epi) {
         { int rc = encode_out(&maps.c, g.C, g.M, glu ? g.N / 2 : g.N, g.ldc, g.cmap); if (rc) return rc; }
         if (g.residual) { int rc = encode_out(&maps.r, g.residual, g.M, g.N, g.ldr, g.cmap); if (rc) return rc; }

@@ -7,6 +7,7 @@ int d4_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 // tcgen05 path: terms = 1 (tf32) or 3 (tf32x3 split: A split in shared memory, W_lo supplied)
 int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream);
 int d4_gemm_tc_supported(const GemmArgs& g);
+int d4_gemm_pair_default(void);
 // persistent warp-specialised tcgen05 kernel (gemm_tc2.cu); bn = 128 / 256 / 0 (auto)
 int d4_gemm_tc2(const GemmArgs& g, int terms, int bn, cudaStream_t stream);
 // CTA-pair (cta_group::2) persistent kernel (gemm_tc3.cu): 256 x bn output tiles, bn = 128 / 256 / 0 (auto)
@@ -26,6 +27,7 @@ struct AssembleArgs {
     const float* task_emb; const long long* tasks;
 };
 int d4_row_rstd(const float* x, long long ldx, RowMap map, int M, int D, float* out, cudaStream_t s);
+int d4_row_sumsq(const float* x, long long ldx, int M, int D, float* out, cudaStream_t s);     // out[m] = sum_d x[m][d]^2
 int d4_rmsnorm_rows(const float* x, long long ldx, RowMap map, const float* w, int M, int D, float* out, long long ldo, cudaStream_t s);
 int d4_ln_act_rows(const float* x, long long ldx, const float* w, const float* b, int M, int D, float* out, long long ldo, int act,
                    float* save_mean, float* save_rstd, cudaStream_t s);
@@ -59,6 +61,7 @@ struct SmallAttnArgs {
     // gate_rstd[b] * (gate_x[b] . gate_w[h]) instead of being read from `gate` (keeps the 4 gate rows out of the q GEMM,
     // whose N then is exactly 256)
     const float* gate_x; long long gate_x_ld; const float* gate_rstd; const float* gate_w; int gate_D;
+    int gate_rstd_is_ss;    // gate_rstd holds the sum of squares of the token row: rstd = rsqrt(ss / gate_D + eps)
     int allow_tensor;       // space attention: 3xTF32 mma.sync tiles allowed (tf32x3 / tf32 engine modes); 0 = exact-fp32 FMA
 };
 int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s);

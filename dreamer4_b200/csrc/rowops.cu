@@ -26,6 +26,13 @@ __global__ void row_rstd_kernel(const float* __restrict__ x, long long ldx, RowM
     if (lane == 0) out[m] = rsqrtf(ss / (float)D + D4_RMS_EPS);
 }
 
+__global__ void row_sumsq_kernel(const float* __restrict__ x, long long ldx, int M, int D, float* __restrict__ out) {
+    const int m = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float ss = row_sumsq(x + (long long)m * ldx, D, lane);
+    if (lane == 0) out[m] = ss;
+}
+
 // out[m] = x[map(m)] * rstd * w        nn.RMSNorm (reference dreamer4.py:1906, 2089, 2822, 4831)
 __global__ void rmsnorm_rows_kernel(const float* __restrict__ x, long long ldx, RowMap map, const float* __restrict__ w,
                                     int M, int D, float* __restrict__ out, long long ldo) {
@@ -206,6 +213,11 @@ inline int nblk(long long n, int per) { return (int)((n + per - 1) / per); }
 int d4_row_rstd(const float* x, long long ldx, RowMap map, int M, int D, float* out, cudaStream_t s) {
     if (M <= 0) return 0;
     row_rstd_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, map, M, D, out);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
+}
+int d4_row_sumsq(const float* x, long long ldx, int M, int D, float* out, cudaStream_t s) {
+    if (M <= 0) return 0;
+    row_sumsq_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, M, D, out);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_rmsnorm_rows(const float* x, long long ldx, RowMap map, const float* w, int M, int D, float* out, long long ldo, cudaStream_t s) {

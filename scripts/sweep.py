@@ -5,7 +5,7 @@ import json
 import subprocess
 import sys
 
-POINTS = [(256, 8), (256, 64), (2048, 8), (2048, 64), (2048, 128), (8192, 8), (8192, 32)]
+POINTS = [(256, 64), (2048, 8), (2048, 64), (8192, 32)] if len(sys.argv) > 2 and sys.argv[2] == "short" else [(256, 8), (256, 64), (2048, 8), (2048, 64), (2048, 128), (8192, 8), (8192, 32)]
 out = open(sys.argv[1], 'w') if len(sys.argv) > 1 else None
 for b, h in POINTS:
     r = subprocess.run([sys.executable, 'bench.py', '--batch', str(b), '--horizon', str(h), '--steps', '1', '--warmup', '1', '--no-cpu-baseline'],

@@ -45,8 +45,9 @@ typedef struct d4_config {
     int32_t num_tasks;
     float   softclamp;                               /* attn_softclamp_value (50) */
     int32_t max_batch, max_time;                     /* KV cache / workspace capacity */
-    int32_t precision;                               /* D4_PREC_* for the transformer; heads always run exact fp32 */
-    int32_t time_attn_variant;                       /* 0 ld.global staged, 1 cp.async.bulk ring */
+    int32_t precision;                               /* D4_PREC_* of every dense layer (transformer, heads, d4_learn); the final
+                                                        action unembedding and ragged / tiny GEMMs always run exact fp32 FMA */
+    int32_t time_attn_variant;                       /* K1: 1 cp.async.bulk ring (default of the host class), 0 ld.global staged */
 } d4_config;
 
 typedef struct d4_ctx d4_ctx;

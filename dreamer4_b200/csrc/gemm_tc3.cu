@@ -113,7 +113,7 @@ template <int TERMS, int BN, int BK> struct Cfg3 {
     static constexpr int STAGE = (TERMS == 3) ? 2 * A_TILE + 2 * W_TILE : A_TILE + W_TILE;
     static constexpr int NS = (192 * 1024) / STAGE;                     // BK 32: 3 (x3, BN 256), 4 (x3, 128), 6 / 8 (x1); BK 16: twice that
     static constexpr int STG_BYTES = 4 * 2 * 4096;                      // per epilogue warp: two 32 x 32 fp32 tiles (128B-swizzled)
-    static constexpr int NBARS = 5 * NS + 4 + 8;                        // full | fullA | empty | split | aready | tfull[2] | tempty[2] | resid[4][2]
+    static constexpr int NBARS = 4 * NS + 4 + 8;                        // full | fullA | empty | split | tfull[2] | tempty[2] | resid[4][2]
     static constexpr int SMEM = NS * STAGE + STG_BYTES + NBARS * 8 + 64 + 1024;
     // instruction descriptor: D=f32, A=B=tf32, K-major, N>>3 at bit 17, M>>4 at bit 24 with M = 256 (the pair's rows)
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -130,8 +130,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * K::STAGE + K::STG_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + K::NBARS);
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
-    constexpr int B_FULL = 0, B_FULLA = NS, B_EMPTY = 2 * NS, B_SPLIT = 3 * NS, B_AREADY = 4 * NS, B_TFULL = 5 * NS, B_TEMPTY = 5 * NS + 2,
-                  B_RES = 5 * NS + 4;
+    constexpr int B_FULL = 0, B_FULLA = NS, B_EMPTY = 2 * NS, B_SPLIT = 3 * NS, B_TFULL = 4 * NS, B_TEMPTY = 4 * NS + 2, B_RES = 4 * NS + 4;
     constexpr int T_A = 0, T_ALO = A_TILE, T_W = (TERMS == 3) ? 2 * A_TILE : A_TILE, T_WLO = T_W + K::W_TILE;
     auto tile = [&](int stage, int off) { return smem + stage * K::STAGE + off; };
 
@@ -149,7 +148,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc3_kernel(const __grid_c
         if (e.tma_epi && e.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.r) : "memory");
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_FULLA + s), 1); mbar_init(bar(B_EMPTY + s), 1); mbar_init(bar(B_SPLIT + s), 2);
-            mbar_init(bar(B_AREADY + s), 2);       // (unused: kept so the barrier block layout stays put)
         }
         for (int b = 0; b < 2; ++b) { mbar_init(bar(B_TFULL + b), 1); mbar_init(bar(B_TEMPTY + b), 8); }
         for (int b = 0; b < 8; ++b) mbar_init(bar(B_RES + b), 1);

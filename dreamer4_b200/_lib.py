@@ -68,8 +68,13 @@ class d4_learn_io(C.Structure):
         ('grad_policy_w', _PTR_ARR), ('grad_policy_b', _PTR_ARR), ('grad_policy_lnw', _PTR_ARR), ('grad_policy_lnb', _PTR_ARR),
         ('grad_unembed', C.c_void_p), ('grad_unembed_ld', C.c_int64),
         ('grad_value_w', _PTR_ARR), ('grad_value_b', _PTR_ARR), ('grad_value_lnw', _PTR_ARR), ('grad_value_lnb', _PTR_ARR),
+        ('objective', C.c_int32), ('pmpo_reverse_kl', C.c_int32),
+        ('pmpo_pos_to_neg_weight', C.c_float), ('pmpo_kl_div_loss_weight', C.c_float),
+        ('old_action_unembeds', C.c_void_p), ('old_action_unembeds_ld', C.c_int64),
     ]
 
+
+OBJECTIVES = {'ppo': 0, 'spo': 1, 'pmpo': 2}      # D4_OBJECTIVE_* in include/d4b200.h
 
 # every symbol include/d4b200.h declares: (name, restype, argtypes)
 _i, _i64, _f, _p = C.c_int, C.c_int64, C.c_float, C.c_void_p

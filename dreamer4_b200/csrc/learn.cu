@@ -102,12 +102,15 @@ __global__ void adv_stats_kernel(long long R, const float* __restrict__ returns,
     if (threadIdx.x == 0) { stats[0] = n; stats[1] = mean; stats[2] = var; }
 }
 
-// ---- PPO row kernel: per (b,t) row -> surrogate / entropy loss terms and d(total_policy_loss)/d(logits)
+// ---- policy row kernel: per (b,t) row -> surrogate / entropy loss terms and d(total_policy_loss)/d(logits)
+// objective: D4_OBJECTIVE_PPO (clipped ratio, 6200-6212), _SPO (quadratic trust region, 6184-6198), _PMPO (sign-weighted
+// log-likelihood + KL to the stored unembeds, 6127-6182)
 struct PpoArgs {
     int R, na, A_total; const int* sizes_offs;
     const float* logits; long long ld;
     const long long* actions; const float* old_logp; const float* adv; const unsigned char* mask; const float* stats;
     float eps_clip, entropy_weight, delight_temp; int use_gate;
+    int objective; float pmpo_alpha, pmpo_kl_weight; int pmpo_reverse_kl; const float* old_logits; long long ld_old;
     float* dlogits; float* row_pl; float* row_ent;
 };
 __global__ void ppo_row_kernel(PpoArgs p) {
@@ -140,15 +143,27 @@ __global__ void ppo_row_kernel(PpoArgs p) {
         ent_sum += h;
     }
     const float A = p.adv[r];
-    const float ratio = expf(logp - oldlp);
-    const float clipped = fminf(fmaxf(ratio, 1.f - p.eps_clip), 1.f + p.eps_clip);
-    const float s1 = ratio * A, s2 = clipped * A;
-    float pl = -fminf(s1, s2);
-    const float gate = p.use_gate ? sigmoidf_((-logp * A) / p.delight_temp) : 1.f;
-    pl *= gate;
-    // d(-min(s1,s2))/dlogp: the unclipped branch (or the tie inside the clip range) passes A*ratio, the clipped branch 0
-    const bool pass = (s1 <= s2);
-    const float dlogp = pass ? -gate * A * ratio * inv_n : 0.f;
+    const float gate = p.use_gate ? sigmoidf_((-logp * A) / p.delight_temp) : 1.f;      // detached in the reference (6119-6120)
+    float pl, dlogp;
+    if (p.objective == D4_OBJECTIVE_PMPO) {
+        // -alpha * (sum_{A>=0} g*logp*|tanh A| - sum_{A<0} g*logp*|tanh A|) / n
+        const float w = p.pmpo_alpha * fabsf(tanhf(A)) * gate * (A >= 0.f ? 1.f : -1.f);
+        pl = -w * logp;
+        dlogp = -w * inv_n;
+    } else {
+        const float ratio = expf(logp - oldlp);
+        if (p.objective == D4_OBJECTIVE_SPO) {
+            const float q = fabsf(A) / (2.f * p.eps_clip), d = ratio - 1.f;
+            pl = -(ratio * A - q * d * d) * gate;
+            dlogp = -(A - 2.f * q * d) * ratio * gate * inv_n;
+        } else {
+            const float clipped = fminf(fmaxf(ratio, 1.f - p.eps_clip), 1.f + p.eps_clip);
+            const float s1 = ratio * A, s2 = clipped * A;
+            pl = -fminf(s1, s2) * gate;
+            // d(-min(s1,s2))/dlogp: the unclipped branch (or the tie inside the clip range) passes A*ratio, the clipped branch 0
+            dlogp = (s1 <= s2) ? -gate * A * ratio * inv_n : 0.f;
+        }
+    }
     // pass 2: gradients
     for (int t = 0; t < p.na; ++t) {
         const int sz = p.sizes_offs[t], off = p.sizes_offs[p.na + t];
@@ -160,6 +175,30 @@ __global__ void ppo_row_kernel(PpoArgs p) {
             gl += p.entropy_weight * inv_n * pj * (lp + H_t[t]);
             dl[off + i] = gl;
         }
+    }
+    if (p.objective == D4_OBJECTIVE_PMPO && p.pmpo_kl_weight > 0.f) {
+        // KL between the stored and the replayed unembeds, taken as the reference takes it: ONE categorical over the
+        // flat (A_total) logits (6160-6169 pass the unsplit tensors to kl_div)
+        const float* o = p.old_logits + (long long)r * p.ld_old;
+        float mxn = -INFINITY, mxo = -INFINITY;
+        for (int i = lane; i < p.A_total; i += 32) { mxn = fmaxf(mxn, l[i]); mxo = fmaxf(mxo, o[i]); }
+        mxn = warp_max(mxn); mxo = warp_max(mxo);
+        float sn = 0.f, so = 0.f;
+        for (int i = lane; i < p.A_total; i += 32) { sn += expf(l[i] - mxn); so += expf(o[i] - mxo); }
+        const float lsn = mxn + logf(warp_sum(sn)), lso = mxo + logf(warp_sum(so));
+        float kl = 0.f;
+        for (int i = lane; i < p.A_total; i += 32) {
+            const float ln = l[i] - lsn, lo = o[i] - lso;
+            kl += p.pmpo_reverse_kl ? expf(lo) * (lo - ln) : expf(ln) * (ln - lo);
+        }
+        kl = warp_sum(kl);
+        const float wk = p.pmpo_kl_weight * inv_n;
+        __syncwarp();       // pass 2 stored dl[] per action type: a different lane owns each flat index here
+        for (int i = lane; i < p.A_total; i += 32) {
+            const float ln = l[i] - lsn, lo = o[i] - lso, pn = expf(ln);
+            dl[i] += wk * (p.pmpo_reverse_kl ? pn - expf(lo) : pn * (ln - lo - kl));
+        }
+        pl += p.pmpo_kl_weight * kl;
     }
     if (lane == 0) { p.row_pl[r] = on ? pl : 0.f; p.row_ent[r] = on ? -ent_sum : 0.f; }
 }
@@ -479,6 +518,10 @@ extern "C" int d4_learn(d4_ctx* c, const d4_learn_io* io, void* workspace, int64
     if (!c->has_actions) return d4_fail("d4_learn: the model has no discrete actions");
     const int B = io->B, T = io->T;
     if (B <= 0 || T <= 0) return d4_fail("d4_learn: empty experience");
+    if (io->objective < D4_OBJECTIVE_PPO || io->objective > D4_OBJECTIVE_PMPO) return d4_fail("d4_learn: unknown objective %d", io->objective);
+    if (io->objective == D4_OBJECTIVE_PMPO && io->pmpo_kl_div_loss_weight > 0.f &&
+        (!io->old_action_unembeds || io->old_action_unembeds_ld < c->A_total))
+        return d4_fail("d4_learn: the pmpo KL term needs old_action_unembeds (B, T, >=%d)", c->A_total);
     const LearnPlan p = plan_learn(c, B, T);
     if (workspace_bytes < p.total) return d4_fail("d4_learn: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)p.total);
     if (reinterpret_cast<uintptr_t>(workspace) & 255) return d4_fail("d4_learn: workspace must be 256-byte aligned");
@@ -523,6 +566,10 @@ extern "C" int d4_learn(d4_ctx* c, const d4_learn_io* io, void* workspace, int64
         a.actions = reinterpret_cast<const long long*>(io->actions) + r0 * c->na; a.old_logp = io->old_log_probs + r0 * c->na;
         a.adv = io->advantages + r0; a.mask = lmask + r0; a.stats = stats;
         a.eps_clip = io->eps_clip; a.entropy_weight = io->entropy_weight; a.delight_temp = io->delight_temperature; a.use_gate = io->use_delight_gating;
+        a.objective = io->objective; a.pmpo_alpha = io->pmpo_pos_to_neg_weight; a.pmpo_kl_weight = io->pmpo_kl_div_loss_weight;
+        a.pmpo_reverse_kl = io->pmpo_reverse_kl;
+        a.old_logits = io->old_action_unembeds ? io->old_action_unembeds + r0 * io->old_action_unembeds_ld : nullptr;
+        a.ld_old = io->old_action_unembeds_ld;
         a.dlogits = dlogits; a.row_pl = row_pl + r0; a.row_ent = row_ent + r0;
         ppo_row_kernel<<<nblk(Rc, RPB), 32 * RPB, 0, s>>>(a);
         D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());

@@ -135,7 +135,7 @@ class DynamicsWorldModel(nn.Module):
                  multi_token_pred_len=8, value_head_mlp_depth=3, policy_head_mlp_depth=3, predict_terminals=True,
                  predict_terminal_mlp_kwargs: dict = dict(depth=1), gae_discount_factor=0.997, gae_lambda=0.95, ppo_eps_clip=0.2,
                  use_delight_gating=True, delight_temperature=1., normalize_advantages=None, policy_entropy_weight=.01,
-                 gae_use_accelerated=False, precision='tf32x3', time_attn_variant=1, **kwargs):
+                 pmpo_pos_to_neg_weight=0.5, pmpo_reverse_kl=True, pmpo_kl_div_loss_weight=.3, gae_use_accelerated=False, precision='tf32x3', time_attn_variant=1, **kwargs):
         super().__init__()
         for k, v in kwargs.items():
             if k not in _UNSUPPORTED_DEFAULTS:
@@ -173,6 +173,8 @@ class DynamicsWorldModel(nn.Module):
         self.ppo_eps_clip, self.policy_entropy_weight = ppo_eps_clip, policy_entropy_weight
         self.use_delight_gating, self.delight_temperature = use_delight_gating, delight_temperature
         self.normalize_advantages = normalize_advantages
+        self.pmpo_pos_to_neg_weight, self.pmpo_reverse_kl = pmpo_pos_to_neg_weight, pmpo_reverse_kl     # reference :5227-5231
+        self.pmpo_kl_div_loss_weight = pmpo_kl_div_loss_weight
         self.latent_shape = (num_latent_tokens, dim_latent)
         self.video_tokenizer = None
         self._build_parameters()
@@ -542,8 +544,8 @@ class DynamicsWorldModel(nn.Module):
         """Actor/critic losses with gradients (reference dreamer4.py:5893-6305).  Both losses and every head-parameter
         gradient are produced by one native call; the returned scalars carry an autograd node that deposits those
         gradients on `.backward()` exactly like the reference's graph would."""
-        if objective != 'ppo':
-            raise NotImplementedError(f"objective={objective!r}: pmpo / spo are a 'next' row (SURVEY.md section 8f)")
+        if objective not in _lib.OBJECTIVES:
+            raise ValueError(f'unknown objective {objective}')              # reference dreamer4.py:6214-6215
         if not only_learn_policy_value_heads:
             raise NotImplementedError('only_learn_policy_value_heads=False needs the world-model backward (outside this path)')
         c = self.cfg
@@ -555,7 +557,7 @@ class DynamicsWorldModel(nn.Module):
         dev = self.device
         use_gate = default(use_delight_gating, self.use_delight_gating)
         temp = default(delight_temperature, self.delight_temperature)
-        norm_adv = default(default(normalize_advantages, self.normalize_advantages), True)
+        norm_adv = default(default(normalize_advantages, self.normalize_advantages), objective != 'pmpo')    # reference :6021
 
         f32 = dict(device=dev, dtype=torch.float32)
         cont = lambda t, dt: t.detach().to(device=dev, dtype=dt).contiguous()
@@ -589,6 +591,16 @@ class DynamicsWorldModel(nn.Module):
         io.value_sigma_sqrt2, io.hl_eps = sigma_sqrt2, c.hl_gauss_eps
         io.value_lo, io.value_hi = c.value_range
         io.losses, io.returns, io.advantages = ptr(losses), ptr(returns), ptr(adv)
+        io.objective = _lib.OBJECTIVES[objective]
+        if objective == 'pmpo':                                             # reference dreamer4.py:6127-6182
+            io.pmpo_pos_to_neg_weight, io.pmpo_kl_div_loss_weight = self.pmpo_pos_to_neg_weight, self.pmpo_kl_div_loss_weight
+            io.pmpo_reverse_kl = int(bool(self.pmpo_reverse_kl))
+            if self.pmpo_kl_div_loss_weight > 0.:
+                old = exp.old_action_unembeds
+                assert exists(old) and exists(old.discrete), 'pmpo with a KL weight needs generate(store_old_action_unembeds=True)'
+                old_logits = cont(old.discrete, torch.float32)
+                assert old_logits.shape == (B, T, sum(c.num_discrete_actions)), f'old_action_unembeds {tuple(old_logits.shape)}'
+                io.old_action_unembeds, io.old_action_unembeds_ld = ptr(old_logits), old_logits.stride(1)
 
         def fill(head, nl, arrs):
             for l in range(nl):

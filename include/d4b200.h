@@ -137,8 +137,11 @@ int d4_linear(int precision, int M, int N, int K, const float* A, int64_t lda, c
 int d4_gae(int B, int T, const float* rewards, const float* values, const uint8_t* masks, const uint8_t* learn_masks,
            float gamma, float lam, float* returns, void* stream);
 
-/* ---- learn_from_experience (D4:5893-6305), objective 'ppo', heads only.
+/* ---- learn_from_experience (D4:5893-6305), objective 'ppo' | 'spo' | 'pmpo' (D4:6127-6212), heads only.
  * Computes both losses and the gradients of every policy-head / unembed / value-head parameter in one call. */
+#define D4_OBJECTIVE_PPO  0
+#define D4_OBJECTIVE_SPO  1
+#define D4_OBJECTIVE_PMPO 2
 typedef struct d4_learn_io {
     int32_t B, T;
     const float* agent_embed;       /* (B, T, D) */
@@ -163,6 +166,13 @@ typedef struct d4_learn_io {
     float* grad_unembed; int64_t grad_unembed_ld;   /* (A_total, 4D) rows with leading dim (the [:, 0] slice of (A, mtp, 4D)) */
     float* grad_value_w[D4_MAX_MLP_LAYERS]; float* grad_value_b[D4_MAX_MLP_LAYERS];
     float* grad_value_lnw[D4_MAX_MLP_LAYERS]; float* grad_value_lnb[D4_MAX_MLP_LAYERS];
+    /* surrogate objective (zero-initialised = ppo).  pmpo (D4:6127-6182): weight of the sign-split log-likelihood term,
+     * weight and direction of the KL to the logits stored at rollout time (Experience.old_action_unembeds, D4:5868-5869);
+     * the KL is one categorical over the flat A_total logits, as the reference calls it (D4:6160-6169). */
+    int32_t objective;              /* D4_OBJECTIVE_* */
+    int32_t pmpo_reverse_kl;        /* 1: KL(old || new) (reference default), 0: KL(new || old) */
+    float pmpo_pos_to_neg_weight, pmpo_kl_div_loss_weight;
+    const float* old_action_unembeds; int64_t old_action_unembeds_ld;   /* (B, T, A_total) rows with leading dim; pmpo only */
 } d4_learn_io;
 
 int64_t d4_learn_workspace_bytes(const d4_ctx* ctx, int B, int T);

@@ -71,6 +71,9 @@ class OracleConfig:
     policy_entropy_weight: float = 0.01
     use_delight_gating: bool = True
     delight_temperature: float = 1.0
+    pmpo_pos_to_neg_weight: float = 0.5
+    pmpo_reverse_kl: bool = True
+    pmpo_kl_div_loss_weight: float = 0.3
 
     def __post_init__(self):
         nda = self.num_discrete_actions
@@ -571,10 +574,11 @@ def masked_mean_all(t, mask):
     return t[mask].mean() if bool(mask.any()) else t[mask].sum()
 
 
-def learn_from_experience(sd, cfg: OracleConfig, exp: OracleExperience, eps=1e-6):
-    """DynamicsWorldModel.learn_from_experience, objective='ppo', only_learn_policy_value_heads=True,
+def learn_from_experience(sd, cfg: OracleConfig, exp: OracleExperience, eps=1e-6, objective='ppo', normalize_advantages=None):
+    """DynamicsWorldModel.learn_from_experience, objective 'ppo' | 'spo' | 'pmpo', only_learn_policy_value_heads=True,
     stored agent embeds, D4:5893-6305.  `sd` tensors that require grad receive gradients.
     Returns (total_policy_loss, value_loss, aux dict)."""
+    assert objective in ('ppo', 'spo', 'pmpo'), f'unknown objective {objective}'             # D4:6214-6215
     B, T = exp.latents.shape[:2]
     rewards, old_values = exp.rewards, exp.values
     mask_for_gae = lens_to_mask(exp.lens, T)                                                 # D4:5946-5950
@@ -589,9 +593,12 @@ def learn_from_experience(sd, cfg: OracleConfig, exp: OracleExperience, eps=1e-6
         gae_masks = gae_masks.masked_fill(term_seq, False)
     returns = calc_gae(rewards, old_values, gae_masks, mask, cfg.gae_discount_factor, cfg.gae_lambda)
     advantage = returns - old_values                                                         # D4:6017
-    mean = masked_mean_all(advantage, mask)                                                  # z_score D4:404-410
-    var = masked_mean_all((advantage - mean).pow(2), mask)
-    advantage = (advantage - mean) / var.clamp(min=eps).sqrt()
+    if normalize_advantages is None:                                                         # D4:6021: pmpo keeps raw advantages
+        normalize_advantages = objective != 'pmpo'
+    if normalize_advantages:
+        mean = masked_mean_all(advantage, mask)                                              # z_score D4:404-410
+        var = masked_mean_all((advantage - mean).pow(2), mask)
+        advantage = (advantage - mean) / var.clamp(min=eps).sqrt()
 
     agent = exp.agent_embed.detach()                                                         # D4:6074-6075
     pe = mlp(sd, 'policy_head.', agent, cfg.head_activation)                                 # D4:6080
@@ -605,12 +612,31 @@ def learn_from_experience(sd, cfg: OracleConfig, exp: OracleExperience, eps=1e-6
     entropies = torch.stack(ents, dim=-1)
     old_log_probs = exp.log_probs.sum(dim=-1)                                                # D4:6113-6114
     gate = ((-log_probs * advantage) / cfg.delight_temperature).sigmoid().detach()           # D4:6119-6120
-    ratio = (log_probs - old_log_probs).exp()                                                # D4:6204-6207
-    clipped = ratio.clamp(1.0 - cfg.ppo_eps_clip, 1.0 + cfg.ppo_eps_clip)
-    policy_loss = -torch.min(ratio * advantage, clipped * advantage)
-    if cfg.use_delight_gating:
-        policy_loss = policy_loss * gate
-    policy_loss = masked_mean_all(policy_loss, mask)                                         # D4:6212
+    if objective == 'pmpo':                                                                  # D4:6127-6182
+        glp = log_probs * gate if cfg.use_delight_gating else log_probs
+        pos = (advantage >= 0.) & mask                                                       # D4:6028-6030, 6137-6142
+        neg = ~(advantage >= 0.) & mask
+        scaled = glp * advantage.tanh().abs()
+        num = max(1., mask.sum().item())
+        policy_loss = -cfg.pmpo_pos_to_neg_weight * (scaled[pos].sum() - scaled[neg].sum()) / num
+        if cfg.pmpo_kl_div_loss_weight > 0.:                                                 # D4:6158-6182
+            # the reference hands kl_div the FLAT (b t A_total) unembeds (D4:6160-6169, no return_split_discrete), so
+            # MultiCategorical sees one categorical over the concatenated action types - restated as called
+            new_flat = torch.cat(logits, dim=-1).log_softmax(dim=-1)
+            old_flat = exp.old_action_unembeds.log_softmax(dim=-1)
+            src, tgt = (old_flat, new_flat) if cfg.pmpo_reverse_kl else (new_flat, old_flat)  # kl_div(src, tgt) D4:1463-1485
+            kl = (src.exp() * (src - tgt)).sum(dim=-1)
+            policy_loss = policy_loss + masked_mean_all(kl, mask) * cfg.pmpo_kl_div_loss_weight
+    else:
+        ratio = (log_probs - old_log_probs).exp()
+        if objective == 'spo':                                                               # D4:6184-6198
+            policy_loss = -(ratio * advantage - advantage.abs() * (ratio - 1.).square() / (2 * cfg.ppo_eps_clip))
+        else:                                                                                # D4:6200-6212
+            clipped = ratio.clamp(1.0 - cfg.ppo_eps_clip, 1.0 + cfg.ppo_eps_clip)
+            policy_loss = -torch.min(ratio * advantage, clipped * advantage)
+        if cfg.use_delight_gating:
+            policy_loss = policy_loss * gate
+        policy_loss = masked_mean_all(policy_loss, mask)
     entropy_loss = masked_mean_all(-entropies.sum(dim=-1), mask)                             # D4:6219-6221
     total_policy_loss = policy_loss + entropy_loss * cfg.policy_entropy_weight               # D4:6238-6242
 
@@ -646,4 +672,6 @@ def config_from_reference_kwargs(**kw) -> OracleConfig:
         gae_discount_factor=kw.get('gae_discount_factor', 0.997), gae_lambda=kw.get('gae_lambda', 0.95),
         ppo_eps_clip=kw.get('ppo_eps_clip', 0.2), policy_entropy_weight=kw.get('policy_entropy_weight', 0.01),
         use_delight_gating=kw.get('use_delight_gating', True), delight_temperature=kw.get('delight_temperature', 1.0),
+        pmpo_pos_to_neg_weight=kw.get('pmpo_pos_to_neg_weight', 0.5), pmpo_reverse_kl=kw.get('pmpo_reverse_kl', True),
+        pmpo_kl_div_loss_weight=kw.get('pmpo_kl_div_loss_weight', 0.3),
     )

@@ -76,6 +76,27 @@ def run_case(ref, name, model_kwargs, gen_kwargs, seed=7):
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     out.update(policy_loss=policy_loss.detach(), value_loss=value_loss.detach(), grads=grads)
 
+    # off-policy replay: nudge the policy head (as an optimizer step would) so the importance ratio leaves 1, the PPO
+    # clip engages and the PMPO KL term is non-zero, then run all three surrogate objectives (D4:6127-6212)
+    torch.manual_seed(seed + 2000)
+    moved = {}
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.startswith('policy_head.') or n == 'action_embedder.discrete_action_unembed':
+                p.add_(torch.randn_like(p) * p.abs().mean() * 0.15)
+                moved[n] = p.detach().clone()
+    out['offpolicy_params'] = moved
+    for objective in ('ppo', 'spo', 'pmpo'):
+        model.zero_grad()
+        pl, vl = model.learn_from_experience(exp, objective=objective)
+        pl.backward(retain_graph=True)
+        vl.backward()
+        # the value loss does not depend on the objective: its gradients are stored once, with 'ppo'
+        out[f'offpolicy_{objective}'] = dict(
+            policy_loss=pl.detach().clone(), value_loss=vl.detach().clone(),
+            grads={n: p.grad.detach().clone() for n, p in model.named_parameters()
+                   if p.grad is not None and (objective == 'ppo' or n in moved)})
+
     fixture = dict(name=name, model_kwargs=model_kwargs, gen_kwargs=gen_kwargs, gen_seed=gen_seed,
                    state_dict=sd, out={k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in out.items()},
                    torch_version=torch.__version__)

@@ -60,3 +60,29 @@ def test_learn_matches_reference(path):
     (pl + vl).backward()
     for name, g in ref['grads'].items():
         torch.testing.assert_close(sd[name].grad, g, atol=1e-6, rtol=1e-4, msg=lambda m, n=name: f'{n}: {m}')
+
+
+@pytest.mark.parametrize('objective', ['ppo', 'spo', 'pmpo'])
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_learn_offpolicy_objectives_match_reference(path, objective):
+    """The three surrogate objectives (D4:6127-6212) replayed after the policy head moved: ratio != 1, the PPO clip
+    engages and the PMPO KL term against old_action_unembeds is non-zero."""
+    fx = load(path)
+    cfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    ref = fx['out']
+    want = ref[f'offpolicy_{objective}']
+    state = dict(fx['state_dict'])
+    state.update(ref['offpolicy_params'])
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and k in want['grads']) for k, v in state.items()}
+    exp = O.OracleExperience(
+        latents=ref['latents'], agent_embed=ref['agent_embed'], rewards=ref['rewards'], values=ref['values'],
+        actions=ref['actions'], log_probs=ref['log_probs'], lens=ref['lens'], is_truncated=ref['is_truncated'],
+        terminals=ref['terminals'], step_size=ref['step_size'], old_action_unembeds=ref['old_action_unembeds'])
+    pl, vl, _ = O.learn_from_experience(sd, cfg, exp, objective=objective)
+    torch.testing.assert_close(pl.detach(), want['policy_loss'], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(vl.detach(), want['value_loss'], atol=1e-6, rtol=1e-5)
+    (pl + vl).backward()
+    for name, g in want['grads'].items():
+        torch.testing.assert_close(sd[name].grad, g, atol=1e-6, rtol=1e-4, msg=lambda m, n=name: f'{n}: {m}')
+    if objective != 'ppo':      # the fixtures must actually separate the objectives
+        assert (want['policy_loss'] - ref['offpolicy_ppo']['policy_loss']).abs() > 1e-3

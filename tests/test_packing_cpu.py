@@ -76,6 +76,30 @@ def test_library_exports_every_declared_symbol():
     assert lib.d4_last_error() is not None
 
 
+def test_ctypes_structs_mirror_the_header(tmp_path):
+    """Every field of every struct the C-ABI passes by pointer sits at the offset gcc gives it from include/d4b200.h."""
+    import ctypes
+    import subprocess
+    from dreamer4_b200 import _lib
+    root = os.path.dirname(os.path.dirname(__file__))
+    structs = {'d4_config': _lib.d4_config, 'd4_frame_io': _lib.d4_frame_io, 'd4_learn_io': _lib.d4_learn_io}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "d4b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got[f'{name}.{field}']) == getattr(cls, field).offset, f'{name}.{field}'
+
+
 def test_no_cpu_fallback():
     from dreamer4_b200._lib import D4Error
     model = DynamicsWorldModel(dim=32, dim_latent=8, num_latent_tokens=6, attn_heads=2, attn_dim_head=16, num_discrete_actions=4)

@@ -5,5 +5,6 @@ classes on this path."""
 from .experience import Actions, Experience, combine_experiences
 from .dynamics import DynamicsWorldModel, ModelConfig, exists, default
 from .trainer import DreamTrainer
+from .env import DynamicsWorldModelWrapper
 
-__all__ = ['Actions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'ModelConfig', 'exists', 'default']
+__all__ = ['Actions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default']

@@ -180,6 +180,7 @@ class DynamicsWorldModel(nn.Module):
         self._build_parameters()
         self._ctx = None
         self._ctx_key = None
+        self._kv_epoch = 0
         self._packed = None
         self._packed_version = None
         self._bufs = {}
@@ -304,12 +305,20 @@ class DynamicsWorldModel(nn.Module):
         return sum(p._version for n, p in self.named_parameters() if not n.startswith(('policy_head.', 'value_head.', 'to_state_terminal_pred.'))
                    and n != 'action_embedder.discrete_action_unembed')
 
-    def _engine(self, batch, max_time, agent_index=0):
-        """(Re)creates the native context for this (batch, max_time) capacity and binds weights."""
+    def _engine(self, batch, max_time, agent_index=0, grow=False):
+        """(Re)creates the native context for this (batch, max_time) capacity and binds weights.  `grow` (prompted /
+        resumed rollouts, whose time_steps creeps up by one per env step): an existing context whose KV capacity already
+        covers max_time is kept, a new one is sized to the next multiple of 64 frames."""
         self._require_cuda()
         lib = _lib.load()
         c = self.cfg
         dev = self.device
+        if grow:
+            k = self._ctx_key
+            if self._ctx is not None and k[0] == batch and k[1] >= max_time and k[2:] == (agent_index, self.precision, self.time_attn_variant, dev.index):
+                max_time = k[1]
+            else:
+                max_time = (max_time + 63) // 64 * 64
         key = (batch, max_time, agent_index, self.precision, self.time_attn_variant, dev.index)
         if self._ctx is not None and self._ctx_key != key:
             self._release()
@@ -432,11 +441,10 @@ class DynamicsWorldModel(nn.Module):
             return_log_probs_and_values = True
             return_rewards_per_frame = True
             return_terminals = return_terminals or self.predict_terminals
-        for name, v in dict(prompt=prompt, prompt_latents=prompt_latents, prompt_proprio=prompt_proprio, time_cache=time_cache,
-                            prompt_discrete_actions=prompt_discrete_actions, prompt_continuous_actions=prompt_continuous_actions,
-                            prompt_rewards=prompt_rewards, latent_gene_ids=latent_gene_ids).items():
+        for name, v in dict(prompt=prompt, prompt_proprio=prompt_proprio, prompt_continuous_actions=prompt_continuous_actions,
+                            latent_gene_ids=latent_gene_ids).items():
             if exists(v):
-                raise NotImplementedError(f'generate({name}=...): prompted / resumed rollouts are a "next" row (SURVEY.md section 8f)')
+                raise NotImplementedError(f'generate({name}=...): video prompts / proprioception / continuous actions are "next" rows (SURVEY.md section 8f)')
         if return_decoded_video:
             raise NotImplementedError('return_decoded_video needs the VideoTokenizer, a "next" row (SURVEY.md section 8f)')
         if not use_time_cache:
@@ -447,8 +455,38 @@ class DynamicsWorldModel(nn.Module):
             raise ValueError('num_steps=1 indexes step_size_embed out of range in the reference (SURVEY.md section 8a); use >= 2')
         c = self.cfg
         B, T, N, Dl, D = batch_size, time_steps, c.num_latent_tokens, c.dim_latent, c.dim
-        lib, ctx = self._engine(B, T, agent_index)
         dev = self.device
+        f32 = dict(device=dev, dtype=torch.float32)
+
+        # ---- prompt and resumed cache (reference dreamer4.py:6377-6402; env.py:464-484)
+        P, prompt_lat = 0, None
+        if exists(prompt_latents):
+            prompt_lat = prompt_latents[:, :, 0] if prompt_latents.ndim == 5 else prompt_latents      # lone view dim (6394)
+            assert prompt_lat.shape[0] == B and tuple(prompt_lat.shape[2:]) == (N, Dl), f'prompt_latents {tuple(prompt_latents.shape)}'
+            prompt_lat = prompt_lat.to(**f32).contiguous()
+            P = prompt_lat.shape[1]
+            assert P < T, f'time_steps={T} must exceed the {P} prompt frames'
+        resumed_kv = None
+        if exists(time_cache):
+            resumed_kv = time_cache.main.next_kv_cache if exists(time_cache.main) else None
+            cached = time_cache.main.token_count if exists(time_cache.main) else 0
+            assert cached == P, f'time_cache holds {cached} frames but the prompt has {P}: pass the latents of exactly the cached frames'
+        prompted = P > 0 or exists(time_cache)
+        lib, ctx = self._engine(B, T, agent_index, grow=prompted)
+        kv = self._bufs['kv']
+        L, BS = c.num_time_layers, B * c.tokens_per_frame
+        if exists(resumed_kv) and P > 0 and L > 0:
+            dst = kv[:L, :, :BS, :, :P]
+            assert tuple(resumed_kv.shape) == tuple(dst.shape), f'time_cache kv {tuple(resumed_kv.shape)} != {tuple(dst.shape)}'
+            if resumed_kv.untyped_storage().data_ptr() == kv.untyped_storage().data_ptr():
+                # a view of the live in-place cache: only valid if no other rollout has written the buffer since
+                if getattr(resumed_kv, '_d4_epoch', None) != self._kv_epoch or resumed_kv.data_ptr() != dst.data_ptr() or resumed_kv.stride() != dst.stride():
+                    raise ValueError('stale time_cache: it is a view of the in-place KV buffer, which a later generate() has '
+                                     'overwritten; clone next_kv_cache to keep a cache across rollouts')
+            else:
+                dst.copy_(resumed_kv.to(**f32))
+        self._kv_epoch += 1
+
         return_agent_actions = (return_agent_actions or return_log_probs_and_values) and c.has_actions
         want_heads = return_agent_actions
         should_term = return_terminals and self.predict_terminals
@@ -460,23 +498,63 @@ class DynamicsWorldModel(nn.Module):
 
         A = c.total_actions
         na = len(c.num_discrete_actions)
-        f32 = dict(device=dev, dtype=torch.float32)
         latents = torch.empty(B, T, N, Dl, **f32)
         agent_embed = torch.empty(B, T, D, **f32)
         rewards = torch.empty(B, T, **f32)
         values = torch.empty(B, T, **f32) if want_heads else None
-        actions = torch.empty(B, T, na, device=dev, dtype=torch.long) if want_heads else None
         log_probs = torch.empty(B, T, na, **f32) if want_heads else None
         logits = torch.empty(B, T, A, **f32) if want_heads else None
         lens = torch.full((B,), T, device=dev, dtype=torch.long)
         terminals = torch.zeros(B, device=dev, dtype=torch.bool)
         term_u8 = terminals.view(torch.uint8)
+        # The action history `decoded` that conditions frame t is decoded[:, :t] right-padded with index 0, shifted by one
+        # frame, and a zero token when there is no history at all (reference dreamer4.py:6519-6522, 7111-7126): rows past
+        # n_dec stay zero here, and frame t reads row t-1.  Sampled actions append at row n_dec (6645) - row t unless the
+        # prompt's action count differs from its frame count.
+        n_dec = 0
+        actions = None
+        if exists(prompt_discrete_actions):
+            assert c.has_actions and prompt_discrete_actions.shape[0] == B
+            pa = prompt_discrete_actions if prompt_discrete_actions.ndim == 3 else prompt_discrete_actions[..., None]
+            assert pa.shape[-1] == na, f'prompt_discrete_actions {tuple(prompt_discrete_actions.shape)}'
+            n_dec = pa.shape[1]
+        if want_heads or n_dec > 0:
+            actions = torch.zeros(B, max(T, n_dec + T - P), na, device=dev, dtype=torch.long)
+            if n_dec > 0:
+                actions[:, :n_dec] = pa.to(dev, torch.long)
+        if P > 0:
+            latents[:, :P] = prompt_lat.clamp(-1., 1.)                        # the final clamp covers the prompt too (6686)
+            if exists(prompt_rewards):
+                assert tuple(prompt_rewards.shape) == (B, P), f'prompt_rewards {tuple(prompt_rewards.shape)} != {(B, P)}'
+                rewards[:, :P] = prompt_rewards.to(**f32)
+            else:
+                assert not (return_rewards_per_frame or return_agent_actions), \
+                    'prompt_rewards (b, prompt frames) is required to return an Experience from a prompted rollout (reference :6741-6743)'
 
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+        def prev_actions_of(t):
+            if t == 0 or n_dec == 0:
+                return None, 0
+            return C.c_void_p(actions[:, t - 1].data_ptr()), actions.stride(0)
+
+        if P > 0 and not exists(time_cache):
+            # Cold prompt.  The reference re-runs its uncached multi-frame forward over [prompt, new frame] on every pass
+            # of the first new frame (6529-6546).  Prompt frames sit at signal level max_steps-1 with context noise equal to
+            # themselves (6400, 6497) and time attention is causal, so that is one clean pass per prompt frame appending
+            # its keys/values - the same pass d4_frame ends every frame with.
+            step_log2 = int(math.log2(self.max_steps // num_steps))
+            scratch = torch.empty(B, D, **f32)
+            for p in range(P):
+                pa_ptr, pa_stride = prev_actions_of(p)
+                frame = prompt_lat[:, p].contiguous()
+                check(lib.d4_pass(ctx, B, ptr(frame), self.max_steps - 1, step_log2, pa_ptr, pa_stride, ptr(tasks), p, 1,
+                                  None, ptr(scratch), stream))
+
         io = _lib.d4_frame_io()
-        frames = 0
+        frames = P
         keep = []
-        for t in range(T):
+        for t in range(P, T):
             if exists(noise):
                 nl = noise['latent'][t]
                 au = noise['action_uniform'][t] if want_heads else None
@@ -490,23 +568,22 @@ class DynamicsWorldModel(nn.Module):
             tu = tu.to(**f32).contiguous() if exists(tu) else None
             keep = [nl, au, tu]
             io.noise_latent, io.action_uniform, io.terminal_uniform = ptr(nl), ptr(au), ptr(tu)
-            if want_heads and t > 0:
-                io.prev_actions, io.pa_stride = C.c_void_p(actions[:, t - 1].data_ptr()), actions.stride(0)
-            else:
-                io.prev_actions, io.pa_stride = None, 0
+            io.prev_actions, io.pa_stride = prev_actions_of(t)
             io.tasks = ptr(tasks)
             io.latents, io.latents_bs = C.c_void_p(latents[:, t].data_ptr()), latents.stride(0)
             io.agent_embed, io.agent_bs = C.c_void_p(agent_embed[:, t].data_ptr()), agent_embed.stride(0)
             io.rewards, io.rewards_bs = C.c_void_p(rewards[:, t].data_ptr()), rewards.stride(0)
             if want_heads:
                 io.values, io.values_bs = C.c_void_p(values[:, t].data_ptr()), values.stride(0)
-                io.actions, io.actions_bs = C.c_void_p(actions[:, t].data_ptr()), actions.stride(0)
+                io.actions, io.actions_bs = C.c_void_p(actions[:, n_dec].data_ptr()), actions.stride(0)
                 io.log_probs, io.log_probs_bs = C.c_void_p(log_probs[:, t].data_ptr()), log_probs.stride(0)
                 io.logits, io.logits_bs = C.c_void_p(logits[:, t].data_ptr()), logits.stride(0)
             else:
                 io.values = io.actions = io.log_probs = io.logits = None
             io.lens, io.terminals = ptr(lens), ptr(term_u8)
             check(lib.d4_frame(ctx, B, t, num_steps, float(discrete_temperature), C.byref(io), stream))
+            if want_heads:
+                n_dec += 1
             if not exists(noise) and context_signal_noise > 0.:
                 torch.randn(B, N, Dl, **f32)            # dreamer4.py:6670: consumed by the reference, numerically dead with the KV cache
             frames = t + 1
@@ -516,25 +593,29 @@ class DynamicsWorldModel(nn.Module):
 
         Tg = frames
         latents = latents[:, :Tg]
-        kv = self._bufs['kv']
-        tc = DynamicsIntermediates(main=TransformerIntermediates(
-            next_kv_cache=kv[:c.num_time_layers, :, :, :, :Tg] if c.num_time_layers > 0 else None, token_count=Tg))
+        next_kv = None
+        if L > 0:
+            next_kv = kv[:L, :, :, :, :Tg]
+            next_kv._d4_epoch = self._kv_epoch          # lets a resumed call recognise this view as current (see above)
+        tc = DynamicsIntermediates(main=TransformerIntermediates(next_kv_cache=next_kv, token_count=Tg))
         if not (return_rewards_per_frame or return_agent_actions):
             return (latents, tc) if return_time_cache else latents
 
+        # prompt frames carry latents, rewards and actions only; everything decoded off the agent token covers the new
+        # frames (reference dreamer4.py:6620-6662 accumulate from empty)
         rewards = rewards[:, :Tg]
         step_mask = (torch.arange(Tg, device=dev)[None, :] < lens[:, None]).float()
         gen = Experience(
             latents=latents,
-            agent_embed=agent_embed[:, :Tg] if store_agent_embed else None,
-            old_action_unembeds=Actions(logits[:, :Tg], None) if (want_heads and store_old_action_unembeds) else None,
+            agent_embed=agent_embed[:, P:Tg] if store_agent_embed else None,
+            old_action_unembeds=Actions(logits[:, P:Tg], None) if (want_heads and store_old_action_unembeds) else None,
             step_size=self.max_steps // num_steps, agent_index=agent_index, lens=lens, is_truncated=~terminals, terminals=terminals,
             is_from_world_model=True,
             episode_return=(rewards * step_mask).sum(dim=-1),
             rewards=rewards if return_rewards_per_frame else None,
-            actions=Actions(actions[:, :Tg], None) if return_agent_actions else None,
-            log_probs=Actions(log_probs[:, :Tg], None) if (return_log_probs_and_values and want_heads) else None,
-            values=values[:, :Tg] if (return_log_probs_and_values and want_heads) else None)
+            actions=Actions(actions[:, :n_dec], None) if return_agent_actions else None,
+            log_probs=Actions(log_probs[:, P:Tg], None) if (return_log_probs_and_values and want_heads) else None,
+            values=values[:, P:Tg] if (return_log_probs_and_values and want_heads) else None)
         return (gen, tc) if return_time_cache else gen
 
     # ------------------------------------------------------------------ learn_from_experience

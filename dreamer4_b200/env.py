@@ -1,0 +1,74 @@
+"""Gym-style stepping of a `DynamicsWorldModel` (reference dreamer4/env.py:353-553, `DynamicsWorldModelWrapper`).
+
+Each `step` is one prompted `generate` call for a single new frame over the time cache of everything imagined so far
+(reference env.py:464-484) - on this path the cache is the engine's in-place KV buffer, so a step costs the five passes
+of one frame and no copy.  Without a video tokenizer (a "next" row) the observation is the newest
+frame's latent `(b, n, d)`, which is what the reference returns when `gen_out.video` is absent (env.py:441, 505)."""
+from __future__ import annotations
+
+import torch
+
+from .dynamics import DynamicsWorldModel, exists
+
+
+class DynamicsWorldModelWrapper:
+    def __init__(self, world_model: DynamicsWorldModel, prompt=None, num_generation_steps=4, max_steps=1000, device=None, image_size=None):
+        if exists(prompt):
+            raise NotImplementedError('video prompts need the VideoTokenizer, a "next" row (SURVEY.md section 8f)')
+        self.world_model = world_model.eval()
+        self.num_generation_steps = num_generation_steps
+        self.max_steps = max_steps
+        self.device = device if exists(device) else world_model.device
+        self.image_size = image_size
+        self.clear()
+
+    def clear(self):
+        self._latents = self._discrete_actions = self._rewards = self._time_cache = None
+        self._current_step = 0
+
+    # the flags env.py:405-417 / 464-484 pass on every call (decoded video excepted, see the module docstring)
+    _FLAGS = dict(return_rewards_per_frame=True, return_terminals=True, use_time_cache=True, return_time_cache=True)
+
+    def reset(self, batch_size=None, seed=None):
+        batch_size = batch_size if exists(batch_size) else 1
+        if exists(seed):
+            torch.manual_seed(seed)
+        self.clear()
+        gen, self._time_cache = self.world_model.generate(time_steps=1, batch_size=batch_size, num_steps=self.num_generation_steps, **self._FLAGS)
+        self._latents, self._rewards = gen.latents, gen.rewards
+        na = len(self.world_model.cfg.num_discrete_actions)
+        if na > 0:
+            self._discrete_actions = torch.empty(batch_size, 0, na, dtype=torch.long, device=self.device)
+        return gen.latents[:, -1], dict()
+
+    def step(self, action):
+        assert exists(self._latents), 'call reset() first'
+        self._current_step += 1
+        action = self._parse_action(action)
+        if exists(action) and exists(self._discrete_actions):
+            self._discrete_actions = torch.cat((self._discrete_actions, action), dim=1)
+        batch, frames = self._latents.shape[:2]
+        gen, self._time_cache = self.world_model.generate(
+            time_steps=frames + 1, batch_size=batch, num_steps=self.num_generation_steps, prompt_latents=self._latents,
+            prompt_discrete_actions=self._discrete_actions, prompt_rewards=self._rewards, time_cache=self._time_cache, **self._FLAGS)
+        self._latents, self._rewards = gen.latents, gen.rewards
+        reward = gen.rewards[:, -1]
+        terminated = gen.terminals if exists(gen.terminals) else torch.zeros(batch, dtype=torch.bool, device=self.device)
+        truncated = torch.full((batch,), self._current_step >= self.max_steps, dtype=torch.bool, device=self.device)
+        return gen.latents[:, -1], reward, terminated, truncated, dict(experience=gen)
+
+    def _parse_action(self, action):
+        """Unbatched or batched discrete actions -> (b, 1, na) int64 (env.py:511-553): a 1-D input is one action vector when
+        the env holds a single episode and one scalar action per episode otherwise; a 2-D input is (b, na)."""
+        if not exists(action) or len(self.world_model.cfg.num_discrete_actions) == 0:
+            return None
+        action = torch.atleast_1d(torch.as_tensor(action, device=self.device)).long()
+        batch = self._latents.shape[0]
+        if action.ndim == 1:
+            action = action[None, None, :] if batch == 1 else action[:, None, None]
+        elif action.ndim == 2:
+            action = action[:, None, :]
+        else:
+            raise ValueError(f'action must be 1D or 2D, but got {action.ndim}D')
+        assert action.shape[0] == batch, f'action batch size {action.shape[0]} must match environment batch size {batch}'
+        return action

@@ -456,13 +456,29 @@ def _log(t, eps=1e-20):
     return t.clamp(min=eps).log()
 
 
+def cache_from_reference(next_kv_cache):
+    """Reference time_cache.main.next_kv_cache (y 2 b*S h T d), D4:3255-3265 -> the oracle's per-time-layer [(k, v)]."""
+    if next_kv_cache is None:
+        return None
+    return [(layer[0], layer[1]) for layer in next_kv_cache]
+
+
 @torch.no_grad()
 def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=None, tasks=None,
-             return_terminals=False, discrete_temperature=1.0):
-    """DynamicsWorldModel.generate with the DreamTrainer flags (return_rewards_per_frame,
-    return_agent_actions, return_log_probs_and_values; TR:1422-1428), use_time_cache=True, no prompt.
-    D4:6307-6774.  Unlike the reference it embeds only the newest frame on each pass; outputs are
-    identical because cached passes discard everything but the last frame (D4:2960-2961, 6560)."""
+             return_terminals=False, discrete_temperature=1.0, prompt_latents=None, prompt_actions=None,
+             prompt_rewards=None, kv_cache=None, return_agent_actions=True):
+    """DynamicsWorldModel.generate, use_time_cache=True, D4:6307-6774: the DreamTrainer flags
+    (return_rewards_per_frame, return_agent_actions, return_log_probs_and_values; TR:1422-1428) by default;
+    `return_agent_actions=False` is the env wrapper's call (env.py:464-484: rewards per frame, actions supplied).
+    Unlike the reference it embeds only the newest frame on each pass; outputs are identical because cached
+    passes discard everything but the last frame (D4:2960-2961, 6560).
+
+    Prompted rollouts (D4:6377-6402): `prompt_latents` (b P N Dl), `prompt_actions` (b a na), `prompt_rewards` (b P).
+    With `kv_cache` (the cache returned for those P frames) decoding resumes at frame P.  Without it the reference
+    runs its uncached multi-frame forward over [prompt, new frame] on every pass of the first new frame; the prompt
+    frames sit at signal level max_steps-1 with context noise == themselves (6400: past noise is a clone of the prompt,
+    so the lerp at 6497 is the identity) and time attention is causal, so that equals one clean pass per prompt frame
+    appending to the cache - restated here as that prefill."""
     noise = noise or TorchRNGNoise()
     if isinstance(noise, InjectedNoise):
         noise._splits = list(cfg.num_discrete_actions)
@@ -473,15 +489,32 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
     reward_codec = HLGauss(cfg.reward_range, cfg.reward_num_bins, cfg.hl_gauss_sigma_to_bin_ratio, cfg.hl_gauss_eps)
     value_codec = HLGauss(cfg.value_range, cfg.value_num_bins, cfg.hl_gauss_sigma_to_bin_ratio, cfg.hl_gauss_eps)
     should_term = return_terminals and cfg.predict_terminals
+    want_heads = return_agent_actions and cfg.has_actions
+    na = len(cfg.num_discrete_actions)
 
-    latents, agent_embeds, rewards, values = [], [], [], []
-    actions, log_probs, policy_embeds = [], [], []
+    P = 0 if prompt_latents is None else prompt_latents.shape[1]
+    latents = [] if P == 0 else [prompt_latents[:, p].reshape(B, N, Dl) for p in range(P)]  # D4:6393-6396
+    rewards = [] if prompt_rewards is None else [prompt_rewards[:, p] for p in range(prompt_rewards.shape[1])]   # D4:6444-6447
+    # the action history that conditions frame t is decoded[:, :t] right-padded with index 0 (D4:6519-6522); the
+    # forward shifts it by one (7111-7120) and uses a zero token when there is no history at all (7124-7126)
+    decoded = torch.empty(B, 0, na, dtype=torch.long) if prompt_actions is None else prompt_actions.clone()      # D4:6420-6428
+
+    def prev_actions_for(t):
+        if t == 0 or decoded.shape[1] == 0:
+            return None
+        return decoded[:, t - 1] if t - 1 < decoded.shape[1] else torch.zeros(B, na, dtype=torch.long)
+
+    agent_embeds, values, log_probs, policy_embeds = [], [], [], []
     terminals = torch.zeros(B, dtype=torch.bool)
     lens = torch.full((B,), time_steps)
-    kv_cache = None
-    prev_actions = None
+    if kv_cache is None:
+        for p in range(P):                                                                   # prefill: see the docstring
+            _, _, kv_cache = forward_step(sd, cfg, latents[p], cfg.max_steps - 1, step_log2, prev_actions_for(p), kv_cache, p, tasks)
+    elif P > 0:
+        assert kv_cache[0][0].shape[-2] == P, 'the time cache must cover exactly the prompt frames'
 
-    for frame in range(time_steps):
+    for frame in range(P, time_steps):
+        prev_actions = prev_actions_for(frame)
         x = noise.latent(frame, (B, 1, 1, N, Dl)).reshape(B, N, Dl)                          # D4:6475
         for step in range(num_steps + 1):                                                    # D4:6484-6486
             is_last = step == num_steps
@@ -503,7 +536,7 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
             lens = lens.masked_fill(just, frame + 1)
             terminals = terminals | is_term
         agent_embeds.append(agent)
-        if cfg.has_actions:
+        if want_heads:
             pe = mlp(sd, 'policy_head.', agent, cfg.head_activation)                         # D4:6628
             policy_embeds.append(pe)
             logits = unembed_logits(sd, pe).split(list(cfg.num_discrete_actions), dim=-1)     # D4:1330-1334
@@ -514,8 +547,7 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
                 idx = ((l / max(discrete_temperature, 1e-10)) + g).argmax(dim=-1)
                 sampled.append(idx)
                 lps.append(l.log_softmax(dim=-1).gather(-1, idx[:, None])[:, 0])
-            prev_actions = torch.stack(sampled, dim=-1)
-            actions.append(prev_actions)
+            decoded = torch.cat((decoded, torch.stack(sampled, dim=-1)[:, None]), dim=1)      # D4:6645
             log_probs.append(torch.stack(lps, dim=-1))
             vb = mlp(sd, 'value_head.', agent, cfg.head_activation)                          # D4:6659-6660
             values.append(value_codec.from_logits(vb))
@@ -525,22 +557,23 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
             break
 
     T = len(latents)
-    lat = torch.stack(latents, dim=1).clamp(-1.0, 1.0)                                       # D4:6686
-    rew = torch.stack(rewards, dim=1)
+    lat = torch.stack(latents, dim=1).clamp(-1.0, 1.0) if T > 0 else torch.empty(B, 0, N, Dl)  # D4:6686 (prompt frames included)
+    rew = torch.stack(rewards, dim=1) if rewards else torch.empty(B, 0)
     step_mask = torch.arange(T)[None, :] < lens[:, None]
     exp = OracleExperience(
         latents=lat,
-        agent_embed=torch.stack(agent_embeds, dim=1),
+        agent_embed=torch.stack(agent_embeds, dim=1) if agent_embeds else None,              # new frames only (D4:6620-6621)
         rewards=rew,
         lens=lens, is_truncated=~terminals, terminals=terminals, step_size=step_size,
-        episode_return=(rew * step_mask.float()).sum(dim=-1),                                # D4:6741-6743
+        episode_return=(rew * step_mask.float()).sum(dim=-1) if rew.shape[1] == T else None,  # D4:6741-6743
         kv_cache=kv_cache,
     )
-    if cfg.has_actions:
-        exp.actions = torch.stack(actions, dim=1)
-        exp.log_probs = torch.stack(log_probs, dim=1)
-        exp.values = torch.stack(values, dim=1)
-        exp.old_action_unembeds = unembed_logits(sd, torch.stack(policy_embeds, dim=1))      # D4:6749-6750
+    if want_heads:
+        exp.actions = decoded                                                                # prompt + sampled (D4:6764)
+        if log_probs:
+            exp.log_probs = torch.stack(log_probs, dim=1)
+            exp.values = torch.stack(values, dim=1)
+            exp.old_action_unembeds = unembed_logits(sd, torch.stack(policy_embeds, dim=1))  # D4:6749-6750
     return exp
 
 

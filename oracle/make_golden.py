@@ -42,6 +42,35 @@ CASES = {
 }
 
 
+def _experience_dict(exp, time_cache):
+    get = lambda a: None if a is None else a.discrete
+    return dict(latents=exp.latents, agent_embed=exp.agent_embed, rewards=exp.rewards, values=exp.values,
+                actions=get(exp.actions), log_probs=get(exp.log_probs), old_action_unembeds=get(exp.old_action_unembeds),
+                lens=exp.lens, is_truncated=exp.is_truncated, terminals=exp.terminals, episode_return=exp.episode_return,
+                kv_cache=time_cache.main.next_kv_cache, token_count=time_cache.main.token_count)
+
+
+def run_prompted(model, gen_kwargs, seed, P=2):
+    """Three continuations of a P-frame rollout, each from its own seed:
+    resume   - prompt + the time cache of those frames, the policy keeps acting (DreamTrainer flags)
+    cold     - the same prompt without a cache: the reference's uncached multi-frame forward rebuilds the context
+    env_step - env.py's DynamicsWorldModelWrapper.step: one new frame from prompt + cache, the action supplied by the caller"""
+    B, T = gen_kwargs['batch_size'], gen_kwargs['time_steps']
+    flags = dict(return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True, return_time_cache=True)
+    torch.manual_seed(seed + 3000)
+    head, head_cache = model.generate(time_steps=P, batch_size=B, **flags)
+    prompt = dict(prompt_latents=head.latents, prompt_discrete_actions=head.actions.discrete, prompt_rewards=head.rewards)
+    res = dict(P=P, head_seed=seed + 3000, head=_experience_dict(head, head_cache))
+    torch.manual_seed(seed + 3001)
+    res['resume'] = dict(seed=seed + 3001, **_experience_dict(*model.generate(time_steps=T, batch_size=B, time_cache=head_cache, **prompt, **flags)))
+    torch.manual_seed(seed + 3002)
+    res['cold'] = dict(seed=seed + 3002, **_experience_dict(*model.generate(time_steps=T, batch_size=B, **prompt, **flags)))
+    torch.manual_seed(seed + 3003)
+    res['env_step'] = dict(seed=seed + 3003, **_experience_dict(*model.generate(
+        time_steps=P + 1, batch_size=B, time_cache=head_cache, return_rewards_per_frame=True, return_time_cache=True, **prompt)))
+    return res
+
+
 def run_case(ref, name, model_kwargs, gen_kwargs, seed=7):
     torch.manual_seed(seed)
     model = ref.DynamicsWorldModel(**model_kwargs)
@@ -96,6 +125,11 @@ def run_case(ref, name, model_kwargs, gen_kwargs, seed=7):
             policy_loss=pl.detach().clone(), value_loss=vl.detach().clone(),
             grads={n: p.grad.detach().clone() for n, p in model.named_parameters()
                    if p.grad is not None and (objective == 'ppo' or n in moved)})
+
+    # prompted / resumed rollouts (D4:6377-6402, env.py:464-484) from the first `P` frames of the rollout above
+    model.load_state_dict(sd)             # undo the off-policy nudge
+    if not gen_kwargs.get('return_terminals'):
+        out['prompted'] = run_prompted(model, gen_kwargs, seed)
 
     fixture = dict(name=name, model_kwargs=model_kwargs, gen_kwargs=gen_kwargs, gen_seed=gen_seed,
                    state_dict=sd, out={k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in out.items()},

@@ -1,0 +1,178 @@
+"""Host-side bookkeeping of DynamicsWorldModel.generate and DynamicsWorldModelWrapper on CPU: the native calls are routed
+to tests/fake_engine.py (the oracle's arithmetic behind the C-ABI's signatures), so every output must equal
+oracle.generate's BIT FOR BIT - any difference is a host bug (prompt handling, action history, time-cache hand-back,
+capacity growth, slicing), not rounding.  The CUDA kernels behind the same calls are covered by the -m gpu tests."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import dreamer4_oracle as O
+from fake_engine import install
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.pt')))
+IDS = [os.path.basename(p)[:-3] for p in GOLDEN]
+
+
+@pytest.fixture
+def setup(monkeypatch):
+    """setup(path) -> (fixture, product model on CPU, oracle config, fake engine).  The model's fake context is released
+    before monkeypatch restores the real loader (a fake handle must never reach the real d4_ctx_destroy)."""
+    from dreamer4_b200 import DynamicsWorldModel
+    made = []
+
+    def make(path):
+        fx = torch.load(path, map_location='cpu', weights_only=False)
+        model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+        model.load_state_dict(fx['state_dict'], strict=True)
+        ocfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+        made.append(model)
+        return fx, model, ocfg, install(monkeypatch, model, ocfg)
+
+    yield make
+    for model in made:
+        model._release()
+
+
+def make_noise(cfg, T, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = sum(cfg.num_discrete_actions)
+    return dict(latent=torch.randn(T, B, cfg.num_latent_tokens, cfg.dim_latent, generator=g),
+                action_uniform=torch.rand(T, B, max(A, 1), generator=g)[..., :A],
+                terminal_uniform=torch.rand(T, B, generator=g))
+
+
+def injected(noise):
+    return O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform'])
+
+
+def same(exp, ref, tc=None):
+    assert torch.equal(exp.latents, ref.latents)
+    assert torch.equal(exp.rewards, ref.rewards)
+    assert torch.equal(exp.lens, ref.lens) and torch.equal(exp.terminals, ref.terminals) and torch.equal(exp.is_truncated, ref.is_truncated)
+    assert torch.equal(exp.episode_return, ref.episode_return)
+    if ref.agent_embed is None:
+        assert exp.agent_embed is None or exp.agent_embed.shape[1] == 0
+    else:
+        assert torch.equal(exp.agent_embed, ref.agent_embed)
+    if ref.actions is None:
+        assert exp.actions is None
+    else:
+        assert torch.equal(exp.actions.discrete, ref.actions)
+        assert torch.equal(exp.log_probs.discrete, ref.log_probs) and torch.equal(exp.values, ref.values)
+        # the oracle unembeds all frames in one matmul (dreamer4.py:6749-6750), the engine frame by frame: same values up to blocking
+        torch.testing.assert_close(exp.old_action_unembeds.discrete, ref.old_action_unembeds, atol=1e-5, rtol=1e-5)
+    if tc is not None:
+        kv = torch.stack([torch.stack(layer) for layer in ref.kv_cache])
+        assert tc.main.token_count == ref.latents.shape[1]
+        assert torch.equal(tc.main.next_kv_cache, kv)
+
+
+class ProductOrderNoise(O.TorchRNGNoise):
+    """torch's global generator in the product's draw order: the terminal draw is rand < p (the oracle's default mirrors
+    the reference's torch.bernoulli, which consumes the CPU generator differently)."""
+
+    def terminal(self, frame, probs):
+        return torch.rand(probs.shape) < probs
+
+
+FLAGS = dict(return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True, return_time_cache=True)
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_plain_rollout(path, setup):
+    fx, model, ocfg, _ = setup(path)
+    gk = dict(fx['gen_kwargs'])
+    T, B = gk.pop('time_steps'), gk.pop('batch_size')
+    noise = make_noise(ocfg, T, B, 1)
+    ref = O.generate(fx['state_dict'], ocfg, T, B, noise=injected(noise), **gk)
+    exp, tc = model.generate(T, batch_size=B, noise=noise, **FLAGS, **gk)
+    same(exp, ref, tc)
+
+
+@pytest.mark.parametrize('keep_view', [True, False], ids=['in_place', 'cloned_cache'])
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_resumed_rollout(path, keep_view, setup):
+    """generate(P) then generate(T, prompt..., time_cache) == one oracle rollout resumed the same way; the cache is taken
+    either as the live view of the KV buffer (no copy) or as a clone (copied in)."""
+    fx, model, ocfg, fake = setup(path)
+    B, T, P = fx['gen_kwargs']['batch_size'], 5, 2
+    term = dict(return_terminals=True) if fx['gen_kwargs'].get('return_terminals') else {}
+    noise = make_noise(ocfg, T, B, 2)
+    head_ref = O.generate(fx['state_dict'], ocfg, P, B, noise=injected(noise))
+    ref = O.generate(fx['state_dict'], ocfg, T, B, noise=injected(noise), prompt_latents=head_ref.latents, prompt_actions=head_ref.actions,
+                     prompt_rewards=head_ref.rewards, kv_cache=head_ref.kv_cache, **term)
+    head, tc = model.generate(P, batch_size=B, noise=noise, **FLAGS)
+    same(head, head_ref, tc)
+    if not keep_view:
+        tc = type(tc)(main=type(tc.main)(next_kv_cache=tc.main.next_kv_cache.clone(), token_count=tc.main.token_count))
+    exp, tc2 = model.generate(T, batch_size=B, noise=noise, prompt_latents=head.latents, prompt_discrete_actions=head.actions.discrete,
+                              prompt_rewards=head.rewards, time_cache=tc, **FLAGS, **term)
+    same(exp, ref, tc2)
+    assert fake.calls['pass_'] == 0                      # resumed: no prefill
+    assert exp.agent_embed.shape[1] == exp.latents.shape[1] - P and exp.actions.discrete.shape[1] == exp.latents.shape[1]
+
+
+@pytest.mark.parametrize('n_prompt_actions', [2, 1, 0], ids=['actions_P', 'actions_P-1', 'no_actions'])
+@pytest.mark.parametrize('path', [p for p in GOLDEN if 'terminals' not in p], ids=[i for i in IDS if 'terminals' not in i])
+def test_cold_prompt(path, n_prompt_actions, setup):
+    """No cache: one clean d4_pass per prompt frame rebuilds it; the action history follows the reference's right-pad /
+    shift rule for every prompt-action count (dreamer4.py:6519-6522, 7111-7126)."""
+    fx, model, ocfg, fake = setup(path)
+    B, T, P = fx['gen_kwargs']['batch_size'], 4, 2
+    noise = make_noise(ocfg, T, B, 3)
+    head = O.generate(fx['state_dict'], ocfg, P, B, noise=injected(noise))
+    pa = head.actions[:, :n_prompt_actions] if n_prompt_actions > 0 else None
+    ref = O.generate(fx['state_dict'], ocfg, T, B, noise=injected(noise), prompt_latents=head.latents, prompt_actions=pa, prompt_rewards=head.rewards)
+    exp, tc = model.generate(T, batch_size=B, noise=noise, prompt_latents=head.latents, prompt_discrete_actions=pa, prompt_rewards=head.rewards, **FLAGS)
+    same(exp, ref, tc)
+    assert fake.calls['pass_'] == P and fake.calls['frame'] == T - P
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_env_wrapper_steps(path, setup):
+    """reset() + step(action) x n == the oracle resumed one frame at a time with the same supplied actions; the context is
+    created once for the 1-frame reset and once more (64-frame capacity) for all the steps."""
+    from dreamer4_b200 import DynamicsWorldModelWrapper
+    fx, model, ocfg, fake = setup(path)
+    B, steps = 2, 4
+    sizes = ocfg.num_discrete_actions
+    g = torch.Generator().manual_seed(5)
+    supplied = torch.stack([torch.randint(0, n, (steps, B), generator=g) for n in sizes], dim=-1)       # (steps, B, na)
+    env = DynamicsWorldModelWrapper(model, num_generation_steps=4)
+
+    torch.manual_seed(11)
+    obs, info = env.reset(batch_size=B)
+    outs = [env.step(supplied[i]) for i in range(steps)]
+
+    torch.manual_seed(11)
+    ref = O.generate(fx['state_dict'], ocfg, 1, B, noise=ProductOrderNoise(), return_terminals=True, return_agent_actions=False)
+    assert torch.equal(obs, ref.latents[:, -1])
+    for i in range(steps):
+        ref = O.generate(fx['state_dict'], ocfg, i + 2, B, noise=ProductOrderNoise(), return_terminals=True, return_agent_actions=False, prompt_latents=ref.latents,
+                         prompt_actions=supplied[:i + 1].transpose(0, 1), prompt_rewards=ref.rewards, kv_cache=ref.kv_cache)
+        obs, reward, terminated, truncated, info = outs[i]
+        assert torch.equal(obs, ref.latents[:, -1]) and torch.equal(reward, ref.rewards[:, -1])
+        assert torch.equal(terminated, ref.terminals) and not truncated.any()
+        assert info['experience'].actions is None
+    same(outs[-1][-1]['experience'], ref, env._time_cache)
+    assert fake.calls['ctx_create'] == 2 and fake.calls['pass_'] == 0
+
+
+def test_stale_view_is_rejected_and_capacity_grows(setup):
+    fx, model, ocfg, fake = setup(GOLDEN[0])
+    B = 2
+    args = lambda e: dict(prompt_latents=e.latents, prompt_discrete_actions=e.actions.discrete, prompt_rewards=e.rewards)
+    torch.manual_seed(0)
+    a, tc_a = model.generate(2, batch_size=B, **FLAGS)
+    b, tc_b = model.generate(3, batch_size=B, time_cache=tc_a, **args(a), **FLAGS)            # grows to a 64-frame buffer, copies
+    assert model._ctx_key[1] == 64 and fake.calls['ctx_create'] == 2
+    c, tc_c = model.generate(4, batch_size=B, time_cache=tc_b, **args(b), **FLAGS)            # in place
+    assert fake.calls['ctx_create'] == 2
+    with pytest.raises(ValueError, match='stale'):                                            # tc_b's frames were extended since
+        model.generate(5, batch_size=B, time_cache=tc_b, **args(b), **FLAGS)
+    with pytest.raises(AssertionError):                                                       # cache / prompt length mismatch
+        model.generate(5, batch_size=B, time_cache=tc_c, **args(b), **FLAGS)
+    with pytest.raises(AssertionError):                                                       # nothing to generate
+        model.generate(4, batch_size=B, time_cache=tc_c, **args(c), **FLAGS)

@@ -86,3 +86,43 @@ def test_learn_offpolicy_objectives_match_reference(path, objective):
         torch.testing.assert_close(sd[name].grad, g, atol=1e-6, rtol=1e-4, msg=lambda m, n=name: f'{n}: {m}')
     if objective != 'ppo':      # the fixtures must actually separate the objectives
         assert (want['policy_loss'] - ref['offpolicy_ppo']['policy_loss']).abs() > 1e-3
+
+
+PROMPTED = [p for p in GOLDEN if 'prompted' in load(p)['out']]
+
+
+@pytest.mark.parametrize('flow', ['resume', 'cold', 'env_step'])
+@pytest.mark.parametrize('path', PROMPTED, ids=[os.path.basename(p)[:-3] for p in PROMPTED])
+def test_prompted_generate_matches_reference(path, flow):
+    """generate(prompt_latents=..., prompt_discrete_actions=..., prompt_rewards=...[, time_cache=...]) (D4:6377-6402):
+    resumed over the cache, rebuilt cold from the prompt (the reference's uncached multi-frame forward vs the oracle's
+    per-frame prefill), and the env wrapper's single step with a caller-supplied action (env.py:464-484)."""
+    fx = load(path)
+    cfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    pr = fx['out']['prompted']
+    head, ref = pr['head'], pr[flow]
+    B = fx['gen_kwargs']['batch_size']
+    torch.manual_seed(ref['seed'])
+    exp = O.generate(
+        fx['state_dict'], cfg, ref['latents'].shape[1], B,
+        prompt_latents=head['latents'], prompt_actions=head['actions'], prompt_rewards=head['rewards'],
+        kv_cache=None if flow == 'cold' else O.cache_from_reference(head['kv_cache']),
+        return_agent_actions=flow != 'env_step')
+    tol = dict(atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(exp.latents, ref['latents'], **tol)
+    assert torch.equal(exp.latents[:, :pr['P']], head['latents'])                 # prompt frames pass through
+    torch.testing.assert_close(exp.agent_embed, ref['agent_embed'], **tol)
+    torch.testing.assert_close(exp.rewards, ref['rewards'], **tol)
+    torch.testing.assert_close(exp.episode_return, ref['episode_return'], **tol)
+    assert torch.equal(exp.lens, ref['lens'])
+    if flow == 'env_step':
+        assert ref['actions'] is None and exp.actions is None
+    else:
+        assert torch.equal(exp.actions, ref['actions'])
+        torch.testing.assert_close(exp.log_probs, ref['log_probs'], **tol)
+        torch.testing.assert_close(exp.values, ref['values'], **tol)
+        torch.testing.assert_close(exp.old_action_unembeds, ref['old_action_unembeds'], **tol)
+    kv = torch.stack([torch.stack(layer) for layer in exp.kv_cache])
+    assert kv.shape == ref['kv_cache'].shape
+    torch.testing.assert_close(kv, ref['kv_cache'], **tol)
+    assert ref['token_count'] == exp.latents.shape[1]

@@ -285,15 +285,18 @@ class HLGauss:
 # the transformer pass for ONE new frame over a time-KV cache
 
 
-def transformer_step(sd, cfg: OracleConfig, tokens, kv_cache, token_count):
+def transformer_step(sd, cfg, tokens, kv_cache, token_count, prefix='transformer.', num_special=1, final_norm=False):
     """AxialSpaceTimeTransformer.forward for a single new frame (time == 1 after the slice at
     D4:2960-2961), default branches.  tokens (b S D); kv_cache list over time layers of (k, v)
-    each (b*S, h, t, d) or None; returns (out tokens (b S D), new per-time-layer (k, v))."""
-    p = 'transformer.'
+    each (b*S, h, t, d) or None; returns (out tokens (b S D), new per-time-layer (k, v)).
+    `cfg` supplies is_time / depth / attn_heads / attn_dim_head / attn_softclamp_value / ff_activation / pool_dim_head.
+    The dynamics model's transformer has one special (agent) token and no final norm (D4:5183); the video tokenizer's
+    encoder / decoder pass their own prefix, special-token count and final_norm=True (oracle/tokenizer_oracle.py)."""
+    p = prefix
     b, S, D = tokens.shape
     d, h = cfg.attn_dim_head, cfg.attn_heads
     rot = rotary_angles(sd[p + 'time_rotary.inv_freq'], 1, token_count)                    # D4:3010
-    mask = space_mask(S, 1)                                                                  # D4:2971-2973
+    mask = space_mask(S, num_special)                                                        # D4:2971-2973
     # value residual D4:3026-3027
     v0 = rmsnorm(tokens, sd[p + 'to_value_residual.0.weight']) @ sd[p + 'to_value_residual.1.weight'].T
     v0 = v0.reshape(b, S, h, d)
@@ -323,12 +326,14 @@ def transformer_step(sd, cfg: OracleConfig, tokens, kv_cache, token_count):
         if i != cfg.depth - 1:                                                               # D4:2875, 3222
             tokens = attention_pool(sd, p + f'attn_pools.{i}.', tokens, layer_hiddens, cfg)
     # final agent cross attention + ff, D4:3227-3238 (SDPA branch: no softclamp, no mask, no belief)
-    non_special, special = tokens[:, :-1], tokens[:, -1:]
+    non_special, special = tokens[:, :-num_special], tokens[:, -num_special:]
     out, _ = attention(sd, p + 'final_special_cross_attn.fn.', special, d, context=non_special, belief=False)
     special = special + out
     special = special + feedforward(sd, p + 'final_special_ff.fn.', special, cfg.ff_activation)
     tokens = torch.cat((non_special, special), dim=1)
     tokens = attention_pool(sd, p + 'final_attn_pool.', tokens, layer_hiddens, cfg)         # D4:3242-3243
+    if final_norm:
+        tokens = rmsnorm(tokens, sd[p + 'final_norm.weight'])                                # D4:3247
     return tokens, new_cache
 
 
@@ -402,14 +407,20 @@ class TorchRNGNoise:
     def context(self, frame, shape):
         return torch.randn(shape)
 
+    def decoder(self, shape):
+        return torch.randn(shape)          # VideoTokenizer.decode's start noise, D4:4204 (drawn after the whole rollout)
+
 
 class InjectedNoise:
     """Pre-generated noise shared verbatim between the oracle and the CUDA path.
     latent (H b N Dl) normal, action_u (H b A_total) uniform, terminal_u (H b) uniform."""
 
-    def __init__(self, latent, action_u=None, terminal_u=None):
-        self.lat, self.act, self.term = latent, action_u, terminal_u
+    def __init__(self, latent, action_u=None, terminal_u=None, decoder_noise=None):
+        self.lat, self.act, self.term, self.dec = latent, action_u, terminal_u, decoder_noise
         self._splits = None
+
+    def decoder(self, shape):
+        return self.dec.reshape(shape)
 
     def latent(self, frame, shape):
         return self.lat[frame].reshape(shape).clone()
@@ -445,6 +456,7 @@ class OracleExperience:
     step_size: int = 16
     episode_return: Optional[torch.Tensor] = None
     kv_cache: list = field(default_factory=list)           # per time layer (k, v) each (b*S h T d)
+    video: Optional[torch.Tensor] = None                   # (b c t h w) when decoded through a tokenizer
 
 
 def unembed_logits(sd, policy_embed):
@@ -466,7 +478,8 @@ def cache_from_reference(next_kv_cache):
 @torch.no_grad()
 def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=None, tasks=None,
              return_terminals=False, discrete_temperature=1.0, prompt_latents=None, prompt_actions=None,
-             prompt_rewards=None, kv_cache=None, return_agent_actions=True):
+             prompt_rewards=None, kv_cache=None, return_agent_actions=True, tokenizer=None, prompt=None,
+             return_decoded_video=False):
     """DynamicsWorldModel.generate, use_time_cache=True, D4:6307-6774: the DreamTrainer flags
     (return_rewards_per_frame, return_agent_actions, return_log_probs_and_values; TR:1422-1428) by default;
     `return_agent_actions=False` is the env wrapper's call (env.py:464-484: rewards per frame, actions supplied).
@@ -491,6 +504,13 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
     should_term = return_terminals and cfg.predict_terminals
     want_heads = return_agent_actions and cfg.has_actions
     na = len(cfg.num_discrete_actions)
+
+    # `tokenizer` = (state_dict, oracle.tokenizer_oracle.TokenizerConfig) of the attached VideoTokenizer: a video `prompt`
+    # (b c t h w) is tokenized into prompt_latents (D4:6377-6387) and the finished rollout decoded back (D4:6699-6711)
+    if prompt is not None:
+        from . import tokenizer_oracle
+        assert prompt_latents is None, 'cannot pass in both prompt video and prompt latents'
+        prompt_latents = tokenizer_oracle.tokenize(*tokenizer, prompt)
 
     P = 0 if prompt_latents is None else prompt_latents.shape[1]
     latents = [] if P == 0 else [prompt_latents[:, p].reshape(B, N, Dl) for p in range(P)]  # D4:6393-6396
@@ -568,6 +588,11 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
         episode_return=(rew * step_mask.float()).sum(dim=-1) if rew.shape[1] == T else None,  # D4:6741-6743
         kv_cache=kv_cache,
     )
+    if return_decoded_video:
+        from . import tokenizer_oracle
+        tcfg = tokenizer[1]
+        start = noise.decoder((B, tcfg.channels, T, tcfg.image_height, tcfg.image_width))
+        exp.video = tokenizer_oracle.decode(*tokenizer, lat, noise=start)                    # the clamped latents, D4:6686-6711
     if want_heads:
         exp.actions = decoded                                                                # prompt + sampled (D4:6764)
         if log_probs:

@@ -42,6 +42,78 @@ CASES = {
 }
 
 
+# name -> VideoTokenizer kwargs (lpips off: its network is a torchvision download)
+TOKENIZER_CASES = {
+    # square image, one time layer of two per stack, the default single flow step of the decoder
+    'tokenizer_tiny': dict(dim=32, dim_latent=8, patch_size=4, image_size=16, num_latent_tokens=6, encoder_depth=2, decoder_depth=2,
+                           time_block_every=2, attn_heads=2, attn_dim_head=16, lpips_loss_weight=0.),
+    # non-square image, every layer a time layer, GEGLU, two decoder flow steps, one channel
+    'tokenizer_rect_flow2': dict(dim=32, dim_latent=4, patch_size=4, image_height=8, image_width=16, num_latent_tokens=3, encoder_depth=2,
+                                 decoder_depth=3, time_block_every=1, attn_heads=2, attn_dim_head=16, channels=1, decoder_flow_steps=2,
+                                 ff_kwargs=dict(activation='gelu'), lpips_loss_weight=0.),
+}
+
+
+def run_tokenizer_case(ref, name, kwargs, seed=17, batch=2, frames=3):
+    """VideoTokenizer.tokenize and .decode (D4:4107-4113, 4183-4237) on a seeded random video."""
+    torch.manual_seed(seed)
+    tok = ref.VideoTokenizer(**kwargs)
+    with torch.no_grad():
+        for n, p in tok.named_parameters():
+            if n.endswith('gamma') or ('norm' in n and n.endswith('weight')):
+                p.add_(torch.randn_like(p) * 0.1)
+            if n == 'latent_tokens':
+                p.mul_(30.)
+    tok.eval()
+    sd = {k: v.detach().clone() for k, v in tok.state_dict().items()}
+    channels = kwargs.get('channels', 3)
+    video = torch.rand(batch, channels, frames, tok.image_height, tok.image_width)
+    latents = tok.tokenize(video)
+    decode_seed = seed + 1
+    torch.manual_seed(decode_seed)
+    recon = tok.decode(latents)
+    image_latents = tok.tokenize(video[:, :, 0])          # (b c h w) input
+    fixture = dict(name=name, tokenizer_kwargs=kwargs, state_dict=sd, video=video, latents=latents.detach().clone(),
+                   decode_seed=decode_seed, recon=recon.detach().clone(), image_latents=image_latents.detach().clone(),
+                   torch_version=torch.__version__)
+    os.makedirs(os.path.join(GOLDEN_DIR, 'tokenizer'), exist_ok=True)     # a directory of its own: tests glob golden/*.pt for the dynamics cases
+    path = os.path.join(GOLDEN_DIR, 'tokenizer', f'{name}.pt')
+    torch.save(fixture, path)
+    print(f'{name}: latents {tuple(latents.shape)} recon {tuple(recon.shape)} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)')
+
+
+def run_world_with_tokenizer(ref, name='world_with_tokenizer', seed=23):
+    """DynamicsWorldModel with its VideoTokenizer attached: generate(prompt=video) -> video (D4:6377-6387, 6699-6724) and the
+    DreamTrainer-flag rollout with return_decoded_video (Experience.video)."""
+    tk = TOKENIZER_CASES['tokenizer_tiny']
+    mk = dict(dim=32, dim_latent=8, depth=4, time_block_every=4, attn_heads=2, attn_dim_head=16, num_discrete_actions=4, predict_terminals=False)
+    torch.manual_seed(seed)
+    tok = ref.VideoTokenizer(**tk)
+    model = ref.DynamicsWorldModel(video_tokenizer=tok, **mk)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('gamma') or ('norm' in n and n.endswith('weight')) or '.1.weight' in n:
+                p.add_(torch.randn_like(p) * 0.1)
+            if 'unembed' in n or n.endswith('queries') or 'learned_embed' in n or n in ('register_tokens', 'video_tokenizer.latent_tokens'):
+                p.mul_(30.)
+    model.eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    B, T, P = 2, 4, 2
+    prompt = torch.rand(B, 3, P, tok.image_height, tok.image_width)
+    torch.manual_seed(seed + 1)
+    prompted_video = model.generate(time_steps=T, batch_size=B, prompt=prompt)
+    torch.manual_seed(seed + 2)
+    exp = model.generate(time_steps=3, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
+    fixture = dict(name=name, tokenizer_kwargs=tk, model_kwargs=mk, state_dict=sd, prompt=prompt,
+                   prompted=dict(seed=seed + 1, time_steps=T, video=prompted_video.detach().clone()),
+                   dream=dict(seed=seed + 2, time_steps=3, video=exp.video.detach().clone(), latents=exp.latents.detach().clone(),
+                              actions=exp.actions.discrete.clone(), rewards=exp.rewards.detach().clone()),
+                   torch_version=torch.__version__)
+    path = os.path.join(GOLDEN_DIR, 'tokenizer', f'{name}.pt')
+    torch.save(fixture, path)
+    print(f'{name}: prompted video {tuple(prompted_video.shape)} dream video {tuple(exp.video.shape)} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)')
+
+
 def _experience_dict(exp, time_cache):
     get = lambda a: None if a is None else a.discrete
     return dict(latents=exp.latents, agent_embed=exp.agent_embed, rewards=exp.rewards, values=exp.values,
@@ -145,3 +217,6 @@ if __name__ == '__main__':
     ref = import_reference()
     for name, (mk, gk) in CASES.items():
         run_case(ref, name, mk, gk)
+    for name, kw in TOKENIZER_CASES.items():
+        run_tokenizer_case(ref, name, kw)
+    run_world_with_tokenizer(ref)

@@ -602,6 +602,95 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
     return exp
 
 
+@torch.no_grad()
+def interact_with_env(sd, cfg: OracleConfig, tokenizer, env, num_steps=4, max_timesteps=16, env_is_vectorized=False, seed=None, noise=None):
+    """DynamicsWorldModel.interact_with_env (D4:5470-5889) for image observations through the attached VideoTokenizer
+    (`tokenizer` = (state_dict, TokenizerConfig)), discrete actions, use_time_cache=True: per env step, tokenize the newest
+    frame over the tokenizer's own time cache (5588), one clean pass of the world model over its time cache conditioned on
+    the previous action (5612-5628), value (5647-5650), policy -> sample -> log-prob (5652-5673), env.step; when the episode
+    is cut by max_timesteps the final observation is evaluated once more for the bootstrap value and every per-step record
+    is right-padded by one (5790-5853).  Returns an OracleExperience (lens = episode lengths, is_from_world_model False)."""
+    from . import tokenizer_oracle
+    tsd, tcfg = tokenizer
+    noise = noise or TorchRNGNoise()
+    step_size = cfg.max_steps // num_steps
+    step_log2 = int(math.log2(step_size))
+    value_codec = HLGauss(cfg.value_range, cfg.value_num_bins, cfg.hl_gauss_sigma_to_bin_ratio, cfg.hl_gauss_eps)
+    sizes = list(cfg.num_discrete_actions)
+
+    obs = env.reset(seed=seed)
+    obs = obs[0] if isinstance(obs, tuple) else obs
+    image = lambda o: torch.as_tensor(o, dtype=torch.float32) if env_is_vectorized else torch.as_tensor(o, dtype=torch.float32)[None]
+    frame = image(obs)                                                                       # (b c h w)
+    B = frame.shape[0]
+    latents, agent_embeds, policy_embeds, rewards, values, actions, log_probs = [], [], [], [], [], [], []
+    terminated_any = torch.zeros(B, dtype=torch.bool)
+    truncated_any = torch.zeros(B, dtype=torch.bool)
+    done = torch.zeros(B, dtype=torch.bool)
+    lens = torch.zeros(B, dtype=torch.long)
+    kv_cache = tok_cache = None
+    step = 0
+
+    def observe(frame, t, prev):
+        nonlocal kv_cache, tok_cache
+        lat, tok_cache = tokenizer_oracle.tokenize_step(tsd, tcfg, frame, tok_cache, t)
+        _, agent, kv_cache = forward_step(sd, cfg, lat, cfg.max_steps - 1, step_log2, prev, kv_cache, t, None)
+        return lat, agent
+
+    while not bool(done.all()):
+        step += 1
+        lat, agent = observe(frame, step - 1, actions[-1] if actions else None)
+        latents.append(lat)
+        values.append(value_codec.from_logits(mlp(sd, 'value_head.', agent, cfg.head_activation)))
+        pe = mlp(sd, 'policy_head.', agent, cfg.head_activation)
+        policy_embeds.append(pe)
+        sampled, lps = [], []
+        for ti, l in enumerate(unembed_logits(sd, pe).split(sizes, dim=-1)):
+            u = noise.action_uniform(step - 1, ti, (B, 1, l.shape[-1])).reshape(B, -1)
+            idx = (l - _log(-_log(u))).argmax(dim=-1)                                        # temperature 1 (5657)
+            sampled.append(idx)
+            lps.append(l.log_softmax(dim=-1).gather(-1, idx[:, None])[:, 0])
+        act = torch.stack(sampled, dim=-1)
+        actions.append(act)
+        log_probs.append(torch.stack(lps, dim=-1))
+        out_action = act.numpy() if env_is_vectorized else act[0].numpy()                    # 5679-5690
+        if not env_is_vectorized and out_action.size == 1:
+            out_action = int(out_action.item())
+        next_obs, reward, terminated, truncated, *_ = env.step(out_action)
+        terminated = torch.as_tensor(terminated).reshape(B)
+        truncated = torch.as_tensor(truncated).reshape(B)
+        lens = torch.where(done, lens, lens + 1)                                             # 5726
+        terminated_any |= terminated
+        truncated_any |= truncated
+        if step >= max_timesteps:
+            truncated_any |= ~terminated_any                                                 # 5731-5732
+        done |= terminated_any | truncated_any
+        rewards.append(torch.as_tensor(reward, dtype=torch.float32).reshape(B))
+        agent_embeds.append(agent)
+        frame = image(next_obs)
+        need_bootstrap = truncated_any & ~terminated_any
+        if bool(done.all()) and bool(need_bootstrap.any()):                                  # 5790-5853
+            lat, agent = observe(frame, step, actions[-1])
+            values.append(value_codec.from_logits(mlp(sd, 'value_head.', agent, cfg.head_activation)))
+            rewards.append(torch.zeros(B))
+            actions.append(torch.zeros_like(actions[-1]))
+            log_probs.append(torch.zeros_like(log_probs[-1]))
+            latents.append(lat)
+            agent_embeds.append(agent)
+            policy_embeds.append(mlp(sd, 'policy_head.', agent, cfg.head_activation))
+            lens = torch.where(need_bootstrap, lens + 1, lens)
+            break
+
+    rew = torch.stack(rewards, dim=1)
+    T = rew.shape[1]
+    step_mask = torch.arange(T)[None, :] < lens[:, None]
+    return OracleExperience(
+        latents=torch.stack(latents, dim=1), agent_embed=torch.stack(agent_embeds, dim=1), rewards=rew,
+        values=torch.stack(values, dim=1), actions=torch.stack(actions, dim=1), log_probs=torch.stack(log_probs, dim=1),
+        old_action_unembeds=unembed_logits(sd, torch.stack(policy_embeds, dim=1)), lens=lens, is_truncated=truncated_any,
+        terminals=terminated_any, step_size=step_size, episode_return=(rew * step_mask.float()).sum(dim=-1), kv_cache=kv_cache)
+
+
 # --------------------------------------------------------------------------------------
 # learn_from_experience
 

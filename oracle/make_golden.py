@@ -104,7 +104,22 @@ def run_world_with_tokenizer(ref, name='world_with_tokenizer', seed=23):
     prompted_video = model.generate(time_steps=T, batch_size=B, prompt=prompt)
     torch.manual_seed(seed + 2)
     exp = model.generate(time_steps=3, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
-    fixture = dict(name=name, tokenizer_kwargs=tk, model_kwargs=mk, state_dict=sd, prompt=prompt,
+    # interact_with_env (D4:5470-5889) on oracle/toy_env.py: vectorized with one episode terminating early, one never (cut by
+    # max_timesteps -> bootstrap branch) and one late; all terminated (no bootstrap); a single non-vectorized env both ways
+    from toy_env import ToyImageEnv
+    interact = []
+    for i, (vectorized, terminate_at) in enumerate(((True, [2, 0, 4]), (True, [1, 2, 3]), (False, None), (False, [3]))):
+        env = ToyImageEnv(batch=3 if vectorized else None, terminate_at=terminate_at)
+        torch.manual_seed(seed + 10 + i)
+        e = model.interact_with_env(env, max_timesteps=5, env_is_vectorized=vectorized)
+        interact.append(dict(
+            vectorized=vectorized, terminate_at=terminate_at, max_timesteps=5, seed=seed + 10 + i,
+            latents=e.latents, agent_embed=e.agent_embed, rewards=e.rewards, values=e.values, actions=e.actions.discrete,
+            log_probs=e.log_probs.discrete, old_action_unembeds=e.old_action_unembeds.discrete, lens=e.lens,
+            is_truncated=e.is_truncated, terminals=e.terminals, episode_return=e.episode_return, video=e.video))
+    interact = [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in d.items()} for d in interact]
+
+    fixture = dict(name=name, tokenizer_kwargs=tk, model_kwargs=mk, state_dict=sd, prompt=prompt, interact=interact,
                    prompted=dict(seed=seed + 1, time_steps=T, video=prompted_video.detach().clone()),
                    dream=dict(seed=seed + 2, time_steps=3, video=exp.video.detach().clone(), latents=exp.latents.detach().clone(),
                               actions=exp.actions.discrete.clone(), rewards=exp.rewards.detach().clone()),

@@ -99,21 +99,27 @@ def patch_tokens(sd, prefix, frame, p):
 
 
 @torch.no_grad()
+def tokenize_step(sd, cfg: TokenizerConfig, frame, cache, t):
+    """One frame (b c h w) through the encoder over its time-KV cache `cache` (None at t = 0) -> (latents (b n dl), cache):
+    the incremental call interact_with_env makes per env step (D4:5588, forward(..., time_cache=, return_time_cache=True))."""
+    N = cfg.num_latent_tokens
+    latent_tokens = sd['latent_tokens'][None].expand(frame.shape[0], -1, -1)                 # D4:4349
+    tokens = torch.cat((patch_tokens(sd, 'patch_to_tokens.', frame, cfg.patch_size), latent_tokens), dim=1)                   # D4:4360
+    # encoder: the N latent tokens are the special tokens - patches cannot attend to them, they attend to everything,
+    # and cross-attend to the patches once more at the end (D4:3912-3918, 1769-1783, 3227-3238)
+    tokens, cache = O.transformer_step(sd, cfg.encoder, tokens, cache, t, prefix='encoder_transformer.', num_special=N, final_norm=True)
+    return (tokens[:, -N:] @ sd['encoded_to_latents.weight'].T).tanh(), cache               # D4:4413, 4426
+
+
+@torch.no_grad()
 def tokenize(sd, cfg: TokenizerConfig, video):
     """VideoTokenizer.tokenize = forward(video, return_latents=True) in eval mode (no patch masking): (b c t h w) -> (b t n dl)."""
     if video.ndim == 4:                                                                      # D4:4258-4260
         video = video[:, :, None]
-    b, _, T, H, W = video.shape
-    N = cfg.num_latent_tokens
-    tcfg = cfg.encoder
-    latent_tokens = sd['latent_tokens'][None].expand(b, -1, -1)                              # D4:4349
     cache, out = None, []
-    for t in range(T):
-        tokens = torch.cat((patch_tokens(sd, 'patch_to_tokens.', video[:, :, t], cfg.patch_size), latent_tokens), dim=1)     # D4:4360
-        # encoder: the N latent tokens are the special tokens - patches cannot attend to them, they attend to everything,
-        # and cross-attend to the patches once more at the end (D4:3912-3918, 1769-1783, 3227-3238)
-        tokens, cache = O.transformer_step(sd, tcfg, tokens, cache, t, prefix='encoder_transformer.', num_special=N, final_norm=True)
-        out.append((tokens[:, -N:] @ sd['encoded_to_latents.weight'].T).tanh())              # D4:4413, 4426
+    for t in range(video.shape[2]):
+        latents, cache = tokenize_step(sd, cfg, video[:, :, t], cache, t)
+        out.append(latents)
     return torch.stack(out, dim=1)
 
 

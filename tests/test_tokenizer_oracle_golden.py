@@ -96,3 +96,20 @@ def test_dream_with_decoded_video_matches_reference():
     torch.testing.assert_close(exp.latents, ref['latents'], **TOL)
     torch.testing.assert_close(exp.rewards, ref['rewards'], **TOL)
     torch.testing.assert_close(exp.video, ref['video'], **TOL)
+
+
+@pytest.mark.parametrize('case', range(4), ids=['vec_mixed_bootstrap', 'vec_all_terminated', 'single_truncated', 'single_terminated'])
+def test_interact_with_env_matches_reference(case):
+    """interact_with_env (D4:5470-5889) on the deterministic toy image env: per-step incremental tokenize + one clean world-model
+    pass + value / policy / sampling, termination and truncation bookkeeping, the bootstrap step and its right-padding."""
+    from oracle.toy_env import ToyImageEnv
+    fx, sd, cfg, tokenizer = _world()
+    ref = fx['interact'][case]
+    env = ToyImageEnv(batch=3 if ref['vectorized'] else None, terminate_at=ref['terminate_at'])
+    torch.manual_seed(ref['seed'])
+    exp = O.interact_with_env(sd, cfg, tokenizer, env, max_timesteps=ref['max_timesteps'], env_is_vectorized=ref['vectorized'])
+    assert torch.equal(exp.actions, ref['actions'])
+    assert torch.equal(exp.lens, ref['lens']) and torch.equal(exp.is_truncated, ref['is_truncated']) and torch.equal(exp.terminals, ref['terminals'])
+    for name in ('latents', 'agent_embed', 'rewards', 'values', 'log_probs', 'old_action_unembeds', 'episode_return'):
+        torch.testing.assert_close(getattr(exp, name), ref[name], **TOL, msg=lambda m, n=name: f'{n}: {m}')
+    assert ref['video'].shape[2] == exp.rewards.shape[1]            # frames the env showed, bootstrap frame included (D4:5856)

@@ -126,7 +126,7 @@ class DynamicsWorldModel(nn.Module):
 
     Extra keyword arguments (not in the reference): `precision` in {'tf32x3' (default), 'fp32', 'tf32'} — arithmetic of the
     dense layers: 3-term TF32 split on the tensor cores (fp32-accurate), exact-fp32 FMA, or single-pass TF32 (reduced
-    precision); the policy head always runs exact fp32.  `time_attn_variant`: K1 kernel (1 = bulk-copy ring, 0 = ld.global)."""
+    precision); the final action unembedding always runs exact fp32.  `time_attn_variant`: K1 kernel (1 = bulk-copy ring, 0 = ld.global)."""
 
     def __init__(self, dim, dim_latent, *, num_latent_tokens=None, max_steps=64, num_register_tokens=8, num_spatial_tokens=4,
                  num_agents=1, num_tasks=0, reward_encoder_kwargs: dict = dict(), value_encoder_kwargs: Optional[dict] = None,

@@ -91,6 +91,7 @@ SYMBOLS = {
     'd4_set_buffers': (_i, [_p, _p, _i64, _p, _i64]),
     'd4_pass': (_i, [_p, _i, _p, _i, _i, _p, _i64, _p, _i, _i, _p, _p, _p]),
     'd4_frame': (_i, [_p, _i, _i, _i, _f, C.POINTER(d4_frame_io), _p]),
+    'd4_observe': (_i, [_p, _i, _i, _i, _f, C.POINTER(d4_frame_io), _p]),
     'd4_profile': (_i, [_p, _i]),
     'd4_profile_read': (_i, [_p, C.POINTER(C.c_double)]),
     'd4_time_attn_decode': (_i, [_i, _i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _f, _i, _i, _p]),

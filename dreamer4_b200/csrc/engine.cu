@@ -575,7 +575,10 @@ extern "C" int d4_pass(d4_ctx* c, int B, const float* latent, int signal_level, 
                     static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int d4_frame(d4_ctx* c, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream) {
+// One frame at cache position t: passes first_step..num_steps of the denoising schedule (the last one is the clean pass that
+// commits the frame's keys/values), then the heads.  first_step = 0 is d4_frame; first_step = num_steps is d4_observe, where
+// io->noise_latent already holds the clean latent and only that last pass runs.
+static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream, int first_step) {
     D4_TRY(check_ready(c, B, t));
     if (!io || !io->noise_latent || !io->latents) return d4_fail("d4_frame: noise_latent and latents are required");
     if (num_steps < 1 || num_steps > c->cfg.max_steps || (num_steps & (num_steps - 1)) || c->cfg.max_steps % num_steps)
@@ -588,7 +591,7 @@ extern "C" int d4_frame(d4_ctx* c, int B, int t, int num_steps, float discrete_t
     float* x = c->b.lat_x;
     D4_CUDA_OK(cudaMemcpyAsync(x, io->noise_latent, nlat * 4, cudaMemcpyDeviceToDevice, s));
     // denoising passes + the clean pass that commits this frame's keys/values (reference dreamer4.py:6484-6580)
-    for (int step = 0; step <= num_steps; ++step) {
+    for (int step = first_step; step <= num_steps; ++step) {
         const bool last = (step == num_steps);
         const int signal = std::min(step * step_size, c->cfg.max_steps - 1);
         D4_TRY(run_pass(c, B, x, signal, step_log2, io->prev_actions, io->pa_stride, io->tasks, t, last ? 1 : 0,
@@ -636,6 +639,14 @@ extern "C" int d4_frame(d4_ctx* c, int B, int t, int num_steps, float discrete_t
         }
     }
     return 0;
+}
+
+extern "C" int d4_frame(d4_ctx* c, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream) {
+    return frame_impl(c, B, t, num_steps, discrete_temperature, io, stream, 0);
+}
+
+extern "C" int d4_observe(d4_ctx* c, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream) {
+    return frame_impl(c, B, t, num_steps, discrete_temperature, io, stream, num_steps);
 }
 
 // ------------------------------------------------------------------------------------------------ stand-alone operators

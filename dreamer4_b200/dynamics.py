@@ -618,6 +618,143 @@ class DynamicsWorldModel(nn.Module):
             values=values[:, P:Tg] if (return_log_probs_and_values and want_heads) else None)
         return (gen, tc) if return_time_cache else gen
 
+    # ------------------------------------------------------------------ interact_with_env
+
+    @torch.no_grad()
+    def interact_with_env(self, env, seed=None, agent_index=0, num_steps=4, max_timesteps=16, env_is_vectorized=False,
+                          use_time_cache=True, store_agent_embed=True, store_old_action_unembeds=True, obs_to_latents_fn=None):
+        """One real-environment episode (batch of episodes when vectorized) driven by the policy head (reference
+        dreamer4.py:5470-5889).  Per env step: `obs_to_latents_fn(self, obs, cache) -> (latents (b, 1, n, d), cache)`, one
+        native `d4_observe` (the clean pass over the time cache conditioned on the previous action, value head, policy head,
+        gumbel-argmax sample, log-prob), `env.step`.  Episodes cut by `max_timesteps` get the reference's bootstrap step: the
+        final observation is evaluated once more for its value and every per-step record is right-padded by one (:5790-5853).
+
+        Without a VideoTokenizer on this path `obs_to_latents_fn` is required; it is called with the same
+        (self, obs, cache) arguments at the bootstrap step (the reference drops `self` there, :5793)."""
+        if not exists(obs_to_latents_fn):
+            raise NotImplementedError('interact_with_env needs obs_to_latents_fn: image / state observations go through the '
+                                      'VideoTokenizer / state_to_latents, "next" rows (SURVEY.md section 8f)')
+        if not use_time_cache:
+            raise NotImplementedError('use_time_cache=False: the native path always runs over the in-place KV cache')
+        c = self.cfg
+        assert c.has_actions, 'interact_with_env needs a model with discrete actions'
+        assert self.max_steps % num_steps == 0
+        dev = self.device
+        N, Dl, D, A, na = c.num_latent_tokens, c.dim_latent, c.dim, c.total_actions, len(c.num_discrete_actions)
+        f32 = dict(device=dev, dtype=torch.float32)
+        as_f32 = lambda v: torch.as_tensor(v, dtype=torch.float32).to(dev)
+
+        def as_obs(obs):                                      # reference :5513-5521, :5712-5720
+            if isinstance(obs, dict):
+                return obs
+            obs = obs if torch.is_tensor(obs) else as_f32(obs)
+            return dict(image=obs) if obs.ndim >= 3 else dict(state=obs)
+
+        def frames_of(obs):                                   # (image (b c 1 h w) | None, state (b d) | None), reference :5528-5541
+            image = as_f32(obs['image']) if 'image' in obs else None
+            state = as_f32(obs['state']) if 'state' in obs else None
+            if not env_is_vectorized:
+                image, state = (t[None] if exists(t) else None for t in (image, state))
+            return (image[:, :, None] if exists(image) else None), state
+
+        obs = env.reset(seed=seed)
+        obs = as_obs(obs[0] if isinstance(obs, tuple) else obs)
+        assert 'image' in obs or 'state' in obs
+        image, state = frames_of(obs)
+        B = image.shape[0] if exists(image) else state.shape[0]
+        video_frames, states = ([image] if exists(image) else []), ([state] if exists(state) else [])
+
+        T = max_timesteps + 1                                 # + the bootstrap frame
+        lib, ctx = self._engine(B, T, agent_index, grow=True)
+        self._kv_epoch += 1
+        latents = torch.zeros(B, T, N, Dl, **f32)
+        agent_embed = torch.zeros(B, T, D, **f32)
+        values = torch.zeros(B, T, **f32)
+        rewards = torch.zeros(B, T, **f32)
+        actions = torch.zeros(B, T, na, device=dev, dtype=torch.long)
+        log_probs = torch.zeros(B, T, na, **f32)
+        logits = torch.zeros(B, T, A, **f32)
+        scratch = torch.empty(B, N, Dl, **f32)
+        terminated_any = torch.zeros(B, dtype=torch.bool, device=dev)
+        truncated_any = torch.zeros(B, dtype=torch.bool, device=dev)
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        lens = torch.zeros(B, dtype=torch.long, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        io = _lib.d4_frame_io()
+
+        def observe(t, obs, cache, uniform):
+            """latents of `obs` -> frame t of the records; returns the tokenizer-side cache."""
+            lat, cache = obs_to_latents_fn(self, obs, cache)
+            lat = lat.to(**f32).reshape(B, N, Dl).contiguous()
+            latents[:, t] = lat
+            io.noise_latent, io.action_uniform, io.terminal_uniform = ptr(lat), ptr(uniform), None
+            io.prev_actions, io.pa_stride = (C.c_void_p(actions[:, t - 1].data_ptr()), actions.stride(0)) if t > 0 else (None, 0)
+            io.tasks = None
+            io.latents, io.latents_bs = ptr(scratch), scratch.stride(0)
+            io.agent_embed, io.agent_bs = C.c_void_p(agent_embed[:, t].data_ptr()), agent_embed.stride(0)
+            io.rewards, io.rewards_bs = None, 0
+            io.values, io.values_bs = C.c_void_p(values[:, t].data_ptr()), values.stride(0)
+            io.actions, io.actions_bs = C.c_void_p(actions[:, t].data_ptr()), actions.stride(0)
+            io.log_probs, io.log_probs_bs = C.c_void_p(log_probs[:, t].data_ptr()), log_probs.stride(0)
+            io.logits, io.logits_bs = C.c_void_p(logits[:, t].data_ptr()), logits.stride(0)
+            io.lens = io.terminals = None
+            check(lib.d4_observe(ctx, B, t, num_steps, 1., C.byref(io), stream))
+            return cache
+
+        cache = None
+        step = 0
+        while not bool(done.all()):
+            step += 1
+            t = step - 1
+            uniform = torch.cat([torch.rand(B, n, **f32) for n in c.num_discrete_actions], dim=-1)      # the sampler's draws (:5657)
+            cache = observe(t, obs, cache, uniform)
+            act = actions[:, t].cpu().numpy()                 # (b, na); the reference's host sync, :5679-5690
+            if not env_is_vectorized:
+                act = act[0]
+                if act.size == 1:
+                    act = int(act.item())
+            out = env.step(act)
+            assert 2 <= len(out) <= 5, f'env.step returned {len(out)} values'
+            next_obs, reward = out[0], out[1]
+            flag = lambda i: torch.as_tensor(out[i]).to(dev).reshape(B).bool() if len(out) > i else torch.zeros(B, dtype=torch.bool, device=dev)
+            terminated, truncated = flag(2), flag(3)
+            lens = torch.where(done, lens, lens + 1)          # :5726
+            terminated_any |= terminated
+            truncated_any |= truncated
+            if step >= max_timesteps:
+                truncated_any |= ~terminated_any              # :5731-5732
+            done |= terminated_any | truncated_any
+            rewards[:, t] = as_f32(reward).reshape(B)
+            obs = as_obs(next_obs)
+            assert 'image' in obs or 'state' in obs
+            image, state = frames_of(obs)
+            if exists(state):
+                states.append(state)
+            if exists(image):
+                video_frames.append(image)
+            need_bootstrap = truncated_any & ~terminated_any
+            if bool(done.all()) and bool(need_bootstrap.any()):                                           # :5790-5853
+                # value of the state the episode was cut at; its reward / action / log-prob rows stay zero (the right-pad)
+                observe(step, obs, cache, torch.full((B, A), 0.5, **f32))
+                actions[:, step] = 0
+                log_probs[:, step] = 0.
+                lens = torch.where(need_bootstrap, lens + 1, lens)
+                step += 1
+                break
+
+        Tg = step
+        step_mask = (torch.arange(Tg, device=dev)[None, :] < lens[:, None]).float()
+        return Experience(
+            latents=latents[:, :Tg],
+            video=torch.cat(video_frames, dim=2)[:, :, :Tg] if video_frames else None,
+            critic_state=torch.stack(states, dim=1)[:, :Tg] if states else None,
+            rewards=rewards[:, :Tg], actions=Actions(actions[:, :Tg], None), log_probs=Actions(log_probs[:, :Tg], None),
+            values=values[:, :Tg],
+            old_action_unembeds=Actions(logits[:, :Tg], None) if store_old_action_unembeds else None,
+            agent_embed=agent_embed[:, :Tg] if store_agent_embed else None,
+            step_size=self.max_steps // num_steps, agent_index=agent_index, is_truncated=truncated_any, terminals=terminated_any,
+            lens=lens, is_from_world_model=False, episode_return=(rewards[:, :Tg] * step_mask).sum(dim=-1))
+
     # ------------------------------------------------------------------ learn_from_experience
 
     def learn_from_experience(self, experience: Experience, policy_optim=None, value_optim=None, only_learn_policy_value_heads=True,

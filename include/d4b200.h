@@ -112,6 +112,12 @@ typedef struct d4_frame_io {
  * + action sampling.  Replaces one iteration of the frame loop of DynamicsWorldModel.generate (D4:6458-6684). */
 int d4_frame(d4_ctx* ctx, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream);
 
+/* One OBSERVED frame: io->noise_latent holds the clean latent of a real observation (not noise); runs only the clean pass at
+ * signal level max_steps-1 with the step-size embedding of `num_steps` (appending the frame's keys/values at position t) and
+ * the same heads as d4_frame.  Replaces one iteration of DynamicsWorldModel.interact_with_env's loop between the tokenizer
+ * and env.step (D4:5612-5673).  io->latents receives the clamped copy of the input (scratch for most callers). */
+int d4_observe(d4_ctx* ctx, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream);
+
 /* ---- in-situ kernel timing (bench.py's roofline): CUDA events recorded around every launch of the four kernel
  * classes on the launching stream while enabled.  d4_profile_read() synchronises the recorded events and returns,
  * per class [gemm, time_attn (K1), small_attn, other-marked], {milliseconds, launches, algorithmic work} where work is

@@ -613,6 +613,8 @@ def interact_with_env(sd, cfg: OracleConfig, tokenizer, env, num_steps=4, max_ti
     from . import tokenizer_oracle
     tsd, tcfg = tokenizer
     noise = noise or TorchRNGNoise()
+    if isinstance(noise, InjectedNoise):
+        noise._splits = list(cfg.num_discrete_actions)
     step_size = cfg.max_steps // num_steps
     step_log2 = int(math.log2(step_size))
     value_codec = HLGauss(cfg.value_range, cfg.value_num_bins, cfg.hl_gauss_sigma_to_bin_ratio, cfg.hl_gauss_eps)

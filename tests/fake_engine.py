@@ -108,14 +108,18 @@ class FakeEngine:
         self.calls['pass_'] += 1
         return 0
 
-    def d4_frame(self, ctx, B, t, num_steps, temperature, io, stream):
+    def d4_observe(self, ctx, B, t, num_steps, temperature, io, stream):
+        self.calls['observe'] = self.calls.get('observe', 0) + 1
+        return self.d4_frame(ctx, B, t, num_steps, temperature, io, stream, first_step=num_steps)
+
+    def d4_frame(self, ctx, B, t, num_steps, temperature, io, stream, first_step=0):
         io, c, sd = io._obj, self.cfg, self.sd
         N, Dl, D = c.num_latent_tokens, c.dim_latent, c.dim
         step_size = c.max_steps // num_steps
         step_log2 = int(math.log2(step_size))
         pa, tk = self._inputs(B, io.prev_actions, io.pa_stride, io.tasks)
         x = _flat(io.noise_latent, B * N * Dl).view(B, N, Dl).clone()
-        for step in range(num_steps + 1):
+        for step in range(first_step, num_steps + 1):
             signal = min(step * step_size, c.max_steps - 1)
             pred, agent = self._pass(B, x, signal, step_log2, pa, tk, t, step == num_steps)
             if step < num_steps:

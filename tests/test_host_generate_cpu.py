@@ -176,3 +176,53 @@ def test_stale_view_is_rejected_and_capacity_grows(setup):
         model.generate(5, batch_size=B, time_cache=tc_c, **args(b), **FLAGS)
     with pytest.raises(AssertionError):                                                       # nothing to generate
         model.generate(4, batch_size=B, time_cache=tc_c, **args(c), **FLAGS)
+
+
+WORLD = os.path.join(os.path.dirname(__file__), 'golden', 'tokenizer', 'world_with_tokenizer.pt')
+
+
+@pytest.mark.parametrize('case', range(4), ids=['vec_mixed_bootstrap', 'vec_all_terminated', 'single_truncated', 'single_terminated'])
+def test_interact_with_env(case, monkeypatch):
+    """interact_with_env's bookkeeping (termination / truncation / bootstrap padding, previous-action conditioning, record
+    slicing, env action formatting) against oracle.interact_with_env on the deterministic toy env, observations tokenized by
+    the oracle's incremental tokenizer through `obs_to_latents_fn`.  One d4_observe per env step (+1 for the bootstrap)."""
+    from dreamer4_b200 import DynamicsWorldModel
+    from oracle import tokenizer_oracle as TO
+    from oracle.toy_env import ToyImageEnv
+    fx = torch.load(WORLD, map_location='cpu', weights_only=False)
+    ref_case = fx['interact'][case]
+    vectorized, terminate_at, max_timesteps = ref_case['vectorized'], ref_case['terminate_at'], ref_case['max_timesteps']
+    tk = fx['tokenizer_kwargs']
+    mk = dict(fx['model_kwargs'], num_latent_tokens=tk['num_latent_tokens'])
+    sd = {k: v for k, v in fx['state_dict'].items() if not k.startswith('video_tokenizer.')}
+    tsd = {k[len('video_tokenizer.'):]: v for k, v in fx['state_dict'].items() if k.startswith('video_tokenizer.')}
+    ocfg, tcfg = O.config_from_reference_kwargs(**mk), TO.config_from_reference_kwargs(**tk)
+    model = DynamicsWorldModel(**mk, precision='fp32')
+    model.load_state_dict(sd, strict=True)
+    fake = install(monkeypatch, model, ocfg)
+
+    def obs_to_latents(world_model, obs, cache):
+        assert world_model is model
+        frame = obs['image'] if vectorized else obs['image'][None]
+        tok_cache, t = cache if cache is not None else (None, 0)
+        lat, tok_cache = TO.tokenize_step(tsd, tcfg, frame, tok_cache, t)
+        return lat[:, None], (tok_cache, t + 1)
+
+    try:
+        torch.manual_seed(ref_case['seed'])
+        exp = model.interact_with_env(ToyImageEnv(batch=3 if vectorized else None, terminate_at=terminate_at), max_timesteps=max_timesteps,
+                                      env_is_vectorized=vectorized, obs_to_latents_fn=obs_to_latents)
+        torch.manual_seed(ref_case['seed'])
+        ref = O.interact_with_env(fx['state_dict'], ocfg, (tsd, tcfg), ToyImageEnv(batch=3 if vectorized else None, terminate_at=terminate_at),
+                                  max_timesteps=max_timesteps, env_is_vectorized=vectorized)
+        for name in ('latents', 'agent_embed', 'rewards', 'values', 'episode_return', 'lens', 'terminals', 'is_truncated'):
+            assert torch.equal(getattr(exp, name), getattr(ref, name)), name
+        assert torch.equal(exp.actions.discrete, ref.actions) and torch.equal(exp.log_probs.discrete, ref.log_probs)
+        torch.testing.assert_close(exp.old_action_unembeds.discrete, ref.old_action_unembeds, atol=1e-5, rtol=1e-5)
+        assert not exp.is_from_world_model and exp.video.shape[2] == exp.rewards.shape[1]
+        # ... and, transitively, the reference's own episode (the oracle is pinned to it in test_tokenizer_oracle_golden.py)
+        assert torch.equal(exp.actions.discrete, ref_case['actions']) and torch.equal(exp.lens, ref_case['lens'])
+        torch.testing.assert_close(exp.values, ref_case['values'], atol=2e-5, rtol=1e-4)
+        assert fake.calls['observe'] == exp.latents.shape[1] and fake.calls['pass_'] == 0
+    finally:
+        model._release()

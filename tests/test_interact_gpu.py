@@ -2,10 +2,8 @@
 the deterministic toy env (oracle/toy_env.py) with observations tokenized by the oracle's incremental tokenizer through
 `obs_to_latents_fn` (there is no CUDA tokenizer yet).
 
-STATUS: written after round 1's GPU budget was spent.  The host logic is held bit-for-bit to the oracle on CPU
-(tests/test_host_generate_cpu.py::test_interact_with_env) and d4_observe is d4_frame's body entered at its last pass, but this
-file has not run on hardware yet - hence the non-strict xfail: it reports XPASS / XFAIL without gating the suite until a first
-run on a B200 confirms it, after which the marker goes."""
+First hardware run: profiles/r1_interact_tests.log (4 cases green on a B200, together with the d4_frame golden tests after the
+frame_impl refactor)."""
 import os
 
 import pytest
@@ -15,7 +13,7 @@ from oracle import dreamer4_oracle as O
 from oracle import tokenizer_oracle as TO
 from oracle.toy_env import ToyImageEnv
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='first hardware run pending (GPU budget of round 1 spent)')]
+pytestmark = pytest.mark.gpu
 
 WORLD = os.path.join(os.path.dirname(__file__), 'golden', 'tokenizer', 'world_with_tokenizer.pt')
 TOL = dict(atol=5e-5, rtol=2e-4)

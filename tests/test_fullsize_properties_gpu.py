@@ -1,0 +1,112 @@
+"""Parity at BASELINE.json's FULL size (config 4: dim 512, depth 8, 64 x 32 latents, 2048 dreams x 64 frames per GPU), where the
+CPU oracle cannot follow: size-independent properties of the path that tie the full-size run back to the small runs the
+oracle does check.
+
+  * dreams are independent: the first dreams of the 2048-dream rollout equal a 32-dream rollout on the same noise rows;
+  * rollouts are causal: the first 16 frames of the 64-frame rollout equal a 16-frame rollout (another KV capacity / stride);
+  * the update is a mean over (dream, step): with advantage normalisation off, losses and gradients of the full batch equal
+    the average of those of its two halves.
+
+A sampled action that flips (two logits + gumbel within reassociation noise; the fused sum-of-squares uses atomics, so even a
+re-run of the same shape is not bit-identical) forks that one dream from there on, so floats are compared on the dreams whose
+actions agree throughout and at most a small fraction may fork.
+
+STATUS: written after round 1's GPU budget was spent; not yet run on hardware, hence the non-strict xfail (reports XPASS /
+XFAIL without gating the suite).  The marker goes after the first run on a B200."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='first hardware run pending (GPU budget of round 1 spent)')]
+
+B_FULL, H_FULL, B_SMALL, H_SHORT = 2048, 64, 32, 16
+FLAGS = dict(return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
+TOL = dict(atol=2e-4, rtol=2e-4)            # the tf32x3 bar of tests/test_gpu_parity.py at the BASELINE widths
+
+
+def full_model():
+    from bench import WORKLOADS
+    from dreamer4_b200 import DynamicsWorldModel
+    torch.manual_seed(0)
+    model = DynamicsWorldModel(**WORKLOADS['config4']['model'])         # class default precision: tf32x3, what bench.py measures
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'unembed' in n:
+                p.mul_(30.)                                              # logits of O(1..10): sampling is not uniform
+    return model.cuda()
+
+
+def cuda_noise(cfg, T, B, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return dict(latent=torch.randn(T, B, cfg.num_latent_tokens, cfg.dim_latent, device='cuda', generator=g),
+                action_uniform=torch.rand(T, B, sum(cfg.num_discrete_actions), device='cuda', generator=g),
+                terminal_uniform=torch.rand(T, B, device='cuda', generator=g))
+
+
+def compare_dreams(a, b, frames, max_forked):
+    """a, b: Experiences over the same dreams; compares the first `frames` frames."""
+    same = (a.actions.discrete[:, :frames] == b.actions.discrete[:, :frames]).flatten(1).all(dim=1)
+    forked = int((~same).sum())
+    assert forked <= max_forked, f'{forked} of {same.numel()} dreams forked on a sampled action'
+    for name in ('latents', 'rewards', 'values', 'agent_embed'):
+        x, y = getattr(a, name)[same, :frames], getattr(b, name)[same, :frames]
+        torch.testing.assert_close(x, y, **TOL, msg=lambda m, n=name: f'{n}: {m}')
+    torch.testing.assert_close(a.log_probs.discrete[same, :frames], b.log_probs.discrete[same, :frames], **TOL)
+
+
+@pytest.fixture(scope='module')
+def full():
+    model = full_model()
+    noise = cuda_noise(model.cfg, H_FULL, B_FULL, seed=1)
+    exp = model.generate(H_FULL, batch_size=B_FULL, noise=noise, **FLAGS)
+    assert exp.latents.shape == (B_FULL, H_FULL, model.cfg.num_latent_tokens, model.cfg.dim_latent)
+    assert bool(torch.isfinite(exp.latents).all()) and bool(torch.isfinite(exp.values).all())
+    return model, noise, exp
+
+
+def batch_slice(exp, sl):
+    from dreamer4_b200 import Actions, Experience
+    cut = lambda t: t[sl] if torch.is_tensor(t) else t
+    return Experience(latents=cut(exp.latents), agent_embed=cut(exp.agent_embed), rewards=cut(exp.rewards), values=cut(exp.values),
+                      actions=Actions(cut(exp.actions.discrete), None), log_probs=Actions(cut(exp.log_probs.discrete), None),
+                      old_action_unembeds=Actions(cut(exp.old_action_unembeds.discrete), None), lens=cut(exp.lens),
+                      is_truncated=cut(exp.is_truncated), terminals=cut(exp.terminals), step_size=exp.step_size,
+                      agent_index=exp.agent_index, episode_return=cut(exp.episode_return))
+
+
+def test_dreams_are_independent_at_full_size(full):
+    model, noise, exp = full
+    small_noise = {k: v[:, :B_SMALL].contiguous() for k, v in noise.items()}
+    small_model = full_model()
+    small = small_model.generate(H_FULL, batch_size=B_SMALL, noise=small_noise, **FLAGS)
+    compare_dreams(batch_slice(exp, slice(0, B_SMALL)), small, H_FULL, max_forked=2)
+
+
+def test_rollout_prefix_at_full_size(full):
+    model, noise, exp = full
+    short_model = full_model()
+    short = short_model.generate(H_SHORT, batch_size=B_FULL, noise={k: v[:H_SHORT] for k, v in noise.items()}, **FLAGS)
+    compare_dreams(exp, short, H_SHORT, max_forked=B_FULL // 200)
+
+
+def test_update_is_a_mean_over_dreams_at_full_size(full):
+    model, _, exp = full
+
+    def update(e):
+        model.zero_grad()
+        pl, vl = model.learn_from_experience(e, normalize_advantages=False)
+        pl.backward()
+        vl.backward()
+        names = [n for n, p in model.named_parameters() if p.grad is not None]
+        return pl.detach().clone(), vl.detach().clone(), {n: dict(model.named_parameters())[n].grad.clone() for n in names}
+
+    half = B_FULL // 2
+    pl, vl, g = update(exp)
+    pl1, vl1, g1 = update(batch_slice(exp, slice(0, half)))
+    pl2, vl2, g2 = update(batch_slice(exp, slice(half, B_FULL)))
+    # every dream runs the full horizon (no terminal head in config 4): both halves hold the same number of learnable steps
+    torch.testing.assert_close(pl, (pl1 + pl2) / 2, atol=1e-6, rtol=1e-4)
+    torch.testing.assert_close(vl, (vl1 + vl2) / 2, atol=1e-6, rtol=1e-4)
+    assert set(g) == set(g1) == set(g2) and len(g) > 0
+    for n in g:
+        scale = float(g[n].abs().max())
+        torch.testing.assert_close(g[n], (g1[n] + g2[n]) / 2, atol=1e-4 * scale + 1e-12, rtol=1e-3, msg=lambda m, k=n: f'{k}: {m}')

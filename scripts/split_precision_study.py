@@ -8,6 +8,9 @@ Splits of  D = A @ W^T  (A activations (M, K) fp32, W weights (N, K) fp32):
               w_hi = rna_tf32(w), w_lo = rna_tf32(w - w_hi);  D = a_hi.w_hi + a_lo.w_hi + a_hi.w_lo        (3 TF32 MMAs = 3 units)
   f16x3       the same three terms on kind::f16 (twice the TF32 rate): hi = fp16(x), lo = fp16(2^11 (x - hi)), the lo terms
               accumulated apart and scaled by 2^-11 (Ootomo & Yokota's error-corrected fp16 GEMM)             (3 F16 MMAs = 1.5 units)
+  f16x3p      fp16 without the 2^11 trick and with ONE accumulator: rows of A and the whole of W are first multiplied by a power
+              of two that brings their rms to ~1 (exact exponent shifts, undone by the epilogue's row scale), then
+              hi = fp16(x), lo = fp16(x - hi);  D = hi.hi + lo.hi + hi.lo                                     (3 F16 MMAs = 1.5 units)
   tf32+f16x2  main term on TF32, the two corrections on kind::f16 as above                                     (2 units)
   bf16x3      hi / lo in bf16 (8-bit significands), for reference                                              (1.5 units)
   tf32x1      single TF32 pass, for reference                                                                  (1 unit)
@@ -53,6 +56,12 @@ def variants(a, w):
     ah, wh = f16(a), f16(w)
     al, wl = f16((a - ah) * s), f16((w - wh) * s)
     out['f16x3'] = mm(ah, wh) + (mm(al, wh) + mm(ah, wl)) / s
+    pow2 = lambda x: 2.0 ** torch.round(torch.log2(x))
+    p = 1.0 / pow2(a.pow(2).mean(dim=1, keepdim=True).sqrt().clamp(min=1e-30))          # per row of A
+    q = 1.0 / pow2(w.pow(2).mean().sqrt())                                             # per weight matrix
+    ap, wp = a * p, w * q
+    aph, wph = f16(ap), f16(wp)
+    out['f16x3p'] = (mm(aph, wph) + mm(f16(ap - aph), wph) + mm(aph, f16(wp - wph))) / (p.double() * float(q))
     al2, wl2 = f16((a - a_hi) * s), f16((w - w_hi) * s)
     out['tf32+f16x2'] = mm(a_hi, w_hi) + (mm(al2, f16(w_hi)) + mm(f16(a_hi), wl2)) / s
     bh, bwh = bf16(a), bf16(w)
@@ -85,8 +94,10 @@ def main():
     for scale in (1e-6, 1e-4, 1e-2, 1., 1e2, 1e4):
         report(f'K={K} activation scale {scale:g}', torch.randn(256, K) * scale, w)
     a = torch.randn(256, K) * 3e4                              # a few elements beyond fp16's 65504
+    v = variants(a, w)
     print(f'fp16 overflow: {int((a.abs() > 65504).sum())} of {a.numel()} activations exceed 65504 at scale 3e4 ->',
-          'f16x3 finite' if torch.isfinite(variants(a, w)['f16x3']).all() else 'f16x3 produces inf/nan (needs a per-row power-of-two pre-scale)')
+          'f16x3 finite' if torch.isfinite(v['f16x3']).all() else 'f16x3 produces inf/nan',
+          '; f16x3p (pre-scaled rows) finite' if torch.isfinite(v['f16x3p']).all() else '; f16x3p inf/nan')
 
 
 if __name__ == '__main__':

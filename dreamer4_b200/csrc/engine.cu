@@ -670,6 +670,10 @@ extern "C" int d4_linear(int precision, int M, int N, int K, const float* A, int
     g.bias = bias; g.row_scale = row_scale; g.residual = residual; g.ldr = ldr; g.act = act; g.W_lo = W_lo;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (precision == D4_PREC_FP32) return d4_gemm_simt(g, s);
+    if (precision == D4_PREC_F16X3) {          // experimental: W / W_lo point to fp16 (N, ldw) hi / lo words of weights pre-scaled to rms ~ 1
+        if (!W_lo) return d4_fail("d4_linear: f16x3 needs W_lo");
+        return d4_gemm_f16x3(g, 1.f, 0, s);    // the caller folds 1 / q into row_scale
+    }
     if (!d4_gemm_tc_supported(g)) return d4_fail("d4_linear: shape/alignment not supported by the tcgen05 path (need K%%4==0, 16B-aligned rows)");
     if (precision == D4_PREC_TF32X3) { if (!W_lo) return d4_fail("d4_linear: tf32x3 needs W_lo"); return d4_gemm_tc(g, 3, s); }
     return d4_gemm_tc(g, 1, s);

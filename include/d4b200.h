@@ -27,7 +27,8 @@ extern "C" {
 #define D4_MAX_MLP_LAYERS 8
 
 /* precision of the dense layers: exact fp32 FMA, tcgen05 TF32, or tcgen05 3xTF32 split (fp32-accurate) */
-enum { D4_PREC_FP32 = 0, D4_PREC_TF32 = 1, D4_PREC_TF32X3 = 2 };
+enum { D4_PREC_FP32 = 0, D4_PREC_TF32 = 1, D4_PREC_TF32X3 = 2,
+       D4_PREC_F16X3 = 3 /* experimental, d4_linear only: 3-term fp16 split, see dreamer4_b200/csrc/gemm_f16.cu */ };
 
 /* Mirrors the subset of DynamicsWorldModel.__init__ kwargs (D4:4662-4778) that shapes the imagination path. */
 typedef struct d4_config {
@@ -134,7 +135,9 @@ int d4_time_attn_decode(int M, int heads, int query_heads, int dim_head, int t, 
                         const float* qkvgm, int64_t ld, const float* v0, const float* k_gamma, const float* inv_freq,
                         float* kcache, float* vcache, float* out, float softclamp, int commit, int variant, void* stream);
 
-/* C = epilogue(A @ W^T): precision D4_PREC_*; act 0 none / 1 GLU-silu / 2 GLU-gelu (W rows interleaved x,g) */
+/* C = epilogue(A @ W^T): precision D4_PREC_*; act 0 none / 1 GLU-silu / 2 GLU-gelu (W rows interleaved x,g).
+ * D4_PREC_F16X3: W / W_lo point to fp16 (N, ldw) arrays hi = fp16(q W), lo = fp16(q W - hi) with q a power of two that brings
+ * rms(q W) to ~1; the caller folds 1 / q into row_scale. */
 int d4_linear(int precision, int M, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_lo,
               const float* bias, const float* row_scale, const float* residual, int64_t ldr, int act,
               float* C, int64_t ldc, void* stream);

@@ -100,6 +100,26 @@ def test_ctypes_structs_mirror_the_header(tmp_path):
             assert int(got[f'{name}.{field}']) == getattr(cls, field).offset, f'{name}.{field}'
 
 
+def test_sass_is_native_blackwell():
+    """The built library is sm_100a code whose hot kernels use the Blackwell units the design claims: tcgen05 MMAs (UTCHMMA, incl.
+    the CTA-pair form), TMEM loads (LDTM), TMA tile loads / stores (UTMALDG / UTMASTG), bulk copies (UBLKCP: the K1 ring), and no
+    kernel spills registers to local memory.  (Mnemonics per /opt/skills/guides/B200_PROFILING.md.)"""
+    import shutil
+    import subprocess
+    from dreamer4_b200 import _lib
+    if not shutil.which('cuobjdump'):
+        pytest.skip('cuobjdump not on PATH')
+    sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    assert 'arch = sm_100a' in sass and 'arch = sm_90' not in sass
+    for opcode in ('UTCHMMA.2CTA', 'UTCHMMA', 'LDTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'UTCBAR'):
+        assert sass.count(opcode) > 0, opcode
+    usage = subprocess.run(['cuobjdump', '-res-usage', _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    names = re.findall(r'Function (\S+):\n\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)', usage)
+    assert len(names) > 20
+    hot = [(n, int(reg), int(local)) for n, reg, stack, local in names if re.search(r'gemm_tc3_kernel|gemm_tc2_kernel|time_attn_bulk_kernel|gemm_f16x3_kernel', n)]
+    assert hot and all(local == 0 for _, _, local in hot), [h for h in hot if h[2]]
+
+
 def test_no_cpu_fallback():
     from dreamer4_b200._lib import D4Error
     model = DynamicsWorldModel(dim=32, dim_latent=8, num_latent_tokens=6, attn_heads=2, attn_dim_head=16, num_discrete_actions=4)

@@ -8,7 +8,9 @@ a CUDA device and libd4b200.so must be built, otherwise the calls raise."""
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
+import pickle
 from dataclasses import dataclass
 from typing import Optional
 
@@ -17,7 +19,7 @@ from torch import nn
 
 from . import _lib
 from ._lib import D4Error, check, ptr
-from .experience import Actions, DynamicsIntermediates, Experience, TransformerIntermediates
+from .experience import Actions, DynamicsIntermediates, Embeds, Experience, Predictions, TransformerIntermediates
 from .packing import hl_gauss_tables, mlp_param_names, pack, tf32_split
 
 
@@ -121,6 +123,16 @@ _UNSUPPORTED_DEFAULTS = dict(
 )
 
 
+def _records_config(init):
+    """Keeps the constructor arguments on the instance, as `torch_einops_utils.save_load` does for the reference class
+    (reference dreamer4.py:72, 4660) - what .save / .init_and_load pickle next to the state_dict."""
+    @functools.wraps(init)
+    def wrapped(self, *args, **kwargs):
+        self._config = (args, kwargs)
+        init(self, *args, **kwargs)
+    return wrapped
+
+
 class DynamicsWorldModel(nn.Module):
     """Drop-in for the reference class on the imagination path (generate + learn_from_experience).
 
@@ -128,6 +140,7 @@ class DynamicsWorldModel(nn.Module):
     dense layers: 3-term TF32 split on the tensor cores (fp32-accurate), exact-fp32 FMA, or single-pass TF32 (reduced
     precision); the final action unembedding always runs exact fp32.  `time_attn_variant`: K1 kernel (1 = bulk-copy ring, 0 = ld.global)."""
 
+    @_records_config
     def __init__(self, dim, dim_latent, *, num_latent_tokens=None, max_steps=64, num_register_tokens=8, num_spatial_tokens=4,
                  num_agents=1, num_tasks=0, reward_encoder_kwargs: dict = dict(), value_encoder_kwargs: Optional[dict] = None,
                  depth=4, time_block_every=4, attn_kwargs: dict = dict(), transformer_kwargs: dict = dict(), attn_heads=8,
@@ -289,11 +302,36 @@ class DynamicsWorldModel(nn.Module):
     def _named(self, prefixes):
         return [p for n, p in self.named_parameters() if n.startswith(prefixes)]
 
-    def policy_head_parameters(self):      # reference dreamer4.py:5343-5352
-        return self._named(('policy_head.', 'action_embedder.'))
+    def policy_head_parameters(self):      # reference dreamer4.py:5343-5352: the policy MLP + the action UNembedding (1249-1250), not the embedding
+        unembeds = ('action_embedder.discrete_action_unembed', 'action_embedder.continuous_action_unembed')
+        return self._named(('policy_head.',)) + [p for n, p in self.named_parameters() if n in unembeds]
+
+    def muon_parameters(self):             # reference dreamer4.py:5335-5341, 2918-2925, 1960-1966, 2099-2103: to_v / to_out / proj_in / proj_out weights
+        ends = ('.to_v.weight', '.to_out.weight', '.proj_in.weight', '.proj_out.weight')
+        return [p for n, p in self.named_parameters() if n.startswith('transformer.') and n.endswith(ends)]
 
     def value_head_parameters(self):       # reference dreamer4.py:5354-5363
         return self._named(('value_head.',))
+
+    # .save / .load / .init_and_load of the reference's @save_load (dreamer4.py:4660; used at cli.py:329, tests/test_dreamer.py:2243-2247):
+    # one torch.save'd dict {model: state_dict, config: pickled (args, kwargs)}
+
+    def save(self, path, overwrite=True):
+        import os
+        assert overwrite or not os.path.exists(str(path)), f'{path} already exists'
+        torch.save(dict(model=self.state_dict(), config=pickle.dumps(self._config)), str(path))
+
+    def load(self, path, strict=True):
+        pkg = torch.load(str(path), map_location='cpu', weights_only=False)
+        self.load_state_dict(pkg['model'], strict=strict)
+
+    @classmethod
+    def init_and_load(cls, path, strict=True):
+        pkg = torch.load(str(path), map_location='cpu', weights_only=False)
+        args, kwargs = pickle.loads(pkg['config'])
+        model = cls(*args, **kwargs)
+        model.load_state_dict(pkg['model'], strict=strict)
+        return model
 
     # ------------------------------------------------------------------ engine plumbing
 
@@ -423,6 +461,26 @@ class DynamicsWorldModel(nn.Module):
 
     # ------------------------------------------------------------------ generate
 
+    def _adopt_time_cache(self, resumed_kv, P, B, T, agent_index, grow):
+        """Engine context with KV capacity >= T whose first P frames hold `resumed_kv` (None: nothing to adopt): a view of the
+        live in-place buffer is taken as is - if no other rollout has written the buffer since it was handed out - anything
+        else is copied in.  Returns (lib, ctx, kv buffer)."""
+        c = self.cfg
+        lib, ctx = self._engine(B, T, agent_index, grow=grow)
+        kv = self._bufs['kv']
+        L, BS = c.num_time_layers, B * c.tokens_per_frame
+        if exists(resumed_kv) and P > 0 and L > 0:
+            dst = kv[:L, :, :BS, :, :P]
+            assert tuple(resumed_kv.shape) == tuple(dst.shape), f'time_cache kv {tuple(resumed_kv.shape)} != {tuple(dst.shape)}'
+            if resumed_kv.untyped_storage().data_ptr() == kv.untyped_storage().data_ptr():
+                # a view of the live in-place cache: only valid if no other rollout has written the buffer since
+                if getattr(resumed_kv, '_d4_epoch', None) != self._kv_epoch or resumed_kv.data_ptr() != dst.data_ptr() or resumed_kv.stride() != dst.stride():
+                    raise ValueError('stale time_cache: it is a view of the in-place KV buffer, which a later generate() has '
+                                     'overwritten; clone next_kv_cache to keep a cache across rollouts')
+            else:
+                dst.copy_(resumed_kv.to(device=self.device, dtype=torch.float32))
+        return lib, ctx, kv
+
     @torch.no_grad()
     def generate(self, time_steps, num_steps=4, batch_size=1, agent_index=0, tasks=None, latent_gene_ids=None, image_height=None,
                  image_width=None, return_decoded_video=None, context_signal_noise=0.1, time_cache=None, use_time_cache=True,
@@ -471,20 +529,8 @@ class DynamicsWorldModel(nn.Module):
             resumed_kv = time_cache.main.next_kv_cache if exists(time_cache.main) else None
             cached = time_cache.main.token_count if exists(time_cache.main) else 0
             assert cached == P, f'time_cache holds {cached} frames but the prompt has {P}: pass the latents of exactly the cached frames'
-        prompted = P > 0 or exists(time_cache)
-        lib, ctx = self._engine(B, T, agent_index, grow=prompted)
-        kv = self._bufs['kv']
-        L, BS = c.num_time_layers, B * c.tokens_per_frame
-        if exists(resumed_kv) and P > 0 and L > 0:
-            dst = kv[:L, :, :BS, :, :P]
-            assert tuple(resumed_kv.shape) == tuple(dst.shape), f'time_cache kv {tuple(resumed_kv.shape)} != {tuple(dst.shape)}'
-            if resumed_kv.untyped_storage().data_ptr() == kv.untyped_storage().data_ptr():
-                # a view of the live in-place cache: only valid if no other rollout has written the buffer since
-                if getattr(resumed_kv, '_d4_epoch', None) != self._kv_epoch or resumed_kv.data_ptr() != dst.data_ptr() or resumed_kv.stride() != dst.stride():
-                    raise ValueError('stale time_cache: it is a view of the in-place KV buffer, which a later generate() has '
-                                     'overwritten; clone next_kv_cache to keep a cache across rollouts')
-            else:
-                dst.copy_(resumed_kv.to(**f32))
+        lib, ctx, kv = self._adopt_time_cache(resumed_kv, P, B, T, agent_index, grow=P > 0 or exists(time_cache))
+        L = c.num_time_layers
         self._kv_epoch += 1
 
         return_agent_actions = (return_agent_actions or return_log_probs_and_values) and c.has_actions

@@ -16,6 +16,8 @@ Actions = namedtuple('Actions', ['discrete', 'continuous'])
 
 TransformerIntermediates = namedtuple('TransformerIntermediates', ['next_kv_cache', 'token_count'])
 DynamicsIntermediates = namedtuple('DynamicsIntermediates', ['main'])
+Predictions = namedtuple('Predictions', ['flow', 'proprioception', 'state'])              # reference dreamer4.py:128
+Embeds = namedtuple('Embeds', ['agent', 'state_pred', 'actor', 'critic'], defaults=(None, None, None))    # reference dreamer4.py:130
 
 
 def _map_tensors(fn, v):

@@ -192,6 +192,10 @@ def run_case(ref, name, model_kwargs, gen_kwargs, seed=7):
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     out.update(policy_loss=policy_loss.detach(), value_loss=value_loss.detach(), grads=grads)
 
+    # parameter groups the trainers hand to their optimizers (D4:5335-5363)
+    names = {id(p): n for n, p in model.named_parameters()}
+    out['param_groups'] = {fn: [names[id(p)] for p in getattr(model, fn)()] for fn in ('muon_parameters', 'policy_head_parameters', 'value_head_parameters')}
+
     # off-policy replay: nudge the policy head (as an optimizer step would) so the importance ratio leaves 1, the PPO
     # clip engages and the PMPO KL term is non-zero, then run all three surrogate objectives (D4:6127-6212)
     torch.manual_seed(seed + 2000)

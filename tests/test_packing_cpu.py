@@ -56,6 +56,38 @@ def test_packed_dataflow_matches_oracle(path):
         prev = torch.stack([torch.randint(0, n, (B,)) for n in cfg.num_discrete_actions], dim=-1)
 
 
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_parameter_groups_match_reference(path):
+    """muon_parameters / policy_head_parameters / value_head_parameters name the same tensors as the reference's (D4:5335-5363);
+    the policy group is the policy MLP + the action UNembeddings (a set in the reference, 1249-1250), not the action embedding."""
+    fx = torch.load(path, map_location='cpu', weights_only=False)
+    model = DynamicsWorldModel(**fx['model_kwargs'])
+    names = {id(p): n for n, p in model.named_parameters()}
+    for fn, want in fx['out']['param_groups'].items():
+        got = [names[id(p)] for p in getattr(model, fn)()]
+        assert sorted(got) == sorted(want), fn
+        if fn != 'policy_head_parameters':
+            assert got == want, fn
+
+
+def test_save_and_init_and_load_round_trip(tmp_path):
+    """.save / .load / .init_and_load of the reference's @save_load (D4:4660; tests/test_dreamer.py:2243-2247 of the reference):
+    the constructor arguments travel with the state_dict, so a checkpoint rebuilds the same architecture and weights."""
+    fx = torch.load(GOLDEN[1], map_location='cpu', weights_only=False)
+    model = DynamicsWorldModel(**fx['model_kwargs'])
+    path = tmp_path / 'world.pt'
+    model.save(path)
+    with pytest.raises(AssertionError):
+        model.save(path, overwrite=False)
+    clone = DynamicsWorldModel.init_and_load(path)
+    assert clone.cfg == model.cfg
+    sd, sd2 = model.state_dict(), clone.state_dict()
+    assert list(sd) == list(sd2) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+    other = DynamicsWorldModel(**fx['model_kwargs'])
+    other.load(path)
+    assert all(torch.equal(sd[k], v) for k, v in other.state_dict().items())
+
+
 def test_tf32_split_round_to_nearest():
     """w = hi + lo with both words TF32-representable (so the tensor core's operand truncation is a no-op), hi the NEAREST
     TF32 value (|lo| <= 2^-11 |w|: half a TF32 ulp) and a residual of at most 2^-23 |w|: an fp32 ulp."""

@@ -229,7 +229,9 @@ def run_native(args):
                                      f'{B} dreams x {H} frames per GPU, 4 denoise + 1 clean pass per frame, generate + learn_from_experience + AdamW',
                             dreams_per_gpu=B, horizon=H, global_dreams=world * B, precision=args.precision,
                             precision_note={'tf32x3': 'fp32 in / fp32 out; every dense product = 3 TF32 tensor-core MMAs (hi/lo split), fp32 accumulate: fp32-level accuracy',
-                                            'fp32': 'exact fp32 FMA on CUDA cores', 'tf32': 'single-pass TF32 operands (reduced precision)'}[args.precision],
+                                            'fp32': 'exact fp32 FMA on CUDA cores', 'tf32': 'single-pass TF32 operands (reduced precision)',
+                                            'f16x3': 'EXPERIMENTAL: fp32 in / fp32 out; transformer dense products = 3 fp16 tensor-core MMAs (hi/lo split of '
+                                                     'power-of-two pre-scaled operands), fp32 accumulate; heads and learn on 3xTF32'}[args.precision],
                             time_attn_variant=args.variant,
                             parallelism=f'dp{world} (dream batch sharded, one flat gradient all-reduce)',
                             l2='inputs larger than L2 (KV cache + activations per pass >> 126 MB)' if B * H >= 4096 else 'small problem: L2 resident'),
@@ -245,14 +247,14 @@ def run_native(args):
         # GEMM roofline: `achieved` counts ALGORITHMIC FLOPs (2*M*N*K per layer).  The fp32-accurate path executes 3 TF32
         # tensor-core products per algorithmic one, and TF32 runs at half the bf16 rate the measured peak is quoted in, so the
         # tensor pipe's own bound for this arithmetic is peak / 6 (peak / 2 for single-pass tf32): `frac_of_arith_bound`.
-        terms = {'tf32x3': 3, 'tf32': 1}.get(args.precision)
+        terms = {'tf32x3': 3, 'tf32': 1, 'f16x3': 1.5}.get(args.precision)      # f16x3: 3 fp16 MMAs at the bf16 rate = 1.5 TF32 units
         roof_gemm = dict(bound='tensor', kernel='gemm (all linear layers)', achieved=gemm_tf, peak=pk['tensor_sustained'], unit='TFLOP/s',
                          frac=gemm_tf / pk['tensor_sustained'], traffic=None, launches=int(prof[0][1]), share_of_step=shares['gemm'],
                          peak_is='measured cuBLAS bf16 dense, sustained')
         if terms:
             roof_gemm.update(executed_tensor_tflops=gemm_tf * terms, tf32_peak_est=pk['tensor_sustained'] / 2,
                              frac_of_arith_bound=gemm_tf * terms / (pk['tensor_sustained'] / 2),
-                             note=f'{args.precision}: {terms} TF32 MMA(s) per algorithmic product; TF32 = half the bf16 rate')
+                             note=f'{args.precision}: {terms} TF32-MMA unit(s) per algorithmic product; TF32 = half the bf16 rate')
         roof_attn = dict(bound='hbm', kernel='time_attn (K1, KV-cache decode)', achieved=attn_gbs, peak=pk['hbm'], unit='GB/s',
                          frac=attn_gbs / pk['hbm'], traffic=None, launches=int(prof[1][1]), share_of_step=shares['time_attn'],
                          traffic_note='ncu dram bytes == algorithmic bytes at t=40 (profiles/r1a_ncu_k1_t40_raw.csv: 5.29 GB read per launch)')
@@ -346,7 +348,7 @@ def main():
     ap.add_argument('--workload', default='config4', choices=list(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='dreams per GPU (default: the workload\'s)')
     ap.add_argument('--horizon', type=int, default=0)
-    ap.add_argument('--precision', default=os.environ.get('D4_BENCH_PRECISION', 'tf32x3'), choices=['fp32', 'tf32', 'tf32x3'],
+    ap.add_argument('--precision', default=os.environ.get('D4_BENCH_PRECISION', 'tf32x3'), choices=['fp32', 'tf32', 'tf32x3', 'f16x3'],
                     help='tf32x3 (default): 3-term TF32 split on tcgen05, fp32-accurate; fp32: SIMT FMA; tf32: single-pass (reduced precision)')
     ap.add_argument('--variant', type=int, default=1, help='K1 kernel variant (0 ld.global staged, 1 cp.async.bulk ring)')
     ap.add_argument('--cpu-sample', default='16x16', help='CPU baseline sample: dreams x frames')

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, 'csrc', 'libd4b200.so')
 
 D4_MAX_ACTION_TYPES = 8
 D4_MAX_MLP_LAYERS = 8
-PREC = dict(fp32=0, tf32=1, tf32x3=2)
+PREC = dict(fp32=0, tf32=1, tf32x3=2, f16x3=3)      # f16x3: experimental, see include/d4b200.h
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -85,6 +85,7 @@ SYMBOLS = {
     'd4_ctx_create': (_i, [C.POINTER(d4_config), C.POINTER(_p)]),
     'd4_ctx_destroy': (None, [_p]),
     'd4_set_weight': (_i, [_p, C.c_char_p, _p, _i64]),
+    'd4_set_weight_scale': (_i, [_p, C.c_char_p, _f]),
     'd4_bind': (_i, [_p]),
     'd4_workspace_bytes': (_i64, [_p]),
     'd4_kv_bytes': (_i64, [_p]),

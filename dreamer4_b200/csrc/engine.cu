@@ -87,6 +87,13 @@ extern "C" int d4_set_weight(d4_ctx* c, const char* name, const float* p, int64_
     c->bound = false;
     return 0;
 }
+extern "C" int d4_set_weight_scale(d4_ctx* c, const char* name, float scale) {
+    if (!c || !name) return d4_fail("d4_set_weight_scale: null argument");
+    if (!(scale > 0.f) || !(scale < 3.0e38f)) return d4_fail("d4_set_weight_scale: '%s' needs a positive finite scale", name);
+    c->scales[name] = scale;
+    c->bound = false;
+    return 0;
+}
 
 int d4_engine_plan(d4_ctx* c) {
     const long long B = c->cfg.max_batch, M = B * c->S;
@@ -156,9 +163,18 @@ struct Binder {
     }
     LinW lin(const std::string& name, int64_t numel) {
         LinW w; w.w = get(name, numel);
-        const bool optional = c->cfg.precision != D4_PREC_TF32X3;
+        const bool optional = !d4_prec_split(c->cfg.precision);
         w.hi = get(name + ".hi", numel, optional);
         w.lo = get(name + ".lo", numel, optional);
+        if (c->cfg.precision == D4_PREC_F16X3) {
+            // fp16 words of the pre-scaled weight (same element count, 2 bytes each) and 1 / q; a weight registered without
+            // them simply stays on the 3xTF32 kernel
+            w.h_hi = get(name + ".h16hi", numel, true);
+            w.h_lo = get(name + ".h16lo", numel, true);
+            auto it = c->scales.find(name);
+            if (w.h_hi && w.h_lo && it != c->scales.end()) w.h_scale = it->second;
+            else w.h_hi = w.h_lo = nullptr;
+        }
         return w;
     }
 };
@@ -279,8 +295,12 @@ int d4_engine_gemm(d4_ctx* c, GemmArgs g, const LinW& w, int force_fp32, cudaStr
     const int prec = force_fp32 ? D4_PREC_FP32 : c->cfg.precision;
     const int ph = d4_prof_begin(c, D4_CLS_GEMM, 2.0 * g.M * g.N * g.K, s);
     int rc;
-    if (prec != D4_PREC_FP32 && d4_gemm_tc_supported(g)) {
-        if (prec == D4_PREC_TF32X3 && w.hi && w.lo) { g.W = w.hi; g.W_lo = w.lo; rc = d4_gemm_tc(g, 3, s); }
+    if (prec == D4_PREC_F16X3 && w.h_hi && w.h_lo && d4_gemm_f16x3_supported(g, w.h_hi, w.h_lo)) {
+        // fp16 3-term split on kind::f16 (gemm_f16.cu); the fp16 arrays share the fp32 weight's (N, ldw) shape
+        g.W = static_cast<const float*>(w.h_hi); g.W_lo = static_cast<const float*>(w.h_lo);
+        rc = d4_gemm_f16x3(g, w.h_scale, 0, s);
+    } else if (prec != D4_PREC_FP32 && d4_gemm_tc_supported(g)) {
+        if (d4_prec_split(prec) && w.hi && w.lo) { g.W = w.hi; g.W_lo = w.lo; rc = d4_gemm_tc(g, 3, s); }
         else rc = d4_gemm_tc(g, 1, s);
     } else {
         rc = d4_gemm_simt(g, s);
@@ -303,7 +323,7 @@ int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, in
         GemmArgs g = gemm_args(cur, ldc, mlp.w[l], mlp.dims[l], dst, ldd, M, mlp.dims[l + 1], mlp.dims[l]);
         g.bias = mlp.b[l];
         LinW lw; lw.w = mlp.w[l]; lw.hi = mlp.hi[l]; lw.lo = mlp.lo[l];
-        const int exact = !(allow_tensor && c->cfg.precision == D4_PREC_TF32X3 && lw.hi && lw.lo);
+        const int exact = !(allow_tensor && d4_prec_split(c->cfg.precision) && lw.hi && lw.lo);
         D4_TRY(d4_engine_gemm(c, g, lw, exact, s));
         if (!last) D4_TRY(d4_ln_act_rows(dst, ldd, mlp.lnw[l], mlp.lnb[l], M, mlp.dims[l + 1], dst, ldd, D4_ACT_SILU, nullptr, nullptr, s));
         cur = dst; ldc = ldd;
@@ -418,7 +438,7 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
     // RMS statistics.  Fused mode (CTA-pair tensor-core GEMMs, D <= 512 so a row spans at most two column tiles and the two
     // atomic partial sums commute): every GEMM that produces a residual-stream snapshot accumulates the rows' sums of squares in
     // its epilogue and every consumer turns them into rstd on the fly — no separate pass re-reads the 63 MB snapshots.
-    const int fss = (c->fuse_ss && c->cfg.precision == D4_PREC_TF32X3 && M > 128 && D <= 512 && (D % 4) == 0 && d4_gemm_pair_default()) ? 1 : 0;
+    const int fss = (c->fuse_ss && d4_prec_split(c->cfg.precision) && M > 128 && D <= 512 && (D % 4) == 0 && d4_gemm_pair_default()) ? 1 : 0;
     auto xss = [&](int j) { return c->b.x_rstd + (long long)j * M; };
     if (fss) {
         D4_CUDA_OK(cudaMemsetAsync(hrs(1), 0, (size_t)(c->n_hid - 1) * M * 4, s));

@@ -6,7 +6,11 @@
 #include "../../include/d4b200.h"
 #include "kernels.h"
 
-struct LinW { const float* w = nullptr; const float* hi = nullptr; const float* lo = nullptr; };   // GEMM weight (+ its tf32 hi/lo split for tf32x3)
+// GEMM weight, its tf32 hi/lo split (tf32x3), and - f16x3 engine mode only - the fp16 hi/lo words of q W with h_scale = 1 / q
+struct LinW { const float* w = nullptr; const float* hi = nullptr; const float* lo = nullptr;
+              const void* h_hi = nullptr; const void* h_lo = nullptr; float h_scale = 1.f; };
+// the two engine modes whose dense layers are fp32-accurate tensor-core split products
+static inline bool d4_prec_split(int p) { return p == D4_PREC_TF32X3 || p == D4_PREC_F16X3; }
 
 struct AttnLayerW { LinW w; const float* b; const float* k_gamma; LinW w_out; };
 struct FFW { LinW w_in; const float* b_in; LinW w_out; const float* b_out; };
@@ -29,6 +33,7 @@ struct d4_ctx {
     int act_off[D4_MAX_ACTION_TYPES];
 
     std::unordered_map<std::string, std::pair<const float*, int64_t>> table;
+    std::unordered_map<std::string, float> scales;      // d4_set_weight_scale: 1 / q of the fp16-split weights
     bool bound = false;
 
     // bound weights

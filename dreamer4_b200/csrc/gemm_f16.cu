@@ -424,6 +424,22 @@ int encode_out32(CUtensorMap* map, const float* base, long long M, long long N, 
 }
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// What the kernel can take: the TMA epilogue only (16-byte aligned rows, row maps whose groups tile the 32-row warp slices),
+// fp16 weight rows of ldw elements (a multiple of 8 = 16 bytes), sum-of-squares output on identity rows without GLU.
+bool operands_ok(const GemmArgs& g, const void* whi, const void* wlo) {
+    const bool glu = (g.act == D4_ACT_GLU_SILU || g.act == D4_ACT_GLU_GELU);
+    const int grp = g.cmap.grp;
+    if (g.M < 1 || g.N < 1 || g.K < 1 || (glu && (g.N & 1)) || g.act == D4_ACT_SILU) return false;
+    bool ok = whi && wlo && al16(g.A) && (g.lda % 4 == 0) && al16(whi) && al16(wlo) && (g.ldw % 8 == 0) && al16(g.C) && (g.ldc % 4 == 0) && (!g.bias || al16(g.bias)) &&
+              (grp == 0 || (32 % grp == 0 && g.M % grp == 0 && (((long long)g.cmap.goff * g.ldc) % 4 == 0) && (((long long)g.cmap.gstride * g.ldc) % 4 == 0))) &&
+              (g.amap.grp == 0 || (BM % g.amap.grp == 0 && g.M % g.amap.grp == 0 && g.amap.grp <= 256 && (((long long)g.amap.goff * g.lda) % 4 == 0))) &&
+              !g.transA && !g.transW;
+    if (g.residual) ok = ok && al16(g.residual) && (g.ldr % 4 == 0) &&
+                         (grp == 0 || ((((long long)g.cmap.goff * g.ldr) % 4 == 0) && (((long long)g.cmap.gstride * g.ldr) % 4 == 0)));
+    if (g.ss_out) ok = ok && grp == 0 && !glu && (g.N % 4) == 0;
+    return ok;
+}
+
 template <int BN>
 int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
     using K = CfgH<BN>;
@@ -440,15 +456,7 @@ int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
     }
     if (maxc <= 0) return d4_fail("gemm_f16: no CTA pair of %d bytes of shared memory can be scheduled on this device", K::SMEM);
     const bool glu = (g.act == D4_ACT_GLU_SILU || g.act == D4_ACT_GLU_GELU);
-    const int grp = g.cmap.grp;
-    // this draft has the TMA epilogue only: 16-byte aligned rows, row maps whose groups tile the 32-row warp slices
-    bool ok = al16(g.A) && (g.lda % 4 == 0) && al16(g.W) && al16(g.W_lo) && (g.ldw % 8 == 0) && al16(g.C) && (g.ldc % 4 == 0) && (!g.bias || al16(g.bias)) &&
-              (grp == 0 || (32 % grp == 0 && g.M % grp == 0 && (((long long)g.cmap.goff * g.ldc) % 4 == 0) && (((long long)g.cmap.gstride * g.ldc) % 4 == 0))) &&
-              (g.amap.grp == 0 || (BM % g.amap.grp == 0 && g.M % g.amap.grp == 0)) && !g.transA && !g.transW;
-    if (g.residual) ok = ok && al16(g.residual) && (g.ldr % 4 == 0) &&
-                         (grp == 0 || ((((long long)g.cmap.goff * g.ldr) % 4 == 0) && (((long long)g.cmap.gstride * g.ldr) % 4 == 0)));
-    if (!ok) return d4_fail("gemm_f16: operand alignment / row map not supported by this kernel");
-    if (g.ss_out && (grp != 0 || glu || (g.N % 4) != 0)) return d4_fail("gemm_f16: ss_out needs identity output rows, no GLU and N %% 4 == 0");
+    if (!operands_ok(g, g.W, g.W_lo)) return d4_fail("gemm_f16: operand alignment / row map not supported by this kernel");
     TmaMapsH maps; memset(&maps, 0, sizeof(maps));
     { int rc = encode_a32(&maps.a, g.A, g.M, g.K, g.lda, g.amap); if (rc) return rc; }
     { int rc = encode_w16(&maps.w, g.W, g.N, g.K, g.ldw, K::BNH); if (rc) return rc; }
@@ -472,6 +480,13 @@ int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// 1 if the engine may route this GEMM here given the fp16 hi / lo arrays of its weight: the pair kernel's shapes (more rows than
+// one CTA's 128, like gemm_tc3.cu), whole 64-column K steps (K = dim, ff_inner_pad, pool width ... of every BASELINE config), and
+// the operand rules above.  g.W still points to the fp32 weight; only its leading dimension is read.
+int d4_gemm_f16x3_supported(const GemmArgs& g, const void* whi, const void* wlo) {
+    return (g.M > BM && (g.K % 32) == 0 && g.K >= BK && operands_ok(g, whi, wlo)) ? 1 : 0;
+}
 
 // g.W / g.W_lo point to fp16 arrays (N, ldw) holding hi = fp16(q W), lo = fp16(q W - hi); w_scale = 1 / q.  bn = 128 | 256 (0: by padding).
 int d4_gemm_f16x3(const GemmArgs& g, float w_scale, int bn, cudaStream_t stream) {

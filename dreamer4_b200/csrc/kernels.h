@@ -14,6 +14,7 @@ int d4_gemm_tc2(const GemmArgs& g, int terms, int bn, cudaStream_t stream);
 int d4_gemm_tc3(const GemmArgs& g, int terms, int bn, cudaStream_t stream);
 // experimental fp16 3-term split (gemm_f16.cu): g.W / g.W_lo are fp16 (N, ldw) arrays of the pre-scaled weights, w_scale = 1 / q
 int d4_gemm_f16x3(const GemmArgs& g, float w_scale, int bn, cudaStream_t stream);
+int d4_gemm_f16x3_supported(const GemmArgs& g, const void* whi, const void* wlo);
 
 // ---- row-wise kernels (rowops.cu)
 struct AssembleArgs {

@@ -359,7 +359,7 @@ LearnPlan plan_learn(const d4_ctx* c, int B, int T) {
     const int ldl = std::max(c->ldlog, (c->cfg.value_bins + 3) / 4 * 4);
     p.logits = take((long long)p.Rc * ldl * 4); p.dlogits = take((long long)p.Rc * ldl * 4);
     p.g0 = take((long long)p.Rc * H * 4); p.g1 = take((long long)p.Rc * H * 4);
-    if (c->cfg.precision == D4_PREC_TF32X3) {
+    if (d4_prec_split(c->cfg.precision)) {
         p.dyT = take((long long)p.Rc * H * 4); p.xT_hi = take((long long)p.Rc * H * 4); p.xT_lo = take((long long)p.Rc * H * 4);
     }
     p.total = off;
@@ -403,7 +403,7 @@ int transpose_rows(int R, int C, const float* in, long long ld, float* out, floa
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }
-inline bool learn_tc(const d4_ctx* c) { return c->cfg.precision == D4_PREC_TF32X3; }
+inline bool learn_tc(const d4_ctx* c) { return d4_prec_split(c->cfg.precision); }   // f16x3 mode: the heads stay on 3xTF32
 
 // forward of one head on a chunk of rows, keeping what the backward needs
 int mlp_forward_saved(d4_ctx* c, const MlpW& mlp, const float* x0, int Rc, unsigned char* ws, const LearnPlan& p, float* out, long long ldo,

@@ -136,7 +136,7 @@ def _records_config(init):
 class DynamicsWorldModel(nn.Module):
     """Drop-in for the reference class on the imagination path (generate + learn_from_experience).
 
-    Extra keyword arguments (not in the reference): `precision` in {'tf32x3' (default), 'fp32', 'tf32'} — arithmetic of the
+    Extra keyword arguments (not in the reference): `precision` in {'tf32x3' (default), 'fp32', 'tf32', 'f16x3' (experimental)} — arithmetic of the
     dense layers: 3-term TF32 split on the tensor cores (fp32-accurate), exact-fp32 FMA, or single-pass TF32 (reduced
     precision); the final action unembedding always runs exact fp32.  `time_attn_variant`: K1 kernel (1 = bulk-copy ring, 0 = ld.global)."""
 
@@ -394,7 +394,10 @@ class DynamicsWorldModel(nn.Module):
         ver = (self._frozen_version(), agent_index)
         if self._packed_version != ver:
             sd = {k: v for k, v in self.state_dict().items()}
-            self._packed = pack(sd, c, dev, agent_index=agent_index, split=self.precision == 'tf32x3')
+            split = self.precision in ('tf32x3', 'f16x3')       # f16x3: the heads, d4_learn and odd shapes stay on 3xTF32
+            self._packed = pack(sd, c, dev, agent_index=agent_index, split=split, split_f16=self.precision == 'f16x3')
+            for name, scale in self._packed.pop('h16scales', {}).items():
+                check(lib.d4_set_weight_scale(self._ctx, name.encode(), scale))
             for name, t in self._packed.items():
                 check(lib.d4_set_weight(self._ctx, name.encode(), ptr(t), t.numel()))
             params = dict(self.named_parameters())
@@ -407,7 +410,7 @@ class DynamicsWorldModel(nn.Module):
                     t = params[key_]
                     assert t.is_contiguous()
                     check(lib.d4_set_weight(self._ctx, f'{short}.{pname}'.encode(), ptr(t), t.numel()))
-                    if self.precision == 'tf32x3' and pname.endswith('.w') and short != 'terminal':
+                    if split and pname.endswith('.w') and short != 'terminal':
                         # trained head weights change every optimizer step: their tf32 hi/lo split lives in persistent
                         # buffers that _refresh_head_splits() rewrites in place when the parameter version moves
                         hi, lo = torch.empty_like(t), torch.empty_like(t)

@@ -16,7 +16,8 @@ Packed names (what d4_bind() resolves; shapes in the reference's nn.Linear (out,
   policy.{l}.{w,b,lnw,lnb}, value.{l}.*, terminal.{l}.*, unembed            borrowed parameter pointers (no copy: optimizer steps stay visible)
 
 Every GEMM weight `name` also gets `name.hi` / `name.lo` (tf32 split: hi has 10 explicit mantissa bits, lo = w - hi) when
-the engine runs in tf32x3 precision.
+the engine runs in tf32x3 precision, and on top of those `name.h16hi` / `name.h16lo` + a scale (f16_split) in the experimental
+f16x3 precision.
 
 Folding gamma:  rmsnorm(x; gamma) @ W^T == rstd(x) * (x @ (W * gamma)^T): the engine computes rstd per row and applies it as
 the GEMM's row scale, so normalised activations never round-trip through HBM."""
@@ -44,15 +45,28 @@ def tf32_split(w):
     return hi, tf32_round(w - hi)
 
 
+def f16_split(w):
+    """fp16 operand split of the experimental f16x3 mode (csrc/gemm_f16.cu): q = the power of two that brings rms(q w) to ~1,
+    hi = fp16(q w), lo = fp16(q w - hi) - both round-to-nearest, so hi + lo carries ~22 significand bits of q w wherever lo stays
+    a normal fp16 number.  Returns (hi, lo, 1 / q); the GEMM's epilogue multiplies by 1 / q (an exact exponent shift)."""
+    rms = w.float().pow(2).mean().sqrt().clamp_min(1e-30)
+    q = torch.exp2(torch.round(torch.log2(1.0 / rms)))
+    wq = w.float() * q
+    hi = wq.half()
+    lo = (wq - hi.float()).half()
+    return hi.contiguous(), lo.contiguous(), float(1.0 / q)
+
+
 def hl_gauss_tables(lo, hi, num_bins, device):
     support = torch.linspace(lo, hi, num_bins + 1).float()
     centers = (support[:-1] + support[1:]) / 2
     return support.to(device), centers.to(device)
 
 
-def pack(sd, cfg, device, agent_index=0, split=False):
+def pack(sd, cfg, device, agent_index=0, split=False, split_f16=False):
     """sd: reference-layout state_dict (tensors on `device`); cfg: dreamer4_b200.dynamics.ModelConfig.
-    Returns {packed name: fp32 contiguous tensor}."""
+    Returns {packed name: fp32 contiguous tensor}; with `split_f16` also `name.h16hi` / `name.h16lo` (fp16) per GEMM weight and
+    their 1 / q under the key 'h16scales' (a {name: float} dict, not a tensor)."""
     g = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
     out = {}
     D, Dl = cfg.dim, cfg.dim_latent
@@ -134,6 +148,12 @@ def pack(sd, cfg, device, agent_index=0, split=False):
         for k in list(out):
             if k.endswith(GEMM_WEIGHTS_SUFFIXES) and not k.startswith('reward.'):
                 out[k + '.hi'], out[k + '.lo'] = (t.contiguous() for t in tf32_split(out[k]))
+    if split_f16:
+        scales = {}
+        for k in list(out):
+            if k.endswith(GEMM_WEIGHTS_SUFFIXES) and not k.startswith('reward.'):
+                out[k + '.h16hi'], out[k + '.h16lo'], scales[k] = f16_split(out[k])
+        out['h16scales'] = scales
     return out
 
 

@@ -28,7 +28,8 @@ extern "C" {
 
 /* precision of the dense layers: exact fp32 FMA, tcgen05 TF32, or tcgen05 3xTF32 split (fp32-accurate) */
 enum { D4_PREC_FP32 = 0, D4_PREC_TF32 = 1, D4_PREC_TF32X3 = 2,
-       D4_PREC_F16X3 = 3 /* experimental, d4_linear only: 3-term fp16 split, see dreamer4_b200/csrc/gemm_f16.cu */ };
+       D4_PREC_F16X3 = 3 /* experimental (never run on hardware in round 1): 3-term fp16 split on kind::f16 for the transformer's
+                            dense layers, 3xTF32 for the heads and d4_learn; see dreamer4_b200/csrc/gemm_f16.cu */ };
 
 /* Mirrors the subset of DynamicsWorldModel.__init__ kwargs (D4:4662-4778) that shapes the imagination path. */
 typedef struct d4_config {
@@ -66,6 +67,11 @@ void d4_ctx_destroy(d4_ctx* ctx);
  * how each is derived from the reference state_dict).  d4_bind() resolves every name the configuration needs
  * and fails with the first missing one. */
 int d4_set_weight(d4_ctx* ctx, const char* name, const float* dev_ptr, int64_t numel);
+/* D4_PREC_F16X3 only (experimental): a GEMM weight `name` may also be registered as `name.h16hi` / `name.h16lo` - fp16 arrays of
+ * the same (out, in) shape holding hi = fp16(q W), lo = fp16(q W - hi), q a power of two that brings rms(q W) to ~1 (dev_ptr
+ * cast to const float*, numel counted in ELEMENTS) - together with scale = 1 / q here.  Weights without them, and shapes the
+ * fp16 kernel does not take, stay on the 3xTF32 kernel (their `.hi` / `.lo` are required in this mode as well). */
+int d4_set_weight_scale(d4_ctx* ctx, const char* name, float scale);
 int d4_bind(d4_ctx* ctx);
 
 /* Workspace (activations of one pass) and the time-KV cache are caller-allocated.

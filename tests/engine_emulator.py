@@ -164,3 +164,68 @@ def emulate_pass(P, cfg, latent, signal, step_log2, prev_actions, kv_cache, t):
                              gate=P['lp.gate'][None].expand(B, -1, -1))
         pred = (o.reshape(B * N, Dq) @ P['lp.w_comb'].T).reshape(B, N, -1)
     return pred, agent, new_kv
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Operand-split emulation: a packed GEMM weight wrapped so that `x @ W.T` inside emulate_pass computes what the tensor-core
+# kernels compute - each operand split into two narrow words, three of the four cross products summed (exact products; the
+# fp32 accumulation is emulated in fp64, i.e. its rounding is left out: it is common to every mode).  `pow2_rows`: rows of x
+# are first scaled by 2^round(log2(rstd(x))) as gemm_f16.cu does in rs_mode 1 (undone exactly afterwards).
+
+def _tf32_rna(x):
+    return ((x.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+
+
+def pow2_near(x):
+    return ((x.contiguous().view(torch.int32) + 0x00400000) & 0x7F800000).view(torch.float32)
+
+
+class SplitWeight:
+    def __init__(self, w, mode, pow2_rows=True):
+        self.mode, self.pow2_rows, self.shape = mode, pow2_rows, w.shape
+        if mode == 'tf32x3':
+            self.hi = _tf32_rna(w)
+            self.lo = _tf32_rna(w - self.hi)
+            self.inv_q = 1.0
+        elif mode == 'f16x3':
+            from dreamer4_b200.packing import f16_split
+            self.hi, self.lo, self.inv_q = f16_split(w)
+        else:
+            raise ValueError(mode)
+
+    @property
+    def T(self):
+        return self
+
+    def __rmatmul__(self, x):                      # x (M, K) @ W^T -> (M, N)
+        lead = x.shape[:-1]
+        x = x.float().reshape(-1, x.shape[-1])
+        if self.mode == 'tf32x3':
+            a_hi = _tf32_rna(x)
+            a_lo = _tf32_rna(x - a_hi)
+            p = None
+        else:
+            p = pow2_near(rstd(x)) if self.pow2_rows else torch.ones(x.shape[0])
+            a = x * p[:, None]
+            a_hi = a.half()
+            a_lo = (a - a_hi.float()).half()
+        wh, wl = self.hi.double(), self.lo.double()
+        out = a_lo.double() @ wh.T + a_hi.double() @ wl.T + a_hi.double() @ wh.T
+        if p is not None:
+            out = out / p.double()[:, None] * self.inv_q
+        return out.float().reshape(*lead, -1)
+
+
+def split_packed(P, mode, pow2_rows='engine'):
+    """The packed dict with every GEMM weight the engine sends to the tensor cores wrapped in a SplitWeight.  pow2_rows:
+    True / False for every weight, or 'engine': only the GEMMs whose rows the engine scales by an RMS statistic (rs_mode 1 of
+    the pair kernels - the fused q/k/v, value-residual, feed-forward-in and pool q / kv projections); the projections that
+    consume attention outputs or GLU activations see their rows as they are."""
+    from dreamer4_b200.packing import GEMM_WEIGHTS_SUFFIXES
+    normed = ('.attn.w', '.w_in', '.w_qg', '.w_kv')
+
+    def rows(k):
+        if pow2_rows != 'engine':
+            return bool(pow2_rows)
+        return k == 'vr.w' or (k.endswith(normed) and k != 'lp.w_kv')
+    return {k: (SplitWeight(v, mode, rows(k)) if k.endswith(GEMM_WEIGHTS_SUFFIXES) and not k.startswith('reward.') else v) for k, v in P.items()}

@@ -2,6 +2,7 @@
 dreamer4_b200/packing.py (through tests/engine_emulator.py, which mirrors engine.cu's dataflow) against the oracle,
 and that the C-ABI library loads and exports every symbol include/d4b200.h declares."""
 import glob
+import math
 import os
 import re
 
@@ -9,9 +10,9 @@ import pytest
 import torch
 
 from dreamer4_b200 import DynamicsWorldModel
-from dreamer4_b200.packing import pack, tf32_split
+from dreamer4_b200.packing import f16_split, pack, tf32_split
 from oracle import dreamer4_oracle as O
-from engine_emulator import emulate_pass
+from engine_emulator import emulate_pass, split_packed
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.pt')))
 IDS = [os.path.basename(p)[:-3] for p in GOLDEN]
@@ -86,6 +87,49 @@ def test_save_and_init_and_load_round_trip(tmp_path):
     other = DynamicsWorldModel(**fx['model_kwargs'])
     other.load(path)
     assert all(torch.equal(sd[k], v) for k, v in other.state_dict().items())
+
+
+def test_f16_split_words():
+    """f16x3 packing (experimental mode): q is a power of two bringing rms(q w) into [2^-0.5, 2^0.5], hi + lo reproduces q w to
+    2^-22 relative (or fp16's subnormal spacing), both words finite for weights of any sane scale."""
+    torch.manual_seed(1)
+    for scale in (1e-4, 0.02, 1.0, 300.0):
+        w = torch.randn(96, 512) * scale
+        hi, lo, inv_q = f16_split(w)
+        assert hi.dtype == lo.dtype == torch.float16 and torch.isfinite(hi).all() and torch.isfinite(lo).all()
+        q = 1.0 / inv_q
+        assert math.log2(q) == round(math.log2(q))
+        rms = (w * q).pow(2).mean().sqrt().item()
+        assert 2 ** -0.51 <= rms <= 2 ** 0.51
+        err = (hi.double() + lo.double() - w.double() * q).abs()
+        # |lo| <= 2^-11 |x| is itself rounded to 11 bits (2^-22 |x|) or, where it falls below fp16's normal range, to the
+        # subnormal grid (spacing 2^-24)
+        assert (err <= torch.maximum((w.double() * q).abs() * 2.0 ** -22, torch.tensor(2.0 ** -25, dtype=torch.float64))).all()
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=IDS)
+def test_f16x3_dataflow_keeps_fp32_accuracy(path):
+    """The engine dataflow with every tensor-core GEMM replaced by its operand-split emulation (tests/engine_emulator.py:
+    SplitWeight) against the same dataflow in fp64: the fp16 3-term split with power-of-two pre-scales (f16x3, experimental)
+    stays within 2x of what plain fp32 arithmetic loses - the bar the 3xTF32 split meets - on pred and agent embedding."""
+    fx = load(path)
+    model = DynamicsWorldModel(**fx['model_kwargs'])
+    cfg = model.cfg
+    P = pack(fx['state_dict'], cfg, torch.device('cpu'))
+    P64 = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in P.items()}
+    torch.manual_seed(0)
+    x = torch.randn(4, cfg.num_latent_tokens, cfg.dim_latent)
+    torch.set_default_dtype(torch.float64)
+    try:
+        pr, ar, _ = emulate_pass(P64, cfg, x.double(), 48, 4, None, None, 0)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    err = {}
+    for mode in ('fp32', 'tf32x3', 'f16x3'):
+        pe, ae, _ = emulate_pass(P if mode == 'fp32' else split_packed(P, mode), cfg, x, 48, 4, None, None, 0)
+        err[mode] = max((pe.double() - pr).abs().max().item() / pr.abs().max().item(), (ae.double() - ar).abs().max().item() / ar.abs().max().item())
+    assert err['f16x3'] <= 2 * err['fp32'] + 1e-7, err
+    assert err['tf32x3'] <= 2 * err['fp32'] + 1e-7, err
 
 
 def test_tf32_split_round_to_nearest():

@@ -1,7 +1,8 @@
 """EXPERIMENTAL kernel, first hardware run pending: the fp16 3-term split GEMM (dreamer4_b200/csrc/gemm_f16.cu) through
 d4_linear(precision = D4_PREC_F16X3), against fp64, held to the SAME tolerance as the 3xTF32 kernel in
 tests/test_gpu_parity.py::test_linear_tcgen05 - the point of the kernel is that accuracy at half the tensor-core cost
-(scripts/split_precision_study.py).  The engine does not dispatch to it yet.
+(scripts/split_precision_study.py) - and the engine in its f16x3 mode (DynamicsWorldModel(precision='f16x3')), which routes the
+transformer's dense layers to that kernel, against the oracle at the tf32x3 mode's tolerances.
 
 STATUS: written after round 1's GPU budget was spent - compiled for sm_100a, never executed.  It therefore runs only when asked
 for (D4_EXPERIMENTAL=1): a never-run kernel that traps (its barrier waits trap instead of hanging) would poison the CUDA context
@@ -62,3 +63,39 @@ def test_linear_f16x3(M, N, K, act):
     tol = 1e-5 * max(1.0, K / 256)
     err = (Cc.double() - ref).abs().max().item()
     assert err < tol * max(1.0, ref.abs().max().item()), f'max abs err {err}'
+
+
+# ------------------------------------------------------------------------------------------------ the engine in f16x3 mode
+# DynamicsWorldModel(precision='f16x3'): every transformer GEMM the fp16 kernel takes (M > 128 rows, K a multiple of 32) runs on
+# it, the rest - heads, d4_learn, odd shapes - on 3xTF32.  Same oracle, same tolerances as the tf32x3 mode in test_gpu_parity.py.
+
+@pytest.mark.parametrize('name', ['config2_mnist', 'config4_256px'])
+def test_f16x3_engine_matches_oracle(name):
+    import test_gpu_parity as G
+    from dreamer4_b200 import DynamicsWorldModel
+    from oracle import dreamer4_oracle as O
+    kwargs = G.BASELINE_MODELS[name]
+    torch.manual_seed(21)
+    model = DynamicsWorldModel(**kwargs, precision='f16x3')
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('gamma') or n.endswith('norm.weight') or n.endswith('norm_context.weight'):
+                p.add_(torch.randn_like(p) * 0.1)
+            if 'unembed' in n or n.endswith('queries') or 'learned_embed' in n or n == 'register_tokens':
+                p.mul_(30.)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    ocfg = O.config_from_reference_kwargs(**kwargs)
+    T, B = 3, 20                                      # B * S = 300 rows: the pair kernels are the ones dispatched
+    noise = G.make_noise(model.cfg, T, B, seed=17)
+    ref = O.generate(sd, ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform']))
+    exp, tc = model.generate(T, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
+                             return_log_probs_and_values=True, return_time_cache=True, noise=G.to_cuda(noise))
+    ref_kv = torch.stack([torch.stack(layer) for layer in ref.kv_cache])
+    G.compare_experience(exp, ref, tc.main.next_kv_cache, ref_kv, TOL=dict(atol=2e-4, rtol=2e-4), LOGIT_TOL=dict(atol=4e-4, rtol=2e-4))
+    keys = [k for k in sd if k.startswith(('policy_head.', 'value_head.')) or k == 'action_embedder.discrete_action_unembed']
+    sdg = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd.items()}
+    rpl, rvl, _ = O.learn_from_experience(sdg, ocfg, ref)
+    pl, vl = model.learn_from_experience(exp)
+    torch.testing.assert_close(pl.detach().cpu(), rpl.detach(), atol=2e-6, rtol=1e-4)
+    torch.testing.assert_close(vl.detach().cpu(), rvl.detach(), atol=2e-6, rtol=1e-4)

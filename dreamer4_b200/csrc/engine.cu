@@ -70,12 +70,19 @@ extern "C" int d4_ctx_create(const d4_config* cfg, d4_ctx** out) {
     { const char* f = getenv("D4_FUSE_POOLS"); c->fuse_pools = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_SPACE_MMA"); c->space_mma = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_FUSE_SS"); c->fuse_ss = f ? atoi(f) != 0 : true; }
+    { const char* f = getenv("D4_GRAPH"); c->use_graphs = f ? atoi(f) != 0 : false; }
+    { const char* f = getenv("D4_GRAPH_MAX_ROWS"); if (f && atoi(f) > 0) c->graph_max_rows = atoi(f); }
     d4_engine_plan(c);
     *out = c;
     return 0;
 }
+static void drop_graphs(d4_ctx* c) {
+    for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    c->graphs.clear();
+}
 extern "C" void d4_ctx_destroy(d4_ctx* ctx) {
     if (!ctx) return;
+    drop_graphs(ctx);
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& r : ctx->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     delete ctx;
@@ -85,6 +92,7 @@ extern "C" int d4_set_weight(d4_ctx* c, const char* name, const float* p, int64_
     if (!c || !name) return d4_fail("d4_set_weight: null argument");
     c->table[name] = std::make_pair(p, numel);
     c->bound = false;
+    drop_graphs(c);           // captured frames hold the old pointers
     return 0;
 }
 extern "C" int d4_set_weight_scale(d4_ctx* c, const char* name, float scale) {
@@ -114,6 +122,17 @@ int d4_engine_plan(d4_ctx* c) {
     };
     for (auto& it : items) *it.p = reinterpret_cast<float*>(take(it.n));   // offsets for now; rebased in d4_set_buffers
     c->b.sizes_offs = reinterpret_cast<int*>(take(2 * D4_MAX_ACTION_TYPES));
+    if (c->use_graphs) {      // dense staging rows of one frame's inputs / outputs (offsets for now, like the rest)
+        const long long A = std::max(c->A_total, 1), na = std::max(c->na, 1);
+        auto& g = c->gio;
+        g.noise = reinterpret_cast<float*>(take(B * c->N * c->Dl)); g.latents = reinterpret_cast<float*>(take(B * c->N * c->Dl));
+        g.act_u = reinterpret_cast<float*>(take(B * A)); g.logits = reinterpret_cast<float*>(take(B * A));
+        g.term_u = reinterpret_cast<float*>(take(B)); g.rewards = reinterpret_cast<float*>(take(B)); g.values = reinterpret_cast<float*>(take(B));
+        g.agent = reinterpret_cast<float*>(take(B * c->D)); g.logp = reinterpret_cast<float*>(take(B * na));
+        g.prev_actions = reinterpret_cast<long long*>(take(2 * B * na)); g.actions = reinterpret_cast<long long*>(take(2 * B * na));
+        g.tasks = reinterpret_cast<long long*>(take(2 * B)); g.lens = reinterpret_cast<long long*>(take(2 * B));
+        g.terminals = reinterpret_cast<unsigned char*>(take((B + 3) / 4));
+    }
     c->ws_need = off;
     return 0;
 }
@@ -136,6 +155,11 @@ extern "C" int d4_set_buffers(d4_ctx* c, void* workspace, int64_t workspace_byte
     const int nptr = (int)(offsetof(decltype(c->b), sizes_offs) / sizeof(float*));
     for (int i = 0; i < nptr; ++i) ptrs[i] = reinterpret_cast<float*>(base + reinterpret_cast<uintptr_t>(ptrs[i]));
     c->b.sizes_offs = reinterpret_cast<int*>(base + reinterpret_cast<uintptr_t>(c->b.sizes_offs));
+    if (c->use_graphs) {
+        void** gp = reinterpret_cast<void**>(&c->gio);
+        for (size_t i = 0; i < sizeof(c->gio) / sizeof(void*); ++i) gp[i] = base + reinterpret_cast<uintptr_t>(gp[i]);
+    }
+    drop_graphs(c);
     c->ws = base; c->ws_bytes = workspace_bytes; c->kv = kv; c->kv_bytes_ = kv_bytes;
     // ff_mid pad columns must read as zero (they meet zero-padded weight columns)
     D4_CUDA_OK(cudaMemset(c->b.ff_mid, 0, (size_t)c->cfg.max_batch * c->S * c->inner_pad * 4));
@@ -598,7 +622,7 @@ extern "C" int d4_pass(d4_ctx* c, int B, const float* latent, int signal_level, 
 // One frame at cache position t: passes first_step..num_steps of the denoising schedule (the last one is the clean pass that
 // commits the frame's keys/values), then the heads.  first_step = 0 is d4_frame; first_step = num_steps is d4_observe, where
 // io->noise_latent already holds the clean latent and only that last pass runs.
-static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream, int first_step) {
+static int frame_body(d4_ctx* c, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream, int first_step) {
     D4_TRY(check_ready(c, B, t));
     if (!io || !io->noise_latent || !io->latents) return d4_fail("d4_frame: noise_latent and latents are required");
     if (num_steps < 1 || num_steps > c->cfg.max_steps || (num_steps & (num_steps - 1)) || c->cfg.max_steps % num_steps)
@@ -657,6 +681,91 @@ static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_tem
             D4_TRY(d4_mlp_forward(c, c->value, c->b.agent, D, B, c->b.hbuf0, c->b.hbuf1, c->b.bins, c->cfg.value_bins, 1, s));
             D4_TRY(d4_hl_gauss_decode(c->b.bins, c->cfg.value_bins, B, c->cfg.value_bins, c->value_centers, io->values, io->values_bs, s));
         }
+    }
+    return 0;
+}
+
+// ---- CUDA-graph replay of a frame (see d4_ctx::use_graphs)
+namespace {
+// rows of `width` bytes between a dense staging buffer and the caller's strided rows
+inline cudaError_t rows_copy(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, int rows, cudaStream_t s) {
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, cudaMemcpyDeviceToDevice, s);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToDevice, s);
+}
+}  // namespace
+
+static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_temperature, const d4_frame_io* io, void* stream, int first_step) {
+    if (!c || !c->use_graphs || c->prof_on || !io || (long long)B * c->S > c->graph_max_rows || c->graphs.size() >= 4096)
+        return frame_body(c, B, t, num_steps, discrete_temperature, io, stream, first_step);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool term = c->cfg.predict_terminals && io->terminal_uniform && io->lens && io->terminals;
+    const bool act = c->has_actions && io->actions;
+    long long flags = 0;
+    const void* opt[] = {io->prev_actions, io->tasks, io->agent_embed, io->rewards, io->values, io->logits, io->action_uniform, io->log_probs};
+    for (int i = 0; i < 8; ++i) flags |= (long long)(opt[i] != nullptr) << i;
+    flags |= (long long)term << 8 | (long long)act << 9;
+    uint32_t tbits; memcpy(&tbits, &discrete_temperature, 4);
+    const std::array<long long, 6> key = {first_step == 0 ? 0 : 1, B, t, num_steps, (long long)tbits, flags};
+    auto& fg = c->graphs[key];
+    if (!fg.seen) {           // first use of this key: run directly
+        fg.seen = true;
+        return frame_body(c, B, t, num_steps, discrete_temperature, io, stream, first_step);
+    }
+    const auto& g = c->gio;
+    const long long nl = (long long)c->N * c->Dl, A = c->A_total, na = c->na;
+    d4_frame_io st; memset(&st, 0, sizeof(st));
+    st.noise_latent = g.noise; st.latents = g.latents; st.latents_bs = nl;
+    if (io->action_uniform) st.action_uniform = g.act_u;
+    if (io->terminal_uniform) st.terminal_uniform = g.term_u;
+    if (io->prev_actions) { st.prev_actions = reinterpret_cast<const int64_t*>(g.prev_actions); st.pa_stride = na; }
+    if (io->tasks) st.tasks = reinterpret_cast<const int64_t*>(g.tasks);
+    if (io->agent_embed) { st.agent_embed = g.agent; st.agent_bs = c->D; }
+    if (io->rewards) { st.rewards = g.rewards; st.rewards_bs = 1; }
+    if (io->values) { st.values = g.values; st.values_bs = 1; }
+    if (io->actions) { st.actions = reinterpret_cast<int64_t*>(g.actions); st.actions_bs = na; }
+    if (io->log_probs) { st.log_probs = g.logp; st.log_probs_bs = na; }
+    if (io->logits) { st.logits = g.logits; st.logits_bs = A; }
+    if (term) { st.lens = reinterpret_cast<int64_t*>(g.lens); st.terminals = g.terminals; }
+    if (!fg.exec) {           // second use: capture the frame on the staging rows, instantiate
+        if (!c->bound || !c->ws) return frame_body(c, B, t, num_steps, discrete_temperature, io, stream, first_step);   // reports the error
+        const long long l0 = d4_launches_;
+        D4_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int rc = frame_body(c, B, t, num_steps, discrete_temperature, &st, stream, first_step);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const long long captured = d4_launches_ - l0;
+        d4_launches_ = l0;                                   // nothing ran yet
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+        if (ce != cudaSuccess || !graph) { cudaGetLastError(); return d4_fail("d4_frame: stream capture failed: %s", cudaGetErrorString(ce)); }
+        const cudaError_t ie = cudaGraphInstantiate(&fg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { fg.exec = nullptr; cudaGetLastError(); return d4_fail("d4_frame: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+        fg.launches = captured;
+    }
+    // copy in -> replay -> copy out, all on the caller's stream
+    D4_CUDA_OK(cudaMemcpyAsync(g.noise, io->noise_latent, (size_t)B * nl * 4, cudaMemcpyDeviceToDevice, s));
+    if (io->action_uniform) D4_CUDA_OK(cudaMemcpyAsync(g.act_u, io->action_uniform, (size_t)B * A * 4, cudaMemcpyDeviceToDevice, s));
+    if (io->terminal_uniform) D4_CUDA_OK(cudaMemcpyAsync(g.term_u, io->terminal_uniform, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+    if (io->prev_actions) D4_CUDA_OK(rows_copy(g.prev_actions, na * 8, io->prev_actions, (size_t)io->pa_stride * 8, na * 8, B, s));
+    if (io->tasks) D4_CUDA_OK(cudaMemcpyAsync(g.tasks, io->tasks, (size_t)B * 8, cudaMemcpyDeviceToDevice, s));
+    if (term) {
+        D4_CUDA_OK(cudaMemcpyAsync(g.lens, io->lens, (size_t)B * 8, cudaMemcpyDeviceToDevice, s));
+        D4_CUDA_OK(cudaMemcpyAsync(g.terminals, io->terminals, (size_t)B, cudaMemcpyDeviceToDevice, s));
+    }
+    D4_CUDA_OK(cudaGraphLaunch(fg.exec, s));
+    d4_launches_ += fg.launches; ++c->graph_replays;
+    D4_CUDA_OK(rows_copy(io->latents, (size_t)io->latents_bs * 4, g.latents, nl * 4, nl * 4, B, s));
+    if (io->agent_embed) D4_CUDA_OK(rows_copy(io->agent_embed, (size_t)io->agent_bs * 4, g.agent, (size_t)c->D * 4, (size_t)c->D * 4, B, s));
+    if (io->rewards) D4_CUDA_OK(rows_copy(io->rewards, (size_t)io->rewards_bs * 4, g.rewards, 4, 4, B, s));
+    if (act) {
+        D4_CUDA_OK(rows_copy(io->actions, (size_t)io->actions_bs * 8, g.actions, na * 8, na * 8, B, s));
+        if (io->log_probs) D4_CUDA_OK(rows_copy(io->log_probs, (size_t)io->log_probs_bs * 4, g.logp, na * 4, na * 4, B, s));
+        if (io->logits) D4_CUDA_OK(rows_copy(io->logits, (size_t)io->logits_bs * 4, g.logits, A * 4, A * 4, B, s));
+        if (io->values) D4_CUDA_OK(rows_copy(io->values, (size_t)io->values_bs * 4, g.values, 4, 4, B, s));
+    }
+    if (term) {
+        D4_CUDA_OK(cudaMemcpyAsync(io->lens, g.lens, (size_t)B * 8, cudaMemcpyDeviceToDevice, s));
+        D4_CUDA_OK(cudaMemcpyAsync(io->terminals, g.terminals, (size_t)B, cudaMemcpyDeviceToDevice, s));
     }
     return 0;
 }

@@ -1,5 +1,7 @@
 // d4_ctx: configuration, bound weight pointers and the workspace plan of one model on one device.
 #pragma once
+#include <array>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -65,6 +67,18 @@ struct d4_ctx {
     bool fuse_ss = true;         // RMS statistics accumulated in the producing GEMM's epilogue (D4_FUSE_SS=0: separate row pass)
     bool space_mma = true;       // space attention on mma.sync 3xTF32 tiles in the tensor-core engine modes (D4_SPACE_MMA=0: FMA kernel)
     bool fuse_pools = true;      // fused latent<->space pool kernels (fused_pools.cu); D4_FUSE_POOLS=0 keeps the GEMM + attention path
+    // CUDA-graph replay of whole frames (D4_GRAPH=1, off by default; small batches are launch-bound: ~570 launches per imagined
+    // frame).  One instantiated graph per (entry point, B, t, num_steps, temperature, which optional io fields are present),
+    // captured the SECOND time a key is seen (the first use runs directly, which also gets every lazy one-time setup out of
+    // the way); the graph works on dense staging rows inside the workspace, copied in / out around the launch, so it does not
+    // depend on the caller's pointers.  Dropped whenever weights or buffers are re-registered.
+    bool use_graphs = false;
+    int graph_max_rows = 4096;   // frames with more than this many token rows (B * S) always run directly
+    struct GraphIO { float *noise, *act_u, *term_u, *latents, *agent, *rewards, *values, *logp, *logits;
+                     long long *prev_actions, *tasks, *actions, *lens; unsigned char* terminals; } gio = {};
+    struct FrameGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; bool seen = false; };
+    std::map<std::array<long long, 6>, FrameGraph> graphs;
+    long long graph_replays = 0;
     struct ProfRec { cudaEvent_t a, b; int cls; double work; };
     std::vector<ProfRec> prof;          // records in use
     std::vector<ProfRec> prof_pool;     // created events, reused

@@ -6,5 +6,7 @@ from .experience import Actions, Experience, combine_experiences
 from .dynamics import DynamicsWorldModel, ModelConfig, exists, default
 from .trainer import DreamTrainer
 from .env import DynamicsWorldModelWrapper
+from .tokenizer import VideoTokenizer, TokenizerConfig
 
-__all__ = ['Actions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default']
+__all__ = ['Actions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default',
+           'VideoTokenizer', 'TokenizerConfig']

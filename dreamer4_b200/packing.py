@@ -63,6 +63,54 @@ def hl_gauss_tables(lo, hi, num_bins, device):
     return support.to(device), centers.to(device)
 
 
+def _attn_qg(g, p, queries=None):
+    wq, wg, nw = g(p + 'to_q.weight'), g(p + 'to_gates.0.weight'), g(p + 'norm.weight')
+    if queries is not None:          # learned queries: the query side is input independent -> precompute
+        xq = _rms(queries, nw)
+        return xq @ wq.T, xq @ wg.T
+    return torch.cat((wq, wg)) * nw[None, :]
+
+
+def _pack_transformer(g, out, tp, depth, ff_inner_pad, device, attn_qg=None):
+    """Packed weights of one AxialSpaceTimeTransformer whose state_dict keys start with `tp` (the dynamics model's
+    'transformer.', the video tokenizer's 'encoder_transformer.' / 'decoder.transformer.'): vr.w, L{i}.attn.*, L{i}.ff.*,
+    P{i}.*, PF.*, FA.*, FAFF.* (names in the module docstring)."""
+    attn_qg = attn_qg or (lambda p, queries=None: _attn_qg(g, p, queries))
+    out['vr.w'] = g(tp + 'to_value_residual.1.weight') * g(tp + 'to_value_residual.0.weight')[None, :]
+
+    def pack_ff(p, name):
+        nw = g(p + 'norm.weight')
+        w_in, b_in = g(p + 'proj_in.weight'), g(p + 'proj_in.bias')
+        inner = w_in.shape[0] // 2
+        xw, gw = w_in[:inner], w_in[inner:]
+        out[name + '.w_in'] = torch.stack((xw, gw), dim=1).reshape(2 * inner, -1) * nw[None, :]
+        out[name + '.b_in'] = torch.stack((b_in[:inner], b_in[inner:]), dim=1).reshape(-1)
+        out[name + '.w_out'] = F.pad(g(p + 'proj_out.weight'), (0, ff_inner_pad - inner))
+        out[name + '.b_out'] = g(p + 'proj_out.bias')
+
+    def pack_pool(p, name):
+        out[name + '.w_qg'] = attn_qg(p)
+        out[name + '.w_kv'] = torch.cat((g(p + 'to_k.weight'), g(p + 'to_v.weight'))) * g(p + 'norm_context.weight')[None, :]
+        out[name + '.k_gamma'] = g(p + 'k_heads_rmsnorm.gamma')
+        out[name + '.w_out'] = g(p + 'to_out.weight')
+
+    for i in range(depth):
+        p = f'{tp}layers.{i}.2.fn.'
+        nw = g(p + 'norm.weight')
+        mixw, mixb = g(p + 'to_learned_value_residual_mix.0.weight'), g(p + 'to_learned_value_residual_mix.0.bias')
+        w = torch.cat((g(p + 'to_q.weight'), g(p + 'to_k.weight'), g(p + 'to_v.weight'), g(p + 'to_gates.0.weight'), mixw))
+        out[f'L{i}.attn.w'] = w * nw[None, :]
+        out[f'L{i}.attn.b'] = torch.cat((torch.zeros(w.shape[0] - mixb.shape[0], device=device), mixb))
+        out[f'L{i}.attn.k_gamma'] = g(p + 'k_heads_rmsnorm.gamma')
+        out[f'L{i}.attn.w_out'] = g(p + 'to_out.weight')
+        pack_ff(f'{tp}layers.{i}.3.fn.', f'L{i}.ff')
+        if i != depth - 1:
+            pack_pool(f'{tp}attn_pools.{i}.fn.attn.', f'P{i}')
+    pack_pool(tp + 'final_attn_pool.fn.attn.', 'PF')
+    pack_pool(tp + 'final_special_cross_attn.fn.', 'FA')
+    pack_ff(tp + 'final_special_ff.fn.', 'FAFF')
+
+
 def pack(sd, cfg, device, agent_index=0, split=False, split_f16=False):
     """sd: reference-layout state_dict (tensors on `device`); cfg: dreamer4_b200.dynamics.ModelConfig.
     Returns {packed name: fp32 contiguous tensor}; with `split_f16` also `name.h16hi` / `name.h16lo` (fp16) per GEMM weight and
@@ -81,12 +129,7 @@ def pack(sd, cfg, device, agent_index=0, split=False, split_f16=False):
         out['task_emb'] = g('task_embed.weight')
     out['inv_freq'] = g('transformer.time_rotary.inv_freq')
 
-    def attn_qg(p, queries=None):
-        wq, wg, nw = g(p + 'to_q.weight'), g(p + 'to_gates.0.weight'), g(p + 'norm.weight')
-        if queries is not None:          # learned queries: the query side is input independent -> precompute
-            xq = _rms(queries, nw)
-            return xq @ wq.T, xq @ wg.T
-        return torch.cat((wq, wg)) * nw[None, :]
+    attn_qg = lambda p, queries=None: _attn_qg(g, p, queries)
 
     if cfg.same_len:
         out['l2s.w'] = g('latents_to_spatial_tokens.weight')
@@ -105,39 +148,7 @@ def pack(sd, cfg, device, agent_index=0, split=False, split_f16=False):
         out['lp.k_gamma'] = g(p + 'k_heads_rmsnorm.gamma')
         out['lp.w_comb'] = g('to_latent_pred.2.weight') @ g(p + 'to_out.weight')
     out['lp.norm0'] = g('to_latent_pred.0.weight')
-    out['vr.w'] = g('transformer.to_value_residual.1.weight') * g('transformer.to_value_residual.0.weight')[None, :]
-
-    def pack_ff(p, name):
-        nw = g(p + 'norm.weight')
-        w_in, b_in = g(p + 'proj_in.weight'), g(p + 'proj_in.bias')
-        inner = w_in.shape[0] // 2
-        xw, gw = w_in[:inner], w_in[inner:]
-        out[name + '.w_in'] = torch.stack((xw, gw), dim=1).reshape(2 * inner, -1) * nw[None, :]
-        out[name + '.b_in'] = torch.stack((b_in[:inner], b_in[inner:]), dim=1).reshape(-1)
-        out[name + '.w_out'] = F.pad(g(p + 'proj_out.weight'), (0, cfg.ff_inner_pad - inner))
-        out[name + '.b_out'] = g(p + 'proj_out.bias')
-
-    def pack_pool(p, name):
-        out[name + '.w_qg'] = attn_qg(p)
-        out[name + '.w_kv'] = torch.cat((g(p + 'to_k.weight'), g(p + 'to_v.weight'))) * g(p + 'norm_context.weight')[None, :]
-        out[name + '.k_gamma'] = g(p + 'k_heads_rmsnorm.gamma')
-        out[name + '.w_out'] = g(p + 'to_out.weight')
-
-    for i in range(cfg.depth):
-        p = f'transformer.layers.{i}.2.fn.'
-        nw = g(p + 'norm.weight')
-        mixw, mixb = g(p + 'to_learned_value_residual_mix.0.weight'), g(p + 'to_learned_value_residual_mix.0.bias')
-        w = torch.cat((g(p + 'to_q.weight'), g(p + 'to_k.weight'), g(p + 'to_v.weight'), g(p + 'to_gates.0.weight'), mixw))
-        out[f'L{i}.attn.w'] = w * nw[None, :]
-        out[f'L{i}.attn.b'] = torch.cat((torch.zeros(w.shape[0] - mixb.shape[0], device=device), mixb))
-        out[f'L{i}.attn.k_gamma'] = g(p + 'k_heads_rmsnorm.gamma')
-        out[f'L{i}.attn.w_out'] = g(p + 'to_out.weight')
-        pack_ff(f'transformer.layers.{i}.3.fn.', f'L{i}.ff')
-        if i != cfg.depth - 1:
-            pack_pool(f'transformer.attn_pools.{i}.fn.attn.', f'P{i}')
-    pack_pool('transformer.final_attn_pool.fn.attn.', 'PF')
-    pack_pool('transformer.final_special_cross_attn.fn.', 'FA')
-    pack_ff('transformer.final_special_ff.fn.', 'FAFF')
+    _pack_transformer(g, out, 'transformer.', cfg.depth, cfg.ff_inner_pad, device, attn_qg)
 
     out['reward.w'] = g('to_reward_pred.nets.0.1.weight') * g('to_reward_pred.nets.0.0.weight')[None, :]
     _, out['reward.centers'] = hl_gauss_tables(*cfg.reward_range, cfg.reward_num_bins, device)
@@ -165,3 +176,63 @@ def mlp_param_names(prefix, n_layers):
         if l < n_layers - 1:
             pairs += [(f'{l}.lnw', f'{prefix}.layers.{l}.1.weight'), (f'{l}.lnb', f'{prefix}.layers.{l}.1.bias')]
     return pairs
+
+
+# ------------------------------------------------------------------------------------------------ video tokenizer
+
+def _split_all(out, split):
+    out = {k: v.contiguous() for k, v in out.items()}
+    if split:
+        for k in list(out):
+            if k.endswith(GEMM_WEIGHTS_SUFFIXES):
+                out[k + '.hi'], out[k + '.lo'] = (t.contiguous() for t in tf32_split(out[k]))
+    return out
+
+
+def _mlp_eval(g, p, x, act):
+    """x-mlps normed MLP (Linear -> LayerNorm -> act)* -> Linear on the host: only for input-independent tables at pack time."""
+    fn = F.silu if act == 'silu' else F.gelu
+    i = 0
+    while True:
+        try:
+            w, b = g(p + f'layers.{i}.0.weight'), g(p + f'layers.{i}.0.bias')
+        except KeyError:
+            return x
+        x = x @ w.T + b
+        try:
+            x = fn(F.layer_norm(x, (x.shape[-1],), g(p + f'layers.{i}.1.weight'), g(p + f'layers.{i}.1.bias')))
+        except KeyError:
+            pass
+        i += 1
+
+
+def pack_tokenizer(sd, cfg, device, split=False):
+    """Packed weights of the VideoTokenizer's inference paths (reference dreamer4.py:3686-4237, default branches), from a
+    reference-layout state_dict; cfg: dreamer4_b200.tokenizer.TokenizerConfig.  Returns {'enc': {...}, 'dec': {...}, 'io': {...}}:
+
+      enc / dec   one transformer each (_pack_transformer names + inv_freq + final_norm), what d4_tf_bind resolves
+      io          patch.{w, b, ln}       patch_to_tokens: Linear(p*p*c -> D) + LayerNorm(no bias) (3833-3838)
+                  latent_tokens (N, D)   the encoder's special tokens (4349)
+                  to_latents.w (Dl, D)   encoded_to_latents, followed by tanh (4413, 4426)
+                  npatch.{w, b, ln}      noised_patch_to_tokens of the flow decoder (3881-3886)
+                  pos_emb (hp*wp, D)     to_decoder_pos_emb(coords): input independent -> evaluated here (3618-3623)
+                  lat_in.w (D, Dl)       latents_to_decoder (4148-4154); time_embed (steps, D) is its per-flow-step bias
+                  to_patch.{w, b}        decoder.tokens_to_patch (3569-3572)"""
+    g = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+    enc, dec, io = {}, {}, {}
+    for out, tp, depth in ((enc, 'encoder_transformer.', cfg.encoder_depth), (dec, 'decoder.transformer.', cfg.decoder_depth)):
+        _pack_transformer(g, out, tp, depth, cfg.ff_inner_pad, device)
+        out['inv_freq'] = g(tp + 'time_rotary.inv_freq')
+        out['final_norm'] = g(tp + 'final_norm.weight')
+    io['patch.w'], io['patch.b'], io['patch.ln'] = g('patch_to_tokens.1.weight'), g('patch_to_tokens.1.bias'), g('patch_to_tokens.2.weight')
+    io['latent_tokens'] = g('latent_tokens')
+    io['to_latents.w'] = g('encoded_to_latents.weight')
+    io['npatch.w'], io['npatch.b'], io['npatch.ln'] = (g('noised_patch_to_tokens.1.weight'), g('noised_patch_to_tokens.1.bias'),
+                                                       g('noised_patch_to_tokens.2.weight'))
+    hp, wp = cfg.image_height // cfg.patch_size, cfg.image_width // cfg.patch_size
+    coords = torch.stack(torch.meshgrid(torch.linspace(-1., 1., hp), torch.linspace(-1., 1., wp), indexing='ij'), dim=-1).to(device)
+    io['pos_emb'] = _mlp_eval(g, 'decoder.to_decoder_pos_emb.', coords.reshape(hp * wp, 2), cfg.decoder_pos_emb_mlp_activation)
+    io['lat_in.w'] = g('latents_to_decoder.weight')
+    io['time_embed'] = g('time_embed.weight')
+    io['to_patch.w'], io['to_patch.b'] = g('decoder.tokens_to_patch.0.weight'), g('decoder.tokens_to_patch.0.bias')
+    return dict(enc=_split_all(enc, split), dec=_split_all(dec, split), io=_split_all(io, split))

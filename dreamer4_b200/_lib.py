@@ -51,6 +51,17 @@ class d4_frame_io(C.Structure):
     ]
 
 
+class d4_tf_config(C.Structure):
+    _fields_ = [
+        ('dim', C.c_int32), ('depth', C.c_int32), ('time_block_every', C.c_int32),
+        ('heads', C.c_int32), ('query_heads', C.c_int32), ('dim_head', C.c_int32), ('pool_heads', C.c_int32), ('pool_dim_head', C.c_int32),
+        ('ff_inner', C.c_int32), ('ff_inner_pad', C.c_int32), ('ff_act', C.c_int32),
+        ('tokens_per_frame', C.c_int32), ('num_special', C.c_int32), ('final_norm', C.c_int32),
+        ('softclamp', C.c_float),
+        ('max_batch', C.c_int32), ('max_time', C.c_int32), ('precision', C.c_int32), ('time_attn_variant', C.c_int32),
+    ]
+
+
 _PTR_ARR = C.c_void_p * D4_MAX_MLP_LAYERS
 
 
@@ -100,6 +111,13 @@ SYMBOLS = {
     'd4_gae': (_i, [_i, _i, _p, _p, _p, _p, _f, _f, _p, _p]),
     'd4_learn_workspace_bytes': (_i64, [_p, _i, _i]),
     'd4_learn': (_i, [_p, C.POINTER(d4_learn_io), _p, _i64, _p]),
+    'd4_tf_create': (_i, [C.POINTER(d4_tf_config), C.POINTER(_p)]),
+    'd4_tf_step': (_i, [_p, _i, _p, _i, _p, _p]),
+    'd4_linear_rows': (_i, [_i, _i, _i, _i, _p, _i64, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _i64, _p]),
+    'd4_patchify': (_i, [_i, _i, _i, _i, _i, _p, _i64, _i64, _p, _p]),
+    'd4_unpatchify_flow': (_i, [_i, _i, _i, _i, _i, _p, _p, _i64, _i64, _f, _p]),
+    'd4_tok_assemble': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p]),
+    'd4_tanh_rows': (_i, [_p, _i64, _p]),
 }
 
 _lib = None

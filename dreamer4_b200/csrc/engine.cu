@@ -122,6 +122,10 @@ int d4_engine_plan(d4_ctx* c) {
     };
     for (auto& it : items) *it.p = reinterpret_cast<float*>(take(it.n));   // offsets for now; rebased in d4_set_buffers
     c->b.sizes_offs = reinterpret_cast<int*>(take(2 * D4_MAX_ACTION_TYPES));
+    if (c->tf_mode) {
+        c->tfb.fa_q = reinterpret_cast<float*>(take(B * c->tf_ns * c->ldfa)); c->tfb.fa_att = reinterpret_cast<float*>(take(B * c->tf_ns * c->Dq));
+        c->tfb.sp_rstd = reinterpret_cast<float*>(take(B * c->tf_ns));
+    }
     if (c->use_graphs) {      // dense staging rows of one frame's inputs / outputs (offsets for now, like the rest)
         const long long A = std::max(c->A_total, 1), na = std::max(c->na, 1);
         auto& g = c->gio;
@@ -155,6 +159,10 @@ extern "C" int d4_set_buffers(d4_ctx* c, void* workspace, int64_t workspace_byte
     const int nptr = (int)(offsetof(decltype(c->b), sizes_offs) / sizeof(float*));
     for (int i = 0; i < nptr; ++i) ptrs[i] = reinterpret_cast<float*>(base + reinterpret_cast<uintptr_t>(ptrs[i]));
     c->b.sizes_offs = reinterpret_cast<int*>(base + reinterpret_cast<uintptr_t>(c->b.sizes_offs));
+    if (c->tf_mode) {
+        void** tp = reinterpret_cast<void**>(&c->tfb);
+        for (size_t i = 0; i < sizeof(c->tfb) / sizeof(void*); ++i) tp[i] = base + reinterpret_cast<uintptr_t>(tp[i]);
+    }
     if (c->use_graphs) {
         void** gp = reinterpret_cast<void**>(&c->gio);
         for (size_t i = 0; i < sizeof(c->gio) / sizeof(void*); ++i) gp[i] = base + reinterpret_cast<uintptr_t>(gp[i]);
@@ -204,8 +212,10 @@ struct Binder {
 };
 }  // namespace
 
+static int tf_bind(d4_ctx* c);
 extern "C" int d4_bind(d4_ctx* c) {
     if (!c) return d4_fail("d4_bind: null ctx");
+    if (c->tf_mode) return tf_bind(c);
     Binder B{c};
     const int D = c->D, Dl = c->Dl, Dq = c->Dq, Dkv = c->Dkv, h = c->h, hq = c->hq, d = c->d, Dp = c->Dp, hp = c->hp;
     const int half = D / 2;
@@ -807,3 +817,228 @@ extern "C" int d4_linear(int precision, int M, int N, int K, const float* A, int
     if (precision == D4_PREC_TF32X3) { if (!W_lo) return d4_fail("d4_linear: tf32x3 needs W_lo"); return d4_gemm_tc(g, 3, s); }
     return d4_gemm_tc(g, 1, s);
 }
+
+// ================================================================================================ generic transformer context
+// The video tokenizer's encoder and decoder are AxialSpaceTimeTransformers like the dynamics model's (reference
+// dreamer4.py:3908-3929, 3595-3607) with other token counts: S = patches + latents per frame, the last num_special of them
+// special (the encoder's latent tokens: patches cannot attend to them, they cross-attend to the patches once more at the end,
+// 3912-3918 / 3227-3238; the decoder keeps the library default of one), and a final RMSNorm (2774, 3247).  d4_tf_step is the
+// layer loop of run_pass on caller-assembled tokens, with the attention inside a frame on frame_attn.cu and the RMS statistics
+// as separate row passes.  STATUS: drafted in round 1 after the GPU budget was spent - compiles, not yet run on hardware.
+
+extern "C" int d4_tf_create(const d4_tf_config* cfg, d4_ctx** out) {
+    if (!cfg || !out) return d4_fail("d4_tf_create: null argument");
+    d4_ctx* c = new d4_ctx();
+    memset(&c->cfg, 0, sizeof(c->cfg));
+    c->cfg.dim = cfg->dim; c->cfg.depth = cfg->depth; c->cfg.time_block_every = cfg->time_block_every;
+    c->cfg.heads = cfg->heads; c->cfg.query_heads = cfg->query_heads; c->cfg.dim_head = cfg->dim_head;
+    c->cfg.pool_heads = cfg->pool_heads; c->cfg.pool_dim_head = cfg->pool_dim_head;
+    c->cfg.ff_inner = cfg->ff_inner; c->cfg.ff_inner_pad = cfg->ff_inner_pad; c->cfg.ff_act = cfg->ff_act;
+    c->cfg.softclamp = cfg->softclamp; c->cfg.max_batch = cfg->max_batch; c->cfg.max_time = cfg->max_time;
+    c->cfg.precision = cfg->precision == D4_PREC_F16X3 ? D4_PREC_TF32X3 : cfg->precision; c->cfg.time_attn_variant = cfg->time_attn_variant;
+    c->cfg.max_steps = 1;
+    c->tf_mode = true; c->tf_ns = cfg->num_special; c->tf_final_norm = cfg->final_norm;
+    c->D = cfg->dim; c->Dl = 0; c->N = 0; c->nsp = 0; c->nreg = 0; c->L = cfg->depth; c->h = cfg->heads; c->hq = cfg->query_heads; c->d = cfg->dim_head;
+    c->hp = cfg->pool_heads; c->dp = cfg->pool_dim_head; c->Dp = c->hp * c->dp;
+    c->Dq = c->hq * c->d; c->Dkv = c->h * c->d;
+    c->inner = cfg->ff_inner; c->inner_pad = cfg->ff_inner_pad;
+    c->na = 0; c->has_actions = 0; c->A_total = 0; c->same_len = 0;
+    c->S = cfg->tokens_per_frame;
+    c->n_hid = 2 * c->L + 1;
+    c->y = 0;
+    const char* bad = nullptr;
+    if (cfg->depth < 1 || cfg->time_block_every < 1) bad = "depth and time_block_every must be positive";
+    else if (c->h < 1 || c->hq % c->h != 0) bad = "query_heads must be a multiple of heads";
+    else if (c->d % 4 != 0 || c->d > 128) bad = "dim_head must be a multiple of 4, <= 128";
+    else if (c->D % 4 != 0) bad = "dim must be a multiple of 4";
+    else if (c->S < 2 || c->tf_ns < 1 || c->tf_ns >= c->S) bad = "need 1 <= num_special < tokens_per_frame";
+    else if (c->n_hid > 64) bad = "depth > 31 unsupported";
+    else if (c->inner_pad < c->inner || c->inner_pad % 4 != 0) bad = "ff_inner_pad must be >= ff_inner and a multiple of 4";
+    else if (cfg->max_batch < 1 || cfg->max_time < 1) bad = "max_batch / max_time must be positive";
+    if (bad) { delete c; return d4_fail("d4_tf_create: %s", bad); }
+    for (int i = 0; i < c->L; ++i) { const int it = ((i + 1) % cfg->time_block_every) == 0; c->is_time.push_back(it); c->y += it; }
+    c->NQ = c->Dq + 2 * c->Dkv + c->hq + c->h; c->ldq = round_up(c->NQ, 4);
+    c->ldpq = round_up(c->Dp + c->hp, 4);
+    c->ldfa = round_up(c->Dq + c->hq, 4);
+    c->ldlog = 4;
+    c->fuse_pools = false; c->space_mma = false; c->fuse_ss = false; c->use_graphs = false;
+    d4_engine_plan(c);
+    *out = c;
+    return 0;
+}
+
+static int tf_bind(d4_ctx* c) {
+    Binder B{c};
+    const int D = c->D, Dq = c->Dq, Dkv = c->Dkv, h = c->h, hq = c->hq, d = c->d, Dp = c->Dp, hp = c->hp;
+    c->vr_w = B.lin("vr.w", (int64_t)Dkv * D);
+    c->inv_freq = B.get("inv_freq", d / 2);
+    c->tf_final_norm_w = B.get("final_norm", D, !c->tf_final_norm);
+    auto bind_ff = [&](const std::string& p, FFW& f) {
+        f.w_in = B.lin(p + ".w_in", (int64_t)2 * c->inner * D); f.b_in = B.get(p + ".b_in", 2 * c->inner);
+        f.w_out = B.lin(p + ".w_out", (int64_t)D * c->inner_pad); f.b_out = B.get(p + ".b_out", D);
+    };
+    auto bind_pool = [&](const std::string& p, PoolW& w) {
+        w.w_qg = B.lin(p + ".w_qg", (int64_t)(Dp + hp) * D); w.w_kv = B.lin(p + ".w_kv", (int64_t)2 * Dp * D);
+        w.k_gamma = B.get(p + ".k_gamma", (int64_t)hp * c->dp); w.w_out = B.lin(p + ".w_out", (int64_t)D * Dp);
+    };
+    c->attn.assign(c->L, AttnLayerW()); c->ff.assign(c->L, FFW()); c->pools.assign(c->L > 0 ? c->L - 1 : 0, PoolW());
+    for (int i = 0; i < c->L; ++i) {
+        const std::string p = "L" + std::to_string(i);
+        c->attn[i].w = B.lin(p + ".attn.w", (int64_t)c->NQ * D); c->attn[i].b = B.get(p + ".attn.b", c->NQ);
+        c->attn[i].k_gamma = B.get(p + ".attn.k_gamma", (int64_t)h * d); c->attn[i].w_out = B.lin(p + ".attn.w_out", (int64_t)D * Dq);
+        bind_ff(p + ".ff", c->ff[i]);
+        if (i != c->L - 1) bind_pool("P" + std::to_string(i), c->pools[i]);
+    }
+    bind_pool("PF", c->pool_final);
+    c->fa.w_qg = B.lin("FA.w_qg", (int64_t)(Dq + hq) * D); c->fa.w_kv = B.lin("FA.w_kv", (int64_t)2 * Dkv * D);
+    c->fa.k_gamma = B.get("FA.k_gamma", (int64_t)h * d); c->fa.w_out = B.lin("FA.w_out", (int64_t)D * Dq);
+    bind_ff("FAFF", c->fa_ff);
+    if (B.missing) return d4_fail("d4_bind: weight '%s' missing or mis-sized", B.missing);
+    c->bound = true;
+    return 0;
+}
+
+extern "C" int d4_tf_step(d4_ctx* c, int B, const float* tokens_in, int t, float* tokens_out, void* stream) {
+    D4_TRY(check_ready(c, B, t));
+    if (!c->tf_mode) return d4_fail("d4_tf_step: not a d4_tf_create context");
+    if (!tokens_in || !tokens_out) return d4_fail("d4_tf_step: null tokens");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int S = c->S, D = c->D, Dq = c->Dq, Dkv = c->Dkv, h = c->h, hq = c->hq, d = c->d, L = c->L, ns = c->tf_ns;
+    const int M = B * S, Ms = B * ns;
+    const long long MD = (long long)M * D;
+    auto hid = [&](int j) { return c->b.hid + (long long)j * MD; };
+    auto hrs = [&](int j) { return c->b.hid_rstd + (long long)j * M; };
+    auto xss = [&](int j) { return c->b.x_rstd + (long long)j * M; };
+    const float att_scale = 1.f / sqrtf((float)d);
+    auto attend = [&](const SmallAttnArgs& a) {
+        const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_frame_attn(a, s); d4_prof_end(c, ph, s); return rc;
+    };
+
+    D4_CUDA_OK(cudaMemcpyAsync(hid(0), tokens_in, MD * 4, cudaMemcpyDeviceToDevice, s));
+    D4_TRY(d4_row_rstd(hid(0), D, rowmap_identity(), M, D, hrs(0), s));
+    {   // value residual (reference dreamer4.py:3026-3027)
+        GemmArgs g = gemm_args(hid(0), D, nullptr, D, c->b.v0, Dkv, M, Dkv, D);
+        g.row_scale = hrs(0);
+        D4_TRY(d4_engine_gemm(c, g, c->vr_w, 0, s));
+    }
+    const float* x_in = hid(0); const float* x_in_rstd = hrs(0);
+    int ti = 0;
+    for (int i = 0; i < L; ++i) {
+        {   // fused q | k | v | gate logits | value-residual mix logits of the normed layer input
+            GemmArgs g = gemm_args(x_in, D, nullptr, D, c->b.qkvgm, c->ldq, M, c->NQ, D);
+            g.row_scale = x_in_rstd; g.bias = c->attn[i].b;
+            D4_TRY(d4_engine_gemm(c, g, c->attn[i].w, 0, s));
+        }
+        const int off_k = Dq, off_v = Dq + Dkv, off_g = Dq + 2 * Dkv, off_m = Dq + 2 * Dkv + hq;
+        if (c->is_time[i]) {
+            TimeAttnArgs a; memset(&a, 0, sizeof(a));
+            a.M = M; a.hkv = h; a.g = hq / h; a.d = d; a.t = t; a.Tmax = c->cfg.max_time;
+            a.qkvgm = c->b.qkvgm; a.ld = c->ldq; a.off_k = off_k; a.off_v = off_v; a.off_g = off_g; a.off_m = off_m;
+            a.v0 = c->b.v0; a.ldv0 = Dkv; a.k_gamma = c->attn[i].k_gamma; a.inv_freq = c->inv_freq;
+            const long long per = (long long)c->cfg.max_batch * S * h * c->cfg.max_time * d;
+            a.kcache = c->kv + (long long)(ti * 2 + 0) * per; a.vcache = c->kv + (long long)(ti * 2 + 1) * per;
+            a.out = c->b.attn_o; a.ldo = Dq; a.scale = att_scale; a.softclamp = c->cfg.softclamp; a.commit = 1;
+            a.variant = c->cfg.time_attn_variant;
+            const int ph = d4_prof_begin(c, D4_CLS_TIME_ATTN, (double)M * h * d * 4.0 * (2.0 * t + 6.0), s);
+            const int rc = d4_time_attn(a, s);
+            d4_prof_end(c, ph, s);
+            D4_TRY(rc);
+            ++ti;
+        } else {
+            SmallAttnArgs a; memset(&a, 0, sizeof(a));
+            a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = S; a.n = S;
+            a.q = c->b.qkvgm; a.q_sb = (long long)S * c->ldq; a.q_si = c->ldq;
+            a.k = c->b.qkvgm + off_k; a.k_sb = a.q_sb; a.k_sj = c->ldq;
+            a.v = c->b.qkvgm + off_v; a.v_sb = a.q_sb; a.v_sj = c->ldq;
+            a.k_gamma = c->attn[i].k_gamma;
+            a.v0 = c->b.v0; a.v0_sb = (long long)S * Dkv; a.v0_sj = Dkv;
+            a.mix = c->b.qkvgm + off_m; a.mix_sb = a.q_sb; a.mix_sj = c->ldq;
+            a.gate = c->b.qkvgm + off_g; a.gate_sb = a.q_sb; a.gate_si = c->ldq;
+            a.out = c->b.attn_o; a.out_sb = (long long)S * Dq; a.out_si = Dq;
+            a.scale = att_scale; a.softclamp = c->cfg.softclamp; a.mask_agent = ns; a.belief = 1;
+            D4_TRY(attend(a));
+        }
+        {
+            GemmArgs g = gemm_args(c->b.attn_o, Dq, nullptr, Dq, hid(2 * i + 1), D, M, D, Dq);
+            g.residual = x_in; g.ldr = D;
+            D4_TRY(d4_engine_gemm(c, g, c->attn[i].w_out, 0, s));
+        }
+        D4_TRY(d4_row_rstd(hid(2 * i + 1), D, rowmap_identity(), M, D, hrs(2 * i + 1), s));
+        D4_TRY(run_ff(c, c->ff[i], M, hid(2 * i + 1), D, rowmap_identity(), hrs(2 * i + 1), 0, hid(2 * i + 2), D, rowmap_identity(), nullptr, s));
+        D4_TRY(d4_row_rstd(hid(2 * i + 2), D, rowmap_identity(), M, D, hrs(2 * i + 2), s));
+        if (i != L - 1) {
+            D4_TRY(run_pool(c, c->pools[i], M, hid(2 * i + 2), hrs(2 * i + 2), 0, 0, 2 * i + 3, c->b.x_cur, nullptr, s));
+            D4_TRY(d4_row_rstd(c->b.x_cur, D, rowmap_identity(), M, D, xss(i), s));
+            x_in = c->b.x_cur; x_in_rstd = xss(i);
+        }
+    }
+
+    // ---- the special tokens cross-attend to the others once more, then their feed-forward (reference dreamer4.py:3227-3238)
+    float* xf = c->b.x_cur;
+    D4_CUDA_OK(cudaMemcpyAsync(xf, hid(2 * L), MD * 4, cudaMemcpyDeviceToDevice, s));
+    const RowMap sp_rows = rowmap(ns, S, S - ns);
+    D4_TRY(d4_row_rstd(xf, D, sp_rows, Ms, D, c->tfb.sp_rstd, s));
+    {
+        GemmArgs g = gemm_args(xf, D, nullptr, D, c->tfb.fa_q, c->ldfa, Ms, Dq + hq, D);
+        g.amap = sp_rows; g.row_scale = c->tfb.sp_rstd;
+        D4_TRY(d4_engine_gemm(c, g, c->fa.w_qg, 0, s));
+        GemmArgs g2 = gemm_args(hid(2 * L), D, nullptr, D, c->b.fa_kv, 2 * Dkv, M, 2 * Dkv, D);
+        g2.row_scale = hrs(2 * L);
+        D4_TRY(d4_engine_gemm(c, g2, c->fa.w_kv, 0, s));
+        SmallAttnArgs a; memset(&a, 0, sizeof(a));
+        a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = ns; a.n = S - ns;
+        a.q = c->tfb.fa_q; a.q_sb = (long long)ns * c->ldfa; a.q_si = c->ldfa;
+        a.k = c->b.fa_kv; a.k_sb = (long long)S * 2 * Dkv; a.k_sj = 2 * Dkv;
+        a.v = c->b.fa_kv + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+        a.k_gamma = c->fa.k_gamma;
+        a.gate = c->tfb.fa_q + Dq; a.gate_sb = a.q_sb; a.gate_si = c->ldfa;
+        a.out = c->tfb.fa_att; a.out_sb = (long long)ns * Dq; a.out_si = Dq;
+        a.scale = att_scale;
+        D4_TRY(attend(a));
+        GemmArgs g3 = gemm_args(c->tfb.fa_att, Dq, nullptr, Dq, xf, D, Ms, D, Dq);
+        g3.residual = xf; g3.ldr = D; g3.cmap = sp_rows;
+        D4_TRY(d4_engine_gemm(c, g3, c->fa.w_out, 0, s));
+    }
+    D4_TRY(d4_row_rstd(xf, D, sp_rows, Ms, D, c->tfb.sp_rstd, s));
+    D4_TRY(run_ff(c, c->fa_ff, Ms, xf, D, sp_rows, c->tfb.sp_rstd, 0, xf, D, sp_rows, nullptr, s));
+    // final attention-residual pool over all 2L+1 hiddens (reference dreamer4.py:3242-3243), final norm (3247)
+    D4_TRY(d4_row_rstd(xf, D, rowmap_identity(), M, D, xss(L), s));
+    if (c->tf_final_norm) {
+        D4_TRY(run_pool(c, c->pool_final, M, xf, xss(L), 0, 0, c->n_hid, xf, nullptr, s));
+        return d4_rmsnorm_rows(xf, D, rowmap_identity(), c->tf_final_norm_w, M, D, tokens_out, D, s);
+    }
+    return run_pool(c, c->pool_final, M, xf, xss(L), 0, 0, c->n_hid, tokens_out, nullptr, s);
+}
+
+// ---- stand-alone operators of the tokenizer's front / back end
+extern "C" int d4_linear_rows(int precision, int M, int N, int K, const float* A, int64_t lda, int a_grp, int a_gstride, int a_goff,
+                              const float* W, int64_t ldw, const float* W_lo, const float* W_exact, const float* bias, float* C, int64_t ldc,
+                              void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GemmArgs g = gemm_args(A, lda, W_exact ? W_exact : W, ldw, C, ldc, M, N, K);
+    g.bias = bias;
+    if (a_grp > 0) g.amap = rowmap(a_grp, a_gstride, a_goff);
+    if (precision == D4_PREC_FP32 || !d4_gemm_tc_supported(g)) {
+        if (!W_exact) return d4_fail("d4_linear_rows: this shape runs on the exact-fp32 kernel and needs W_exact");
+        return d4_gemm_simt(g, s);
+    }
+    if (precision == D4_PREC_TF32X3 || precision == D4_PREC_F16X3) {
+        if (!W || !W_lo) return d4_fail("d4_linear_rows: tf32x3 needs the hi / lo words of W");
+        g.W = W; g.W_lo = W_lo;
+        return d4_gemm_tc(g, 3, s);
+    }
+    return d4_gemm_tc(g, 1, s);
+}
+extern "C" int d4_patchify(int B, int C, int H, int W, int p, const float* frame, int64_t stride_b, int64_t stride_c, float* out, void* stream) {
+    return d4_patchify_launch(B, C, H, W, p, frame, stride_b, stride_c, out, static_cast<cudaStream_t>(stream));
+}
+extern "C" int d4_unpatchify_flow(int B, int C, int H, int W, int p, const float* patches, float* frame, int64_t stride_b, int64_t stride_c,
+                                  float scale, void* stream) {
+    return d4_unpatchify_flow_launch(B, C, H, W, p, patches, frame, stride_b, stride_c, scale, static_cast<cudaStream_t>(stream));
+}
+extern "C" int d4_tok_assemble(int B, int S, int P, int D, const float* lin, const float* ln_w, const float* pos_emb, const float* special,
+                               int64_t special_bstride, int num_special, float* tokens, void* stream) {
+    if (P + num_special != S) return d4_fail("d4_tok_assemble: %d patches + %d special tokens != %d tokens per frame", P, num_special, S);
+    return d4_tok_assemble_launch(B, S, P, D, lin, ln_w, pos_emb, special, special_bstride, tokens, static_cast<cudaStream_t>(stream));
+}
+extern "C" int d4_tanh_rows(float* x, int64_t n, void* stream) { return d4_tanh_launch(x, n, static_cast<cudaStream_t>(stream)); }

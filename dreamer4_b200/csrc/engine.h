@@ -67,6 +67,11 @@ struct d4_ctx {
     bool fuse_ss = true;         // RMS statistics accumulated in the producing GEMM's epilogue (D4_FUSE_SS=0: separate row pass)
     bool space_mma = true;       // space attention on mma.sync 3xTF32 tiles in the tensor-core engine modes (D4_SPACE_MMA=0: FMA kernel)
     bool fuse_pools = true;      // fused latent<->space pool kernels (fused_pools.cu); D4_FUSE_POOLS=0 keeps the GEMM + attention path
+    // generic transformer context (d4_tf_create: the video tokenizer's encoder / decoder): S tokens per frame of which the last
+    // tf_ns are special, final RMSNorm; uses attn / ff / pools / pool_final / fa / fa_ff / vr_w / inv_freq and the buffers below
+    bool tf_mode = false; int tf_ns = 1; int tf_final_norm = 0; const float* tf_final_norm_w = nullptr;
+    struct { float *fa_q, *fa_att, *sp_rstd; } tfb = {};
+
     // CUDA-graph replay of whole frames (D4_GRAPH=1, off by default; small batches are launch-bound: ~570 launches per imagined
     // frame).  One instantiated graph per (entry point, B, t, num_steps, temperature, which optional io fields are present),
     // captured the SECOND time a key is seen (the first use runs directly, which also gets every lazy one-time setup out of

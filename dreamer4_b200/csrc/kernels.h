@@ -115,3 +115,14 @@ struct LpArgs {
 };
 int d4_lp_fused_supported(const LpArgs& a);
 int d4_lp_fused(const LpArgs& a, cudaStream_t s);
+
+// ---- attention within a frame of more than 64 tokens (frame_attn.cu; video tokenizer).  a.mask_agent = number of special tokens.
+int d4_frame_attn(const SmallAttnArgs& a, cudaStream_t s);
+
+// ---- video tokenizer front / back end (tokenizer.cu)
+int d4_patchify_launch(int B, int C, int H, int W, int p, const float* frame, long long sb, long long sc, float* out, cudaStream_t s);
+int d4_unpatchify_flow_launch(int B, int C, int H, int W, int p, const float* patches, float* frame, long long sb, long long sc, float scale,
+                              cudaStream_t s);
+int d4_tok_assemble_launch(int B, int S, int P, int D, const float* lin, const float* ln_w, const float* pos_emb, const float* special,
+                           long long special_bstride, float* tokens, cudaStream_t s);
+int d4_tanh_launch(float* x, long long n, cudaStream_t s);

@@ -193,6 +193,53 @@ typedef struct d4_learn_io {
 int64_t d4_learn_workspace_bytes(const d4_ctx* ctx, int B, int T);
 int d4_learn(d4_ctx* ctx, const d4_learn_io* io, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- video tokenizer (VideoTokenizer.tokenize / .decode, D4:4107-4113, 4183-4237; both of its
+ * transformers run one frame per step over a time-KV cache, like the dynamics model).  STATUS: drafted in round 1, not yet run
+ * on hardware. */
+
+/* A generic AxialSpaceTimeTransformer context: the tokenizer's encoder (D4:3908-3929: num_special = num_latent_tokens) or decoder
+ * (D4:3595-3607: library defaults, num_special = 1); S = tokens_per_frame = patches + latent tokens, the special tokens last.
+ * The returned d4_ctx is used with d4_set_weight / d4_bind / d4_workspace_bytes / d4_kv_bytes / d4_set_buffers / d4_ctx_destroy
+ * exactly like a d4_ctx_create one; packed weight names: vr.w, inv_freq, final_norm, L{i}.attn.*, L{i}.ff.*, P{i}.*, PF.*, FA.*,
+ * FAFF.* (dreamer4_b200/packing.py: _pack_transformer). */
+typedef struct d4_tf_config {
+    int32_t dim, depth, time_block_every;
+    int32_t heads, query_heads, dim_head, pool_heads, pool_dim_head;
+    int32_t ff_inner, ff_inner_pad, ff_act;
+    int32_t tokens_per_frame, num_special, final_norm;
+    float   softclamp;
+    int32_t max_batch, max_time, precision, time_attn_variant;
+} d4_tf_config;
+int d4_tf_create(const d4_tf_config* cfg, d4_ctx** out);
+
+/* One frame through the transformer over its time-KV cache (appended at position t): replaces
+ * AxialSpaceTimeTransformer.forward (D4:2927-3267) for time == 1.  tokens_in / tokens_out (B, S, D). */
+int d4_tf_step(d4_ctx* ctx, int B, const float* tokens_in, int t, float* tokens_out, void* stream);
+
+/* C (M, N) = A[rows] @ W^T + bias, the rows of A taken through a grouped row map: compact row m -> (m / a_grp) * a_gstride +
+ * a_goff + m % a_grp (a_grp = 0: identity) - e.g. the latent-token rows of every frame of a (B, S, D) token tensor.
+ * W / W_lo: the tf32 hi / lo words (D4_PREC_TF32X3) or W itself; W_exact: the fp32 weight, used by the exact-fp32 kernel when
+ * precision is D4_PREC_FP32 or the shape does not fit the tensor-core path.  Replaces the nn.Linear layers either side of the
+ * tokenizer's transformers (D4:3836, 3884, 4413, 4148, 3569). */
+int d4_linear_rows(int precision, int M, int N, int K, const float* A, int64_t lda, int a_grp, int a_gstride, int a_goff,
+                   const float* W, int64_t ldw, const float* W_lo, const float* W_exact, const float* bias, float* C, int64_t ldc,
+                   void* stream);
+
+/* 'b c (h p1) (w p2) -> (b h w) (p1 p2 c)' of one frame (D4:3835, 3883); frame element (b, c, y, x) at frame[b * stride_b +
+ * c * stride_c + y * W + x] (a [:, :, t] slice of a (b c t h w) video); out (B * H/p * W/p, p * p * C). */
+int d4_patchify(int B, int C, int H, int W, int p, const float* frame, int64_t stride_b, int64_t stride_c, float* out, void* stream);
+/* frame <- frame + (pred - frame) * scale with pred the un-patched rows '(b h w) (p1 p2 c) -> b c (h p1) (w p2)' (D4:3571) and
+ * scale = 1 / (1 - tau) / steps: one Euler step of the decoder's flow (D4:4223-4227). */
+int d4_unpatchify_flow(int B, int C, int H, int W, int p, const float* patches, float* frame, int64_t stride_b, int64_t stride_c,
+                       float scale, void* stream);
+/* tokens (B, S, D) of one frame: rows i < P = LayerNorm(lin[b * P + i]) * ln_w (nn.LayerNorm(bias=False), D4:3837, 3885)
+ * + pos_emb[i] (decoder only, D4:3618-3628; NULL otherwise); rows P .. S-1 = the num_special special tokens
+ * special[b * special_bstride + j * D] (special_bstride = 0: one learned set for every b, D4:4349). */
+int d4_tok_assemble(int B, int S, int P, int D, const float* lin, const float* ln_w, const float* pos_emb, const float* special,
+                    int64_t special_bstride, int num_special, float* tokens, void* stream);
+/* x <- tanh(x) over n elements (D4:4426). */
+int d4_tanh_rows(float* x, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

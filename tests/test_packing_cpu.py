@@ -158,7 +158,7 @@ def test_ctypes_structs_mirror_the_header(tmp_path):
     import subprocess
     from dreamer4_b200 import _lib
     root = os.path.dirname(os.path.dirname(__file__))
-    structs = {'d4_config': _lib.d4_config, 'd4_frame_io': _lib.d4_frame_io, 'd4_learn_io': _lib.d4_learn_io}
+    structs = {'d4_config': _lib.d4_config, 'd4_frame_io': _lib.d4_frame_io, 'd4_learn_io': _lib.d4_learn_io, 'd4_tf_config': _lib.d4_tf_config}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "d4b200.h"', 'int main(void) {']
     for name, cls in structs.items():
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')

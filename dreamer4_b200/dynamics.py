@@ -150,12 +150,18 @@ class DynamicsWorldModel(nn.Module):
                  use_delight_gating=True, delight_temperature=1., normalize_advantages=None, policy_entropy_weight=.01,
                  pmpo_pos_to_neg_weight=0.5, pmpo_reverse_kl=True, pmpo_kl_div_loss_weight=.3, gae_use_accelerated=False, precision='tf32x3', time_attn_variant=1, **kwargs):
         super().__init__()
+        video_tokenizer = kwargs.pop('video_tokenizer', None)
+        if exists(video_tokenizer):             # reference dreamer4.py:4790-4801
+            assert hasattr(video_tokenizer, 'tokenize') and hasattr(video_tokenizer, 'decode'), 'video_tokenizer must be a dreamer4_b200.VideoTokenizer'
+            num_latent_tokens = default(num_latent_tokens, video_tokenizer.num_latent_tokens)
+            assert video_tokenizer.num_latent_tokens == num_latent_tokens and video_tokenizer.dim_latent == dim_latent, \
+                'the tokenizer and the dynamics model disagree on the latent shape'
         for k, v in kwargs.items():
             if k not in _UNSUPPORTED_DEFAULTS:
                 continue                    # training-only knobs (loss weights, ssl kwargs, ...) do not touch this path
             if v != _UNSUPPORTED_DEFAULTS[k]:
                 raise NotImplementedError(f'{k}={v!r}: this branch of the reference is outside the B200 hot path (SURVEY.md section 8)')
-        assert exists(num_latent_tokens), 'num_latent_tokens is required (no video tokenizer is attached on this path)'
+        assert exists(num_latent_tokens), '`num_latent_tokens` must be set (or attach a video_tokenizer)'
         assert precision in _lib.PREC, f'precision must be one of {list(_lib.PREC)}'
         if transformer_kwargs:
             raise NotImplementedError('transformer_kwargs overrides are outside the B200 hot path')
@@ -189,8 +195,8 @@ class DynamicsWorldModel(nn.Module):
         self.pmpo_pos_to_neg_weight, self.pmpo_reverse_kl = pmpo_pos_to_neg_weight, pmpo_reverse_kl     # reference :5227-5231
         self.pmpo_kl_div_loss_weight = pmpo_kl_div_loss_weight
         self.latent_shape = (num_latent_tokens, dim_latent)
-        self.video_tokenizer = None
         self._build_parameters()
+        self.video_tokenizer = video_tokenizer.eval() if exists(video_tokenizer) else None      # submodule: state_dict keys video_tokenizer.* (4794)
         self._ctx = None
         self._ctx_key = None
         self._kv_epoch = 0
@@ -502,12 +508,22 @@ class DynamicsWorldModel(nn.Module):
             return_log_probs_and_values = True
             return_rewards_per_frame = True
             return_terminals = return_terminals or self.predict_terminals
-        for name, v in dict(prompt=prompt, prompt_proprio=prompt_proprio, prompt_continuous_actions=prompt_continuous_actions,
+        for name, v in dict(prompt_proprio=prompt_proprio, prompt_continuous_actions=prompt_continuous_actions,
                             latent_gene_ids=latent_gene_ids).items():
             if exists(v):
-                raise NotImplementedError(f'generate({name}=...): video prompts / proprioception / continuous actions are "next" rows (SURVEY.md section 8f)')
-        if return_decoded_video:
-            raise NotImplementedError('return_decoded_video needs the VideoTokenizer, a "next" row (SURVEY.md section 8f)')
+                raise NotImplementedError(f'generate({name}=...): proprioception / continuous actions are "next" rows (SURVEY.md section 8f)')
+        has_tokenizer = exists(self.video_tokenizer)
+        return_decoded_video = default(return_decoded_video, has_tokenizer)          # reference dreamer4.py:6694-6695
+        if return_decoded_video and not has_tokenizer:
+            raise ValueError('return_decoded_video needs a video_tokenizer attached to the model')
+        assert not (exists(prompt) and exists(prompt_latents)), 'cannot pass in both prompt video and prompt latents'
+        if exists(prompt):                                                           # reference dreamer4.py:6377-6387
+            assert has_tokenizer, 'a video prompt needs a video_tokenizer attached to the model'
+            if prompt.ndim == 4:
+                prompt = prompt[:, :, None]
+            if prompt.shape[1] != self.video_tokenizer.channels:
+                prompt = prompt.expand(-1, self.video_tokenizer.channels, -1, -1, -1)
+            prompt_latents = self.video_tokenizer.tokenize(prompt)
         if not use_time_cache:
             raise NotImplementedError('use_time_cache=False: the native path always decodes over the in-place KV cache')
         assert math.log2(num_steps).is_integer(), f'number of steps {num_steps} must be a power of 2'
@@ -647,8 +663,12 @@ class DynamicsWorldModel(nn.Module):
             next_kv = kv[:L, :, :, :, :Tg]
             next_kv._d4_epoch = self._kv_epoch          # lets a resumed call recognise this view as current (see above)
         tc = DynamicsIntermediates(main=TransformerIntermediates(next_kv_cache=next_kv, token_count=Tg))
+        video = None
+        if return_decoded_video:                                                     # reference dreamer4.py:6699-6711
+            video = self.video_tokenizer.decode(latents, height=image_height, width=image_width)
         if not (return_rewards_per_frame or return_agent_actions):
-            return (latents, tc) if return_time_cache else latents
+            out = video if return_decoded_video else latents
+            return (out, tc) if return_time_cache else out
 
         # prompt frames carry latents, rewards and actions only; everything decoded off the agent token covers the new
         # frames (reference dreamer4.py:6620-6662 accumulate from empty)
@@ -656,6 +676,7 @@ class DynamicsWorldModel(nn.Module):
         step_mask = (torch.arange(Tg, device=dev)[None, :] < lens[:, None]).float()
         gen = Experience(
             latents=latents,
+            video=video,
             agent_embed=agent_embed[:, P:Tg] if store_agent_embed else None,
             old_action_unembeds=Actions(logits[:, P:Tg], None) if (want_heads and store_old_action_unembeds) else None,
             step_size=self.max_steps // num_steps, agent_index=agent_index, lens=lens, is_truncated=~terminals, terminals=terminals,
@@ -681,8 +702,16 @@ class DynamicsWorldModel(nn.Module):
         Without a VideoTokenizer on this path `obs_to_latents_fn` is required; it is called with the same
         (self, obs, cache) arguments at the bootstrap step (the reference drops `self` there, :5793)."""
         if not exists(obs_to_latents_fn):
-            raise NotImplementedError('interact_with_env needs obs_to_latents_fn: image / state observations go through the '
-                                      'VideoTokenizer / state_to_latents, "next" rows (SURVEY.md section 8f)')
+            if not exists(self.video_tokenizer):
+                raise NotImplementedError('interact_with_env needs obs_to_latents_fn or an attached video_tokenizer: state observations '
+                                          'go through state_to_latents, a "next" row (SURVEY.md section 8f)')
+
+            def obs_to_latents_fn(model, obs, cache):       # reference dreamer4.py:5588: one frame through the encoder's time cache
+                image = obs['image'] if isinstance(obs, dict) else obs
+                image = torch.as_tensor(image, dtype=torch.float32).to(model.device)
+                if not env_is_vectorized:
+                    image = image[None]
+                return model.video_tokenizer(image[:, :, None], return_latents=True, time_cache=cache, return_time_cache=True)
         if not use_time_cache:
             raise NotImplementedError('use_time_cache=False: the native path always runs over the in-place KV cache')
         c = self.cfg

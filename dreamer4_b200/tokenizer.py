@@ -18,6 +18,7 @@ import ctypes as C
 import functools
 import math
 import pickle
+from collections import namedtuple
 from dataclasses import dataclass
 from typing import Optional
 
@@ -87,6 +88,12 @@ _TRAINING_ONLY = ('lpips_loss_weight', 'lpips_loss_network', 'encoder_add_decor_
                   'latent_ar_loss_weight', 'recon_loss_weight', 'norm_recon_loss', 'time_decorr_loss_weight', 'nd_rotary_kwargs')
 
 
+# what `forward(..., return_time_cache=True)` hands back and `time_cache=` takes: the encoder's keys / values stay in the engine's
+# in-place buffer, the record only says how many frames it holds and which rollout wrote them (a later un-cached call restarts
+# the buffer and makes older records stale - rejected rather than silently mixing rollouts)
+TokenizerTimeCache = namedtuple('TokenizerTimeCache', ['token_count', 'epoch'])
+
+
 def _records_config(init):
     @functools.wraps(init)
     def wrapped(self, *args, **kwargs):
@@ -131,6 +138,7 @@ class VideoTokenizer(nn.Module):
         self._build_parameters()
         self._ctx = {}            # 'enc' / 'dec' -> (ctx, key, buffers)
         self._packed, self._packed_version = None, None
+        self._enc_epoch = 0
 
     # ------------------------------------------------------------------ parameters (reference state_dict layout)
 
@@ -224,20 +232,21 @@ class VideoTokenizer(nn.Module):
             self._packed_version = self._version()
         return self._packed
 
-    def _transformer(self, which, batch, max_time):
-        """Native context of the encoder ('enc') or decoder ('dec') transformer with this (batch, KV capacity)."""
+    def _transformer(self, which, batch, need_time, keep_frames=0):
+        """Native context of the encoder ('enc') or decoder ('dec') transformer for this batch with a KV capacity of at least
+        `need_time` frames (allocated in blocks of 16); when an existing context has to grow, its first `keep_frames` cached
+        frames are carried over."""
         if self.device.type != 'cuda':
             raise D4Error('dreamer4_b200 runs on CUDA only: move the tokenizer to a B200 (`.cuda()`); there is no CPU fallback')
         lib = _lib.load()
         c, dev = self.cfg, self.device
         packed = self._weights()
-        key = (batch, max_time, self.precision, self.time_attn_variant, dev.index)
+        key = (batch, self.precision, self.time_attn_variant, dev.index)
         have = self._ctx.get(which)
-        if have is not None and have[1] == key:
+        if have is not None and have[1] == key and have[2]['max_time'] >= need_time:
             return lib, have[0], have[2]
-        if have is not None:
-            lib.d4_ctx_destroy(have[0])
-            del self._ctx[which]
+        old = have if (have is not None and have[1] == key and keep_frames > 0) else None
+        max_time = (need_time + 15) // 16 * 16
         depth = c.encoder_depth if which == 'enc' else c.decoder_depth
         cc = _lib.d4_tf_config()
         cc.dim, cc.depth, cc.time_block_every = c.dim, depth, c.time_block_every
@@ -255,14 +264,20 @@ class VideoTokenizer(nn.Module):
         ctx = C.c_void_p()
         check(lib.d4_tf_create(C.byref(cc), C.byref(ctx)))
         ws_bytes, kv_bytes = lib.d4_workspace_bytes(ctx), lib.d4_kv_bytes(ctx)
+        y = max(sum(c.is_time(depth)), 1)
         with torch.cuda.device(dev):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            kv = torch.zeros(max(kv_bytes // 4, 4), device=dev)
-            check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv.numel() * 4))
+            kv = torch.zeros(y, 2, batch * c.tokens_per_frame, c.attn_heads, max_time, c.attn_dim_head, device=dev)
+            assert kv.numel() * 4 == kv_bytes
+            if old is not None:
+                kv[..., :keep_frames, :] = old[2]['kv'][..., :keep_frames, :]
+            check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv_bytes))
         for name, t in packed[which].items():
             check(lib.d4_set_weight(ctx, name.encode(), ptr(t), t.numel()))
         check(lib.d4_bind(ctx))
-        bufs = dict(ws=ws, kv=kv)
+        if have is not None:
+            lib.d4_ctx_destroy(have[0])
+        bufs = dict(ws=ws, kv=kv, max_time=max_time)
         self._ctx[which] = (ctx, key, bufs)
         return lib, ctx, bufs
 
@@ -282,15 +297,24 @@ class VideoTokenizer(nn.Module):
     # ------------------------------------------------------------------ tokenize (video -> latents)
 
     @torch.no_grad()
-    def tokenize(self, video):
-        """(b c t h w) or (b c h w) -> (b t n dl): `forward(video, return_latents=True)` in eval mode (reference dreamer4.py:4107-4113)."""
+    def tokenize(self, video, time_cache=None, return_time_cache=False):
+        """(b c t h w) or (b c h w) -> (b t n dl): `forward(video, return_latents=True)` in eval mode (reference dreamer4.py:4107-4113).
+        `time_cache` / `return_time_cache` (as on the reference's forward, used by interact_with_env at :5588): continue over the
+        frames already encoded instead of starting a new video."""
         c = self.cfg
         if video.ndim == 4:                                              # reference dreamer4.py:4258-4260
             video = video[:, :, None]
         b, ch, T, H, W = video.shape
         assert (ch, H, W) == (c.channels, c.image_height, c.image_width), f'video {tuple(video.shape)} does not match the tokenizer'
         video = video.to(device=self.device, dtype=torch.float32).contiguous()
-        lib, ctx, _ = self._transformer('enc', b, (T + 15) // 16 * 16)
+        t0 = 0
+        if time_cache is not None:
+            if time_cache.epoch != self._enc_epoch:
+                raise ValueError('stale tokenizer time_cache: a later un-cached tokenize() restarted the encoder\'s in-place KV buffer')
+            t0 = time_cache.token_count
+        else:
+            self._enc_epoch += 1
+        lib, ctx, _ = self._transformer('enc', b, t0 + T, keep_frames=t0)
         io = self._packed['io']
         P, N, S, D = c.num_patches, c.num_latent_tokens, c.tokens_per_frame, c.dim
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -303,11 +327,13 @@ class VideoTokenizer(nn.Module):
             check(lib.d4_patchify(b, ch, H, W, c.patch_size, ptr(frame), frame.stride(0), frame.stride(1), ptr(patches), stream))
             self._linear(lib, patches, 'patch.w', io['patch.b'], b * P, out=lin)
             check(lib.d4_tok_assemble(b, S, P, D, ptr(lin), ptr(io['patch.ln']), None, ptr(io['latent_tokens']), 0, N, ptr(tok), stream))
-            check(lib.d4_tf_step(ctx, b, ptr(tok), t, ptr(out), stream))
+            check(lib.d4_tf_step(ctx, b, ptr(tok), t0 + t, ptr(out), stream))
             lat_t = torch.empty(b * N, c.dim_latent, device=self.device)
             self._linear(lib, out.view(b * S, D), 'to_latents.w', None, b * N, amap=(N, S, P), out=lat_t)
             check(lib.d4_tanh_rows(ptr(lat_t), lat_t.numel(), stream))
             latents[:, t] = lat_t.view(b, N, c.dim_latent)
+        if return_time_cache:
+            return latents, TokenizerTimeCache(t0 + T, self._enc_epoch)
         return latents
 
     # ------------------------------------------------------------------ decode (latents -> video)
@@ -323,7 +349,7 @@ class VideoTokenizer(nn.Module):
         latents = latents.to(device=self.device, dtype=torch.float32).contiguous()
         b, T, N, Dl = latents.shape
         assert (N, Dl) == (c.num_latent_tokens, c.dim_latent)
-        lib, ctx, _ = self._transformer('dec', b, (T + 15) // 16 * 16)
+        lib, ctx, _ = self._transformer('dec', b, T)
         io = self._packed['io']
         P, S, D, ch = c.num_patches, c.tokens_per_frame, c.dim, c.channels
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -350,9 +376,10 @@ class VideoTokenizer(nn.Module):
         return video
 
     def forward(self, *args, **kwargs):
-        if kwargs.get('return_latents'):
+        if kwargs.pop('return_latents', False):
             assert len(args) == 1, 'forward(video, return_latents=True)'
-            return self.tokenize(args[0])
+            kwargs.pop('mask_patches', None)           # eval mode never masks patches
+            return self.tokenize(args[0], **kwargs)
         raise NotImplementedError('VideoTokenizer training forward is outside the path this package builds (DESIGN.md section 8)')
 
 

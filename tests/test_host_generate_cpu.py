@@ -226,3 +226,87 @@ def test_interact_with_env(case, monkeypatch):
         assert fake.calls['observe'] == exp.latents.shape[1] and fake.calls['pass_'] == 0
     finally:
         model._release()
+
+
+# ------------------------------------------------------------------------------------------------ attached video tokenizer
+# DynamicsWorldModel(video_tokenizer=VideoTokenizer(...)): state_dict layout with the tokenizer as a submodule, generate(prompt=
+# video) and return_decoded_video (reference dreamer4.py:6377-6387, 6694-6724).  The tokenizer's two entry points are replaced by
+# the oracle's here (a fake tokenizer engine, like fake_engine.py for the dynamics model): what is under test is the wiring.
+
+WORLD = os.path.join(os.path.dirname(__file__), 'golden', 'tokenizer', 'world_with_tokenizer.pt')
+
+
+@pytest.fixture
+def world(monkeypatch):
+    from dreamer4_b200 import DynamicsWorldModel, VideoTokenizer
+    from oracle import tokenizer_oracle as TO
+    fx = torch.load(WORLD, map_location='cpu', weights_only=False)
+    tok = VideoTokenizer(**fx['tokenizer_kwargs'])
+    model = DynamicsWorldModel(**fx['model_kwargs'], video_tokenizer=tok, precision='fp32')
+    assert model.cfg.num_latent_tokens == tok.num_latent_tokens                  # taken from the tokenizer (reference :4801)
+    model.load_state_dict(fx['state_dict'], strict=True)                         # video_tokenizer.* keys included
+    tsd = {k[len('video_tokenizer.'):]: v for k, v in fx['state_dict'].items() if k.startswith('video_tokenizer.')}
+    tcfg = TO.config_from_reference_kwargs(**fx['tokenizer_kwargs'])
+    monkeypatch.setattr(tok, 'tokenize', lambda video, **kw: TO.tokenize(tsd, tcfg, video))
+    dec_noise = {}                                                               # test-provided start noise of the flow decoder
+    monkeypatch.setattr(tok, 'decode', lambda latents, height=None, width=None, **kw: TO.decode(tsd, tcfg, latents, noise=dec_noise['x']))
+    ocfg = O.config_from_reference_kwargs(num_latent_tokens=tok.num_latent_tokens, **fx['model_kwargs'])
+    fake = install(monkeypatch, model, ocfg)
+    yield fx, model, ocfg, (tsd, tcfg), dec_noise
+    model._release()
+
+
+def test_video_prompt_and_decoded_video(world):
+    fx, model, ocfg, tokenizer, dec_noise = world
+    sd = fx['state_dict']
+    B, T = fx['prompt'].shape[0], fx['prompted']['time_steps']
+    noise = make_noise(model.cfg, T, B, seed=11)
+    tcfg = tokenizer[1]
+    dec_noise['x'] = torch.randn(B, tcfg.channels, T, tcfg.image_height, tcfg.image_width)        # the decoder's randn (reference :4204)
+    ref = O.generate(sd, ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform'], dec_noise['x']),
+                     tokenizer=tokenizer, prompt=fx['prompt'], return_agent_actions=False, return_decoded_video=True)
+    video = model.generate(T, batch_size=B, prompt=fx['prompt'], noise=noise)    # tokenizer attached: the decoded video comes back (:6694, 6721)
+    assert torch.is_tensor(video) and video.shape == ref.video.shape
+    assert torch.equal(video, ref.video)
+    latents = model.generate(T, batch_size=B, prompt=fx['prompt'], noise=noise, return_decoded_video=False)
+    assert torch.equal(latents, ref.latents)
+
+
+def test_dream_returns_experience_with_video(world):
+    fx, model, ocfg, tokenizer, dec_noise = world
+    sd = fx['state_dict']
+    B, T = 2, 4
+    noise = make_noise(model.cfg, T, B, seed=12)
+    tcfg = tokenizer[1]
+    dec_noise['x'] = torch.randn(B, tcfg.channels, T, tcfg.image_height, tcfg.image_width)
+    ref = O.generate(sd, ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform'], dec_noise['x']),
+                     tokenizer=tokenizer, return_decoded_video=True)
+    exp = model.generate(T, batch_size=B, noise=noise, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
+    same(exp, ref)
+    assert torch.equal(exp.video, ref.video)
+
+
+@pytest.mark.parametrize('case', [0, 2], ids=['vec_mixed_bootstrap', 'single_truncated'])
+def test_interact_with_env_through_the_attached_tokenizer(case, world, monkeypatch):
+    """Without obs_to_latents_fn, image observations go through the attached tokenizer one frame per env step over its time cache
+    (reference dreamer4.py:5588) - same episode as the reference's."""
+    from oracle import tokenizer_oracle as TO
+    from oracle.toy_env import ToyImageEnv
+    fx, model, ocfg, (tsd, tcfg), _ = world
+    ref_case = fx['interact'][case]
+    vectorized = ref_case['vectorized']
+
+    def tokenize(video, time_cache=None, return_time_cache=False):          # the oracle's incremental tokenizer behind the product's signature
+        assert video.ndim == 5 and video.shape[2] == 1 and return_time_cache
+        tok_cache, t = time_cache if time_cache is not None else (None, 0)
+        lat, tok_cache = TO.tokenize_step(tsd, tcfg, video[:, :, 0], tok_cache, t)
+        return lat[:, None], (tok_cache, t + 1)
+
+    monkeypatch.setattr(model.video_tokenizer, 'tokenize', tokenize)
+    torch.manual_seed(ref_case['seed'])
+    exp = model.interact_with_env(ToyImageEnv(batch=3 if vectorized else None, terminate_at=ref_case['terminate_at']),
+                                  max_timesteps=ref_case['max_timesteps'], env_is_vectorized=vectorized)
+    assert torch.equal(exp.actions.discrete, ref_case['actions']) and torch.equal(exp.lens, ref_case['lens'])
+    assert torch.equal(exp.is_truncated, ref_case['is_truncated']) and torch.equal(exp.terminals, ref_case['terminals'])
+    torch.testing.assert_close(exp.latents, ref_case['latents'], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(exp.values, ref_case['values'], atol=2e-5, rtol=1e-4)

@@ -500,7 +500,7 @@ class DynamicsWorldModel(nn.Module):
                  discrete_temperature=1., continuous_temperature=1., noise=None):
         """Imagination rollout (reference dreamer4.py:6307-6774).  `noise` (not in the reference) optionally injects the
         per-frame random draws — dict(latent=(T,B,N,Dl) normal, action_uniform=(T,B,A_total) uniform,
-        terminal_uniform=(T,B) uniform) — so that seeded runs are comparable draw for draw across devices; by default the
+        terminal_uniform=(T,B) uniform, optionally decoder=(B,C,T,H,W) normal for the decoded video) — so that seeded runs are comparable draw for draw across devices; by default the
         draws come from torch's CUDA generator in the reference's per-frame order (randn latent, rand terminal, rand per
         action type, randn context)."""
         if return_for_policy_optimization:            # reference dreamer4.py:6342-6347
@@ -665,7 +665,8 @@ class DynamicsWorldModel(nn.Module):
         tc = DynamicsIntermediates(main=TransformerIntermediates(next_kv_cache=next_kv, token_count=Tg))
         video = None
         if return_decoded_video:                                                     # reference dreamer4.py:6699-6711
-            video = self.video_tokenizer.decode(latents, height=image_height, width=image_width)
+            dec_kw = dict(noise=noise['decoder']) if (exists(noise) and 'decoder' in noise) else {}      # injected start noise (tests)
+            video = self.video_tokenizer.decode(latents, height=image_height, width=image_width, **dec_kw)
         if not (return_rewards_per_frame or return_agent_actions):
             out = video if return_decoded_video else latents
             return (out, tc) if return_time_cache else out

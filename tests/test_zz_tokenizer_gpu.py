@@ -99,3 +99,35 @@ def test_tokenizer_at_config4_size_matches_oracle():
     want_v = TO.decode(sd, ocfg, want, noise=noise)
     got_v = tok.decode(want.cuda(), noise=noise)
     torch.testing.assert_close(got_v.cpu(), want_v, atol=5e-4, rtol=5e-4)
+
+
+def test_world_model_with_attached_tokenizer_matches_oracle():
+    """generate(prompt=video) -> decoded video, and the DreamTrainer-flag rollout with Experience.video, of a DynamicsWorldModel with
+    its tokenizer attached (reference dreamer4.py:6377-6387, 6694-6724) against the oracle on the same injected draws."""
+    from dreamer4_b200 import DynamicsWorldModel, VideoTokenizer
+    from oracle import dreamer4_oracle as O
+    from oracle import tokenizer_oracle as TO
+    fx = load(os.path.join(os.path.dirname(__file__), 'golden', 'tokenizer', 'world_with_tokenizer.pt'))
+    tok = VideoTokenizer(**fx['tokenizer_kwargs'], precision='fp32')
+    model = DynamicsWorldModel(**fx['model_kwargs'], video_tokenizer=tok, precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    model = model.cuda()
+    sd = fx['state_dict']
+    tsd = {k[len('video_tokenizer.'):]: v for k, v in sd.items() if k.startswith('video_tokenizer.')}
+    tcfg = TO.config_from_reference_kwargs(**fx['tokenizer_kwargs'])
+    ocfg = O.config_from_reference_kwargs(num_latent_tokens=tok.num_latent_tokens, **fx['model_kwargs'])
+    B, T = fx['prompt'].shape[0], fx['prompted']['time_steps']
+    g = torch.Generator().manual_seed(4)
+    A = sum(model.cfg.num_discrete_actions)
+    noise = dict(latent=torch.randn(T, B, model.cfg.num_latent_tokens, model.cfg.dim_latent, generator=g), action_uniform=torch.rand(T, B, A, generator=g),
+                 terminal_uniform=torch.rand(T, B, generator=g), decoder=torch.randn(B, tcfg.channels, T, tcfg.image_height, tcfg.image_width, generator=g))
+    inj = O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform'], noise['decoder'])
+    ref = O.generate(sd, ocfg, T, B, noise=inj, tokenizer=(tsd, tcfg), prompt=fx['prompt'], return_agent_actions=False, return_decoded_video=True)
+    cuda_noise = {k: v.cuda() for k, v in noise.items()}
+    video = model.generate(T, batch_size=B, prompt=fx['prompt'].cuda(), noise=cuda_noise)
+    torch.testing.assert_close(video.cpu(), ref.video, atol=1e-4, rtol=2e-4)
+    ref = O.generate(sd, ocfg, T, B, noise=inj, tokenizer=(tsd, tcfg), return_decoded_video=True)
+    exp = model.generate(T, batch_size=B, noise=cuda_noise, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
+    assert torch.equal(exp.actions.discrete.cpu(), ref.actions)
+    torch.testing.assert_close(exp.latents.cpu(), ref.latents, **TOL)
+    torch.testing.assert_close(exp.video.cpu(), ref.video, atol=1e-4, rtol=2e-4)

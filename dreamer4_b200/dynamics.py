@@ -391,7 +391,8 @@ class DynamicsWorldModel(nn.Module):
             self._ctx, self._ctx_key = ctx, key
             ws_bytes, kv_bytes = lib.d4_workspace_bytes(ctx), lib.d4_kv_bytes(ctx)
             with torch.cuda.device(dev):
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+                ws = ws[(-ws.data_ptr()) % 256:][:ws_bytes]      # 256-byte aligned (a no-op offset for CUDA allocations)
                 y = max(c.num_time_layers, 1)
                 kv = torch.zeros(y, 2, batch * c.tokens_per_frame, c.attn_heads, max_time, c.attn_dim_head, device=dev)
                 check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv.numel() * 4))

@@ -224,6 +224,13 @@ class VideoTokenizer(nn.Module):
         self._release()
         return out
 
+    def _require_cuda(self):
+        if self.device.type != 'cuda':
+            raise D4Error('dreamer4_b200 runs on CUDA only: move the tokenizer to a B200 (`.cuda()`); there is no CPU fallback')
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
     def _weights(self):
         if self._packed_version != self._version():
             if self._ctx:
@@ -236,8 +243,7 @@ class VideoTokenizer(nn.Module):
         """Native context of the encoder ('enc') or decoder ('dec') transformer for this batch with a KV capacity of at least
         `need_time` frames (allocated in blocks of 16); when an existing context has to grow, its first `keep_frames` cached
         frames are carried over."""
-        if self.device.type != 'cuda':
-            raise D4Error('dreamer4_b200 runs on CUDA only: move the tokenizer to a B200 (`.cuda()`); there is no CPU fallback')
+        self._require_cuda()
         lib = _lib.load()
         c, dev = self.cfg, self.device
         packed = self._weights()
@@ -265,13 +271,13 @@ class VideoTokenizer(nn.Module):
         check(lib.d4_tf_create(C.byref(cc), C.byref(ctx)))
         ws_bytes, kv_bytes = lib.d4_workspace_bytes(ctx), lib.d4_kv_bytes(ctx)
         y = max(sum(c.is_time(depth)), 1)
-        with torch.cuda.device(dev):
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            kv = torch.zeros(y, 2, batch * c.tokens_per_frame, c.attn_heads, max_time, c.attn_dim_head, device=dev)
-            assert kv.numel() * 4 == kv_bytes
-            if old is not None:
-                kv[..., :keep_frames, :] = old[2]['kv'][..., :keep_frames, :]
-            check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv_bytes))
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws = ws[(-ws.data_ptr()) % 256:][:ws_bytes]                      # the engine wants its workspace 256-byte aligned
+        kv = torch.zeros(y, 2, batch * c.tokens_per_frame, c.attn_heads, max_time, c.attn_dim_head, device=dev)
+        assert kv.numel() * 4 == kv_bytes
+        if old is not None:
+            kv[..., :keep_frames, :] = old[2]['kv'][..., :keep_frames, :]
+        check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv_bytes))
         for name, t in packed[which].items():
             check(lib.d4_set_weight(ctx, name.encode(), ptr(t), t.numel()))
         check(lib.d4_bind(ctx))
@@ -289,7 +295,7 @@ class VideoTokenizer(nn.Module):
         out = torch.empty(M, N, device=A.device) if out is None else out
         lo = io.get(w_name + '.lo')
         Wp = io[w_name + '.hi'] if lo is not None else W
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = self._stream()
         check(lib.d4_linear_rows(_lib.PREC[self.precision], M, N, K, ptr(A), A.stride(-2), amap[0], amap[1], amap[2], ptr(Wp), K, ptr(lo),
                                  ptr(W), ptr(bias), ptr(out), N, stream))
         return out
@@ -317,7 +323,7 @@ class VideoTokenizer(nn.Module):
         lib, ctx, _ = self._transformer('enc', b, t0 + T, keep_frames=t0)
         io = self._packed['io']
         P, N, S, D = c.num_patches, c.num_latent_tokens, c.tokens_per_frame, c.dim
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = self._stream()
         patches = torch.empty(b * P, c.dim_patch, device=self.device)
         lin = torch.empty(b * P, D, device=self.device)
         tok, out = torch.empty(b, S, D, device=self.device), torch.empty(b, S, D, device=self.device)
@@ -352,7 +358,7 @@ class VideoTokenizer(nn.Module):
         lib, ctx, _ = self._transformer('dec', b, T)
         io = self._packed['io']
         P, S, D, ch = c.num_patches, c.tokens_per_frame, c.dim, c.channels
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = self._stream()
         video = (torch.randn(b, ch, T, H, W, device=self.device) if noise is None else noise.to(device=self.device, dtype=torch.float32)).clone()
         steps = c.decoder_flow_steps
         patches = torch.empty(b * P, c.dim_patch, device=self.device)

@@ -1,0 +1,205 @@
+"""The parts of the native library that are plain CUDA C - the engine's orchestration (engine.cu), the row kernels, the SIMT
+GEMM, and the kernels drafted in round 1 without a GPU at hand (frame_attn.cu, tokenizer.cu) - compiled for the HOST by g++ and
+executed under a thread-per-CUDA-thread simulator (tests/cusim/: grids, blocks, shared memory, __syncthreads / __syncwarp, warp
+shuffles; `<<<...>>>` launches rewritten by tests/cusim/transform.py).  The kernels written in PTX (tensor-core GEMMs, K1, the
+mma.sync attention) are outside the simulator: the engine runs in exact-fp32 mode, where its GEMMs use the SIMT kernel, and the
+attention entry points are restated as plain loops from their contract (tests/cusim/cusim_main.cpp).
+
+What this establishes on the CPU: the engine's buffer plumbing, strides and row maps, and the indexing / masking / reductions /
+barriers of the simulated kernels - for the hardware-verified dynamics pass (which validates the harness itself against the
+oracle) and for the tokenizer path that has not run on hardware yet (d4_tf_step and the VideoTokenizer host class end to end,
+against the REFERENCE's golden vectors).  Not performance, not memory-model subtleties, not the PTX kernels: the -m gpu tests
+remain the parity tests proper.  Test infrastructure only - nothing here is linked into the product."""
+import contextlib
+import ctypes as C
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from engine_emulator import patchify, small_attn, tok_assemble, unpatchify
+from oracle import dreamer4_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(HERE), 'dreamer4_b200', 'csrc')
+SIM = os.path.join(HERE, 'cusim')
+sys.path.insert(0, SIM)
+LL = C.c_longlong
+
+
+@pytest.fixture(scope='module')
+def simlib(tmp_path_factory):
+    from transform import transform
+    from dreamer4_b200 import _lib
+    build = tmp_path_factory.mktemp('cusim')
+    srcs = []
+    for name in ('engine', 'rowops', 'gemm_simt', 'frame_attn', 'tokenizer'):
+        out = build / f'{name}.cpp'
+        out.write_text(transform(open(os.path.join(CSRC, name + '.cu')).read()))
+        srcs.append(str(out))
+    lib = build / 'libcusim.so'
+    cmd = ['g++', '-std=c++20', '-O1', '-shared', '-fPIC', '-pthread', '-I', SIM, '-I', CSRC, *srcs, os.path.join(SIM, 'cusim_main.cpp'), '-o', str(lib)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    lib = C.CDLL(str(lib))
+    for name, (res, args) in _lib.SYMBOLS.items():          # the product's own C-ABI, where the simulated sources define it
+        if hasattr(lib, name):
+            getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
+    return lib
+
+
+class _Stream:
+    cuda_stream = 0
+
+
+@pytest.fixture
+def on_simulator(simlib, monkeypatch):
+    """Routes the host classes' native calls to the simulated library and lifts their CUDA-only guards."""
+    from dreamer4_b200 import DynamicsWorldModel, VideoTokenizer, _lib
+    monkeypatch.setattr(_lib, '_lib', simlib)
+    for cls in (DynamicsWorldModel, VideoTokenizer):
+        monkeypatch.setattr(cls, '_require_cuda', lambda self: None)
+    monkeypatch.setattr(VideoTokenizer, '_stream', lambda self: C.c_void_p(0))
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, 'device', lambda device=None: contextlib.nullcontext())
+    return simlib
+
+
+def p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# ------------------------------------------------------------------------------------------------ frame_attn.cu
+
+def frame_attn(sim, q, k, v, k_gamma, scale, v0=None, mix=None, gate=None, softclamp=0., num_special=0, belief=False):
+    """q (b, nq, hq, d); k, v (b, n, h, d) contiguous; returns (b, nq, hq, d)."""
+    b, nq, hq, d = q.shape
+    n, h = k.shape[1], k.shape[2]
+    out = torch.full((b, nq, hq, d), float('nan'))
+    f = sim.sim_frame_attn
+    f.argtypes = [C.c_int] * 6 + [C.c_void_p, LL, LL] * 3 + [C.c_void_p] + [C.c_void_p, LL, LL] * 4 + [C.c_float, C.c_float, C.c_int, C.c_int]
+    rc = f(b, h, hq // h, d, nq, n, p(q), nq * hq * d, hq * d, p(k), n * h * d, h * d, p(v), n * h * d, h * d, p(k_gamma),
+           p(v0), n * h * d, h * d, p(mix), n * h, h, p(gate), nq * hq, hq, p(out), nq * hq * d, hq * d, scale, softclamp, num_special, int(belief))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize('S,ns,h,g,d', [(22, 6, 2, 1, 16), (70, 1, 2, 2, 32), (40, 8, 1, 1, 64), (33, 32, 2, 1, 16)])
+def test_frame_attn_self_attention(simlib, S, ns, h, g, d):
+    """Space attention of one frame: key RMSNorm, softclamp, special-token mask, value-residual lerp, belief projection, gates."""
+    torch.manual_seed(S + ns)
+    b, hq = 2, h * g
+    q, k, v, v0 = torch.randn(b, S, hq, d), torch.randn(b, S, h, d), torch.randn(b, S, h, d), torch.randn(b, S, h, d)
+    mix, gate, gamma = torch.randn(b, S, h), torch.randn(b, S, hq), torch.randn(h, d) * 0.2
+    got = frame_attn(simlib, q, k, v, gamma, d ** -0.5, v0=v0, mix=mix, gate=gate, softclamp=50., num_special=ns, belief=True)
+    want, _, _ = small_attn(q, k, v, gamma, d ** -0.5, gate=gate, softclamp=50., num_special=ns, belief=True, v0=v0, mix=mix)
+    torch.testing.assert_close(got, want, atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize('nq,n,h,d', [(6, 16, 2, 16), (1, 69, 2, 32), (64, 64, 1, 64)])
+def test_frame_attn_cross_attention(simlib, nq, n, h, d):
+    """The special tokens' final cross-attention over the other tokens: no mask, no softclamp, no belief, gated."""
+    torch.manual_seed(nq + n)
+    b = 2
+    q, k, v = torch.randn(b, nq, h, d), torch.randn(b, n, h, d), torch.randn(b, n, h, d)
+    gate, gamma = torch.randn(b, nq, h), torch.randn(h, d) * 0.2
+    got = frame_attn(simlib, q, k, v, gamma, d ** -0.5, gate=gate)
+    want, _, _ = small_attn(q, k, v, gamma, d ** -0.5, gate=gate)
+    torch.testing.assert_close(got, want, atol=2e-5, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ tokenizer.cu through the C-ABI
+
+def test_tokenizer_frame_ops(simlib):
+    """d4_patchify / d4_tok_assemble / d4_unpatchify_flow / d4_tanh_rows / d4_linear_rows (the same calls as
+    tests/test_zz_tokenizer_gpu.py::test_frame_ops_match_torch makes on the GPU)."""
+    lib, s = simlib, C.c_void_p(0)
+    torch.manual_seed(0)
+    B, Cc, T, H, W, pp, D, N = 2, 3, 3, 8, 12, 4, 24, 5
+    P = (H // pp) * (W // pp)
+    video = torch.randn(B, Cc, T, H, W)
+    frame = video[:, :, 1]
+    out = torch.full((B * P, pp * pp * Cc), float('nan'))
+    assert lib.d4_patchify(B, Cc, H, W, pp, p(frame), frame.stride(0), frame.stride(1), p(out), s) == 0
+    assert torch.equal(out, patchify(frame, pp))
+    lin, ln_w, pos, spec = torch.randn(B * P, D), torch.randn(D), torch.randn(P, D), torch.randn(B, N, D)
+    tok = torch.full((B, P + N, D), float('nan'))
+    assert lib.d4_tok_assemble(B, P + N, P, D, p(lin), p(ln_w), p(pos), p(spec), N * D, N, p(tok), s) == 0
+    torch.testing.assert_close(tok, tok_assemble(lin, ln_w, pos, spec, B, P), atol=1e-5, rtol=1e-5)
+    tok.fill_(float('nan'))
+    assert lib.d4_tok_assemble(B, P + N, P, D, p(lin), p(ln_w), None, p(spec[0].contiguous()), 0, N, p(tok), s) == 0
+    torch.testing.assert_close(tok, tok_assemble(lin, ln_w, None, spec[0], B, P), atol=1e-5, rtol=1e-5)
+    assert lib.d4_tok_assemble(B, P + N, P, D, p(lin), p(ln_w), None, p(spec), 0, N + 1, p(tok), s) != 0           # P + num_special != S
+    pred = torch.randn(B * P, pp * pp * Cc)
+    want = frame + (unpatchify(pred, B, pp, Cc, H, W) - frame) * 0.75
+    untouched = video[:, :, 0].clone()
+    assert lib.d4_unpatchify_flow(B, Cc, H, W, pp, p(pred), p(frame), frame.stride(0), frame.stride(1), 0.75, s) == 0
+    torch.testing.assert_close(video[:, :, 1], want, atol=1e-6, rtol=1e-6)
+    assert torch.equal(video[:, :, 0], untouched)
+    x = torch.randn(1000)
+    want = x.tanh()
+    assert lib.d4_tanh_rows(p(x), x.numel(), s) == 0
+    torch.testing.assert_close(x, want, atol=1e-6, rtol=1e-6)
+    S, K, Nn = P + N, 20, 7                       # rows of A through a grouped map: the N special rows of each of B frames of S tokens
+    A, Wt, bias = torch.randn(B * S, K), torch.randn(Nn, K), torch.randn(Nn)
+    Cout = torch.full((B * N, Nn), float('nan'))
+    assert lib.d4_linear_rows(0, B * N, Nn, K, p(A), K, N, S, P, p(Wt), K, None, p(Wt), p(bias), p(Cout), Nn, s) == 0
+    torch.testing.assert_close(Cout, A.view(B, S, K)[:, P:].reshape(B * N, K) @ Wt.T + bias, atol=1e-5, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ the engine, end to end
+
+GOLDEN = sorted(glob.glob(os.path.join(HERE, 'golden', '*.pt')))
+
+
+@pytest.mark.parametrize('path', GOLDEN[:1] + GOLDEN[2:], ids=[os.path.basename(x)[:-3] for x in GOLDEN[:1] + GOLDEN[2:]])
+def test_dynamics_rollout_on_the_simulator_matches_oracle(path, on_simulator):
+    """The hardware-verified path first - DynamicsWorldModel.generate through the real engine.cu on simulated kernels against the
+    oracle: this is what validates the harness (the stand-ins for the PTX kernels included)."""
+    from dreamer4_b200 import DynamicsWorldModel
+    fx = torch.load(path, map_location='cpu', weights_only=False)
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    ocfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    T, B = 2, 2
+    g = torch.Generator().manual_seed(3)
+    A = sum(model.cfg.num_discrete_actions)
+    noise = dict(latent=torch.randn(T, B, model.cfg.num_latent_tokens, model.cfg.dim_latent, generator=g), action_uniform=torch.rand(T, B, A, generator=g),
+                 terminal_uniform=torch.rand(T, B, generator=g))
+    ref = O.generate(fx['state_dict'], ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform']))
+    try:
+        exp = model.generate(T, batch_size=B, noise=noise, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
+    finally:
+        model._release()
+    assert torch.equal(exp.actions.discrete, ref.actions)
+    for name in ('latents', 'rewards', 'values', 'agent_embed'):
+        torch.testing.assert_close(getattr(exp, name), getattr(ref, name), atol=5e-5, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
+
+
+TOK = sorted(glob.glob(os.path.join(HERE, 'golden', 'tokenizer', 'tokenizer_*.pt')))
+
+
+@pytest.mark.parametrize('path', TOK, ids=[os.path.basename(x)[:-3] for x in TOK])
+def test_video_tokenizer_on_the_simulator_reproduces_reference_golden(path, on_simulator):
+    """The path that has NOT run on hardware yet: VideoTokenizer.tokenize / .decode - host class, d4_tf_create / d4_tf_step, frame_attn.cu,
+    tokenizer.cu, d4_linear_rows - against the vectors the reference's own source produced."""
+    from dreamer4_b200 import VideoTokenizer
+    fx = torch.load(path, map_location='cpu', weights_only=False)
+    tok = VideoTokenizer(**fx['tokenizer_kwargs'], precision='fp32')
+    tok.load_state_dict(fx['state_dict'], strict=True)
+    try:
+        latents = tok.tokenize(fx['video'])
+        torch.testing.assert_close(latents, fx['latents'], atol=5e-5, rtol=2e-4)
+        first, cache = tok.tokenize(fx['video'][:, :, :1], return_time_cache=True)                 # resumed over the encoder's time cache
+        rest = tok.tokenize(fx['video'][:, :, 1:], time_cache=cache)
+        torch.testing.assert_close(torch.cat((first, rest), dim=1), fx['latents'], atol=5e-5, rtol=2e-4)
+        b, c, T, H, W = fx['video'].shape
+        torch.manual_seed(fx['decode_seed'])
+        noise = torch.randn(b, c, T, H, W)                                 # the draw at reference dreamer4.py:4204
+        recon = tok.decode(fx['latents'], noise=noise)
+        torch.testing.assert_close(recon, fx['recon'], atol=1e-4, rtol=2e-4)
+    finally:
+        tok._release()

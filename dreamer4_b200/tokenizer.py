@@ -9,9 +9,11 @@ vectors), through the native library: `d4_tf_step` (a generic AxialSpaceTimeTran
 tokens and a final norm) between a patch-embedding front end and a projection back end made of `d4_patchify`,
 `d4_linear_rows`, `d4_tok_assemble`, `d4_tanh_rows` and `d4_unpatchify_flow` (include/d4b200.h).  There is no CPU fallback.
 
-STATUS (round 1): written after the round's GPU budget was spent - the CUDA side compiles for sm_100a but has never run;
-packing and dataflow are held to the oracle on the CPU (tests/test_tokenizer_cpu.py through tests/engine_emulator.py); the
-GPU parity tests (tests/test_zz_tokenizer_gpu.py) run under D4_EXPERIMENTAL=1 until their first hardware run."""
+STATUS (round 1): written after the round's GPU budget was spent - the CUDA side compiles for sm_100a but has never run on
+hardware.  On the CPU, this class + engine.cu's d4_tf_step + the new kernels' device code reproduce the reference's golden
+tokenize / decode vectors under the CUDA-thread simulator (tests/test_kernels_cusim_cpu.py), and the packed dataflow does so
+in torch (tests/test_tokenizer_cpu.py); the GPU parity tests (tests/test_zy_tokenizer_gpu.py) are non-strict xfail until
+their first hardware run."""
 from __future__ import annotations
 
 import ctypes as C

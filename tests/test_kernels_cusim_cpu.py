@@ -115,7 +115,7 @@ def test_frame_attn_cross_attention(simlib, nq, n, h, d):
 
 def test_tokenizer_frame_ops(simlib):
     """d4_patchify / d4_tok_assemble / d4_unpatchify_flow / d4_tanh_rows / d4_linear_rows (the same calls as
-    tests/test_zz_tokenizer_gpu.py::test_frame_ops_match_torch makes on the GPU)."""
+    tests/test_zy_tokenizer_gpu.py::test_frame_ops_match_torch makes on the GPU)."""
     lib, s = simlib, C.c_void_p(0)
     torch.manual_seed(0)
     B, Cc, T, H, W, pp, D, N = 2, 3, 3, 8, 12, 4, 24, 5

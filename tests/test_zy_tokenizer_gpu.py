@@ -1,12 +1,13 @@
 """Video tokenizer on the GPU (dreamer4_b200/tokenizer.py -> d4_tf_step, frame_attn.cu, tokenizer.cu) against the reference's
 golden vectors and the CPU oracle, through the C-ABI.
 
-STATUS: drafted in round 1 after the GPU budget was spent - the CUDA side compiles for sm_100a and has never run, so these
-tests run only under D4_EXPERIMENTAL=1 (a never-run kernel that faults would poison the CUDA context of the whole pytest
-process; the file sorts last for the same reason).  The host call sequence and the packed weights they exercise ARE verified:
-tests/test_tokenizer_cpu.py reproduces the same golden vectors from them with every C-ABI call emulated in torch.
-
-    D4_EXPERIMENTAL=1 python -m pytest tests/test_zz_tokenizer_gpu.py -q -m gpu
+STATUS: drafted in round 1 after the GPU budget was spent - the CUDA side compiles for sm_100a and has never run on hardware.
+What IS verified, on the CPU: the host call sequence, the packed weights, engine.cu's d4_tf_step and the new kernels' device code
+reproduce these same golden vectors under the CUDA-thread simulator (tests/test_kernels_cusim_cpu.py); what is left for the
+hardware is the tensor-core GEMMs at the tokenizer's shapes / row maps, K1 at S = patches + latents rows, and launch limits.
+Hence the non-strict xfail: the tests RUN in the -m gpu suite and report XPASS / XFAIL without gating it; the file sorts after
+every established test (test_zy*) so that a fault here cannot take anything else with it.  The marker goes after the first run
+on a B200.
 """
 import ctypes as C
 import glob
@@ -15,7 +16,7 @@ import os
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('D4_EXPERIMENTAL') != '1', reason='first hardware run pending: set D4_EXPERIMENTAL=1')]
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='first hardware run pending (GPU budget of round 1 spent)')]
 
 FIX = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'tokenizer', 'tokenizer_*.pt')))
 IDS = [os.path.basename(p)[:-3] for p in FIX]

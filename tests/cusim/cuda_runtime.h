@@ -3,7 +3,7 @@
 // without a GPU at hand can be checked on the CPU (tests/test_kernels_cusim_cpu.py).  It models exactly what the simulated code
 // uses: 2-D grids of 1-D blocks, static and dynamic shared memory, __syncthreads / __syncwarp, warp shuffles, float4, __ldg,
 // the usual math intrinsics, and the handful of runtime calls the engine makes ("device" memory is host memory, streams are
-// synchronous).  It is NOT a CUDA emulator (no memory model, no divergence rules beyond "every lane of a warp reaches each
+// synchronous, stream capture records closures).  It is NOT a CUDA emulator (no memory model, no divergence rules beyond "every lane of a warp reaches each
 // shuffle"), kernels written in PTX (tcgen05 / TMA / mma.sync) are outside it, and it is never linked into the product.
 #pragma once
 #include <math.h>
@@ -12,6 +12,7 @@
 #include <string.h>
 #include <barrier>
 #include <functional>
+#include <vector>
 
 #define __global__
 #define __device__
@@ -42,7 +43,7 @@ struct Warp { std::barrier<>* bar; uint64_t slot[32]; };
 extern thread_local Warp* warp;
 extern thread_local std::barrier<>* block_bar;
 extern unsigned char dyn_smem[];
-void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, const std::function<void()>& body);
+void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, std::function<void()> body);
 }
 extern thread_local dim3 threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
@@ -69,16 +70,23 @@ inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }
 inline float __fdividef(float a, float b) { return a / b; }
 
-// ---- the runtime calls the engine and the launch wrappers make
+// ---- the runtime calls the engine and the launch wrappers make.  Stream capture is modelled as "record the closures instead of
+// running them": a graph is the list of kernel launches / copies / memsets enqueued between Begin and EndCapture (the launch
+// rewrite captures kernel arguments BY VALUE, as a real launch does), replayed in order by cudaGraphLaunch.
+namespace cusim {
+struct Graph { std::vector<std::function<void()>> nodes; };
+extern Graph* capturing;
+inline void enqueue(std::function<void()> op) { if (capturing) capturing->nodes.push_back(std::move(op)); else op(); }
+}
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "cusim"; }
-inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { cusim::enqueue([=] { memmove(d, s, n); }); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
-    for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+    cusim::enqueue([=] { for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w); });
     return cudaSuccess;
 }
-inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { cusim::enqueue([=] { memset(d, v, n); }); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
@@ -86,12 +94,11 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
-// stream capture / graphs are not modelled: D4_GRAPH stays off under the simulator
-inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
-inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { *e = nullptr; return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
-inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
-inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { if (cusim::capturing) return 900; cusim::capturing = new cusim::Graph(); return cudaSuccess; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = cusim::capturing; cusim::capturing = nullptr; return *g ? cudaSuccess : 901; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) { *e = new cusim::Graph(*static_cast<cusim::Graph*>(g)); return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete static_cast<cusim::Graph*>(g); return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete static_cast<cusim::Graph*>(e); return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) { for (auto& op : static_cast<cusim::Graph*>(e)->nodes) op(); return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }

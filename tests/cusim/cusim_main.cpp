@@ -16,8 +16,14 @@ thread_local Warp* warp = nullptr;
 thread_local std::barrier<>* block_bar = nullptr;
 alignas(16) unsigned char dyn_smem[1 << 20];
 
-void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, const std::function<void()>& body) {
+Graph* capturing = nullptr;
+
+static void run(dim3 grid, dim3 block, const std::function<void()>& body);
+void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, std::function<void()> body) {
     if (smem > sizeof(dyn_smem)) abort();
+    enqueue([=] { run(grid, block, body); });
+}
+static void run(dim3 grid, dim3 block, const std::function<void()>& body) {
     gridDim = grid; blockDim = block;
     const unsigned nthreads = block.x, nwarps = (nthreads + 31) / 32;
     for (unsigned by = 0; by < grid.y; ++by)
@@ -64,8 +70,14 @@ static inline float lerp_t(float a, float b, float w) { const float d = b - a; r
 // ---- attn.cu's contract (SmallAttnArgs in kernels.h): softmax(q . keynorm(k) * scale [softclamp] [agent mask]) @ lerp(v, v0, sigmoid(mix)),
 // belief projection, head gate.  In-kernel gate logits (gate_w) are declined through d4_pool_attn_ok.
 int d4_pool_attn_ok(const SmallAttnArgs&) { return 0; }
+static void small_attn_host(const SmallAttnArgs& a);
 int d4_small_attn(const SmallAttnArgs& a, cudaStream_t) {
     if (a.gate_w) return d4_fail("cusim: in-kernel gate logits");
+    const SmallAttnArgs copy = a;
+    cusim::enqueue([copy] { small_attn_host(copy); });          // a launch: takes part in stream capture like one
+    return 0;
+}
+static void small_attn_host(const SmallAttnArgs& a) {
     const int d = a.d, n = a.n;
     std::vector<float> K((size_t)n * d), V((size_t)n * d), p(n);
     for (int b = 0; b < a.nb; ++b)
@@ -113,12 +125,17 @@ int d4_small_attn(const SmallAttnArgs& a, cudaStream_t) {
                 }
             }
         }
-    return 0;
 }
 
 // ---- K1's contract (TimeAttnArgs in kernels.h): one new query per (token row, head) over the row's cached keys / values + itself;
 // key = rope(keynorm(k)), query = rope(q) at position t, value = lerp(v, v0, sigmoid(mix)); appended at position t when commit.
+static void time_attn_host(const TimeAttnArgs& a);
 int d4_time_attn(const TimeAttnArgs& a, cudaStream_t) {
+    const TimeAttnArgs copy = a;
+    cusim::enqueue([copy] { time_attn_host(copy); });
+    return 0;
+}
+static void time_attn_host(const TimeAttnArgs& a) {
     const int d = a.d, half = d / 2, t = a.t;
     std::vector<float> kn(d), vn(d), qr(d), p(t + 1), tmp(d);
     auto rope = [&](float* x) {
@@ -172,7 +189,6 @@ int d4_time_attn(const TimeAttnArgs& a, cudaStream_t) {
             if (a.commit) for (int c = 0; c < d; ++c) { kc[(long long)t * d + c] = kn[c]; vc[(long long)t * d + c] = vn[c]; }
         }
     }
-    return 0;
 }
 
 // ---- a direct entry for the one simulated kernel the C-ABI does not expose on its own

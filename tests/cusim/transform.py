@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE - rewrites the CUDA-only syntax of a .cu file so that g++ can compile it against tests/cusim/cuda_runtime.h:
 
-    kernel<T...><<<grid, block, smem, stream>>>(args)   ->   cusim::launch(grid, block, smem, stream, [&] { kernel<T...>(args); })
+    kernel<T...><<<grid, block, smem, stream>>>(args)   ->   cusim::launch(grid, block, smem, stream, [=] { kernel<T...>(args); })
     extern __shared__ [__align__(n)] T name[];          ->   T* name = reinterpret_cast<T*>(cusim::dyn_smem);
 
 Everything else (kernels, device helpers, host launch wrappers) is compiled as written."""
@@ -47,5 +47,5 @@ def transform(src):
         a1 = _balanced(src, a0)
         args = src[a0 + 1:a1 - 1]
         out.append(src[pos:name_start])
-        out.append(f'cusim::launch({cfg}, [&] {{ {name}({args}); }})')
+        out.append(f'cusim::launch({cfg}, [=] {{ {name}({args}); }})')
         pos = a1

@@ -203,3 +203,34 @@ def test_video_tokenizer_on_the_simulator_reproduces_reference_golden(path, on_s
         torch.testing.assert_close(recon, fx['recon'], atol=1e-4, rtol=2e-4)
     finally:
         tok._release()
+
+
+def test_cuda_graph_replay_on_the_simulator(on_simulator, monkeypatch):
+    """engine.cu: frame_impl with D4_GRAPH=1 - first rollout direct, second captured (stream capture modelled as recording the
+    enqueued launches / copies) and replayed over the staging rows, third replayed: identical Experiences, identical launch counts
+    (what tests/test_zx_graph_replay_gpu.py asks of the hardware)."""
+    from dreamer4_b200 import DynamicsWorldModel
+    monkeypatch.setenv('D4_GRAPH', '1')
+    fx = torch.load(GOLDEN[1], map_location='cpu', weights_only=False)         # GQA + two action types
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    T, B = 2, 2
+    g = torch.Generator().manual_seed(3)
+    A = sum(model.cfg.num_discrete_actions)
+    noise = dict(latent=torch.randn(T, B, model.cfg.num_latent_tokens, model.cfg.dim_latent, generator=g), action_uniform=torch.rand(T, B, A, generator=g),
+                 terminal_uniform=torch.rand(T, B, generator=g))
+    runs, launches = [], []
+    try:
+        for _ in range(3):
+            l0 = on_simulator.d4_launch_count()
+            runs.append(model.generate(T, batch_size=B, noise=noise, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True))
+            launches.append(on_simulator.d4_launch_count() - l0)
+    finally:
+        model._release()
+    assert launches[0] == launches[1] == launches[2] > 0
+    for later in runs[1:]:
+        assert torch.equal(later.actions.discrete, runs[0].actions.discrete)
+        for name in ('latents', 'rewards', 'values', 'agent_embed', 'lens', 'terminals'):
+            assert torch.equal(getattr(later, name), getattr(runs[0], name)), name
+        assert torch.equal(later.log_probs.discrete, runs[0].log_probs.discrete)
+        assert torch.equal(later.old_action_unembeds.discrete, runs[0].old_action_unembeds.discrete)

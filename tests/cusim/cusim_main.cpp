@@ -56,8 +56,49 @@ int d4_gemm_pair_default(void) { return 0; }
 int d4_gemm_tc(const GemmArgs&, int, cudaStream_t) { return d4_fail("cusim: tensor-core GEMM"); }
 int d4_gemm_tc2(const GemmArgs&, int, int, cudaStream_t) { return d4_fail("cusim: tensor-core GEMM"); }
 int d4_gemm_tc3(const GemmArgs&, int, int, cudaStream_t) { return d4_fail("cusim: tensor-core GEMM"); }
-int d4_gemm_f16x3(const GemmArgs&, float, int, cudaStream_t) { return d4_fail("cusim: tensor-core GEMM"); }
-int d4_gemm_f16x3_supported(const GemmArgs&, const void*, const void*) { return 0; }
+// ---- gemm_f16.cu's CONTRACT (the kernel itself is tcgen05 PTX): fp16 hi / lo words of q W, rows of A optionally pre-scaled by a
+// power of two and split into fp16 hi / lo, three of the four cross products, fp32 result scaled by rs / p / q.  Lets the engine's
+// f16x3 mode (weight registration, scales, dispatch, epilogue arguments) run end to end on the simulator.
+static long long f16_calls = 0;
+extern "C" long long sim_f16_calls(void) { return f16_calls; }
+int d4_gemm_f16x3_supported(const GemmArgs& g, const void* whi, const void* wlo) {
+    return (whi && wlo && g.K % 8 == 0 && g.ldw % 8 == 0 && !g.transA && !g.transW && g.act != D4_ACT_SILU) ? 1 : 0;
+}
+static inline float pow2_near_h(float x) { return __uint_as_float((__float_as_uint(x) + 0x00400000u) & 0x7F800000u); }
+int d4_gemm_f16x3(const GemmArgs& g0, float w_scale, int, cudaStream_t) {
+    ++f16_calls;
+    const GemmArgs g = g0;
+    cusim::enqueue([g, w_scale] {
+        const _Float16* whi = reinterpret_cast<const _Float16*>(g.W); const _Float16* wlo = reinterpret_cast<const _Float16*>(g.W_lo);
+        const bool glu = g.act == D4_ACT_GLU_SILU || g.act == D4_ACT_GLU_GELU;
+        std::vector<float> acc(g.N);
+        for (int m = 0; m < g.M; ++m) {
+            float p = 1.f, rs = g.row_scale ? g.row_scale[m] : 1.f;
+            if (g.rs_mode && g.row_scale) { rs = 1.0f / sqrtf(rs / (float)g.K + D4_RMS_EPS); p = pow2_near_h(rs); rs /= p; }
+            rs *= w_scale;
+            const float* a = g.A + g.amap(m) * g.lda;
+            for (int n = 0; n < g.N; ++n) {
+                double sum = 0.0;
+                for (int k = 0; k < g.K; ++k) {
+                    const float x = a[k] * p;
+                    const _Float16 ah = (_Float16)x; const _Float16 al = (_Float16)(x - (float)ah);
+                    const float wh = (float)whi[(long long)n * g.ldw + k], wl = (float)wlo[(long long)n * g.ldw + k];
+                    sum += (double)(float)al * wh + (double)(float)ah * wl + (double)(float)ah * wh;
+                }
+                acc[n] = (float)sum * rs + (g.bias ? g.bias[n] : 0.f);
+            }
+            const long long cr = g.cmap(m);
+            const int nout = glu ? g.N / 2 : g.N;
+            for (int j = 0; j < nout; ++j) {
+                float v = acc[j];
+                if (glu) { const float x = acc[2 * j], gt = acc[2 * j + 1]; v = x * (g.act == D4_ACT_GLU_SILU ? gt / (1.f + expf(-gt)) : 0.5f * gt * (1.f + erff(gt * 0.70710678f))); }
+                if (g.residual) v += g.residual[cr * g.ldr + j];
+                g.C[cr * g.ldc + j] = v;
+            }
+        }
+    });
+    return 0;
+}
 // ---- fused pools: report "unsupported", the engine then takes its GEMM + attention path
 int d4_l2s_fused_supported(const L2sArgs&) { return 0; }
 int d4_l2s_fused(const L2sArgs&, cudaStream_t) { return d4_fail("cusim: fused pool"); }

@@ -234,3 +234,30 @@ def test_cuda_graph_replay_on_the_simulator(on_simulator, monkeypatch):
             assert torch.equal(getattr(later, name), getattr(runs[0], name)), name
         assert torch.equal(later.log_probs.discrete, runs[0].log_probs.discrete)
         assert torch.equal(later.old_action_unembeds.discrete, runs[0].old_action_unembeds.discrete)
+
+
+def test_f16x3_engine_mode_plumbing_on_the_simulator(on_simulator):
+    """DynamicsWorldModel(precision='f16x3') through the real engine: fp16 hi / lo weights and their scales registered by the host,
+    resolved by d4_bind, dispatched by d4_engine_gemm with the right epilogue arguments.  The fp16 kernel itself is tcgen05 PTX and
+    is restated from its contract here (tests/cusim/cusim_main.cpp) - this test is about everything around it."""
+    from dreamer4_b200 import DynamicsWorldModel
+    on_simulator.sim_f16_calls.restype = C.c_longlong
+    fx = torch.load(GOLDEN[0], map_location='cpu', weights_only=False)
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='f16x3')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    ocfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    T, B = 2, 2
+    g = torch.Generator().manual_seed(3)
+    A = sum(model.cfg.num_discrete_actions)
+    noise = dict(latent=torch.randn(T, B, model.cfg.num_latent_tokens, model.cfg.dim_latent, generator=g), action_uniform=torch.rand(T, B, A, generator=g),
+                 terminal_uniform=torch.rand(T, B, generator=g))
+    ref = O.generate(fx['state_dict'], ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform']))
+    before = on_simulator.sim_f16_calls()
+    try:
+        exp = model.generate(T, batch_size=B, noise=noise, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
+    finally:
+        model._release()
+    assert on_simulator.sim_f16_calls() - before > 50          # the transformer's dense layers really went through the fp16 entry point
+    assert torch.equal(exp.actions.discrete, ref.actions)
+    for name in ('latents', 'rewards', 'values', 'agent_embed'):
+        torch.testing.assert_close(getattr(exp, name), getattr(ref, name), atol=5e-5, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')

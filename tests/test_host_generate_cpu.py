@@ -310,3 +310,27 @@ def test_interact_with_env_through_the_attached_tokenizer(case, world, monkeypat
     assert torch.equal(exp.is_truncated, ref_case['is_truncated']) and torch.equal(exp.terminals, ref_case['terminals'])
     torch.testing.assert_close(exp.latents, ref_case['latents'], atol=2e-5, rtol=1e-4)
     torch.testing.assert_close(exp.values, ref_case['values'], atol=2e-5, rtol=1e-4)
+
+
+def test_env_wrapper_returns_decoded_frames_with_a_tokenizer(world, monkeypatch):
+    """DynamicsWorldModelWrapper over a model with a tokenizer: observations are the newest DECODED frame (reference env.py:441, 505),
+    a video prompt seeds the episode."""
+    from dreamer4_b200 import DynamicsWorldModelWrapper
+    from oracle import tokenizer_oracle as TO
+    fx, model, ocfg, (tsd, tcfg), _ = world
+    decode = lambda latents, height=None, width=None, **kw: TO.decode(tsd, tcfg, latents, noise=torch.zeros(latents.shape[0], tcfg.channels, latents.shape[1], tcfg.image_height, tcfg.image_width))
+    monkeypatch.setattr(model.video_tokenizer, 'decode', decode)
+    env = DynamicsWorldModelWrapper(model, num_generation_steps=4)
+    assert env.image_size == tcfg.image_height
+    obs, _ = env.reset(batch_size=2, seed=1)
+    assert obs.shape == (2, tcfg.channels, tcfg.image_height, tcfg.image_width)
+    obs, reward, terminated, truncated, info = env.step(torch.tensor([1, 2]))
+    gen = info['experience']
+    assert gen.latents.shape[1] == 2 and torch.equal(obs, decode(gen.latents)[:, :, -1]) and reward.shape == (2,)
+    prompted = DynamicsWorldModelWrapper(model, prompt=fx['prompt'], num_generation_steps=4)
+    obs, _ = prompted.reset()
+    P = fx['prompt'].shape[2]
+    assert prompted._latents.shape[:2] == (fx['prompt'].shape[0], P + 1)
+    torch.testing.assert_close(prompted._latents[:, :P], TO.tokenize(tsd, tcfg, fx['prompt']).clamp(-1, 1))
+    obs2, *_ = prompted.step(torch.zeros(fx['prompt'].shape[0], dtype=torch.long))
+    assert prompted._latents.shape[1] == P + 2 and obs2.shape == obs.shape

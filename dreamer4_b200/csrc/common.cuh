@@ -30,7 +30,11 @@ __device__ __forceinline__ float warp_max(float v) {
 // are then unbiased and <= 2^-24 |x|; a truncating split leaves same-signed errors that add up coherently over K.
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
+#ifdef D4_CUSIM      // host build for the CPU kernel simulator (tests/cusim): the same rounding in integer arithmetic
+    r = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+#else
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+#endif
     return __uint_as_float(r);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

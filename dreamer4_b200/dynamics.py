@@ -912,7 +912,8 @@ class DynamicsWorldModel(nn.Module):
         io.grad_unembed, io.grad_unembed_ld = ptr(grads[un_name]), grads[un_name].stride(0)
 
         ws_bytes = lib.d4_learn_workspace_bytes(ctx, B, T)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws = ws[(-ws.data_ptr()) % 256:][:ws_bytes]          # 256-byte aligned (a no-op offset for CUDA allocations)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         check(lib.d4_learn(ctx, C.byref(io), ptr(ws), ws_bytes, stream))
         ws.record_stream(torch.cuda.current_stream(dev))

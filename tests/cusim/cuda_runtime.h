@@ -6,10 +6,12 @@
 // synchronous, stream capture records closures).  It is NOT a CUDA emulator (no memory model, no divergence rules beyond "every lane of a warp reaches each
 // shuffle"), kernels written in PTX (tcgen05 / TMA / mma.sync) are outside it, and it is never linked into the product.
 #pragma once
+#define D4_CUSIM 1
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
+#include <atomic>
 #include <barrier>
 #include <functional>
 #include <vector>
@@ -62,10 +64,14 @@ template <class T> inline T cusim_shfl(T v, int src) {
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int o) { return cusim_shfl(v, (int)(threadIdx.x & 31) ^ o); }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return cusim_shfl(v, src); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int o) { const int l = threadIdx.x & 31; return cusim_shfl(v, l + o < 32 ? l + o : l); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, int o) { const int l = threadIdx.x & 31; return cusim_shfl(v, l - o >= 0 ? l - o : l); }
 template <class T> inline T __ldg(const T* p) { return *p; }
+inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+template <class T> inline T min(T a, T b) { return b < a ? b : a; }
+template <class T> inline T max(T a, T b) { return a < b ? b : a; }
 inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }
 inline float __fdividef(float a, float b) { return a / b; }

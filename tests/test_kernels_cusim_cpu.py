@@ -36,7 +36,7 @@ def simlib(tmp_path_factory):
     from dreamer4_b200 import _lib
     build = tmp_path_factory.mktemp('cusim')
     srcs = []
-    for name in ('engine', 'rowops', 'gemm_simt', 'frame_attn', 'tokenizer'):
+    for name in ('engine', 'learn', 'rowops', 'gemm_simt', 'frame_attn', 'tokenizer'):
         out = build / f'{name}.cpp'
         out.write_text(transform(open(os.path.join(CSRC, name + '.cu')).read()))
         srcs.append(str(out))
@@ -65,6 +65,7 @@ def on_simulator(simlib, monkeypatch):
     monkeypatch.setattr(VideoTokenizer, '_stream', lambda self: C.c_void_p(0))
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda device=None: _Stream())
     monkeypatch.setattr(torch.cuda, 'device', lambda device=None: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, 'record_stream', lambda self, stream: None)
     return simlib
 
 
@@ -261,3 +262,28 @@ def test_f16x3_engine_mode_plumbing_on_the_simulator(on_simulator):
     assert torch.equal(exp.actions.discrete, ref.actions)
     for name in ('latents', 'rewards', 'values', 'agent_embed'):
         torch.testing.assert_close(getattr(exp, name), getattr(ref, name), atol=5e-5, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
+
+
+def test_learn_from_experience_on_the_simulator_matches_reference_golden(on_simulator):
+    """d4_learn (learn.cu: GAE scan, the three heads' forward / backward, the policy row kernel) through the real engine on simulated
+    kernels against the losses and gradients the reference's own source produced (the test tests/test_gpu_parity.py runs on the GPU)."""
+    from dreamer4_b200 import Actions, DynamicsWorldModel, Experience
+    fx = torch.load(GOLDEN[0], map_location='cpu', weights_only=False)
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    ref = fx['out']
+    exp = Experience(latents=ref['latents'], agent_embed=ref['agent_embed'], rewards=ref['rewards'], values=ref['values'],
+                     actions=Actions(ref['actions'], None), log_probs=Actions(ref['log_probs'], None), lens=ref['lens'],
+                     is_truncated=ref['is_truncated'], terminals=ref['terminals'], step_size=ref['step_size'])
+    try:
+        pl, vl = model.learn_from_experience(exp)
+        torch.testing.assert_close(pl.detach(), ref['policy_loss'], atol=1e-6, rtol=1e-4)
+        torch.testing.assert_close(vl.detach(), ref['value_loss'], atol=1e-6, rtol=1e-4)
+        pl.backward()
+        vl.backward()
+    finally:
+        model._release()
+    params = dict(model.named_parameters())
+    for name, g in ref['grads'].items():
+        assert params[name].grad is not None, name
+        torch.testing.assert_close(params[name].grad, g, atol=2e-6, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')

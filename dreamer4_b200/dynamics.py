@@ -545,11 +545,17 @@ class DynamicsWorldModel(nn.Module):
             P = prompt_lat.shape[1]
             assert P < T, f'time_steps={T} must exceed the {P} prompt frames'
         resumed_kv = None
+        off = 0               # frames in the cache that are not part of this call's output (a time cache without prompt latents)
         if exists(time_cache):
             resumed_kv = time_cache.main.next_kv_cache if exists(time_cache.main) else None
             cached = time_cache.main.token_count if exists(time_cache.main) else 0
-            assert cached == P, f'time_cache holds {cached} frames but the prompt has {P}: pass the latents of exactly the cached frames'
-        lib, ctx, kv = self._adopt_time_cache(resumed_kv, P, B, T, agent_index, grow=P > 0 or exists(time_cache))
+            if P == 0:
+                # the reference's tests/test_dreamer.py::test_cache_generate flow: time_steps NEW frames on top of the cached ones,
+                # at cache positions cached .. cached + T - 1 (their rotary offset, dreamer4.py:3010); only the new frames come back
+                off = cached
+            else:
+                assert cached == P, f'time_cache holds {cached} frames but the prompt has {P}: pass the latents of exactly the cached frames'
+        lib, ctx, kv = self._adopt_time_cache(resumed_kv, P + off, B, T + off, agent_index, grow=P > 0 or exists(time_cache))
         L = c.num_time_layers
         self._kv_epoch += 1
 
@@ -647,7 +653,7 @@ class DynamicsWorldModel(nn.Module):
             else:
                 io.values = io.actions = io.log_probs = io.logits = None
             io.lens, io.terminals = ptr(lens), ptr(term_u8)
-            check(lib.d4_frame(ctx, B, t, num_steps, float(discrete_temperature), C.byref(io), stream))
+            check(lib.d4_frame(ctx, B, t + off, num_steps, float(discrete_temperature), C.byref(io), stream))
             if want_heads:
                 n_dec += 1
             if not exists(noise) and context_signal_noise > 0.:
@@ -659,11 +665,13 @@ class DynamicsWorldModel(nn.Module):
 
         Tg = frames
         latents = latents[:, :Tg]
+        if off > 0 and should_term:
+            lens = torch.where(terminals, lens - off, lens)      # the engine counts frames by cache position
         next_kv = None
         if L > 0:
-            next_kv = kv[:L, :, :, :, :Tg]
+            next_kv = kv[:L, :, :, :, :off + Tg]
             next_kv._d4_epoch = self._kv_epoch          # lets a resumed call recognise this view as current (see above)
-        tc = DynamicsIntermediates(main=TransformerIntermediates(next_kv_cache=next_kv, token_count=Tg))
+        tc = DynamicsIntermediates(main=TransformerIntermediates(next_kv_cache=next_kv, token_count=off + Tg))
         video = None
         if return_decoded_video:                                                     # reference dreamer4.py:6699-6711
             dec_kw = dict(noise=noise['decoder']) if (exists(noise) and 'decoder' in noise) else {}      # injected start noise (tests)

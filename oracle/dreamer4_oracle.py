@@ -532,6 +532,10 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
             _, _, kv_cache = forward_step(sd, cfg, latents[p], cfg.max_steps - 1, step_log2, prev_actions_for(p), kv_cache, p, tasks)
     elif P > 0:
         assert kv_cache[0][0].shape[-2] == P, 'the time cache must cover exactly the prompt frames'
+    # a time cache WITHOUT prompt latents (reference tests/test_dreamer.py::test_cache_generate): the call imagines time_steps NEW
+    # frames on top of the cached ones - their rotary position is offset by the cached count (D4:3010), nothing else changes
+    # (the first new frame has no action history of its own: zero action token, D4:7124-7126)
+    offset = kv_cache[0][0].shape[-2] if (P == 0 and kv_cache) else 0
 
     for frame in range(P, time_steps):
         prev_actions = prev_actions_for(frame)
@@ -539,7 +543,7 @@ def generate(sd, cfg: OracleConfig, time_steps, batch_size, num_steps=4, noise=N
         for step in range(num_steps + 1):                                                    # D4:6484-6486
             is_last = step == num_steps
             signal = min(step * step_size, cfg.max_steps - 1)                                # D4:6492
-            pred, agent, new_kv = forward_step(sd, cfg, x, signal, step_log2, prev_actions, kv_cache, frame, tasks)
+            pred, agent, new_kv = forward_step(sd, cfg, x, signal, step_log2, prev_actions, kv_cache, frame + offset, tasks)
             if is_last:
                 kv_cache = new_kv                                                            # D4:6545-6546
                 break

@@ -334,3 +334,30 @@ def test_env_wrapper_returns_decoded_frames_with_a_tokenizer(world, monkeypatch)
     torch.testing.assert_close(prompted._latents[:, :P], TO.tokenize(tsd, tcfg, fx['prompt']).clamp(-1, 1))
     obs2, *_ = prompted.step(torch.zeros(fx['prompt'].shape[0], dtype=torch.long))
     assert prompted._latents.shape[1] == P + 2 and obs2.shape == obs.shape
+
+
+def test_cache_continuation_without_prompt(monkeypatch):
+    """generate(time_cache=...) without prompt latents (the reference's tests/test_dreamer.py::test_cache_generate): each call returns
+    time_steps NEW frames imagined on top of the cached ones.  Three chained calls against the oracle on the same draws, and - since
+    the oracle is pinned to them - the reference's own chained calls (tests/golden/cache/cache_continue.pt)."""
+    from dreamer4_b200 import DynamicsWorldModel
+    fx = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'cache', 'cache_continue.pt'), map_location='cpu', weights_only=False)
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    ocfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    install(monkeypatch, model, ocfg)
+    try:
+        tc, ocache = None, None
+        for i, call in enumerate(fx['calls']):
+            T = call['time_steps']
+            noise = make_noise(model.cfg, T, 2, seed=40 + i)
+            ref = O.generate(fx['state_dict'], ocfg, T, 2, noise=injected(noise), kv_cache=ocache)
+            ocache = ref.kv_cache
+            exp, tc = model.generate(T, batch_size=2, noise=noise, time_cache=tc, return_time_cache=True, return_rewards_per_frame=True,
+                                     return_agent_actions=True, return_log_probs_and_values=True)
+            assert exp.latents.shape[1] == T and tc.main.token_count == call['token_count']
+            same(exp, ref)
+            kv = torch.stack([torch.stack(layer) for layer in ref.kv_cache])
+            assert torch.equal(tc.main.next_kv_cache, kv)
+    finally:
+        model._release()

@@ -126,3 +126,24 @@ def test_prompted_generate_matches_reference(path, flow):
     assert kv.shape == ref['kv_cache'].shape
     torch.testing.assert_close(kv, ref['kv_cache'], **tol)
     assert ref['token_count'] == exp.latents.shape[1]
+
+
+def test_cache_continuation_matches_reference():
+    """generate(time_cache=...) without prompt latents (the reference's tests/test_dreamer.py::test_cache_generate): each call imagines
+    time_steps NEW frames on top of the cached ones.  Golden: three chained calls of the reference (oracle/make_golden_cache.py)."""
+    import os
+    fx = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'cache', 'cache_continue.pt'), map_location='cpu', weights_only=False)
+    cfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
+    cache = None
+    for call in fx['calls']:
+        torch.manual_seed(call['seed'])
+        exp = O.generate(fx['state_dict'], cfg, call['time_steps'], 2, kv_cache=cache)
+        cache = exp.kv_cache
+        assert torch.equal(exp.actions, call['actions'])
+        for name in ('latents', 'rewards', 'values', 'log_probs', 'agent_embed'):
+            torch.testing.assert_close(getattr(exp, name), call[name], atol=2e-5, rtol=1e-4, msg=lambda m, n=name: f'{n}: {m}')
+        assert cache[0][0].shape[-2] == call['token_count']
+        ref_kv = O.cache_from_reference(call['kv'])
+        for (k, v), (rk, rv) in zip(cache, ref_kv):
+            torch.testing.assert_close(k, rk, atol=2e-5, rtol=1e-4)
+            torch.testing.assert_close(v, rv, atol=2e-5, rtol=1e-4)

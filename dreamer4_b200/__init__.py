@@ -2,11 +2,11 @@
 
 Public names mirror the reference package (`dreamer4/__init__.py:1-15`, `dreamer4/dreamer4.py`) for the
 classes on this path."""
-from .experience import Actions, Experience, combine_experiences
+from .experience import Actions, Embeds, Experience, Predictions, combine_experiences
 from .dynamics import DynamicsWorldModel, ModelConfig, exists, default
 from .trainer import DreamTrainer
 from .env import DynamicsWorldModelWrapper
 from .tokenizer import VideoTokenizer, TokenizerConfig
 
-__all__ = ['Actions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default',
+__all__ = ['Actions', 'Embeds', 'Predictions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default',
            'VideoTokenizer', 'TokenizerConfig']

@@ -18,18 +18,16 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
-import math
 import pickle
 from collections import namedtuple
 from dataclasses import dataclass
-from typing import Optional
 
 import torch
 from torch import nn
 
 from . import _lib
 from ._lib import D4Error, check, ptr
-from .dynamics import _Node, _linear_b, _linear_w
+from .dynamics import _linear_b, _linear_w
 from .packing import pack_tokenizer
 
 

@@ -4,9 +4,9 @@ Public names mirror the reference package (`dreamer4/__init__.py:1-15`, `dreamer
 classes on this path."""
 from .experience import Actions, Embeds, Experience, Predictions, combine_experiences
 from .dynamics import DynamicsWorldModel, ModelConfig, exists, default
-from .trainer import DreamTrainer
+from .trainer import DreamTrainer, SimTrainer
 from .env import DynamicsWorldModelWrapper
 from .tokenizer import VideoTokenizer, TokenizerConfig
 
-__all__ = ['Actions', 'Embeds', 'Predictions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default',
+__all__ = ['Actions', 'Embeds', 'Predictions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'SimTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default',
            'VideoTokenizer', 'TokenizerConfig']

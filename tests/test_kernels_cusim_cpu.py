@@ -287,3 +287,52 @@ def test_learn_from_experience_on_the_simulator_matches_reference_golden(on_simu
     for name, g in ref['grads'].items():
         assert params[name].grad is not None, name
         torch.testing.assert_close(params[name].grad, g, atol=2e-6, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
+
+
+def test_sim_trainer_on_the_simulator(on_simulator):
+    """SimTrainer (reference trainers.py:1472-1790) end to end on the toy image env: episodes through interact_with_env (d4_observe),
+    combined, replayed in shuffled minibatches through d4_learn, both heads stepped.  The first minibatch's losses equal a direct
+    learn_from_experience call on the same rows; only the policy / value heads (and the action unembedding) move."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from dreamer4_b200 import Actions, DynamicsWorldModel, Experience, SimTrainer, combine_experiences
+    from oracle import tokenizer_oracle as TO
+    from oracle.toy_env import ToyImageEnv
+    fx = torch.load(os.path.join(HERE, 'golden', 'tokenizer', 'world_with_tokenizer.pt'), map_location='cpu', weights_only=False)
+    tk = fx['tokenizer_kwargs']
+    mk = dict(fx['model_kwargs'], num_latent_tokens=tk['num_latent_tokens'])
+    sd = {k: v for k, v in fx['state_dict'].items() if not k.startswith('video_tokenizer.')}
+    tsd = {k[len('video_tokenizer.'):]: v for k, v in fx['state_dict'].items() if k.startswith('video_tokenizer.')}
+    tcfg = TO.config_from_reference_kwargs(**tk)
+
+    def obs_to_latents(world_model, obs, cache):
+        tok_cache, t = cache if cache is not None else (None, 0)
+        lat, tok_cache = TO.tokenize_step(tsd, tcfg, obs['image'], tok_cache, t)
+        return lat[:, None], (tok_cache, t + 1)
+
+    model = DynamicsWorldModel(**mk, precision='fp32')
+    model.load_state_dict(sd, strict=True)
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    trainer = SimTrainer(model, batch_size=2, epochs=1, learning_rate=1e-2)
+    env = ToyImageEnv(batch=3, terminate_at=None)
+    try:
+        torch.manual_seed(0)
+        episode = model.interact_with_env(env, env_is_vectorized=True, max_timesteps=2, obs_to_latents_fn=obs_to_latents).cpu()
+        combined = combine_experiences([episode])
+        # the first minibatch the trainer will draw, and its losses computed directly
+        torch.manual_seed(7)
+        first = next(iter(DataLoader(TensorDataset(torch.arange(combined.latents.shape[0])), batch_size=2, shuffle=True)))[0]
+        pick = lambda t: t[first]
+        batch = Experience(latents=pick(combined.latents), actions=Actions(pick(combined.actions.discrete), None),
+                           log_probs=Actions(pick(combined.log_probs.discrete), None), agent_embed=pick(combined.agent_embed),
+                           old_action_unembeds=Actions(pick(combined.old_action_unembeds.discrete), None), values=pick(combined.values),
+                           rewards=pick(combined.rewards), step_size=combined.step_size, agent_index=combined.agent_index)
+        pl, vl = model.learn_from_experience(batch)
+        torch.manual_seed(7)
+        losses = trainer.learn(combined)
+    finally:
+        model._release()
+    assert len(losses) == 2 and int(trainer.step) == 2                      # 3 episodes in minibatches of 2, one epoch
+    torch.testing.assert_close(losses[0][0], pl.detach(), atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(losses[0][1], vl.detach(), atol=1e-6, rtol=1e-5)
+    moved = {k for k, v in model.state_dict().items() if not torch.equal(v, before[k])}
+    assert moved and all(k.startswith(('policy_head.', 'value_head.')) or k == 'action_embedder.discrete_action_unembed' for k in moved), sorted(moved)

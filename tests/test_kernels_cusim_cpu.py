@@ -215,7 +215,7 @@ def test_cuda_graph_replay_on_the_simulator(on_simulator, monkeypatch):
     fx = torch.load(GOLDEN[1], map_location='cpu', weights_only=False)         # GQA + two action types
     model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
     model.load_state_dict(fx['state_dict'], strict=True)
-    T, B = 2, 2
+    T, B = 1, 2          # one cache position: seen directly, then captured, then replayed
     g = torch.Generator().manual_seed(3)
     A = sum(model.cfg.num_discrete_actions)
     noise = dict(latent=torch.randn(T, B, model.cfg.num_latent_tokens, model.cfg.dim_latent, generator=g), action_uniform=torch.rand(T, B, A, generator=g),
@@ -247,7 +247,7 @@ def test_f16x3_engine_mode_plumbing_on_the_simulator(on_simulator):
     model = DynamicsWorldModel(**fx['model_kwargs'], precision='f16x3')
     model.load_state_dict(fx['state_dict'], strict=True)
     ocfg = O.config_from_reference_kwargs(**fx['model_kwargs'])
-    T, B = 2, 2
+    T, B = 1, 2
     g = torch.Generator().manual_seed(3)
     A = sum(model.cfg.num_discrete_actions)
     noise = dict(latent=torch.randn(T, B, model.cfg.num_latent_tokens, model.cfg.dim_latent, generator=g), action_uniform=torch.rand(T, B, A, generator=g),

@@ -132,3 +132,37 @@ def test_world_model_with_attached_tokenizer_matches_oracle():
     assert torch.equal(exp.actions.discrete.cpu(), ref.actions)
     torch.testing.assert_close(exp.latents.cpu(), ref.latents, **TOL)
     torch.testing.assert_close(exp.video.cpu(), ref.video, atol=1e-4, rtol=2e-4)
+
+
+@pytest.mark.parametrize('case', [0, 2], ids=['vec_mixed_bootstrap', 'single_truncated'])
+def test_interact_with_env_through_the_attached_tokenizer(case):
+    """interact_with_env on image observations with NO obs_to_latents_fn: every frame goes through the CUDA tokenizer's encoder over its
+    time cache (reference dreamer4.py:5588), then d4_observe; against the oracle's episode on the same sampler draws."""
+    from dreamer4_b200 import DynamicsWorldModel, VideoTokenizer
+    from oracle import dreamer4_oracle as O
+    from oracle import tokenizer_oracle as TO
+    from oracle.toy_env import ToyImageEnv
+    fx = load(os.path.join(os.path.dirname(__file__), 'golden', 'tokenizer', 'world_with_tokenizer.pt'))
+    ref_case = fx['interact'][case]
+    vectorized, terminate_at, max_timesteps = ref_case['vectorized'], ref_case['terminate_at'], ref_case['max_timesteps']
+    tok = VideoTokenizer(**fx['tokenizer_kwargs'], precision='fp32')
+    model = DynamicsWorldModel(**fx['model_kwargs'], video_tokenizer=tok, precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    model = model.cuda()
+    sd = fx['state_dict']
+    tsd = {k[len('video_tokenizer.'):]: v for k, v in sd.items() if k.startswith('video_tokenizer.')}
+    tcfg = TO.config_from_reference_kwargs(**fx['tokenizer_kwargs'])
+    ocfg = O.config_from_reference_kwargs(num_latent_tokens=tok.num_latent_tokens, **fx['model_kwargs'])
+    B = 3 if vectorized else 1
+    torch.manual_seed(7)
+    exp = model.interact_with_env(ToyImageEnv(batch=B if vectorized else None, terminate_at=terminate_at), max_timesteps=max_timesteps,
+                                  env_is_vectorized=vectorized)
+    torch.manual_seed(7)                                                       # the sampler's draws, in interact_with_env's order
+    draws = torch.stack([torch.cat([torch.rand(B, n, device='cuda') for n in model.cfg.num_discrete_actions], dim=-1)
+                         for _ in range(max_timesteps)]).cpu()
+    ref = O.interact_with_env(sd, ocfg, (tsd, tcfg), ToyImageEnv(batch=B if vectorized else None, terminate_at=terminate_at),
+                              max_timesteps=max_timesteps, env_is_vectorized=vectorized, noise=O.InjectedNoise(None, draws, None))
+    assert torch.equal(exp.actions.discrete.cpu(), ref.actions)
+    assert torch.equal(exp.lens.cpu(), ref.lens) and torch.equal(exp.is_truncated.cpu(), ref.is_truncated)
+    for name in ('latents', 'agent_embed', 'values'):
+        torch.testing.assert_close(getattr(exp, name).cpu(), getattr(ref, name), **TOL, msg=lambda m, n=name: f'{n}: {m}')

@@ -336,3 +336,26 @@ def test_sim_trainer_on_the_simulator(on_simulator):
     torch.testing.assert_close(losses[0][1], vl.detach(), atol=1e-6, rtol=1e-5)
     moved = {k for k, v in model.state_dict().items() if not torch.equal(v, before[k])}
     assert moved and all(k.startswith(('policy_head.', 'value_head.')) or k == 'action_embedder.discrete_action_unembed' for k in moved), sorted(moved)
+
+
+def test_interact_with_env_through_the_attached_tokenizer_on_the_simulator(on_simulator):
+    """interact_with_env on image observations with the VideoTokenizer attached and no obs_to_latents_fn: each frame through the
+    encoder's d4_tf_step over its time cache, then d4_observe - the REFERENCE's own episode (same CPU sampler draws) comes out."""
+    from dreamer4_b200 import DynamicsWorldModel, VideoTokenizer
+    from oracle.toy_env import ToyImageEnv
+    fx = torch.load(os.path.join(HERE, 'golden', 'tokenizer', 'world_with_tokenizer.pt'), map_location='cpu', weights_only=False)
+    ref = fx['interact'][2]                                   # single episode cut by max_timesteps: the bootstrap step runs too
+    tok = VideoTokenizer(**fx['tokenizer_kwargs'], precision='fp32')
+    model = DynamicsWorldModel(**fx['model_kwargs'], video_tokenizer=tok, precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    try:
+        torch.manual_seed(ref['seed'])
+        exp = model.interact_with_env(ToyImageEnv(batch=None, terminate_at=ref['terminate_at']), max_timesteps=ref['max_timesteps'],
+                                      env_is_vectorized=False)
+    finally:
+        model._release()
+        tok._release()
+    assert torch.equal(exp.actions.discrete, ref['actions']) and torch.equal(exp.lens, ref['lens'])
+    assert torch.equal(exp.is_truncated, ref['is_truncated']) and torch.equal(exp.terminals, ref['terminals'])
+    for name in ('latents', 'agent_embed', 'values', 'rewards'):
+        torch.testing.assert_close(getattr(exp, name), ref[name], atol=5e-5, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')

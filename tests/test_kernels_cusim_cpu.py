@@ -359,3 +359,23 @@ def test_interact_with_env_through_the_attached_tokenizer_on_the_simulator(on_si
     assert torch.equal(exp.is_truncated, ref['is_truncated']) and torch.equal(exp.terminals, ref['terminals'])
     for name in ('latents', 'agent_embed', 'values', 'rewards'):
         torch.testing.assert_close(getattr(exp, name), ref[name], atol=5e-5, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
+
+
+def test_world_model_with_tokenizer_on_the_simulator_reproduces_reference_golden(on_simulator):
+    """The reference's own seeded run, drop-in: generate(prompt=video) -> decoded video of a DynamicsWorldModel with its tokenizer
+    attached (reference dreamer4.py:6377-6387, 6694-6724: tokenize the prompt, prefill, roll out, decode).  On the CPU the host classes
+    draw from torch's generator in the reference's order, so the same seed gives the reference's numbers."""
+    from dreamer4_b200 import DynamicsWorldModel, VideoTokenizer
+    fx = torch.load(os.path.join(HERE, 'golden', 'tokenizer', 'world_with_tokenizer.pt'), map_location='cpu', weights_only=False)
+    tok = VideoTokenizer(**fx['tokenizer_kwargs'], precision='fp32')
+    model = DynamicsWorldModel(**fx['model_kwargs'], video_tokenizer=tok, precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    B = fx['prompt'].shape[0]
+    try:
+        ref = fx['prompted']
+        torch.manual_seed(ref['seed'])
+        video = model.generate(ref['time_steps'], batch_size=B, prompt=fx['prompt'])
+        torch.testing.assert_close(video, ref['video'], atol=1e-4, rtol=2e-4)
+    finally:
+        model._release()
+        tok._release()

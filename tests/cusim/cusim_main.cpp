@@ -4,7 +4,9 @@
 // kernel (simulated from its real source), and the attention entry points below restate the kernels' CONTRACT in plain loops.
 // Linked with the transformed rowops / gemm_simt / frame_attn / tokenizer sources and engine.cu compiled as C++.
 #include <float.h>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "engine.h"
@@ -23,9 +25,52 @@ void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, std::function<void
     if (smem > sizeof(dyn_smem)) abort();
     enqueue([=] { run(grid, block, body); });
 }
+// A persistent pool of OS threads (one per CUDA thread of the largest block seen so far): per block the dispatcher publishes a job,
+// the first `active` pool threads run the kernel body as CUDA threads 0..active-1, the dispatcher waits for all of them.
+struct Pool {
+    std::mutex m; std::condition_variable cv_start, cv_done;
+    uint64_t gen = 0; unsigned active = 0, remaining = 0, bx = 0, by = 0;
+    const std::function<void()>* body = nullptr; std::vector<Warp>* warps = nullptr; std::barrier<>* bb = nullptr;
+    unsigned size = 0;
+    void ensure(unsigned n) {
+        std::unique_lock<std::mutex> lk(m);
+        while (size < n) {
+            const unsigned t = size++; const uint64_t seen0 = gen;
+            std::thread([this, t, seen0] {
+                uint64_t seen = seen0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk2(m);
+                    cv_start.wait(lk2, [&] { return gen != seen; });
+                    seen = gen;
+                    if (t >= active) continue;
+                    const std::function<void()>* fn = body; Warp* w = &(*warps)[t / 32]; std::barrier<>* blockbar = bb;
+                    const unsigned x = bx, y = by;
+                    lk2.unlock();
+                    threadIdx = dim3(t); blockIdx = dim3(x, y);
+                    warp = w; block_bar = blockbar;
+                    (*fn)();
+                    w->bar->arrive_and_drop();         // a thread that returned no longer takes part in barriers
+                    blockbar->arrive_and_drop();
+                    lk2.lock();
+                    if (--remaining == 0) cv_done.notify_one();
+                }
+            }).detach();
+        }
+    }
+    void run_block(unsigned nthreads, unsigned x, unsigned y, const std::function<void()>& fn, std::vector<Warp>& w, std::barrier<>& blockbar) {
+        std::unique_lock<std::mutex> lk(m);
+        active = remaining = nthreads; bx = x; by = y; body = &fn; warps = &w; bb = &blockbar;
+        ++gen;
+        cv_start.notify_all();
+        cv_done.wait(lk, [&] { return remaining == 0; });
+    }
+};
+static Pool* pool = new Pool();                        // never destroyed: its threads outlive static destruction
+
 static void run(dim3 grid, dim3 block, const std::function<void()>& body) {
     gridDim = grid; blockDim = block;
     const unsigned nthreads = block.x, nwarps = (nthreads + 31) / 32;
+    pool->ensure(nthreads);
     for (unsigned by = 0; by < grid.y; ++by)
         for (unsigned bx = 0; bx < grid.x; ++bx) {
             std::barrier<> bb((std::ptrdiff_t)nthreads);
@@ -36,16 +81,7 @@ static void run(dim3 grid, dim3 block, const std::function<void()>& body) {
                 wbars.emplace_back(new std::barrier<>((std::ptrdiff_t)lanes));
                 warps[w].bar = wbars[w].get();
             }
-            std::vector<std::thread> threads;
-            for (unsigned t = 0; t < nthreads; ++t)
-                threads.emplace_back([&, t, bx, by] {
-                    threadIdx = dim3(t); blockIdx = dim3(bx, by);
-                    warp = &warps[t / 32]; block_bar = &bb;
-                    body();
-                    warps[t / 32].bar->arrive_and_drop();      // a thread that returned no longer takes part in barriers
-                    bb.arrive_and_drop();
-                });
-            for (auto& th : threads) th.join();
+            pool->run_block(nthreads, bx, by, body, warps, bb);
         }
 }
 }  // namespace cusim

@@ -6,7 +6,7 @@ from .experience import Actions, Embeds, Experience, Predictions, combine_experi
 from .dynamics import DynamicsWorldModel, ModelConfig, exists, default
 from .trainer import DreamTrainer, SimTrainer
 from .env import DynamicsWorldModelWrapper
-from .tokenizer import VideoTokenizer, TokenizerConfig
+from .tokenizer import AxialSpaceTimeTransformer, VideoTokenizer, TokenizerConfig
 
 __all__ = ['Actions', 'Embeds', 'Predictions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'SimTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default',
-           'VideoTokenizer', 'TokenizerConfig']
+           'VideoTokenizer', 'TokenizerConfig', 'AxialSpaceTimeTransformer']

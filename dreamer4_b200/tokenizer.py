@@ -389,6 +389,142 @@ class VideoTokenizer(nn.Module):
         raise NotImplementedError('VideoTokenizer training forward is outside the path this package builds (DESIGN.md section 8)')
 
 
+class AxialSpaceTimeTransformer(nn.Module):
+    """The reference's stand-alone transformer block stack (dreamer4.py:2762-3267, exported by `dreamer4/__init__.py`) on its inference
+    path: same constructor keywords (default branches), same `state_dict` keys, `forward(tokens (b t s d), cache=None,
+    return_intermediates=False)`.  Frames are run one per `d4_tf_step` over the engine's in-place time-KV cache - equal to the
+    reference's multi-frame forward because time attention is causal (golden: tests/golden/cache/axial_transformer.pt); `cache`
+    continues from the frames already seen.  No autograd: training through it is outside the path this package builds."""
+
+    def __init__(self, dim, depth, attn_heads=8, attn_dim_head=64, attn_softclamp_value=50., time_block_every=4, attn_kwargs: dict = dict(),
+                 ff_kwargs: dict = dict(), num_special_tokens=1, final_norm=True, precision='tf32x3', time_attn_variant=1, **kwargs):
+        super().__init__()
+        unsupported = dict(special_attend_only_itself=False, full_spatial_attn=False, spatial_modules=None, value_residual=True, rnn_time=False,
+                           time_attention_use_pope=False, space_attention_use_pope=False, use_attn_pool=True, mot_temporal=False, h_net_layer=None)
+        for k, v in kwargs.items():
+            if k in unsupported and v != unsupported[k]:
+                raise NotImplementedError(f'AxialSpaceTimeTransformer({k}={v!r}) is outside the path this package builds')
+        assert not attn_kwargs and precision in ('fp32', 'tf32', 'tf32x3')
+        self.dim, self.depth, self.num_special_tokens, self.has_final_norm = dim, depth, num_special_tokens, final_norm
+        self.precision, self.time_attn_variant = precision, time_attn_variant
+        # the tokenizer config doubles as the transformer's (only the fields _reg_transformer and the context need)
+        self.cfg = TokenizerConfig(dim=dim, dim_latent=0, patch_size=1, image_height=1, image_width=1, num_latent_tokens=num_special_tokens,
+                                   encoder_depth=depth, decoder_depth=depth, time_block_every=time_block_every, attn_heads=attn_heads,
+                                   attn_dim_head=attn_dim_head, attn_softclamp_value=attn_softclamp_value,
+                                   ff_activation=(ff_kwargs or {}).get('activation', 'silu'))
+        VideoTokenizer._reg_transformer(self, '', depth)
+        if not final_norm:
+            del self._modules['final_norm']
+        self._ctx, self._packed, self._packed_version, self._epoch = None, None, None, 0
+
+    _reg, _reg_attention, _reg_ff = None, None, None      # filled in below
+    _require_cuda = VideoTokenizer._require_cuda
+    _stream = VideoTokenizer._stream
+
+    @property
+    def device(self):
+        return self.to_value_residual._modules['0'].weight.device
+
+    def _release(self):
+        if self._ctx is not None:
+            _lib.load().d4_ctx_destroy(self._ctx[0])
+        self._ctx, self._packed, self._packed_version = None, None, None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._release()           # parameter storage moved: borrowed pointers are stale
+        return out
+
+    def _context(self, batch, tokens_per_frame, need_time, keep_frames):
+        from .packing import _pack_transformer, _split_all
+        self._require_cuda()
+        lib, c, dev = _lib.load(), self.cfg, self.device
+        version = sum(p._version for p in self.parameters())
+        if self._packed_version != version:
+            self._release()
+            g = lambda k: self.state_dict()[k].detach().to(device=dev, dtype=torch.float32)
+            out = {}
+            _pack_transformer(g, out, '', self.depth, c.ff_inner_pad, dev)
+            out['inv_freq'] = g('time_rotary.inv_freq')
+            if self.has_final_norm:
+                out['final_norm'] = g('final_norm.weight')
+            self._packed, self._packed_version = _split_all(out, self.precision == 'tf32x3'), version
+        key = (batch, tokens_per_frame, self.precision, self.time_attn_variant, dev.index)
+        have = self._ctx
+        if have is not None and have[1] == key and have[2]['max_time'] >= need_time:
+            return lib, have[0], have[2]
+        old = have if (have is not None and have[1] == key and keep_frames > 0) else None
+        max_time = (need_time + 15) // 16 * 16
+        cc = _lib.d4_tf_config()
+        cc.dim, cc.depth, cc.time_block_every = c.dim, self.depth, c.time_block_every
+        cc.heads, cc.query_heads, cc.dim_head = c.attn_heads, c.attn_heads, c.attn_dim_head
+        cc.pool_heads, cc.pool_dim_head = c.pool_heads, c.pool_dim_head
+        cc.ff_inner, cc.ff_inner_pad, cc.ff_act = c.ff_inner, c.ff_inner_pad, 1 if c.ff_activation == 'gelu' else 0
+        cc.tokens_per_frame, cc.num_special, cc.final_norm = tokens_per_frame, self.num_special_tokens, int(self.has_final_norm)
+        cc.softclamp = c.attn_softclamp_value
+        cc.max_batch, cc.max_time = batch, max_time
+        cc.precision, cc.time_attn_variant = _lib.PREC[self.precision], self.time_attn_variant
+        ctx = C.c_void_p()
+        check(lib.d4_tf_create(C.byref(cc), C.byref(ctx)))
+        ws_bytes, kv_bytes = lib.d4_workspace_bytes(ctx), lib.d4_kv_bytes(ctx)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws = ws[(-ws.data_ptr()) % 256:][:ws_bytes]
+        y = max(sum(c.is_time(self.depth)), 1)
+        kv = torch.zeros(y, 2, batch * tokens_per_frame, c.attn_heads, max_time, c.attn_dim_head, device=dev)
+        assert kv.numel() * 4 == kv_bytes
+        if old is not None:
+            kv[..., :keep_frames, :] = old[2]['kv'][..., :keep_frames, :]
+        check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv_bytes))
+        for name, t in self._packed.items():
+            check(lib.d4_set_weight(ctx, name.encode(), ptr(t), t.numel()))
+        check(lib.d4_bind(ctx))
+        if have is not None:
+            lib.d4_ctx_destroy(have[0])
+        bufs = dict(ws=ws, kv=kv, max_time=max_time)
+        self._ctx = (ctx, key, bufs)
+        return lib, ctx, bufs
+
+    @torch.no_grad()
+    def forward(self, tokens, time_lens=None, cache=None, return_intermediates=False, **kwargs):
+        """tokens (b t s d) -> (b t s d) [, TransformerIntermediates(next_kv_cache (y 2 b*s h T d), token_count)].  With `cache`, only
+        the LAST frame of `tokens` is new (the reference excises the past ones and hands them back untouched, :2957-2961, 3249-3250)."""
+        from .experience import TransformerIntermediates
+        assert time_lens is None and tokens.ndim == 4, 'tokens (b t s d)'
+        b, T, S, D = tokens.shape
+        tokens = tokens.to(device=self.device, dtype=torch.float32)
+        t0, new = 0, tokens
+        if cache is not None:
+            if getattr(cache.next_kv_cache, '_d4_epoch', self._epoch) != self._epoch:
+                raise ValueError('stale cache: a later un-cached forward restarted the in-place KV buffer')
+            t0 = cache.token_count
+            new = tokens[:, -1:] if T > 1 else tokens
+        else:
+            self._epoch += 1
+        lib, ctx, bufs = self._context(b, S, t0 + new.shape[1], keep_frames=t0)
+        stream = self._stream()
+        out = torch.empty_like(new)
+        for t in range(new.shape[1]):
+            frame_in, frame_out = new[:, t].contiguous(), torch.empty(b, S, D, device=self.device)
+            check(lib.d4_tf_step(ctx, b, ptr(frame_in), t0 + t, ptr(frame_out), stream))
+            out[:, t] = frame_out
+        if cache is not None and T > 1:
+            out = torch.cat((tokens[:, :-1], out), dim=1)
+        if not return_intermediates:
+            return out
+        count = t0 + new.shape[1]
+        y = sum(self.cfg.is_time(self.depth))
+        kv = bufs['kv'][:y, :, :, :, :count] if y > 0 else None
+        if kv is not None:
+            kv._d4_epoch = self._epoch
+        return out, TransformerIntermediates(next_kv_cache=kv, token_count=count)
+
+
 # the reference-layout parameter registration helpers are those of the dynamics model
 from .dynamics import DynamicsWorldModel as _D  # noqa: E402
 
@@ -396,3 +532,6 @@ VideoTokenizer._reg = _D._reg
 VideoTokenizer._reg_attention = _D._reg_attention
 VideoTokenizer._reg_ff = _D._reg_ff
 VideoTokenizer._reg_mlp = _D._reg_mlp
+AxialSpaceTimeTransformer._reg = _D._reg
+AxialSpaceTimeTransformer._reg_attention = _D._reg_attention
+AxialSpaceTimeTransformer._reg_ff = _D._reg_ff

@@ -379,3 +379,27 @@ def test_world_model_with_tokenizer_on_the_simulator_reproduces_reference_golden
     finally:
         model._release()
         tok._release()
+
+
+def test_axial_space_time_transformer_on_the_simulator_reproduces_reference_golden(on_simulator, monkeypatch):
+    """The stand-alone AxialSpaceTimeTransformer (exported by the reference package): state_dict layout, a 3-frame forward with its
+    time-KV cache, and the same frames fed one at a time through `cache=` - against the reference module's own output."""
+    from dreamer4_b200 import AxialSpaceTimeTransformer
+    monkeypatch.setattr(AxialSpaceTimeTransformer, '_require_cuda', lambda self: None)
+    monkeypatch.setattr(AxialSpaceTimeTransformer, '_stream', lambda self: C.c_void_p(0))
+    fx = torch.load(os.path.join(HERE, 'golden', 'cache', 'axial_transformer.pt'), map_location='cpu', weights_only=False)
+    m = AxialSpaceTimeTransformer(**fx['kwargs'], precision='fp32')
+    assert set(m.state_dict()) == set(fx['state_dict'])
+    m.load_state_dict(fx['state_dict'], strict=True)
+    try:
+        out, inter = m(fx['tokens'], return_intermediates=True)
+        torch.testing.assert_close(out, fx['out'], atol=2e-5, rtol=1e-4)
+        assert inter.token_count == fx['token_count']
+        torch.testing.assert_close(inter.next_kv_cache, fx['kv'], atol=2e-5, rtol=1e-4)
+        cache, frames = None, []
+        for t in range(fx['tokens'].shape[1]):                      # the reference's incremental calling convention (:2957-2961)
+            o, cache = m(fx['tokens'][:, :t + 1], cache=cache, return_intermediates=True)
+            frames.append(o[:, -1])
+        torch.testing.assert_close(torch.stack(frames, dim=1), fx['out'], atol=2e-5, rtol=1e-4)
+    finally:
+        m._release()

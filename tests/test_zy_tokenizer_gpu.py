@@ -166,3 +166,21 @@ def test_interact_with_env_through_the_attached_tokenizer(case):
     assert torch.equal(exp.lens.cpu(), ref.lens) and torch.equal(exp.is_truncated.cpu(), ref.is_truncated)
     for name in ('latents', 'agent_embed', 'values'):
         torch.testing.assert_close(getattr(exp, name).cpu(), getattr(ref, name), **TOL, msg=lambda m, n=name: f'{n}: {m}')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+def test_axial_space_time_transformer_matches_reference_golden(precision):
+    """The stand-alone transformer (d4_tf_step on caller tokens) against the reference module's own 3-frame output and time-KV cache."""
+    from dreamer4_b200 import AxialSpaceTimeTransformer
+    fx = load(os.path.join(os.path.dirname(__file__), 'golden', 'cache', 'axial_transformer.pt'))
+    m = AxialSpaceTimeTransformer(**fx['kwargs'], precision=precision)
+    m.load_state_dict(fx['state_dict'], strict=True)
+    m = m.cuda()
+    out, inter = m(fx['tokens'].cuda(), return_intermediates=True)
+    torch.testing.assert_close(out.cpu(), fx['out'], **TOL)
+    torch.testing.assert_close(inter.next_kv_cache.cpu(), fx['kv'], **TOL)
+    cache, frames = None, []
+    for t in range(fx['tokens'].shape[1]):
+        o, cache = m(fx['tokens'][:, :t + 1].cuda(), cache=cache, return_intermediates=True)
+        frames.append(o[:, -1])
+    torch.testing.assert_close(torch.stack(frames, dim=1).cpu(), fx['out'], **TOL)

@@ -717,7 +717,7 @@ static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_tem
     uint32_t tbits; memcpy(&tbits, &discrete_temperature, 4);
     const std::array<long long, 6> key = {first_step == 0 ? 0 : 1, B, t, num_steps, (long long)tbits, flags};
     auto& fg = c->graphs[key];
-    if (!fg.seen) {           // first use of this key: run directly
+    if (!fg.seen || fg.direct) {           // first use of this key (or a stream that cannot be captured): run directly
         fg.seen = true;
         return frame_body(c, B, t, num_steps, discrete_temperature, io, stream, first_step);
     }
@@ -739,7 +739,11 @@ static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_tem
     if (!fg.exec) {           // second use: capture the frame on the staging rows, instantiate
         if (!c->bound || !c->ws) return frame_body(c, B, t, num_steps, discrete_temperature, io, stream, first_step);   // reports the error
         const long long l0 = d4_launches_;
-        D4_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {      // e.g. the legacy default stream
+            cudaGetLastError();
+            fg.direct = true;
+            return frame_body(c, B, t, num_steps, discrete_temperature, io, stream, first_step);
+        }
         const int rc = frame_body(c, B, t, num_steps, discrete_temperature, &st, stream, first_step);
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(s, &graph);

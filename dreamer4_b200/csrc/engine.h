@@ -76,12 +76,13 @@ struct d4_ctx {
     // frame).  One instantiated graph per (entry point, B, t, num_steps, temperature, which optional io fields are present),
     // captured the SECOND time a key is seen (the first use runs directly, which also gets every lazy one-time setup out of
     // the way); the graph works on dense staging rows inside the workspace, copied in / out around the launch, so it does not
-    // depend on the caller's pointers.  Dropped whenever weights or buffers are re-registered.
+    // depend on the caller's pointers.  Dropped whenever weights or buffers are re-registered.  The caller's stream must be
+    // capturable (not the legacy default stream): where cudaStreamBeginCapture refuses, the key stays on direct launches.
     bool use_graphs = false;
     int graph_max_rows = 4096;   // frames with more than this many token rows (B * S) always run directly
     struct GraphIO { float *noise, *act_u, *term_u, *latents, *agent, *rewards, *values, *logp, *logits;
                      long long *prev_actions, *tasks, *actions, *lens; unsigned char* terminals; } gio = {};
-    struct FrameGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; bool seen = false; };
+    struct FrameGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; bool seen = false; bool direct = false; };   // direct: capture refused, keep launching
     std::map<std::array<long long, 6>, FrameGraph> graphs;
     long long graph_replays = 0;
     struct ProfRec { cudaEvent_t a, b; int cls; double work; };

@@ -34,6 +34,8 @@ def main():
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     out = open(os.path.join(ROOT, 'gpurun_out', 'env_step_bench.jsonl'), 'a')
     graphs = os.environ.get('D4_GRAPH') == '1'
+    if graphs:
+        torch.cuda.set_stream(torch.cuda.Stream())          # stream capture needs a non-default stream
     for B in [int(b) for b in args.batches.split(',')]:
         # D4_GRAPH=1: a frame graph is keyed by its cache position, run directly the first time it is seen and captured the
         # second time - so episodes 1 and 2 are preparation and episode 3 (same positions again) is the replay being timed

@@ -24,9 +24,12 @@ def test_cuda_graph_replay_reproduces_direct_frames(monkeypatch):
     noise = G.to_cuda(G.make_noise(model.cfg, T, B, seed=5))
     flags = dict(return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
     runs, launches = [], []
+    side = torch.cuda.Stream()                           # stream capture needs a non-default stream
+    torch.cuda.synchronize()
     for _ in range(3):                                   # direct, capture + replay, replay
         l0 = lib.d4_launch_count()
-        runs.append(model.generate(T, batch_size=B, noise=noise, **flags))
+        with torch.cuda.stream(side):
+            runs.append(model.generate(T, batch_size=B, noise=noise, **flags))
         torch.cuda.synchronize()
         launches.append(lib.d4_launch_count() - l0)
     assert launches[0] == launches[1] == launches[2] > 0

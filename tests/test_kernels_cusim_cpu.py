@@ -204,6 +204,15 @@ def test_video_tokenizer_on_the_simulator_reproduces_reference_golden(path, on_s
         torch.testing.assert_close(recon, fx['recon'], atol=1e-4, rtol=2e-4)
     finally:
         tok._release()
+    # the class default precision: every GEMM weight's tf32 hi / lo words must be registered under the names d4_bind resolves (on the
+    # simulator the GEMMs themselves still take the exact kernel; the point is that binding and the d4_linear_rows arguments hold)
+    tok3 = VideoTokenizer(**fx['tokenizer_kwargs'])
+    assert tok3.precision == 'tf32x3'
+    tok3.load_state_dict(fx['state_dict'], strict=True)
+    try:
+        torch.testing.assert_close(tok3.tokenize(fx['video'][:, :, :1]), fx['latents'][:, :1], atol=5e-5, rtol=2e-4)
+    finally:
+        tok3._release()
 
 
 def test_cuda_graph_replay_on_the_simulator(on_simulator, monkeypatch):

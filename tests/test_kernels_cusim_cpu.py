@@ -41,7 +41,8 @@ def simlib(tmp_path_factory):
         out.write_text(transform(open(os.path.join(CSRC, name + '.cu')).read()))
         srcs.append(str(out))
     lib = build / 'libcusim.so'
-    cmd = ['g++', '-std=c++20', '-O1', '-shared', '-fPIC', '-pthread', '-I', SIM, '-I', CSRC, *srcs, os.path.join(SIM, 'cusim_main.cpp'), '-o', str(lib)]
+    extra = ['-fsanitize=address', '-fno-omit-frame-pointer', '-g'] if os.environ.get('D4_CUSIM_ASAN') == '1' else []      # see tests/cusim/README.md
+    cmd = ['g++', '-std=c++20', '-O1', *extra, '-shared', '-fPIC', '-pthread', '-I', SIM, '-I', CSRC, *srcs, os.path.join(SIM, 'cusim_main.cpp'), '-o', str(lib)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
     lib = C.CDLL(str(lib))

@@ -1022,7 +1022,7 @@ extern "C" int d4_linear_rows(int precision, int M, int N, int K, const float* A
     GemmArgs g = gemm_args(A, lda, W_exact ? W_exact : W, ldw, C, ldc, M, N, K);
     g.bias = bias;
     if (a_grp > 0) g.amap = rowmap(a_grp, a_gstride, a_goff);
-    if (precision == D4_PREC_FP32 || !d4_gemm_tc_supported(g)) {
+    if (precision == D4_PREC_FP32 || N < 16 || !d4_gemm_tc_supported(g)) {      // tiny N: a tensor-core tile would be > 90 % padding
         if (!W_exact) return d4_fail("d4_linear_rows: this shape runs on the exact-fp32 kernel and needs W_exact");
         return d4_gemm_simt(g, s);
     }

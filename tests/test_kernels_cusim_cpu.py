@@ -42,7 +42,7 @@ def simlib(tmp_path_factory):
         srcs.append(str(out))
     lib = build / 'libcusim.so'
     extra = ['-fsanitize=address', '-fno-omit-frame-pointer', '-g'] if os.environ.get('D4_CUSIM_ASAN') == '1' else []      # see tests/cusim/README.md
-    cmd = ['g++', '-std=c++20', '-O1', *extra, '-shared', '-fPIC', '-pthread', '-I', SIM, '-I', CSRC, *srcs, os.path.join(SIM, 'cusim_main.cpp'), '-o', str(lib)]
+    cmd = ['g++', '-std=c++20', '-O2', *extra, '-shared', '-fPIC', '-pthread', '-I', SIM, '-I', CSRC, *srcs, os.path.join(SIM, 'cusim_main.cpp'), '-o', str(lib)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
     lib = C.CDLL(str(lib))
@@ -413,3 +413,29 @@ def test_axial_space_time_transformer_on_the_simulator_reproduces_reference_gold
         torch.testing.assert_close(torch.stack(frames, dim=1), fx['out'], atol=2e-5, rtol=1e-4)
     finally:
         m._release()
+
+
+def test_video_tokenizer_with_64_latent_tokens_on_the_simulator_matches_oracle(on_simulator):
+    """Frames of more than 64 tokens, 64 of them special - config 4's latent-token count (the golden fixtures have 3 and 6): the
+    frame_attn.cu path with several key rounds per lane, the special-token mask over a 64-wide block, 64-row groups in the row maps."""
+    from dreamer4_b200 import VideoTokenizer
+    from oracle import tokenizer_oracle as TO
+    kw = dict(dim=32, dim_latent=8, patch_size=4, image_size=16, num_latent_tokens=64, encoder_depth=2, decoder_depth=2, time_block_every=2,
+              attn_heads=2, attn_dim_head=16)
+    torch.manual_seed(3)
+    tok = VideoTokenizer(**kw, precision='fp32')
+    with torch.no_grad():
+        for n, prm in tok.named_parameters():
+            if n.endswith('gamma') or n.endswith('norm.weight'):
+                prm.add_(torch.randn_like(prm) * 0.1)
+            if n == 'latent_tokens':
+                prm.mul_(30.)
+    sd = {k: v.detach().clone() for k, v in tok.state_dict().items()}
+    ocfg = TO.config_from_reference_kwargs(**kw)
+    video, noise = torch.randn(1, 3, 2, 16, 16), torch.randn(1, 3, 2, 16, 16)
+    want = TO.tokenize(sd, ocfg, video)
+    try:
+        torch.testing.assert_close(tok.tokenize(video), want, atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(tok.decode(want, noise=noise), TO.decode(sd, ocfg, want, noise=noise), atol=5e-5, rtol=1e-4)
+    finally:
+        tok._release()

@@ -7,6 +7,7 @@ from .dynamics import DynamicsWorldModel, ModelConfig, exists, default
 from .trainer import DreamTrainer, SimTrainer
 from .env import DynamicsWorldModelWrapper
 from .tokenizer import AxialSpaceTimeTransformer, VideoTokenizer, TokenizerConfig
+from .registry import register_activation, register_reward_encoder
 
 __all__ = ['Actions', 'Embeds', 'Predictions', 'Experience', 'combine_experiences', 'DynamicsWorldModel', 'DreamTrainer', 'SimTrainer', 'DynamicsWorldModelWrapper', 'ModelConfig', 'exists', 'default',
-           'VideoTokenizer', 'TokenizerConfig', 'AxialSpaceTimeTransformer']
+           'VideoTokenizer', 'TokenizerConfig', 'AxialSpaceTimeTransformer', 'register_activation', 'register_reward_encoder']

@@ -82,6 +82,7 @@ class d4_learn_io(C.Structure):
         ('objective', C.c_int32), ('pmpo_reverse_kl', C.c_int32),
         ('pmpo_pos_to_neg_weight', C.c_float), ('pmpo_kl_div_loss_weight', C.c_float),
         ('old_action_unembeds', C.c_void_p), ('old_action_unembeds_ld', C.c_int64),
+        ('returns_ema', C.c_void_p),
     ]
 
 
@@ -118,6 +119,8 @@ SYMBOLS = {
     'd4_unpatchify_flow': (_i, [_i, _i, _i, _i, _i, _p, _p, _i64, _i64, _f, _p]),
     'd4_tok_assemble': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p]),
     'd4_tanh_rows': (_i, [_p, _i64, _p]),
+    'd4_graph_replays': (_i64, [_p]),
+    'd4_debug_set': (_i, [C.c_char_p, _i]),
 }
 
 _lib = None

@@ -28,6 +28,14 @@ extern "C" const char* d4_last_error(void) { return g_err; }
 extern "C" int d4_version(void) { return 100; }
 long long d4_launches_ = 0;
 extern "C" int64_t d4_launch_count(void) { return d4_launches_; }
+void d4_gemm_f16_debug(int bits);
+// diagnostics switchboard for the bench / profiling scripts (never used by the product path)
+extern "C" int d4_debug_set(const char* key, int value) {
+    if (!key) return d4_fail("d4_debug_set: null key");
+    if (!strcmp(key, "gemm_f16")) { d4_gemm_f16_debug(value); return 0; }
+    return d4_fail("d4_debug_set: unknown key '%s'", key);
+}
+extern "C" int64_t d4_graph_replays(const d4_ctx* c) { return c ? c->graph_replays : 0; }
 
 #define D4_TRY(expr) do { int rc__ = (expr); if (rc__ != 0) return rc__; } while (0)
 

@@ -91,6 +91,7 @@ struct EpiArgsH {
     int rs_mode, kdim;  // rs_mode 1: row_scale holds the sum of squares over kdim columns -> rsqrt(ss / kdim + eps); rows pre-scaled by 2^k
     float* ss_out;
     float w_scale;      // 1 / q of the pre-scaled weights
+    int dbg;            // ablation switches for scripts/gemm_bench.py (results are garbage when set): 1 no epilogue, 2 no split, 4 no MMA
 };
 
 template <int BN> struct CfgH {
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16x3_kernel(const __grid
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t da = make_desc_sw128(smem_u32(tile(s, T_A))), dalo = make_desc_sw128(smem_u32(tile(s, T_ALO)));
                     const uint64_t dw = make_desc_sw128(smem_u32(tile(s, T_W))), dwlo = make_desc_sw128(smem_u32(tile(s, T_WLO)));
+                    if (!(e.dbg & 4))
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {             // small terms first, the hi*hi product last
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16x3_kernel(const __grid
             if (has_res && rows_ok && out0 < n_out && lane == 0) { bulk_wait_read_1(); res_load(g & 1, out0, rbase); }
             mbar_wait(bar(B_TFULL + buf_acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (rows_ok) {
+            if (rows_ok && !(e.dbg & 1)) {
                 auto bias_regs = [&](int nb, float& lo, float& hi) {
                     lo = (biasp && nb + lane < e.N) ? __ldg(biasp + nb + lane) : 0.f;
                     hi = (biasp && glu && nb + 32 + lane < e.N) ? __ldg(biasp + nb + 32 + lane) : 0.f;
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16x3_kernel(const __grid
             for (int kb = 0; kb < nkb; ++kb, ++kc) {
                 const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
                 mbar_wait(bar(B_FULLA + s), ph);
+                if (e.dbg & 2) { if (et == 0) mbar_arrive_cluster(split_leader + (uint32_t)s * 8u); continue; }
                 unsigned char* base = tile(s, T_A);
                 float4 x[4][2];
 #pragma unroll
@@ -440,6 +443,8 @@ bool operands_ok(const GemmArgs& g, const void* whi, const void* wlo) {
     return ok;
 }
 
+int g_dbg = 0;          // d4_debug_set("gemm_f16", bits): 1 no epilogue, 2 no operand split, 4 no MMA (timing ablations only)
+
 template <int BN>
 int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
     using K = CfgH<BN>;
@@ -467,7 +472,7 @@ int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
     e.C = g.C; e.ldc = g.ldc; e.M = g.M; e.N = g.N; e.bias = g.bias; e.row_scale = g.row_scale; e.residual = g.residual; e.ldr = g.ldr;
     e.act = g.act; e.cmap = g.cmap; e.a_grp = g.amap.grp; e.nkb = (g.K + BK - 1) / BK;
     e.n_tiles_m = (g.M + 2 * BM - 1) / (2 * BM); e.n_tiles_n = (g.N + BN - 1) / BN;
-    e.rs_mode = g.rs_mode; e.kdim = g.K; e.ss_out = g.ss_out; e.w_scale = w_scale;
+    e.rs_mode = g.rs_mode; e.kdim = g.K; e.ss_out = g.ss_out; e.w_scale = w_scale; e.dbg = g_dbg;
     const long long tiles = (long long)e.n_tiles_m * e.n_tiles_n;
     const int clusters = (int)std::min<long long>(tiles, maxc);
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
@@ -484,6 +489,7 @@ int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
 // 1 if the engine may route this GEMM here given the fp16 hi / lo arrays of its weight: the pair kernel's shapes (more rows than
 // one CTA's 128, like gemm_tc3.cu), whole 64-column K steps (K = dim, ff_inner_pad, pool width ... of every BASELINE config), and
 // the operand rules above.  g.W still points to the fp32 weight; only its leading dimension is read.
+void d4_gemm_f16_debug(int bits) { g_dbg = bits & 7; }
 int d4_gemm_f16x3_supported(const GemmArgs& g, const void* whi, const void* wlo) {
     return (g.M > BM && (g.K % 32) == 0 && g.K >= BK && operands_ok(g, whi, wlo)) ? 1 : 0;
 }

@@ -79,13 +79,16 @@ __device__ float block_sum(float v, float* sh) {
 
 // advantage = returns - old_values, z-scored over the learnable mask (population variance, eps clamp);
 // stats[0] = number of learnable steps
+// ema (keep_reward_ema_stats, 5987-6013): [mean, std] of the running return statistics - both terms are normalised before the
+// subtraction, in the reference's order
 __global__ void adv_stats_kernel(long long R, const float* __restrict__ returns, const float* __restrict__ values,
-                                 const unsigned char* __restrict__ mask, int normalize, float eps, float* __restrict__ adv,
-                                 float* __restrict__ stats) {
+                                 const unsigned char* __restrict__ mask, int normalize, float eps, const float* __restrict__ ema,
+                                 float* __restrict__ adv, float* __restrict__ stats) {
     __shared__ float sh[32];
     float n = 0.f, s = 0.f;
+    const float em = ema ? ema[0] : 0.f, es = ema ? ema[1] : 1.f;
     for (long long i = threadIdx.x; i < R; i += blockDim.x) {
-        const float a = returns[i] - values[i];
+        const float a = ema ? (returns[i] - em) / es - (values[i] - em) / es : returns[i] - values[i];
         adv[i] = a;
         if (mask[i]) { n += 1.f; s += a; }
     }
@@ -540,7 +543,7 @@ extern "C" int d4_learn(d4_ctx* c, const d4_learn_io* io, void* workspace, int64
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     gae_kernel<<<nblk(B, RPB), 32 * RPB, 0, s>>>(B, T, r_m, v_m, gmask, lmask, io->gamma, io->lam, io->returns);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
-    adv_stats_kernel<<<1, 1024, 0, s>>>(R, io->returns, v_m, lmask, io->normalize_advantages, io->zscore_eps, io->advantages, stats);
+    adv_stats_kernel<<<1, 1024, 0, s>>>(R, io->returns, v_m, lmask, io->normalize_advantages, io->zscore_eps, io->returns_ema, io->advantages, stats);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
 
     const int D = c->D;

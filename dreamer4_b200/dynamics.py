@@ -20,6 +20,7 @@ from torch import nn
 from . import _lib
 from ._lib import D4Error, check, ptr
 from .experience import Actions, DynamicsIntermediates, Embeds, Experience, Predictions, TransformerIntermediates
+from . import registry
 from .packing import hl_gauss_tables, mlp_param_names, pack, tf32_split
 
 
@@ -112,8 +113,10 @@ def _linear_b(out_f, in_f):
     return torch.empty(out_f).uniform_(-bound, bound)
 
 
+# Constructor keywords of the reference (dreamer4.py:4662-4778) that select a branch outside the B200 hot path: accepted at their
+# default value only.
 _UNSUPPORTED_DEFAULTS = dict(
-    video_tokenizer=None, aux_image_encoder=None, num_video_views=1, mot_temporal=False, dim_proprio=None, dim_state=None,
+    aux_image_encoder=None, num_video_views=1, mot_temporal=False, dim_proprio=None, dim_state=None,
     dim_critic_state=None, reward_encoder_type='hl_gauss', critic_state_embedder=None, spatial_pre_encoder_depth=0,
     action_pre_encoder_depth=0, actor_depth=0, critic_depth=0, pred_orig_latent=True, use_time_rnn=False,
     add_reward_embed_to_agent_token=False, add_state_pred_head=False, agent_predicts_state=False, num_continuous_actions=0,
@@ -121,6 +124,24 @@ _UNSUPPORTED_DEFAULTS = dict(
     has_aug_conditioning=False, ssl_lapo=False, ssl_tem=False, actor_spr=False, clip_values=False,
     policy_head_mlp_activation='silu', value_head_mlp_activation='silu', state_terminal_pred_mlp_activation='silu',
 )
+
+# Keywords that only steer the world-model / tokenizer TRAINING losses, dropout or optional heads that are off (reference
+# dreamer4.py:4662-4778): they never enter generate / interact_with_env / learn_from_experience with the heads detached, so they are
+# accepted and recorded but not used.  (`agent_policy_gradient_frac` / `agent_value_gradient_frac` scale the gradient that flows
+# back into the agent embedding, which `only_learn_policy_value_heads=True` detaches: no effect on this path.)  Anything that is
+# in neither table is a TypeError, as it would be for the reference's explicit signature.
+_TRAINING_ONLY = frozenset((
+    'freeze_aux_image_encoder', 'loss_weight_fn', 'prob_shortcut_train', 'add_reward_embed_dropout', 'state_pred_loss_weight',
+    'state_entropy_bonus_weight', 'agent_predicts_state_frac_gradient', 'agent_state_pred_loss_weight', 'eps_latent_pred',
+    'continuous_norm_stats', 'continuous_dist_type', 'continuous_dist_kwargs', 'continuous_target_action_range',
+    'latent_flow_loss_weight', 'shortcut_loss_weight', 'reward_loss_weight', 'terminal_loss_weight', 'discrete_action_loss_weight',
+    'continuous_action_loss_weight', 'value_clip', 'agent_policy_gradient_frac', 'agent_value_gradient_frac', 'use_loss_normalization',
+    'latent_ar_layer', 'latent_ar_action_conditioned', 'latent_ar_loss_weight', 'latent_ar_sigreg_loss_weight',
+    'latent_ar_sigreg_loss_kwargs', 'latent_ar_sigreg_num_subspaces', 'latent_ar_kwargs', 'aug_cfg_dropout_prob',
+    'agent_predict_sem_kwargs', 'lapo_pred_actions', 'lapo_use_fdm', 'tem_first_state_as_init_hidden', 'tem_learn_relative_actions',
+    'lapo_kwargs', 'tem_kwargs', 'lapo_action_loss_weight', 'lapo_fdm_loss_weight', 'lapo_raw_latent_fdm_loss_weight', 'tem_loss_weight',
+    'actor_nlp_kwargs', 'agent_state_pred_mlp_activation',
+))
 
 
 def _records_config(init):
@@ -141,24 +162,33 @@ class DynamicsWorldModel(nn.Module):
     precision); the final action unembedding always runs exact fp32.  `time_attn_variant`: K1 kernel (1 = bulk-copy ring, 0 = ld.global)."""
 
     @_records_config
-    def __init__(self, dim, dim_latent, *, num_latent_tokens=None, max_steps=64, num_register_tokens=8, num_spatial_tokens=4,
+    def __init__(self, dim, dim_latent, video_tokenizer=None, copy_video_tokenizer=True, *, num_latent_tokens=None, max_steps=64,
+                 num_register_tokens=8, num_spatial_tokens=4,
                  num_agents=1, num_tasks=0, reward_encoder_kwargs: dict = dict(), value_encoder_kwargs: Optional[dict] = None,
                  depth=4, time_block_every=4, attn_kwargs: dict = dict(), transformer_kwargs: dict = dict(), attn_heads=8,
                  attn_dim_head=64, attn_softclamp_value=50., ff_kwargs: dict = dict(), num_discrete_actions=0,
                  multi_token_pred_len=8, value_head_mlp_depth=3, policy_head_mlp_depth=3, predict_terminals=True,
-                 predict_terminal_mlp_kwargs: dict = dict(depth=1), gae_discount_factor=0.997, gae_lambda=0.95, ppo_eps_clip=0.2,
+                 predict_terminal_mlp_kwargs: dict = dict(depth=1), keep_reward_ema_stats=False, reward_ema_decay=0.998,
+                 reward_quantile_filter=(0.05, 0.95), gae_discount_factor=0.997, gae_lambda=0.95, ppo_eps_clip=0.2,
                  use_delight_gating=True, delight_temperature=1., normalize_advantages=None, policy_entropy_weight=.01,
                  pmpo_pos_to_neg_weight=0.5, pmpo_reverse_kl=True, pmpo_kl_div_loss_weight=.3, gae_use_accelerated=False, precision='tf32x3', time_attn_variant=1, **kwargs):
         super().__init__()
-        video_tokenizer = kwargs.pop('video_tokenizer', None)
-        if exists(video_tokenizer):             # reference dreamer4.py:4790-4801
+        # `video_tokenizer` is the reference's third positional argument (dreamer4.py:4666); `copy_video_tokenizer` deep-copies and
+        # freezes it (4789-4792)
+        if exists(video_tokenizer):             # reference dreamer4.py:4788-4801
             assert hasattr(video_tokenizer, 'tokenize') and hasattr(video_tokenizer, 'decode'), 'video_tokenizer must be a dreamer4_b200.VideoTokenizer'
+            if copy_video_tokenizer:
+                import copy
+                video_tokenizer = copy.deepcopy(video_tokenizer)
+                video_tokenizer.requires_grad_(False)
             num_latent_tokens = default(num_latent_tokens, video_tokenizer.num_latent_tokens)
             assert video_tokenizer.num_latent_tokens == num_latent_tokens and video_tokenizer.dim_latent == dim_latent, \
                 'the tokenizer and the dynamics model disagree on the latent shape'
         for k, v in kwargs.items():
+            if k in _TRAINING_ONLY:
+                continue                    # recorded in self._config; never read on this path (see _TRAINING_ONLY)
             if k not in _UNSUPPORTED_DEFAULTS:
-                continue                    # training-only knobs (loss weights, ssl kwargs, ...) do not touch this path
+                raise TypeError(f'DynamicsWorldModel.__init__() got an unexpected keyword argument {k!r}')
             if v != _UNSUPPORTED_DEFAULTS[k]:
                 raise NotImplementedError(f'{k}={v!r}: this branch of the reference is outside the B200 hot path (SURVEY.md section 8)')
         assert exists(num_latent_tokens), '`num_latent_tokens` must be set (or attach a video_tokenizer)'
@@ -172,8 +202,9 @@ class DynamicsWorldModel(nn.Module):
         vk = rk if value_encoder_kwargs is None else dict(value_encoder_kwargs)
         ffk = dict(ff_kwargs or {})
         act = ffk.get('activation', 'silu')
-        if act not in ('silu', 'gelu'):
-            raise NotImplementedError(f"feed-forward activation {act!r}: kernels cover the gated silu / gelu variants")
+        if act not in registry.NATIVE_FF_ACTIVATIONS:       # includes names added through register_activation (reference :568-569)
+            assert isinstance(act, str) and act in registry.ACTIVATIONS, f'activation {act} not found in {list(registry.ACTIVATIONS.keys())}'
+            raise NotImplementedError(f"feed-forward activation {act!r}: the GEMM epilogues cover the gated silu / gelu variants")
         self.cfg = cfg = ModelConfig(
             dim=dim, dim_latent=dim_latent, num_latent_tokens=num_latent_tokens, num_spatial_tokens=num_spatial_tokens,
             num_register_tokens=num_register_tokens, depth=depth, time_block_every=time_block_every, attn_heads=attn_heads,
@@ -194,6 +225,8 @@ class DynamicsWorldModel(nn.Module):
         self.normalize_advantages = normalize_advantages
         self.pmpo_pos_to_neg_weight, self.pmpo_reverse_kl = pmpo_pos_to_neg_weight, pmpo_reverse_kl     # reference :5227-5231
         self.pmpo_kl_div_loss_weight = pmpo_kl_div_loss_weight
+        self.keep_reward_ema_stats, self.reward_ema_decay = keep_reward_ema_stats, reward_ema_decay      # reference :5238-5246
+        self._reward_quantile_filter = tuple(float(q) for q in reward_quantile_filter)
         self.latent_shape = (num_latent_tokens, dim_latent)
         self._build_parameters()
         self.video_tokenizer = video_tokenizer.eval() if exists(video_tokenizer) else None      # submodule: state_dict keys video_tokenizer.* (4794)
@@ -256,8 +289,9 @@ class DynamicsWorldModel(nn.Module):
         self._reg('action_learned_embed', torch.randn(c.num_agents, D) * 1e-2)
         self._reg('reward_learned_embed', torch.randn(c.num_agents, D) * 1e-2)
         self._reg('latent_genes', torch.randn(0, D) * 1e-2)
-        for name in ('ema_returns_mean', 'ema_returns_var'):
-            self._reg(name, torch.zeros(()), buffer=True)
+        self._reg('ema_returns_mean', torch.zeros(()), buffer=True)          # reference dreamer4.py:5245-5246
+        self._reg('ema_returns_var', torch.ones(()), buffer=True)
+        self._reg('reward_quantile_filter', torch.tensor(self._reward_quantile_filter), buffer=True, persistent=False)
         for name in ('reward_loss_weight', 'terminal_loss_weight', 'discrete_action_loss_weight', 'continuous_action_loss_weight'):
             self._reg(name, torch.ones(()), buffer=True)
         if c.same_len:          # reference dreamer4.py:4819-4834
@@ -463,6 +497,16 @@ class DynamicsWorldModel(nn.Module):
             self._release()
         except Exception:
             pass
+
+    _NATIVE_STATE = dict(_ctx=None, _ctx_key=None, _bufs={}, _packed=None, _packed_version=None, _head_splits=[], _head_split_version=None)
+
+    def __deepcopy__(self, memo):
+        """A copy owns no native context (the handles borrow this instance's parameter storage): it builds its own on first use."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__dict__ = {k: (copy.deepcopy(self._NATIVE_STATE[k]) if k in self._NATIVE_STATE else copy.deepcopy(v, memo)) for k, v in self.__dict__.items()}
+        return new
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -857,10 +901,27 @@ class DynamicsWorldModel(nn.Module):
         c = self.cfg
         assert c.has_actions, 'learn_from_experience needs a model with discrete actions'
         exp = experience
+        assert isinstance(exp, Experience)
         assert exists(exp.agent_embed), 'the native path learns from stored agent embeds (generate(store_agent_embed=True))'
+        assert all(map(exists, (exp.log_probs, exp.actions, exp.values, exp.rewards, exp.step_size))), \
+            'the generations need to contain the log probs, values, and rewards for policy optimization - world_model.generate(..., return_log_probs_and_values = True)'
+        assert not (exists(exp.actions.continuous) and exp.actions.continuous.numel() > 0), 'continuous actions are a "next" row (SURVEY.md section 8f)'
         B, T = exp.latents.shape[:2]
-        lib, ctx = self._engine(*(self._ctx_key[:2] if self._ctx_key else (B, T)), default(exp.agent_index, 0))
         dev = self.device
+        na, A = len(c.num_discrete_actions), c.total_actions
+        disc = exp.actions.discrete if exp.actions.discrete.ndim == 3 else exp.actions.discrete[..., None]        # reference :6037-6038
+        old_disc = exp.log_probs.discrete if exp.log_probs.discrete.ndim == 3 else exp.log_probs.discrete[..., None]
+        # every per-step record must cover the same (B, T) steps as the latents: the native call reads B*T rows from each.  (A
+        # prompted generate(..., return_for_policy_optimization=True) returns latents / rewards over prompt + new frames but
+        # agent embeds, values and log-probs over the new frames only; the reference fails on that in calc_gae - slice the
+        # Experience to the new frames before learning from it.)
+        for name, t, shape in (('agent_embed', exp.agent_embed, (B, T, c.dim)), ('rewards', exp.rewards, (B, T)), ('values', exp.values, (B, T)),
+                               ('actions.discrete', disc, (B, T, na)), ('log_probs.discrete', old_disc, (B, T, na))):
+            if tuple(t.shape) != shape:
+                raise ValueError(f'learn_from_experience: experience.{name} has shape {tuple(t.shape)}, expected {shape} to match latents {tuple(exp.latents.shape)}')
+        if exists(exp.lens) and tuple(exp.lens.shape) != (B,):
+            raise ValueError(f'learn_from_experience: experience.lens has shape {tuple(exp.lens.shape)}, expected {(B,)}')
+        lib, ctx = self._engine(*(self._ctx_key[:2] if self._ctx_key else (B, T)), default(exp.agent_index, 0))
         use_gate = default(use_delight_gating, self.use_delight_gating)
         temp = default(delight_temperature, self.delight_temperature)
         norm_adv = default(default(normalize_advantages, self.normalize_advantages), objective != 'pmpo')    # reference :6021
@@ -869,9 +930,12 @@ class DynamicsWorldModel(nn.Module):
         cont = lambda t, dt: t.detach().to(device=dev, dtype=dt).contiguous()
         agent = cont(exp.agent_embed, torch.float32)
         rewards, values = cont(exp.rewards, torch.float32), cont(exp.values, torch.float32)
-        actions, old_lp = cont(exp.actions.discrete, torch.long), cont(exp.log_probs.discrete, torch.float32)
+        actions, old_lp = cont(disc, torch.long), cont(old_disc, torch.float32)
         lens = cont(default(exp.lens, torch.full((B,), T, device=dev)), torch.long)
-        is_trunc = cont(default(exp.is_truncated, torch.zeros(B, dtype=torch.bool, device=dev)), torch.bool)
+        # a missing is_truncated means "every episode was cut": the last step is bootstrap-only (reference :5943-5944, :5954)
+        is_trunc = cont(default(exp.is_truncated, torch.ones(B, dtype=torch.bool, device=dev)), torch.bool)
+        if tuple(is_trunc.shape) != (B,):
+            raise ValueError(f'learn_from_experience: experience.is_truncated has shape {tuple(is_trunc.shape)}, expected {(B,)}')
         support, _ = hl_gauss_tables(*c.value_range, c.value_num_bins, dev)
         sigma_sqrt2 = math.sqrt(2.) * c.hl_gauss_sigma_to_bin_ratio * (c.value_range[1] - c.value_range[0]) / c.value_num_bins
 
@@ -898,6 +962,29 @@ class DynamicsWorldModel(nn.Module):
         io.value_lo, io.value_hi = c.value_range
         io.losses, io.returns, io.advantages = ptr(losses), ptr(returns), ptr(adv)
         io.objective = _lib.OBJECTIVES[objective]
+        keep = []
+        if self.keep_reward_ema_stats:                                      # reference dreamer4.py:5987-6013
+            # the running return statistics need this batch's lambda-returns first: the native scan (d4_gae) on the masked rewards /
+            # values, then the quantile-filtered mean / variance and their EMA - a handful of torch ops over (B, T) scalars,
+            # plumbing like the optimizer step - and d4_learn normalises returns and old values by them before subtracting
+            steps = torch.arange(T, device=dev)[None, :]
+            in_len = steps < lens[:, None]
+            learn_mask = steps < (lens - is_trunc.long())[:, None]
+            gae_mask = steps < (lens - 1).clamp(min=0)[:, None]
+            r_m, v_m = (rewards * in_len).contiguous(), (values * in_len).contiguous()
+            gm_u8, lm_u8 = gae_mask.to(torch.uint8).contiguous(), learn_mask.to(torch.uint8).contiguous()      # named: alive across the call
+            stream0 = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            check(lib.d4_gae(B, T, ptr(r_m), ptr(v_m), ptr(gm_u8), ptr(lm_u8), self.gae_discount_factor, self.gae_lambda, ptr(returns), stream0))
+            with torch.no_grad():
+                rs = returns[learn_mask]
+                lo, hi = torch.quantile(rs, self.reward_quantile_filter.to(dev)).unbind()
+                rs = torch.minimum(torch.maximum(rs, lo), hi)
+                decay = 1. - self.reward_ema_decay
+                self.ema_returns_mean.lerp_(rs.mean(), decay)
+                self.ema_returns_var.lerp_(rs.var(correction=0), decay)
+                ema = torch.stack((self.ema_returns_mean, self.ema_returns_var.clamp(min=1e-5).sqrt())).to(**f32).contiguous()
+            keep.append(ema)
+            io.returns_ema = ptr(ema)
         if objective == 'pmpo':                                             # reference dreamer4.py:6127-6182
             io.pmpo_pos_to_neg_weight, io.pmpo_kl_div_loss_weight = self.pmpo_pos_to_neg_weight, self.pmpo_kl_div_loss_weight
             io.pmpo_reverse_kl = int(bool(self.pmpo_reverse_kl))

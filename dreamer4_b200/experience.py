@@ -55,33 +55,41 @@ class Experience:
         return self.to(torch.device('cpu'))
 
 
+def _pad_to(t, dim, size):
+    if t.ndim <= dim or t.shape[dim] == size:
+        return t
+    pad = [0, 0] * (t.ndim - 1 - dim) + [0, size - t.shape[dim]]
+    return torch.nn.functional.pad(t, pad)
+
+
 def combine_experiences(exps):
-    """Concatenates experiences along the batch dimension, right-padding time to the longest
-    (reference dreamer4/dreamer4.py:248-309)."""
+    """Concatenates experiences along the batch dimension (reference dreamer4/dreamer4.py:248-309).  Every tensor field is
+    right-padded with zeros along dims 1 and 2 to the longest among the inputs before the concatenation - dim 1 is time for
+    (b, t, ...) fields and dim 2 is time for `video` (b, c, t, h, w), the reference's `pad_tensors_at_dim_to_max_len(dims = (1, 2))`;
+    missing `lens` default to the full length, missing `is_truncated` to True, a bool `is_from_world_model` becomes a (b,) tensor.
+    Non-tensor fields (step_size, agent_index) must agree."""
     assert len(exps) > 0
-    max_t = max(e.latents.shape[1] for e in exps)
+    for e in exps:
+        payload = e.latents if e.latents is not None else e.video
+        b, t, dev = payload.shape[0], payload.shape[1], payload.device
+        if e.lens is None:
+            e.lens = torch.full((b,), t, device=dev)
+        if e.is_truncated is None:
+            e.is_truncated = torch.full((b,), True, device=dev)
+        if isinstance(e.is_from_world_model, bool):
+            e.is_from_world_model = torch.full((b,), e.is_from_world_model, device=dev, dtype=torch.bool)
 
-    def pad_t(t):
-        if t is None or t.ndim < 2 or t.shape[1] == max_t:
-            return t
-        pad = [0, 0] * (t.ndim - 2) + [0, max_t - t.shape[1]]
-        return torch.nn.functional.pad(t, pad)
-
-    def cat(vals, time_dim=True):
-        if any(v is None for v in vals):
-            return None
+    def join(vals, name):
         if isinstance(vals[0], Actions):
-            return Actions(cat([v.discrete for v in vals]), cat([v.continuous for v in vals]))
-        if not torch.is_tensor(vals[0]):
-            return vals[0]
-        return torch.cat([pad_t(v) if time_dim else v for v in vals], dim=0)
+            assert all(isinstance(v, Actions) for v in vals), f'{name}: some experiences carry it, some do not'
+            return Actions(join([v.discrete for v in vals], name + '.discrete'), join([v.continuous for v in vals], name + '.continuous'))
+        if torch.is_tensor(vals[0]):
+            assert all(torch.is_tensor(v) for v in vals), f'{name}: some experiences carry it, some do not'
+            for dim in (1, 2):
+                size = max((v.shape[dim] for v in vals if v.ndim > dim), default=0)
+                vals = [_pad_to(v, dim, size) for v in vals]
+            return torch.cat(vals) if vals[0].ndim > 0 else torch.stack(vals)
+        assert all(v == vals[0] for v in vals), f'{name}: experiences disagree ({vals})'
+        return vals[0]
 
-    out = {}
-    batch_only = {'lens', 'is_truncated', 'terminals', 'episode_return'}
-    for f in fields(Experience):
-        vals = [getattr(e, f.name) for e in exps]
-        if f.name == 'lens':
-            vals = [v if v is not None else torch.full((e.latents.shape[0],), e.latents.shape[1], device=e.latents.device)
-                    for v, e in zip(vals, exps)]
-        out[f.name] = cat(vals, time_dim=f.name not in batch_only)
-    return Experience(**out)
+    return Experience(**{f.name: join([getattr(e, f.name) for e in exps], f.name) for f in fields(Experience)})

@@ -213,6 +213,15 @@ class VideoTokenizer(nn.Module):
             lib.d4_ctx_destroy(ctx)
         self._ctx, self._packed, self._packed_version = {}, None, None
 
+    def __deepcopy__(self, memo):
+        """A copy (DynamicsWorldModel(copy_video_tokenizer=True), reference dreamer4.py:4789-4792) owns no native context."""
+        import copy
+        fresh = dict(_ctx={}, _packed=None, _packed_version=None)
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__dict__ = {k: (fresh[k] if k in fresh else copy.deepcopy(v, memo)) for k, v in self.__dict__.items()}
+        return new
+
     def __del__(self):
         try:
             self._release()

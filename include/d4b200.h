@@ -148,6 +148,12 @@ int d4_linear(int precision, int M, int N, int K, const float* A, int64_t lda, c
               const float* bias, const float* row_scale, const float* residual, int64_t ldr, int act,
               float* C, int64_t ldc, void* stream);
 
+/* ---- diagnostics (bench / profiling scripts and tests only).
+ * d4_graph_replays: how many frames of this context ran as a CUDA-graph replay (0 = every frame was launched directly).
+ * d4_debug_set: ablation switches of individual kernels, e.g. ("gemm_f16", bits) - results are garbage when set. */
+int64_t d4_graph_replays(const d4_ctx* ctx);
+int d4_debug_set(const char* key, int value);
+
 /* calc_gae (D4:1566-1600): returns = reverse-scan(delta, gamma*lambda*mask) + values.  masks/learn_masks uint8 (B,T). */
 int d4_gae(int B, int T, const float* rewards, const float* values, const uint8_t* masks, const uint8_t* learn_masks,
            float gamma, float lam, float* returns, void* stream);
@@ -188,6 +194,9 @@ typedef struct d4_learn_io {
     int32_t pmpo_reverse_kl;        /* 1: KL(old || new) (reference default), 0: KL(new || old) */
     float pmpo_pos_to_neg_weight, pmpo_kl_div_loss_weight;
     const float* old_action_unembeds; int64_t old_action_unembeds_ld;   /* (B, T, A_total) rows with leading dim; pmpo only */
+    /* keep_reward_ema_stats (D4:5987-6013): device pointer to [ema_returns_mean, ema_returns_std] (already updated with this
+     * batch's returns by the caller) or NULL; advantage = (returns - mean) / std - (old_values - mean) / std. */
+    const float* returns_ema;
 } d4_learn_io;
 
 int64_t d4_learn_workspace_bytes(const d4_ctx* ctx, int B, int T);

@@ -727,10 +727,11 @@ def masked_mean_all(t, mask):
     return t[mask].mean() if bool(mask.any()) else t[mask].sum()
 
 
-def learn_from_experience(sd, cfg: OracleConfig, exp: OracleExperience, eps=1e-6, objective='ppo', normalize_advantages=None):
+def learn_from_experience(sd, cfg: OracleConfig, exp: OracleExperience, eps=1e-6, objective='ppo', normalize_advantages=None, ema_stats=None):
     """DynamicsWorldModel.learn_from_experience, objective 'ppo' | 'spo' | 'pmpo', only_learn_policy_value_heads=True,
     stored agent embeds, D4:5893-6305.  `sd` tensors that require grad receive gradients.
-    Returns (total_policy_loss, value_loss, aux dict)."""
+    `ema_stats` (keep_reward_ema_stats=True, D4:5987-6013): dict(mean, var: 0-d tensors updated in place, decay=reward_ema_decay,
+    quantiles=reward_quantile_filter).  Returns (total_policy_loss, value_loss, aux dict)."""
     assert objective in ('ppo', 'spo', 'pmpo'), f'unknown objective {objective}'             # D4:6214-6215
     B, T = exp.latents.shape[:2]
     rewards, old_values = exp.rewards, exp.values
@@ -745,7 +746,17 @@ def learn_from_experience(sd, cfg: OracleConfig, exp: OracleExperience, eps=1e-6
         term_seq = (torch.arange(T)[None, :] == pos[:, None]) & exp.terminals[:, None]
         gae_masks = gae_masks.masked_fill(term_seq, False)
     returns = calc_gae(rewards, old_values, gae_masks, mask, cfg.gae_discount_factor, cfg.gae_lambda)
-    advantage = returns - old_values                                                         # D4:6017
+    if ema_stats is not None:                                                                # D4:5987-6013
+        decay = 1. - ema_stats['decay']
+        rs = returns[mask]
+        lo, hi = torch.quantile(rs, torch.tensor(ema_stats['quantiles'], dtype=rs.dtype)).tolist()
+        rs = rs.clamp(lo, hi)
+        ema_stats['mean'].lerp_(rs.mean(), decay)
+        ema_stats['var'].lerp_(rs.var(correction=0), decay)
+        std = ema_stats['var'].clamp(min=1e-5).sqrt()
+        advantage = (returns - ema_stats['mean']) / std - (old_values - ema_stats['mean']) / std
+    else:
+        advantage = returns - old_values                                                     # D4:6017
     if normalize_advantages is None:                                                         # D4:6021: pmpo keeps raw advantages
         normalize_advantages = objective != 'pmpo'
     if normalize_advantages:

@@ -97,6 +97,7 @@ int d4_gemm_tc3(const GemmArgs&, int, int, cudaStream_t) { return d4_fail("cusim
 // f16x3 mode (weight registration, scales, dispatch, epilogue arguments) run end to end on the simulator.
 static long long f16_calls = 0;
 extern "C" long long sim_f16_calls(void) { return f16_calls; }
+void d4_gemm_f16_debug(int) {}
 int d4_gemm_f16x3_supported(const GemmArgs& g, const void* whi, const void* wlo) {
     return (whi && wlo && g.K % 8 == 0 && g.ldw % 8 == 0 && !g.transA && !g.transW && g.act != D4_ACT_SILU) ? 1 : 0;
 }

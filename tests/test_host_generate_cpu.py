@@ -242,8 +242,11 @@ def world(monkeypatch):
     from oracle import tokenizer_oracle as TO
     fx = torch.load(WORLD, map_location='cpu', weights_only=False)
     tok = VideoTokenizer(**fx['tokenizer_kwargs'])
-    model = DynamicsWorldModel(**fx['model_kwargs'], video_tokenizer=tok, precision='fp32')
+    model = DynamicsWorldModel(fx['model_kwargs']['dim'], fx['model_kwargs']['dim_latent'], tok, precision='fp32',       # third positional, as the reference (:4666)
+                               **{k: v for k, v in fx['model_kwargs'].items() if k not in ('dim', 'dim_latent')})
     assert model.cfg.num_latent_tokens == tok.num_latent_tokens                  # taken from the tokenizer (reference :4801)
+    assert model.video_tokenizer is not tok and not any(p.requires_grad for p in model.video_tokenizer.parameters())      # copy_video_tokenizer (:4789-4792)
+    tok = model.video_tokenizer
     model.load_state_dict(fx['state_dict'], strict=True)                         # video_tokenizer.* keys included
     tsd = {k[len('video_tokenizer.'):]: v for k, v in fx['state_dict'].items() if k.startswith('video_tokenizer.')}
     tcfg = TO.config_from_reference_kwargs(**fx['tokenizer_kwargs'])

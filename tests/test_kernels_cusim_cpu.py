@@ -299,6 +299,34 @@ def test_learn_from_experience_on_the_simulator_matches_reference_golden(on_simu
         torch.testing.assert_close(params[name].grad, g, atol=2e-6, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
 
 
+def test_reward_ema_stats_on_the_simulator_match_reference_golden(on_simulator):
+    """keep_reward_ema_stats=True (reference dreamer4.py:5987-6013) through the real host class and learn.cu: two consecutive updates of
+    the reference on one dream (oracle/make_golden_learn_ema.py); lens / is_truncated vary per dream."""
+    from dreamer4_b200 import Actions, DynamicsWorldModel, Experience
+    fx = torch.load(os.path.join(HERE, 'golden', 'learn', 'learn_ema.pt'), map_location='cpu', weights_only=False)
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    e = fx['experience']
+    exp = Experience(latents=e['latents'], agent_embed=e['agent_embed'], rewards=e['rewards'], values=e['values'], actions=Actions(e['actions'], None),
+                     log_probs=Actions(e['log_probs'], None), lens=e['lens'], is_truncated=e['is_truncated'], terminals=e['terminals'],
+                     step_size=e['step_size'], old_action_unembeds=Actions(e['old_action_unembeds'], None))
+    params = dict(model.named_parameters())
+    try:
+        for call in fx['calls']:
+            model.zero_grad()
+            pl, vl = model.learn_from_experience(exp, objective=call['objective'])
+            torch.testing.assert_close(model.ema_returns_mean, call['ema_returns_mean'], atol=1e-6, rtol=1e-5)
+            torch.testing.assert_close(model.ema_returns_var, call['ema_returns_var'], atol=1e-6, rtol=1e-5)
+            torch.testing.assert_close(pl.detach(), call['policy_loss'], atol=1e-6, rtol=1e-4)
+            torch.testing.assert_close(vl.detach(), call['value_loss'], atol=1e-6, rtol=1e-4)
+            pl.backward()
+            vl.backward()
+            for name, g in call['grads'].items():
+                torch.testing.assert_close(params[name].grad, g, atol=2e-6, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
+    finally:
+        model._release()
+
+
 def test_sim_trainer_on_the_simulator(on_simulator):
     """SimTrainer (reference trainers.py:1472-1790) end to end on the toy image env: episodes through interact_with_env (d4_observe),
     combined, replayed in shuffled minibatches through d4_learn, both heads stepped.  The first minibatch's losses equal a direct

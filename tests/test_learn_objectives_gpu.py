@@ -111,3 +111,29 @@ def test_unknown_objective_and_missing_unembeds_fail_loudly():
     exp.old_action_unembeds = None
     with pytest.raises(AssertionError):
         model.learn_from_experience(exp, objective='pmpo')
+
+
+def test_reward_ema_stats_match_reference_golden():
+    """keep_reward_ema_stats=True (reference dreamer4.py:5987-6013) through the native path: two consecutive updates of the reference
+    on the same dream (oracle/make_golden_learn_ema.py) - losses, head gradients and the running statistics after each."""
+    from dreamer4_b200 import Actions, DynamicsWorldModel, Experience
+    fx = load(os.path.join(os.path.dirname(__file__), 'golden', 'learn', 'learn_ema.pt'))
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    model = model.cuda()
+    e = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in fx['experience'].items()}
+    exp = Experience(latents=e['latents'], agent_embed=e['agent_embed'], rewards=e['rewards'], values=e['values'], actions=Actions(e['actions'], None),
+                     log_probs=Actions(e['log_probs'], None), lens=e['lens'], is_truncated=e['is_truncated'], terminals=e['terminals'],
+                     step_size=e['step_size'], old_action_unembeds=Actions(e['old_action_unembeds'], None))
+    params = dict(model.named_parameters())
+    for call in fx['calls']:
+        model.zero_grad()
+        pl, vl = model.learn_from_experience(exp, objective=call['objective'])
+        torch.testing.assert_close(model.ema_returns_mean.cpu(), call['ema_returns_mean'], atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(model.ema_returns_var.cpu(), call['ema_returns_var'], atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(pl.detach().cpu(), call['policy_loss'], atol=1e-6, rtol=1e-4)
+        torch.testing.assert_close(vl.detach().cpu(), call['value_loss'], atol=1e-6, rtol=1e-4)
+        pl.backward()
+        vl.backward()
+        for name, g in call['grads'].items():
+            torch.testing.assert_close(params[name].grad.cpu(), g, atol=2e-6, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')

@@ -147,3 +147,26 @@ def test_cache_continuation_matches_reference():
         for (k, v), (rk, rv) in zip(cache, ref_kv):
             torch.testing.assert_close(k, rk, atol=2e-5, rtol=1e-4)
             torch.testing.assert_close(v, rv, atol=2e-5, rtol=1e-4)
+
+
+def test_learn_with_reward_ema_stats_matches_reference():
+    """keep_reward_ema_stats=True (D4:5987-6013): quantile-filtered running mean / variance of the returns normalise returns and old
+    values before the advantage.  Golden: two consecutive updates of the reference (oracle/make_golden_learn_ema.py)."""
+    fx = load(os.path.join(os.path.dirname(__file__), 'golden', 'learn', 'learn_ema.pt'))
+    mk = dict(fx['model_kwargs'])
+    cfg = O.config_from_reference_kwargs(**mk)
+    e = fx['experience']
+    exp = O.OracleExperience(latents=e['latents'], agent_embed=e['agent_embed'], rewards=e['rewards'], values=e['values'], actions=e['actions'],
+                             log_probs=e['log_probs'], lens=e['lens'], is_truncated=e['is_truncated'], terminals=e['terminals'],
+                             step_size=e['step_size'], old_action_unembeds=e['old_action_unembeds'])
+    ema = dict(mean=torch.tensor(0.), var=torch.tensor(1.), decay=mk['reward_ema_decay'], quantiles=mk['reward_quantile_filter'])
+    for call in fx['calls']:
+        sd = {k: v.clone().requires_grad_(v.is_floating_point() and k in call['grads']) for k, v in fx['state_dict'].items()}
+        pl, vl, _ = O.learn_from_experience(sd, cfg, exp, objective=call['objective'], ema_stats=ema)
+        torch.testing.assert_close(ema['mean'], call['ema_returns_mean'], atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(ema['var'], call['ema_returns_var'], atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(pl.detach(), call['policy_loss'], atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(vl.detach(), call['value_loss'], atol=1e-6, rtol=1e-5)
+        (pl + vl).backward()
+        for name, g in call['grads'].items():
+            torch.testing.assert_close(sd[name].grad, g, atol=1e-6, rtol=1e-4, msg=lambda m, n=name: f'{n}: {m}')

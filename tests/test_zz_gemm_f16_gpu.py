@@ -48,10 +48,12 @@ def test_linear_f16x3(M, N, K, act):
     bias, rs = torch.randn(N).cuda(), torch.rand(M).cuda() + 0.5
     nout = N // 2 if act else N
     res = torch.randn(M, nout).cuda() if not act else None
-    Cc = torch.full((M, nout), float('nan')).cuda()
+    ldc = (nout + 3) // 4 * 4                          # output rows are TMA-stored: 16-byte aligned
+    Cc = torch.full((M, ldc), float('nan')).cuda()
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     L.check(lib.d4_linear(D4_PREC_F16X3, M, N, K, L.ptr(A), K, L.ptr(hi), ldw, L.ptr(lo), L.ptr(bias), L.ptr(rs * inv_q), L.ptr(res),
-                          nout, act, L.ptr(Cc), nout, stream))
+                          nout, act, L.ptr(Cc), ldc, stream))
+    Cc = Cc[:, :nout]
     torch.cuda.synchronize()
     ref = (A.double() @ W.double().T) * rs.double()[:, None] + bias.double()
     if act:

@@ -127,8 +127,16 @@ def run_native(args):
     torch.cuda.set_device(dev)
 
     wl = WORKLOADS[args.workload]
-    B = args.batch or wl['batch']
     H = args.horizon or wl['horizon']
+    # BASELINE.json states config 4 as "64-step dream batch=2048 sharded 8xB200": the GLOBAL dream batch is fixed and split over the
+    # ranks (strong scaling, the default).  --scaling weak keeps the per-GPU batch fixed instead (round 1's measurement); with N > 1
+    # the strong run also reports a short weak-scaling measurement under "weak".
+    global_B = args.batch or wl['batch']
+    if args.scaling == 'strong':
+        assert global_B % world == 0, f'global dream batch {global_B} does not split over {world} ranks'
+        B = global_B // world
+    else:
+        B = global_B
     torch.manual_seed(0)
     model = DynamicsWorldModel(**wl['model'], precision=args.precision, time_attn_variant=args.variant).to(dev)
     lib = _lib.load()
@@ -136,7 +144,12 @@ def run_native(args):
     value_optim = torch.optim.AdamW(model.value_head_parameters(), lr=3e-4)
     head_params = model.policy_head_parameters() + model.value_head_parameters()
 
-    host_noise = make_noise(wl['model'], B, H, pinned=True)
+    # every rank draws the noise of the WHOLE global batch from the same seed and keeps its own shard: the dreams a rank imagines do
+    # not depend on how many ranks there are
+    host_noise = make_noise(wl['model'], B * world if args.scaling == 'strong' else B, H, pinned=False)
+    if args.scaling == 'strong' and world > 1:
+        host_noise = {k: (v[:, rank * B:(rank + 1) * B].contiguous() if k != 'terminal_uniform' else v) for k, v in host_noise.items()}
+    host_noise = {k: v.pin_memory() for k, v in host_noise.items()}
     dev_noise = {k: v.to(dev) for k, v in host_noise.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for k, v in host_noise.items() if k != 'terminal_uniform')
 
@@ -147,7 +160,7 @@ def run_native(args):
         ev.record()
         return ev
 
-    def step(e2e):
+    def step(e2e, host_noise=host_noise, dev_noise=dev_noise, B=B):
         ev = [mark()]
         noise = {k: v.to(dev, non_blocking=True) for k, v in host_noise.items()} if e2e else dev_noise
         exp = model.generate(H, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True,
@@ -173,7 +186,7 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(n, e2e, profile=False):
+    def timed(n, e2e, profile=False, step=step):
         barrier()
         if profile:
             _lib.check(lib.d4_profile(model._ctx, 1))
@@ -218,26 +231,44 @@ def run_native(args):
     if not args.no_profile:
         ms_prof, _, prof, _ = timed(1, e2e=False, profile=True)
 
+    # the other scaling regime, measured briefly in the same run (N > 1, strong default only): every rank takes the whole batch
+    weak = None
+    if args.scaling == 'strong' and world > 1 and not args.no_weak:
+        del dev_noise
+        model._release()
+        torch.cuda.empty_cache()
+        wn = make_noise(wl['model'], global_B, H, pinned=False)
+        wdev = {k: v.to(dev) for k, v in wn.items()}
+        wstep = lambda e2e: step(False, wn, wdev, global_B)
+        wstep(False)
+        ms_w, _, _, _ = timed(2, e2e=False, step=wstep)
+        weak = dict(scaling='weak', dreams_per_gpu=global_B, global_dreams=world * global_B, steps=2, warmup=1, ms_per_step=ms_w / 2,
+                    value=world * global_B * H * 2 / (ms_w / 1e3), unit=UNIT)
+        del wdev
+
     frames = world * B * H * args.steps
     value = frames / (ms / 1e3)
     e2e_value = frames / (ms_e2e / 1e3)
     pk = peaks()
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='tf32' if args.precision == 'tf32' else 'f32',
+                higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype='tf32' if args.precision == 'tf32' else 'f32',
                 data='synthetic', impl='native',
                 config=dict(workload=f'{args.workload}: BASELINE.json configs[{dict(config1=0, config2=1, config3=2, config4=3)[args.workload]}] model, '
-                                     f'{B} dreams x {H} frames per GPU, 4 denoise + 1 clean pass per frame, generate + learn_from_experience + AdamW',
+                                     f'{world * B} dreams x {H} frames' + (f' sharded over {world} GPUs ({B} per GPU)' if world > 1 else '') +
+                                     ', 4 denoise + 1 clean pass per frame, generate + learn_from_experience + AdamW',
                             dreams_per_gpu=B, horizon=H, global_dreams=world * B, precision=args.precision,
                             precision_note={'tf32x3': 'fp32 in / fp32 out; every dense product = 3 TF32 tensor-core MMAs (hi/lo split), fp32 accumulate: fp32-level accuracy',
                                             'fp32': 'exact fp32 FMA on CUDA cores', 'tf32': 'single-pass TF32 operands (reduced precision)',
-                                            'f16x3': 'EXPERIMENTAL: fp32 in / fp32 out; transformer dense products = 3 fp16 tensor-core MMAs (hi/lo split of '
-                                                     'power-of-two pre-scaled operands), fp32 accumulate; heads and learn on 3xTF32'}[args.precision],
+                                            'f16x3': 'fp32 in / fp32 out; transformer dense products = 3 fp16 tensor-core MMAs (hi/lo split of power-of-two pre-scaled operands), '
+                                                     'fp32 accumulate: fp32-level accuracy, sampled actions bit-exact vs the oracle over 64 frames at this width; heads and learn on 3xTF32'}[args.precision],
                             time_attn_variant=args.variant,
                             parallelism=f'dp{world} (dream batch sharded, one flat gradient all-reduce)',
                             l2='inputs larger than L2 (KV cache + activations per pass >> 126 MB)' if B * H >= 4096 else 'small problem: L2 resident'),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), clocks=clocks,
                 losses=dict(policy=float(last[0]), value=float(last[1])), peaks=pk['source'], phase_ms_per_step=phases)
+    if weak is not None:
+        line['weak'] = weak
     if prof is not None:
         names = ['gemm', 'time_attn', 'small_attn', 'other']
         total_ms = ms_prof
@@ -332,7 +363,7 @@ def run_reference(args):
     base = cpu_baseline(args, steps=args.steps, warmup=min(args.warmup, 1))
     ms = base['seconds'] / args.steps * 1e3
     line = dict(metric=METRIC, value=base['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=min(args.warmup, 1), ms_per_step=ms,
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
                 config=dict(workload=f'{args.workload} model, bounded CPU sample: {b} dreams x {h} frames per step', dreams=b, horizon=h),
                 cpu_baseline=dict(value=base['value'], unit=UNIT, cores=base['cores'], kind='port', sample=base['sample']),
                 e2e=dict(value=base['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -348,10 +379,14 @@ def main():
     ap.add_argument('--workload', default='config4', choices=list(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='dreams per GPU (default: the workload\'s)')
     ap.add_argument('--horizon', type=int, default=0)
-    ap.add_argument('--precision', default=os.environ.get('D4_BENCH_PRECISION', 'tf32x3'), choices=['fp32', 'tf32', 'tf32x3', 'f16x3'],
-                    help='tf32x3 (default): 3-term TF32 split on tcgen05, fp32-accurate; fp32: SIMT FMA; tf32: single-pass (reduced precision)')
+    ap.add_argument('--precision', default=os.environ.get('D4_BENCH_PRECISION', 'f16x3'), choices=['fp32', 'tf32', 'tf32x3', 'f16x3'],
+                    help='f16x3 (default): 3-term fp16 split of pre-scaled operands on tcgen05 kind::f16, fp32-accurate (held to the tf32x3 parity bars at '
+                         'the benchmark width and horizon, tests/test_horizon_parity_gpu.py); tf32x3: 3-term TF32 split; fp32: SIMT FMA; tf32: single pass (reduced precision)')
     ap.add_argument('--variant', type=int, default=1, help='K1 kernel variant (0 ld.global staged, 1 cp.async.bulk ring)')
     ap.add_argument('--cpu-sample', default='16x16', help='CPU baseline sample: dreams x frames')
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'],
+                    help='strong (default): --batch / the workload batch is the GLOBAL dream batch, sharded over the ranks; weak: per-GPU batch')
+    ap.add_argument('--no-weak', action='store_true', help='skip the extra weak-scaling measurement of a strong N > 1 run')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -119,8 +119,11 @@ SYMBOLS = {
     'd4_unpatchify_flow': (_i, [_i, _i, _i, _i, _i, _p, _p, _i64, _i64, _f, _p]),
     'd4_tok_assemble': (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p, _p]),
     'd4_tanh_rows': (_i, [_p, _i64, _p]),
+    'd4_pass_ex': (_i, [_p, _i, _p, _p, _p, _p, _i64, _p, _i, _i, _p, _p, _p]),
+    'd4_head_forward': (_i, [_p, _i, _p, _i, _p, _p]),
     'd4_graph_replays': (_i64, [_p]),
     'd4_debug_set': (_i, [C.c_char_p, _i]),
+    'd4_debug_get': (_i64, [_p, C.c_char_p]),
 }
 
 _lib = None

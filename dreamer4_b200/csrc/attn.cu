@@ -8,6 +8,7 @@
 //  time_attn_kernel  : K1, the time-decode attention of one new frame over the growing KV cache
 //      (query length 1 per (token, head); reference dreamer4.py:2021-2035, 2848, 3010).  HBM-bound: it streams
 //      2*t*d*4 bytes per (token, kv head) and appends the new key/value in place on the clean pass.
+#include <stdlib.h>
 #include "kernels.h"
 #include <float.h>
 
@@ -861,6 +862,9 @@ int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s) {
     if (a.nq == a.n && a.n <= 16 && a.n >= 1 &&
         ((a.q_sb | a.q_si | a.k_sb | a.k_sj | a.v_sb | a.v_sj | a.v0_sb | a.v0_sj) & 3) == 0 && al16p(a.q) && al16p(a.k) && al16p(a.v) &&
         (!a.v0 || al16p(a.v0)) && al16p(a.k_gamma)) {
+        static int space_v = -1;
+        if (space_v < 0) { const char* v = getenv("D4_SPACE_V"); space_v = v ? atoi(v) : 3; }      // 2: the shared-memory staged version (cross-check)
+        if (a.allow_tensor && space_v == 3 && d4_space_attn_reg_ok(a)) return d4_space_attn_reg(a, s);
         if (a.allow_tensor && a.d == 64 && (a.out_si & 1) == 0 && (a.out_sb & 1) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0)
             return launch_space_mma<64>(a, s);
         if (a.allow_tensor && a.d == 32 && (a.out_si & 1) == 0 && (a.out_sb & 1) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0)

@@ -36,6 +36,14 @@ extern "C" int d4_debug_set(const char* key, int value) {
     return d4_fail("d4_debug_set: unknown key '%s'", key);
 }
 extern "C" int64_t d4_graph_replays(const d4_ctx* c) { return c ? c->graph_replays : 0; }
+extern "C" int64_t d4_debug_get(const d4_ctx* c, const char* key) {
+    if (!c || !key) return -1;
+    if (!strcmp(key, "graph_enabled")) return c->use_graphs ? 1 : 0;
+    if (!strcmp(key, "graph_keys")) return (int64_t)c->graphs.size();
+    if (!strcmp(key, "graph_captured")) { int64_t n = 0; for (auto& kv : c->graphs) n += kv.second.exec != nullptr; return n; }
+    if (!strcmp(key, "graph_capture_refused")) { int64_t n = 0; for (auto& kv : c->graphs) n += kv.second.direct; return n; }
+    return -1;
+}
 
 #define D4_TRY(expr) do { int rc__ = (expr); if (rc__ != 0) return rc__; } while (0)
 
@@ -78,7 +86,8 @@ extern "C" int d4_ctx_create(const d4_config* cfg, d4_ctx** out) {
     { const char* f = getenv("D4_FUSE_POOLS"); c->fuse_pools = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_SPACE_MMA"); c->space_mma = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_FUSE_SS"); c->fuse_ss = f ? atoi(f) != 0 : true; }
-    { const char* f = getenv("D4_GRAPH"); c->use_graphs = f ? atoi(f) != 0 : false; }
+    { const char* f = getenv("D4_GRAPH"); c->use_graphs = f ? atoi(f) != 0 : true; }
+    { const char* f = getenv("D4_SKINNY"); c->skinny = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_GRAPH_MAX_ROWS"); if (f && atoi(f) > 0) c->graph_max_rows = atoi(f); }
     d4_engine_plan(c);
     *out = c;
@@ -88,9 +97,19 @@ static void drop_graphs(d4_ctx* c) {
     for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     c->graphs.clear();
 }
+// the engine's own capture / replay stream and the two events that order it against the caller's stream (any stream, the legacy
+// default stream included, which cannot itself be captured)
+static int graph_stream(d4_ctx* c) {
+    if (c->gstream) return 0;
+    D4_CUDA_OK(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
+    D4_CUDA_OK(cudaEventCreateWithFlags(&c->gev_in, cudaEventDisableTiming));
+    D4_CUDA_OK(cudaEventCreateWithFlags(&c->gev_out, cudaEventDisableTiming));
+    return 0;
+}
 extern "C" void d4_ctx_destroy(d4_ctx* ctx) {
     if (!ctx) return;
     drop_graphs(ctx);
+    if (ctx->gstream) { cudaStreamSynchronize(ctx->gstream); cudaStreamDestroy(ctx->gstream); cudaEventDestroy(ctx->gev_in); cudaEventDestroy(ctx->gev_out); }
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& r : ctx->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     delete ctx;
@@ -337,7 +356,10 @@ int d4_engine_gemm(d4_ctx* c, GemmArgs g, const LinW& w, int force_fp32, cudaStr
     const int prec = force_fp32 ? D4_PREC_FP32 : c->cfg.precision;
     const int ph = d4_prof_begin(c, D4_CLS_GEMM, 2.0 * g.M * g.N * g.K, s);
     int rc;
-    if (prec == D4_PREC_F16X3 && w.h_hi && w.h_lo && d4_gemm_f16x3_supported(g, w.h_hi, w.h_lo)) {
+    if (c->skinny && d4_gemm_skinny_supported(g)) {
+        // a handful of rows (tiny batches; the B-row projections and heads of any batch <= 32): a weight stream, exact fp32
+        rc = d4_gemm_skinny(g, s);
+    } else if (prec == D4_PREC_F16X3 && w.h_hi && w.h_lo && d4_gemm_f16x3_supported(g, w.h_hi, w.h_lo)) {
         // fp16 3-term split on kind::f16 (gemm_f16.cu); the fp16 arrays share the fp32 weight's (N, ldw) shape
         g.W = static_cast<const float*>(w.h_hi); g.W_lo = static_cast<const float*>(w.h_lo);
         rc = d4_gemm_f16x3(g, w.h_scale, 0, s);
@@ -426,7 +448,8 @@ int run_ff(d4_ctx* c, const FFW& F, int M, const float* x, long long ldx, RowMap
 }
 
 int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, const int64_t* prev_actions, int64_t pa_stride,
-             const int64_t* tasks, int t, int commit, float* pred_out, float* agent_out, cudaStream_t s) {
+             const int64_t* tasks, int t, int commit, float* pred_out, float* agent_out, cudaStream_t s,
+             const int64_t* signal_rows = nullptr, const int64_t* step_rows = nullptr) {
     const int S = c->S, D = c->D, Dl = c->Dl, N = c->N, nsp = c->nsp, Dq = c->Dq, Dkv = c->Dkv, h = c->h, hq = c->hq, d = c->d, L = c->L;
     const int M = B * S;
     const long long MD = (long long)M * D;
@@ -475,6 +498,7 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
         a.prev_actions = reinterpret_cast<const long long*>(prev_actions); a.pa_stride = pa_stride;
         for (int i = 0; i < c->na; ++i) a.act_off[i] = c->act_off[i];
         a.task_emb = c->task_emb; a.tasks = (tasks && c->task_emb) ? reinterpret_cast<const long long*>(tasks) : nullptr;
+        a.signal_rows = reinterpret_cast<const long long*>(signal_rows); a.step_rows = reinterpret_cast<const long long*>(step_rows);
         D4_TRY(d4_assemble_tokens(a, s));
     }
     // RMS statistics.  Fused mode (CTA-pair tensor-core GEMMs, D <= 512 so a row spans at most two column tiles and the two
@@ -637,6 +661,28 @@ extern "C" int d4_pass(d4_ctx* c, int B, const float* latent, int signal_level, 
                     static_cast<cudaStream_t>(stream));
 }
 
+// d4_pass with per-dream signal levels / step sizes (DynamicsWorldModel.forward's (b, t) signal_levels and (b) step_sizes, reference
+// dreamer4.py:6912-6942): one frame of the inference branch
+extern "C" int d4_pass_ex(d4_ctx* c, int B, const float* latent, const int64_t* signal_levels, const int64_t* step_sizes_log2,
+                          const int64_t* prev_actions, int64_t pa_stride, const int64_t* tasks, int t, int commit_kv, float* pred_out,
+                          float* agent_out, void* stream) {
+    D4_TRY(check_ready(c, B, t));
+    if (!signal_levels || !step_sizes_log2) return d4_fail("d4_pass_ex: signal_levels and step_sizes_log2 (B) are required");
+    return run_pass(c, B, latent, 0, 0, prev_actions, pa_stride, tasks, t, commit_kv, pred_out, agent_out, static_cast<cudaStream_t>(stream),
+                    signal_levels, step_sizes_log2);
+}
+
+// A head MLP on caller rows (the modules the reference exposes as model.policy_head / model.value_head / the terminal head:
+// x-mlps create_mlp, reference dreamer4.py:4950-4956, 5083-5101): x (M, dim_in) -> out (M, dim_out), M <= max_batch rows per call.
+extern "C" int d4_head_forward(d4_ctx* c, int which, const float* x, int M, float* out, void* stream) {
+    if (!c || !x || !out) return d4_fail("d4_head_forward: null argument");
+    if (!c->bound || !c->ws) return d4_fail("d4_head_forward: context not ready (d4_bind / d4_set_buffers)");
+    const MlpW* m = which == 0 ? &c->policy : which == 1 ? &c->value : which == 2 ? &c->terminal : nullptr;
+    if (!m || m->layers == 0) return d4_fail("d4_head_forward: head %d is not part of this model", which);
+    if (M < 1 || M > c->cfg.max_batch) return d4_fail("d4_head_forward: %d rows outside 1..max_batch=%d", M, c->cfg.max_batch);
+    return d4_mlp_forward(c, *m, x, m->dims[0], M, c->b.hbuf0, c->b.hbuf1, out, m->dims[m->layers], which != 2, static_cast<cudaStream_t>(stream));
+}
+
 // One frame at cache position t: passes first_step..num_steps of the denoising schedule (the last one is the clean pass that
 // commits the frame's keys/values), then the heads.  first_step = 0 is d4_frame; first_step = num_steps is d4_observe, where
 // io->noise_latent already holds the clean latent and only that last pass runs.
@@ -744,17 +790,19 @@ static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_tem
     if (io->log_probs) { st.log_probs = g.logp; st.log_probs_bs = na; }
     if (io->logits) { st.logits = g.logits; st.logits_bs = A; }
     if (term) { st.lens = reinterpret_cast<int64_t*>(g.lens); st.terminals = g.terminals; }
-    if (!fg.exec) {           // second use: capture the frame on the staging rows, instantiate
+    D4_TRY(graph_stream(c));
+    cudaStream_t gs = c->gstream;
+    if (!fg.exec) {           // second use: capture the frame on the staging rows (on the engine's own stream), instantiate
         if (!c->bound || !c->ws) return frame_body(c, B, t, num_steps, discrete_temperature, io, stream, first_step);   // reports the error
         const long long l0 = d4_launches_;
-        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {      // e.g. the legacy default stream
+        if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
             fg.direct = true;
             return frame_body(c, B, t, num_steps, discrete_temperature, io, stream, first_step);
         }
-        const int rc = frame_body(c, B, t, num_steps, discrete_temperature, &st, stream, first_step);
+        const int rc = frame_body(c, B, t, num_steps, discrete_temperature, &st, gs, first_step);
         cudaGraph_t graph = nullptr;
-        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
         const long long captured = d4_launches_ - l0;
         d4_launches_ = l0;                                   // nothing ran yet
         if (rc != 0) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
@@ -764,7 +812,7 @@ static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_tem
         if (ie != cudaSuccess) { fg.exec = nullptr; cudaGetLastError(); return d4_fail("d4_frame: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
         fg.launches = captured;
     }
-    // copy in -> replay -> copy out, all on the caller's stream
+    // copy in (caller's stream) -> replay (engine's stream) -> copy out (caller's stream)
     D4_CUDA_OK(cudaMemcpyAsync(g.noise, io->noise_latent, (size_t)B * nl * 4, cudaMemcpyDeviceToDevice, s));
     if (io->action_uniform) D4_CUDA_OK(cudaMemcpyAsync(g.act_u, io->action_uniform, (size_t)B * A * 4, cudaMemcpyDeviceToDevice, s));
     if (io->terminal_uniform) D4_CUDA_OK(cudaMemcpyAsync(g.term_u, io->terminal_uniform, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
@@ -774,7 +822,13 @@ static int frame_impl(d4_ctx* c, int B, int t, int num_steps, float discrete_tem
         D4_CUDA_OK(cudaMemcpyAsync(g.lens, io->lens, (size_t)B * 8, cudaMemcpyDeviceToDevice, s));
         D4_CUDA_OK(cudaMemcpyAsync(g.terminals, io->terminals, (size_t)B, cudaMemcpyDeviceToDevice, s));
     }
-    D4_CUDA_OK(cudaGraphLaunch(fg.exec, s));
+    // the graph runs on the engine's stream between two events: after everything the caller has queued (inputs, the previous frame),
+    // before anything the caller queues next
+    D4_CUDA_OK(cudaEventRecord(c->gev_in, s));
+    D4_CUDA_OK(cudaStreamWaitEvent(gs, c->gev_in, 0));
+    D4_CUDA_OK(cudaGraphLaunch(fg.exec, gs));
+    D4_CUDA_OK(cudaEventRecord(c->gev_out, gs));
+    D4_CUDA_OK(cudaStreamWaitEvent(s, c->gev_out, 0));
     d4_launches_ += fg.launches; ++c->graph_replays;
     D4_CUDA_OK(rows_copy(io->latents, (size_t)io->latents_bs * 4, g.latents, nl * 4, nl * 4, B, s));
     if (io->agent_embed) D4_CUDA_OK(rows_copy(io->agent_embed, (size_t)io->agent_bs * 4, g.agent, (size_t)c->D * 4, (size_t)c->D * 4, B, s));
@@ -820,7 +874,7 @@ extern "C" int d4_linear(int precision, int M, int N, int K, const float* A, int
     GemmArgs g = gemm_args(A, lda, W, ldw, C, ldc, M, N, K);
     g.bias = bias; g.row_scale = row_scale; g.residual = residual; g.ldr = ldr; g.act = act; g.W_lo = W_lo;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (precision == D4_PREC_FP32) return d4_gemm_simt(g, s);
+    if (precision == D4_PREC_FP32) return d4_gemm_skinny_supported(g) ? d4_gemm_skinny(g, s) : d4_gemm_simt(g, s);      // <= 32 rows: the weight-streaming kernel
     if (precision == D4_PREC_F16X3) {          // experimental: W / W_lo point to fp16 (N, ldw) hi / lo words of weights pre-scaled to rms ~ 1
         if (!W_lo) return d4_fail("d4_linear: f16x3 needs W_lo");
         return d4_gemm_f16x3(g, 1.f, 0, s);    // the caller folds 1 / q into row_scale
@@ -874,6 +928,7 @@ extern "C" int d4_tf_create(const d4_tf_config* cfg, d4_ctx** out) {
     c->ldfa = round_up(c->Dq + c->hq, 4);
     c->ldlog = 4;
     c->fuse_pools = false; c->space_mma = false; c->fuse_ss = false; c->use_graphs = false;
+    { const char* f = getenv("D4_SKINNY"); c->skinny = f ? atoi(f) != 0 : true; }
     d4_engine_plan(c);
     *out = c;
     return 0;

@@ -66,18 +66,19 @@ struct d4_ctx {
     bool prof_on = false;
     bool fuse_ss = true;         // RMS statistics accumulated in the producing GEMM's epilogue (D4_FUSE_SS=0: separate row pass)
     bool space_mma = true;       // space attention on mma.sync 3xTF32 tiles in the tensor-core engine modes (D4_SPACE_MMA=0: FMA kernel)
+    bool skinny = true;          // GEMMs of <= 32 rows on the weight-streaming exact-fp32 kernel (gemm_skinny.cu); D4_SKINNY=0: the tile kernels
     bool fuse_pools = true;      // fused latent<->space pool kernels (fused_pools.cu); D4_FUSE_POOLS=0 keeps the GEMM + attention path
     // generic transformer context (d4_tf_create: the video tokenizer's encoder / decoder): S tokens per frame of which the last
     // tf_ns are special, final RMSNorm; uses attn / ff / pools / pool_final / fa / fa_ff / vr_w / inv_freq and the buffers below
     bool tf_mode = false; int tf_ns = 1; int tf_final_norm = 0; const float* tf_final_norm_w = nullptr;
     struct { float *fa_q, *fa_att, *sp_rstd; } tfb = {};
 
-    // CUDA-graph replay of whole frames (D4_GRAPH=1, off by default; small batches are launch-bound: ~570 launches per imagined
-    // frame).  One instantiated graph per (entry point, B, t, num_steps, temperature, which optional io fields are present),
+    // CUDA-graph replay of whole frames (on by default for frames of <= graph_max_rows token rows, D4_GRAPH=0 disables; small
+    // batches are launch-bound: ~570 launches per imagined frame).  One instantiated graph per (entry point, B, t, num_steps, temperature, which optional io fields are present),
     // captured the SECOND time a key is seen (the first use runs directly, which also gets every lazy one-time setup out of
     // the way); the graph works on dense staging rows inside the workspace, copied in / out around the launch, so it does not
-    // depend on the caller's pointers.  Dropped whenever weights or buffers are re-registered.  The caller's stream must be
-    // capturable (not the legacy default stream): where cudaStreamBeginCapture refuses, the key stays on direct launches.
+    // depend on the caller's pointers.  Dropped whenever weights or buffers are re-registered.  Capture and replay run on a stream
+    // the engine owns, ordered against the caller's stream by two events, so the caller may use any stream (also the legacy default).
     bool use_graphs = false;
     int graph_max_rows = 4096;   // frames with more than this many token rows (B * S) always run directly
     struct GraphIO { float *noise, *act_u, *term_u, *latents, *agent, *rewards, *values, *logp, *logits;
@@ -85,6 +86,7 @@ struct d4_ctx {
     struct FrameGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; bool seen = false; bool direct = false; };   // direct: capture refused, keep launching
     std::map<std::array<long long, 6>, FrameGraph> graphs;
     long long graph_replays = 0;
+    cudaStream_t gstream = nullptr; cudaEvent_t gev_in = nullptr, gev_out = nullptr;    // capture / replay stream, ordered against the caller's by events
     struct ProfRec { cudaEvent_t a, b; int cls; double work; };
     std::vector<ProfRec> prof;          // records in use
     std::vector<ProfRec> prof_pool;     // created events, reused

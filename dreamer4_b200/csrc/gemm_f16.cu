@@ -500,6 +500,11 @@ int d4_gemm_f16x3(const GemmArgs& g, float w_scale, int bn, cudaStream_t stream)
     if (bn == 0) {
         const long long p128 = (long long)(g.N + 127) / 128 * 128, p256 = (long long)(g.N + 255) / 256 * 256;
         bn = (p128 * 10 < p256 * 9) ? 128 : 256;
+        // ... and when 256-wide tiles cannot even give every CTA pair one tile (small batches: M = 3840 rows at 256 dreams), as gemm_tc3.cu
+        static int clusters = 0;
+        if (!clusters) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); clusters = sms > 1 ? sms / 2 : 74; }
+        const long long mt = (g.M + 2 * BM - 1) / (2 * BM);
+        if (mt * (p256 / 256) < clusters && p128 / 128 > p256 / 256) bn = 128;
     }
     return bn == 256 ? launch_h<256>(g, w_scale, stream) : launch_h<128>(g, w_scale, stream);
 }

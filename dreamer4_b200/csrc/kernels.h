@@ -4,6 +4,9 @@
 
 // ---- GEMM (gemm_simt.cu / gemm_tc.cu)
 int d4_gemm_simt(const GemmArgs& g, cudaStream_t stream);
+// M <= 32 rows: exact-fp32 weight-streaming kernel (gemm_skinny.cu), N / 4 CTAs
+int d4_gemm_skinny(const GemmArgs& g, cudaStream_t stream);
+int d4_gemm_skinny_supported(const GemmArgs& g);
 // tcgen05 path: terms = 1 (tf32) or 3 (tf32x3 split: A split in shared memory, W_lo supplied)
 int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream);
 int d4_gemm_tc_supported(const GemmArgs& g);
@@ -28,6 +31,7 @@ struct AssembleArgs {
     const long long* prev_actions; long long pa_stride;   // (B, na) int64 rows with stride, nullptr at frame 0
     int act_off[8];
     const float* task_emb; const long long* tasks;
+    const long long* signal_rows; const long long* step_rows;   // optional (B): per-row signal level / log2 step size (override signal / step)
 };
 int d4_row_rstd(const float* x, long long ldx, RowMap map, int M, int D, float* out, cudaStream_t s);
 int d4_row_sumsq(const float* x, long long ldx, int M, int D, float* out, cudaStream_t s);     // out[m] = sum_d x[m][d]^2
@@ -68,6 +72,9 @@ struct SmallAttnArgs {
     int allow_tensor;       // space attention: 3xTF32 mma.sync tiles allowed (tf32x3 / tf32 engine modes); 0 = exact-fp32 FMA
 };
 int d4_small_attn(const SmallAttnArgs& a, cudaStream_t s);
+// space attention with every operand in registers as MMA fragments (space_attn.cu): head dim 64, S <= 16
+int d4_space_attn_reg(const SmallAttnArgs& a, cudaStream_t s);
+int d4_space_attn_reg_ok(const SmallAttnArgs& a);
 int d4_pool_attn_ok(const SmallAttnArgs& a);      // 1 if `a` takes the one-warp-per-token pool kernel (the only one that honours gate_w)
 
 // K1: time-decode attention over the in-place KV cache (+ append on the clean pass).

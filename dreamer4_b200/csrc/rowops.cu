@@ -84,9 +84,10 @@ __global__ void assemble_tokens_kernel(AssembleArgs a) {
         else { s = a.S - 1; kind = 3; }
         float* o = a.tokens + ((long long)b * a.S + s) * a.D;
         const int half = a.D >> 1;
+        const long long sig = a.signal_rows ? a.signal_rows[b] : a.signal, stp = a.step_rows ? a.step_rows[b] : a.step;
         for (int i = lane; i < a.D; i += 32) {
             float v;
-            if (kind == 0) v = (i < half) ? a.sig_emb[(long long)a.signal * half + i] : a.step_emb[(long long)a.step * half + (i - half)];
+            if (kind == 0) v = (i < half) ? a.sig_emb[sig * half + i] : a.step_emb[stp * half + (i - half)];
             else if (kind == 1) v = a.registers[(long long)(f - 1) * a.D + i];
             else if (kind == 2) {
                 if (a.prev_actions == nullptr) v = 0.f;

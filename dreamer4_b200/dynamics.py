@@ -102,6 +102,17 @@ class _Node(nn.Module):
     """Bare container used to reproduce the reference's state_dict key hierarchy."""
 
 
+class _HeadNode(_Node):
+    """`model.policy_head` / `model.value_head` / the terminal head as callables (the reference exposes them as nn.Modules and its
+    tests call them directly, e.g. `dynamics.policy_head(embeds.agent)`, tests/test_dreamer.py:1262): the MLP runs natively
+    (d4_head_forward); inference only - gradients of the heads come from learn_from_experience."""
+
+    def forward(self, x):
+        model, which = self._d4_model(), self._d4_which
+        assert model is not None, 'the owning DynamicsWorldModel is gone'
+        return model._head_forward(which, x)
+
+
 def _linear_w(out_f, in_f):
     w = torch.empty(out_f, in_f)
     nn.init.kaiming_uniform_(w, a=math.sqrt(5))
@@ -282,8 +293,14 @@ class DynamicsWorldModel(nn.Module):
                 self._reg(f'{p}.layers.{l}.1.bias', torch.zeros(dims[l + 1]))
 
     def _build_parameters(self):
+        import weakref
         c = self.cfg
         D, Dl, h, hq, d = c.dim, c.dim_latent, c.attn_heads, c.query_heads, c.attn_dim_head
+        for which, name in enumerate(('policy_head', 'value_head')):
+            node = _HeadNode()
+            object.__setattr__(node, '_d4_model', weakref.ref(self))
+            object.__setattr__(node, '_d4_which', which)
+            self.add_module(name, node)
         self._reg('register_tokens', torch.randn(c.num_register_tokens, D) * 1e-2)
         self._reg('agent_learned_embed', torch.randn(c.num_agents, D) * 1e-2)
         self._reg('action_learned_embed', torch.randn(c.num_agents, D) * 1e-2)
@@ -391,12 +408,14 @@ class DynamicsWorldModel(nn.Module):
         lib = _lib.load()
         c = self.cfg
         dev = self.device
-        if grow:
-            k = self._ctx_key
-            if self._ctx is not None and k[0] == batch and k[1] >= max_time and k[2:] == (agent_index, self.precision, self.time_attn_variant, dev.index):
-                max_time = k[1]
-            else:
-                max_time = (max_time + 63) // 64 * 64
+        # an existing context of the same batch whose KV capacity already covers max_time is kept (no re-allocation, captured frame
+        # graphs stay valid: env-style stepping alternates 1-frame resets with growing prompted calls); otherwise a new one is sized
+        # exactly (`grow` False: the DreamTrainer path keeps its exact-size KV buffer) or to the next multiple of 64 frames
+        k = self._ctx_key
+        if self._ctx is not None and k[0] == batch and k[1] >= max_time and k[2:] == (agent_index, self.precision, self.time_attn_variant, dev.index):
+            max_time = k[1]
+        elif grow:
+            max_time = (max_time + 63) // 64 * 64
         key = (batch, max_time, agent_index, self.precision, self.time_attn_variant, dev.index)
         if self._ctx is not None and self._ctx_key != key:
             self._release()
@@ -506,12 +525,147 @@ class DynamicsWorldModel(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         new.__dict__ = {k: (copy.deepcopy(self._NATIVE_STATE[k]) if k in self._NATIVE_STATE else copy.deepcopy(v, memo)) for k, v in self.__dict__.items()}
+        import weakref
+        for name in ('policy_head', 'value_head'):          # the callable heads point back at their owner
+            object.__setattr__(new._modules[name], '_d4_model', weakref.ref(new))
         return new
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         self._release()           # parameter storage moved: borrowed pointers are stale
         return out
+
+    @torch.no_grad()
+    def _head_forward(self, which, x):
+        """x (..., dim_in) -> (..., dim_out) through head `which` (0 policy, 1 value, 2 terminal) on the native MLP kernels."""
+        self._require_cuda()
+        c = self.cfg
+        assert c.has_actions or which == 2, 'the model has no policy / value head (no actions)'
+        dim_in = c.dim_latent if which == 2 else c.dim
+        dim_out = (4 * c.dim, c.value_num_bins, 1)[which]
+        assert x.shape[-1] == dim_in, f'head input has {x.shape[-1]} features, expected {dim_in}'
+        rows = x.reshape(-1, dim_in).to(device=self.device, dtype=torch.float32).contiguous()
+        lib, ctx = self._engine(*(self._ctx_key[:2] if self._ctx_key else (min(max(rows.shape[0], 1), 4096), 1)))
+        cap = self._ctx_key[0]
+        out = torch.empty(rows.shape[0], dim_out, device=self.device, dtype=torch.float32)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for r0 in range(0, rows.shape[0], cap):
+            m = min(cap, rows.shape[0] - r0)
+            check(lib.d4_head_forward(ctx, which, C.c_void_p(rows[r0:].data_ptr()), m, C.c_void_p(out[r0:].data_ptr()), stream))
+        return out.reshape(*x.shape[:-1], dim_out)
+
+    # ------------------------------------------------------------------ forward (inference branch)
+
+    @torch.no_grad()
+    def forward(self, *, video=None, latents=None, lens=None, signal_levels=None, step_sizes=None, step_sizes_log2=None, tasks=None,
+                rewards=None, terminals=None, discrete_actions=None, continuous_actions=None, shift_action_tokens=True, proprio=None,
+                time_cache=None, return_pred_only=False, latent_is_noised=False, return_all_losses=False, return_intermediates=False,
+                latent_has_view_dim=False, agent_index=0, seed=None, **unsupported):
+        """The inference branch of the reference's forward (dreamer4.py:6792-7295): `signal_levels` and a step size given, the
+        prediction (and with `return_intermediates` the agent embeddings and the time cache) returned - what `generate`,
+        `interact_with_env` and the reference's parallel-vs-sequential tests (tests/test_dreamer.py:1206-1296) call.  Runs frame by
+        frame over the in-place time-KV cache: time attention is causal, so a T-frame call equals the reference's uncached
+        multi-frame forward, and a call with `time_cache` continues at its cache position.
+
+        latents (b, t, n, d) [or (b, t, 1, n, d) with latent_has_view_dim]; signal_levels int | (b,) | (b, t); step_sizes /
+        step_sizes_log2 int | (b,); discrete_actions (b, t, na) | (b, t-1, na) | None, shifted as the reference does (:7105-7126).
+        Returns Predictions(flow (b, t, 1, n, d)) or (Predictions, (Embeds(agent (b, t, 1, D)), DynamicsIntermediates)).
+
+        The training branch (no signal_levels: flow / shortcut / reward / action losses, :7297-7743) is a "next" row."""
+        for name, v in dict(proprio=proprio, continuous_actions=continuous_actions, **unsupported).items():
+            if exists(v) and v is not False:
+                raise NotImplementedError(f'forward({name}=...) is outside the B200 hot path (SURVEY.md section 8)')
+        assert exists(video) ^ exists(latents)
+        if exists(video):
+            assert exists(self.video_tokenizer), 'video_tokenizer must be passed in if training from raw video on dynamics model'
+            latents = self.video_tokenizer.tokenize(video)
+        if not (exists(signal_levels) and (exists(step_sizes) or exists(step_sizes_log2))):
+            assert not (exists(signal_levels) ^ (exists(step_sizes) or exists(step_sizes_log2)))
+            raise NotImplementedError('forward() without signal_levels / step sizes is the world-model TRAINING branch (flow + shortcut + '
+                                      'reward / action losses, reference :7297-7743): a "next" row (SURVEY.md section 8f-4)')
+        if not (return_pred_only or latent_is_noised):
+            raise NotImplementedError('forward(return_pred_only=False, latent_is_noised=False) computes the training losses: a "next" row')
+        c = self.cfg
+        dev = self.device
+        if latents.ndim == 5:
+            assert latent_has_view_dim and latents.shape[2] == 1, 'multi-view latents are outside the B200 hot path'
+            latents = latents[:, :, 0]
+        assert tuple(latents.shape[-2:]) == self.latent_shape, f'latents must have shape {self.latent_shape}, got {tuple(latents.shape[-2:])}'
+        B, T = latents.shape[:2]
+        N, Dl, D, na = c.num_latent_tokens, c.dim_latent, c.dim, len(c.num_discrete_actions)
+        f32 = dict(device=dev, dtype=torch.float32)
+        latents = latents.to(**f32)
+
+        def per_batch(v, name):
+            v = torch.as_tensor(v, device=dev)
+            assert v.ndim <= 1, f'{name} must be a scalar or (b,)'
+            return v.expand(B) if v.ndim == 0 else v
+        sig = torch.as_tensor(signal_levels, device=dev)
+        sig = sig.expand(B) if sig.ndim == 0 else sig
+        sig = sig[:, None].expand(B, T) if sig.ndim == 1 else sig
+        assert tuple(sig.shape) == (B, T), f'signal_levels {tuple(sig.shape)}'
+        assert not (exists(step_sizes) and exists(step_sizes_log2))
+        if exists(step_sizes):                                   # reference :6936-6942
+            ss = per_batch(step_sizes, 'step_sizes').float()
+            log2 = torch.log2(ss)
+            step_log2 = log2.long()
+            assert bool((step_log2 == log2).all()), '`step_sizes` must be powers of 2'
+        else:
+            step_log2 = per_batch(step_sizes_log2, 'step_sizes_log2').long()
+        sig = sig.long().contiguous()
+        step_log2 = step_log2.contiguous()
+        assert int(sig.min()) >= 0 and int(sig.max()) < self.max_steps and int(step_log2.min()) >= 0 and \
+            int(step_log2.max()) < int(math.log2(self.max_steps)), 'signal level / step size outside the embedding tables'
+        if not latent_is_noised:                                 # reference :6990-7001: noise.lerp(latents, times), times = signal / max_steps
+            gen = torch.Generator(device=dev).manual_seed(seed) if exists(seed) else None
+            times = (sig.float() / self.max_steps)[..., None, None]
+            latents = torch.randn(latents.shape, generator=gen, **f32).lerp(latents, times)
+        latents = latents.contiguous()
+
+        # action tokens (reference :7088-7126): frame i is conditioned on `prev[i]` (None: the zero token)
+        prev = [None] * T
+        if exists(discrete_actions):
+            assert c.has_actions
+            acts = discrete_actions if discrete_actions.ndim == 3 else discrete_actions[..., None]
+            acts = acts.to(dev, torch.long).contiguous()
+            alen = acts.shape[1]
+            sequential = exists(time_cache) and T == 1 and alen == 1
+            if alen == T and shift_action_tokens and not sequential:
+                prev = [None] + [acts[:, i] for i in range(T - 1)]
+            elif alen == T - 1:
+                prev = [None] + [acts[:, i] for i in range(T - 1)]
+            else:
+                assert alen == T, f'discrete_actions cover {alen} steps for {T} frames'
+                prev = [acts[:, i] for i in range(T)]
+        if isinstance(tasks, int):
+            tasks = torch.full((B,), tasks, device=dev, dtype=torch.long)
+        if exists(tasks):
+            tasks = tasks.to(dev, torch.long).contiguous()
+
+        resumed_kv, t0 = None, 0
+        if exists(time_cache) and exists(time_cache.main):
+            resumed_kv, t0 = time_cache.main.next_kv_cache, time_cache.main.token_count
+        lib, ctx, kv = self._adopt_time_cache(resumed_kv, t0, B, t0 + T, agent_index, grow=True)
+        self._kv_epoch += 1
+        flow = torch.empty(B, T, N, Dl, **f32)
+        agent = torch.empty(B, T, D, **f32)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        for i in range(T):
+            frame, s_i = latents[:, i].contiguous(), sig[:, i].contiguous()
+            pa = prev[i].contiguous() if exists(prev[i]) else None
+            pred_i, agent_i = torch.empty(B, N, Dl, **f32), torch.empty(B, D, **f32)
+            check(lib.d4_pass_ex(ctx, B, ptr(frame), ptr(s_i), ptr(step_log2), ptr(pa), na, ptr(tasks), t0 + i, 1, ptr(pred_i), ptr(agent_i), stream))
+            flow[:, i], agent[:, i] = pred_i, agent_i
+        pred = Predictions(flow[:, :, None], None, None)
+        if not return_intermediates:
+            return pred
+        L = c.num_time_layers
+        next_kv = None
+        if L > 0:
+            next_kv = kv[:L, :, :, :, :t0 + T]
+            next_kv._d4_epoch = self._kv_epoch
+        inter = DynamicsIntermediates(main=TransformerIntermediates(next_kv_cache=next_kv, token_count=t0 + T))
+        return pred, (Embeds(agent=agent[:, :, None]), inter)
 
     # ------------------------------------------------------------------ generate
 

@@ -148,11 +148,25 @@ int d4_linear(int precision, int M, int N, int K, const float* A, int64_t lda, c
               const float* bias, const float* row_scale, const float* residual, int64_t ldr, int act,
               float* C, int64_t ldc, void* stream);
 
+/* d4_pass with per-dream conditioning: signal_levels (B) int64 in [0, max_steps), step_sizes_log2 (B) int64 - the (b, t) / (b)
+ * tensors DynamicsWorldModel.forward takes (D4:6792-6827, 6912-6942), one frame t of them per call.  Replaces one frame of the
+ * inference branch of DynamicsWorldModel.forward + get_prediction (D4:6792-7295) for latent_is_noised = True. */
+int d4_pass_ex(d4_ctx* ctx, int B, const float* latent, const int64_t* signal_levels, const int64_t* step_sizes_log2,
+               const int64_t* prev_actions, int64_t pa_stride, const int64_t* tasks, int t, int commit_kv, float* pred_out,
+               float* agent_out, void* stream);
+
+/* A head MLP on caller rows: which = 0 policy_head (D -> 4D), 1 value_head (D -> value bins), 2 terminal head (Dl -> 1); x (M, dim_in)
+ * contiguous, out (M, dim_out) contiguous, M <= max_batch.  Replaces calling the reference's head modules directly
+ * (e.g. dynamics.policy_head(embeds.agent), tests/test_dreamer.py:1262, x-mlps create_mlp D4:4950-4956). */
+int d4_head_forward(d4_ctx* ctx, int which, const float* x, int M, float* out, void* stream);
+
 /* ---- diagnostics (bench / profiling scripts and tests only).
  * d4_graph_replays: how many frames of this context ran as a CUDA-graph replay (0 = every frame was launched directly).
  * d4_debug_set: ablation switches of individual kernels, e.g. ("gemm_f16", bits) - results are garbage when set. */
 int64_t d4_graph_replays(const d4_ctx* ctx);
 int d4_debug_set(const char* key, int value);
+/* counters of a context: "graph_enabled", "graph_keys", "graph_captured", "graph_capture_refused"; -1 for an unknown key */
+int64_t d4_debug_get(const d4_ctx* ctx, const char* key);
 
 /* calc_gae (D4:1566-1600): returns = reverse-scan(delta, gamma*lambda*mask) + values.  masks/learn_masks uint8 (B,T). */
 int d4_gae(int B, int T, const float* rewards, const float* values, const uint8_t* masks, const uint8_t* learn_masks,

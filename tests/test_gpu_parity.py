@@ -144,7 +144,9 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-@pytest.mark.parametrize('M,N,K,act', [(64, 64, 32, 0), (200, 100, 52, 0), (130, 170, 32, 1), (77, 170, 33, 2), (1000, 1552, 512, 0)])
+@pytest.mark.parametrize('M,N,K,act', [(64, 64, 32, 0), (200, 100, 52, 0), (130, 170, 32, 1), (77, 170, 33, 2), (1000, 1552, 512, 0),
+                                      # <= 32 rows: the weight-streaming kernel (gemm_skinny.cu), every row-count template
+                                      (1, 4, 2048, 0), (3, 255, 512, 0), (8, 2730, 512, 1), (15, 1552, 512, 0), (15, 512, 1376, 0), (30, 514, 256, 2), (32, 2048, 2048, 0)])
 def test_linear_fp32(M, N, K, act):
     L, lib = _lib()
     torch.manual_seed(M + N)
@@ -188,8 +190,16 @@ def test_linear_tcgen05(M, N, K, act, grp, terms):
     res = torch.randn(M, nout).cuda() if not act else None
     Cc = torch.full((M, nout), float('nan')).cuda()
     if grp:
-        # engine-internal row map is not exposed by d4_linear: exercise it by a strided A (lda = S*K) per group member instead
-        pytest.skip('row-mapped A is covered by the engine-level parity tests')
+        # A through a grouped row map (compact row m -> token row (m / grp) * S + 1 + m % grp of the (M/grp, S, K) tensor), as the
+        # engine and the tokenizer feed it: d4_linear_rows (bias only)
+        L.check(lib.d4_linear_rows(1 if terms == 1 else 2, M, N, K, L.ptr(full), K, grp, S, 1, L.ptr(W if terms == 1 else hi), K,
+                                   L.ptr(lo) if terms == 3 else None, L.ptr(W), L.ptr(bias), L.ptr(Cc), nout, _stream()))
+        ref = A_ref.double() @ W.double().T + bias.double()
+        assert not torch.isnan(Cc).any()
+        tol = 4e-3 if terms == 1 else 1e-5 * max(1.0, K / 256)
+        err = (Cc.double() - ref).abs().max().item()
+        assert err < tol * max(1.0, ref.abs().max().item()), f'max abs err {err}'
+        return
     prec = 1 if terms == 1 else 2
     Wm = W if terms == 1 else hi
     L.check(lib.d4_linear(prec, M, N, K, L.ptr(full), K, L.ptr(Wm), K, L.ptr(lo) if terms == 3 else None, L.ptr(bias), L.ptr(rs), L.ptr(res),
@@ -347,7 +357,8 @@ def test_generate_midsize_tf32_single_pass():
 
 @pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
 def test_hundred_seeded_dream_steps_losses(precision):
-    """North star: actor/critic losses within 1e-4 relative of the reference over 100 seeded dream steps.
+    """North star: actor/critic losses within 1e-4 relative of the reference over 100 seeded dream steps (bar as tested: 1e-4
+    relative + a small absolute term, stated at the assertion).
 
     One DreamTrainer step (reference trainers.py:1416-1468) = generate(T+1) -> learn_from_experience -> backward ->
     clip(0.5) -> AdamW(3e-4) on the policy head, then on the value head.  Both arms start from the same weights, consume
@@ -402,17 +413,17 @@ def test_hundred_seeded_dream_steps_losses(precision):
         val_opt.step(); val_opt.zero_grad()
 
         assert torch.equal(exp.actions.discrete.cpu(), ref.actions), f'step {step}: sampled action indices diverged'
-        # the policy loss is a masked mean of O(1) terms (z-scored advantages x ratio) that nearly cancel, so its fp32
-        # evaluation carries an absolute error of a few 1e-7 whatever its own magnitude: tolerance 1e-4 relative + 2e-6
-        # (tf32x3: the heads' backward runs on 3xTF32 too, so the two free-running AdamW trajectories separate a little faster:
-        #  1e-4 relative + 1e-5; measured worst case 4.4e-6 absolute on a policy loss of -0.009 at step 19)
-        floor = 2e-2 if precision == 'fp32' else 1e-1
-        ep = abs(pl.item() - rpl.item()) / (abs(rpl.item()) + floor)
-        ev = abs(vl.item() - rvl.item()) / (abs(rvl.item()) + floor)
-        worst_p, worst_v = max(worst_p, ep), max(worst_v, ev)
-        assert ep < 1e-4, f'step {step}: policy loss {pl.item()} vs reference {rpl.item()} (rel {ep:.2e})'
-        assert ev < 1e-4, f'step {step}: value loss {vl.item()} vs reference {rvl.item()} (rel {ev:.2e})'
-    print(f'100 seeded dream steps: worst relative loss error policy {worst_p:.2e}, value {worst_v:.2e}')
+        # Stated bar: |loss - reference| <= 1e-4 * |reference| + abs, abs = 2e-6 (exact fp32) / 1e-5 (tf32x3).  The absolute term is
+        # there because the policy loss is a masked mean of O(1) terms (z-scored advantages x ratio) that nearly cancel: its fp32
+        # evaluation carries an absolute error of a few 1e-7 whatever its own magnitude, and it passes through zero during
+        # training.  (tf32x3: the heads' backward runs on 3xTF32 too, so the two free-running AdamW trajectories separate a little
+        # faster; measured worst case 4.4e-6 absolute on a policy loss of -0.009 at step 19.)
+        abs_tol = 2e-6 if precision == 'fp32' else 1e-5
+        dp, dv = abs(pl.item() - rpl.item()), abs(vl.item() - rvl.item())
+        worst_p, worst_v = max(worst_p, dp / (1e-4 * abs(rpl.item()) + abs_tol)), max(worst_v, dv / (1e-4 * abs(rvl.item()) + abs_tol))
+        assert dp <= 1e-4 * abs(rpl.item()) + abs_tol, f'step {step}: policy loss {pl.item()} vs reference {rpl.item()} (|diff| {dp:.2e})'
+        assert dv <= 1e-4 * abs(rvl.item()) + abs_tol, f'step {step}: value loss {vl.item()} vs reference {rvl.item()} (|diff| {dv:.2e})'
+    print(f'100 seeded dream steps: worst loss error as a fraction of the bar: policy {worst_p:.2f}, value {worst_v:.2f}')
 
 
 def test_learn_tf32x3_matches_oracle():

@@ -1,0 +1,103 @@
+"""Parity at the BENCHMARK's width AND horizon: the config-4 architecture (dim 512, depth 8, 64 x 32 latents; BASELINE.json configs[3]),
+64 frames, every engine precision, against the CPU oracle on the same injected noise - KV cache, sampled actions, heads, and the
+actor / critic update on the resulting dream.  20 dreams (300 token rows: the CTA-pair tensor-core GEMMs, the ring regime of the
+time-attention kernel at contexts up to 63 frames and rotary offsets up to 63 are all exercised inside the full engine).  The
+oracle rollout is computed once per module (~25-45 s of CPU).
+
+Bars: sampled action indices bit-exact over all 64 frames in every mode; floats 5e-5 + 2e-4 rel in exact fp32, 2e-4 + 2e-4 rel in
+the split tensor-core modes (logits 4e-4: this test scales the unembedding x30, logits reach +-10) - the same bars as the 3-frame
+test of tests/test_gpu_parity.py - except the KV cache in the split modes, 3e-4 + 2e-4 rel: keys carry a sqrt(d) = 8 gain (|k| up to
+~5) and over 39.3 M cached elements the tail of the tf32x3 error reaches 2.4e-4 (measured, round 2: ONE element beyond 2e-4)."""
+import pytest
+import torch
+
+from oracle import dreamer4_oracle as O
+import test_gpu_parity as G
+
+pytestmark = pytest.mark.gpu
+
+T, B = 64, 20
+
+
+@pytest.fixture(scope='module')
+def oracle_rollout():
+    from dreamer4_b200 import DynamicsWorldModel
+    kwargs = G.BASELINE_MODELS['config4_256px']
+    torch.manual_seed(21)
+    model = DynamicsWorldModel(**kwargs)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('gamma') or n.endswith('norm.weight') or n.endswith('norm_context.weight'):
+                p.add_(torch.randn_like(p) * 0.1)
+            if 'unembed' in n or n.endswith('queries') or 'learned_embed' in n or n == 'register_tokens':
+                p.mul_(30.)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ocfg = O.config_from_reference_kwargs(**kwargs)
+    noise = G.make_noise(model.cfg, T, B, seed=29)
+    ref = O.generate(sd, ocfg, T, B, noise=O.InjectedNoise(noise['latent'], noise['action_uniform'], noise['terminal_uniform']))
+    keys = [k for k in sd if k.startswith(('policy_head.', 'value_head.')) or k == 'action_embedder.discrete_action_unembed']
+    sdg = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd.items()}
+    rpl, rvl, _ = O.learn_from_experience(sdg, ocfg, ref)
+    (rpl + rvl).backward()
+    grads = {k: sdg[k].grad.detach().clone() for k in keys}
+    return kwargs, sd, noise, ref, rpl.detach(), rvl.detach(), grads
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'f16x3'])
+def test_config4_full_horizon_matches_oracle(oracle_rollout, precision):
+    from dreamer4_b200 import DynamicsWorldModel
+    kwargs, sd, noise, ref, rpl, rvl, rgrads = oracle_rollout
+    model = DynamicsWorldModel(**kwargs, precision=precision)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    exp, tc = model.generate(T, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True,
+                             return_time_cache=True, noise=G.to_cuda(noise))
+    agree = (exp.actions.discrete.cpu() == ref.actions).flatten(1).all(dim=1)
+    assert bool(agree.all()), f'{int((~agree).sum())} of {B} dreams sampled a different action somewhere in {T} frames'
+    ref_kv = torch.stack([torch.stack(layer) for layer in ref.kv_cache])
+    if precision == 'fp32':
+        G.compare_experience(exp, ref, tc.main.next_kv_cache, ref_kv)
+    else:
+        G.compare_experience(exp, ref, TOL=dict(atol=2e-4, rtol=2e-4), LOGIT_TOL=dict(atol=4e-4, rtol=2e-4))
+        torch.testing.assert_close(tc.main.next_kv_cache.cpu(), ref_kv, atol=3e-4, rtol=2e-4)
+    assert tc.main.token_count == T
+    pl, vl = model.learn_from_experience(exp)
+    torch.testing.assert_close(pl.detach().cpu(), rpl, atol=2e-6, rtol=1e-4)
+    torch.testing.assert_close(vl.detach().cpu(), rvl, atol=2e-6, rtol=1e-4)
+    pl.backward()
+    vl.backward()
+    params = dict(model.named_parameters())
+    gtol = dict(atol=2e-6, rtol=2e-4) if precision == 'fp32' else dict(atol=2e-5, rtol=2e-4)
+    for k, g in rgrads.items():
+        assert params[k].grad is not None, k
+        torch.testing.assert_close(params[k].grad.cpu(), g, msg=lambda m, n=k: f'{n}: {m}', **gtol)
+
+
+def test_full_size_rerun_is_bit_identical():
+    """The rollout is deterministic: two runs of the same 2048-dream batch on the same noise agree bit for bit in every output (the
+    only atomics on the path are the fused sums of squares, two partial sums per row that commute).  Measured on hardware in round 2
+    for tf32x3 and f16x3, with and without the fusion (scripts/determinism_check.py)."""
+    from bench import WORKLOADS
+    from dreamer4_b200 import DynamicsWorldModel
+    Bf, Hf = 2048, 8
+    cfgm = WORKLOADS['config4']['model']
+    torch.manual_seed(0)
+    model = DynamicsWorldModel(**cfgm)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'unembed' in n:
+                p.mul_(30.)
+    model = model.cuda()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    noise = dict(latent=torch.randn(Hf, Bf, cfgm['num_latent_tokens'], cfgm['dim_latent'], device='cuda', generator=g),
+                 action_uniform=torch.rand(Hf, Bf, cfgm['num_discrete_actions'], device='cuda', generator=g),
+                 terminal_uniform=torch.rand(Hf, Bf, device='cuda', generator=g))
+    flags = dict(return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True)
+    a = model.generate(Hf, batch_size=Bf, noise=noise, **flags)
+    keep = {k: getattr(a, k).clone() for k in ('latents', 'rewards', 'values', 'agent_embed')}
+    keep.update(actions=a.actions.discrete.clone(), log_probs=a.log_probs.discrete.clone(), logits=a.old_action_unembeds.discrete.clone())
+    b = model.generate(Hf, batch_size=Bf, noise=noise, **flags)
+    for k in ('latents', 'rewards', 'values', 'agent_embed'):
+        assert torch.equal(keep[k], getattr(b, k)), k
+    assert torch.equal(keep['actions'], b.actions.discrete) and torch.equal(keep['log_probs'], b.log_probs.discrete)
+    assert torch.equal(keep['logits'], b.old_action_unembeds.discrete)

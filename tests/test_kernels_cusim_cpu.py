@@ -36,7 +36,7 @@ def simlib(tmp_path_factory):
     from dreamer4_b200 import _lib
     build = tmp_path_factory.mktemp('cusim')
     srcs = []
-    for name in ('engine', 'learn', 'rowops', 'gemm_simt', 'frame_attn', 'tokenizer'):
+    for name in ('engine', 'learn', 'rowops', 'gemm_simt', 'gemm_skinny', 'frame_attn', 'tokenizer'):
         out = build / f'{name}.cpp'
         out.write_text(transform(open(os.path.join(CSRC, name + '.cu')).read()))
         srcs.append(str(out))
@@ -61,6 +61,9 @@ def on_simulator(simlib, monkeypatch):
     """Routes the host classes' native calls to the simulated library and lifts their CUDA-only guards."""
     from dreamer4_b200 import DynamicsWorldModel, VideoTokenizer, _lib
     monkeypatch.setattr(_lib, '_lib', simlib)
+    # the <= 32-row weight-streaming GEMM (one 128-thread block per 4 weight rows, 5-step shuffle trees) is slow to SIMULATE thread by
+    # thread: the engine-level tests keep the tile kernel, test_skinny_gemm_on_the_simulator below covers the kernel itself
+    monkeypatch.setenv('D4_SKINNY', '0')
     for cls in (DynamicsWorldModel, VideoTokenizer):
         monkeypatch.setattr(cls, '_require_cuda', lambda self: None)
     monkeypatch.setattr(VideoTokenizer, '_stream', lambda self: C.c_void_p(0))
@@ -72,6 +75,28 @@ def on_simulator(simlib, monkeypatch):
 
 def p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# ------------------------------------------------------------------------------------------------ gemm_skinny.cu
+
+@pytest.mark.parametrize('M,N,K,act,res', [(1, 8, 16, 0, False), (15, 40, 64, 0, True), (7, 24, 32, 1, False), (32, 10, 48, 0, True), (20, 6, 36, 2, False)])
+def test_skinny_gemm_on_the_simulator(simlib, M, N, K, act, res):
+    """d4_linear(fp32) with <= 32 rows takes gemm_skinny.cu: every row-count template, ragged N, GLU pairs, bias / row scale / residual."""
+    torch.manual_seed(M * 100 + N)
+    A, W = torch.randn(M, K), torch.randn(N, K) / K ** 0.5
+    bias, rs = torch.randn(N), torch.rand(M) + 0.5
+    nout = N // 2 if act else N
+    R = torch.randn(M, nout) if res else None
+    Cc = torch.full((M, nout), float('nan'))
+    rc = simlib.d4_linear(0, M, N, K, p(A), K, p(W), K, None, p(bias), p(rs), p(R), nout, act, p(Cc), nout, None)
+    assert rc == 0, simlib.d4_last_error()
+    ref = (A.double() @ W.double().T) * rs.double()[:, None] + bias.double()
+    if act:
+        x, g = ref[:, 0::2], ref[:, 1::2]
+        ref = x * (torch.nn.functional.silu(g) if act == 1 else torch.nn.functional.gelu(g))
+    elif res:
+        ref = ref + R.double()
+    torch.testing.assert_close(Cc.double(), ref, atol=1e-5, rtol=1e-5)
 
 
 # ------------------------------------------------------------------------------------------------ frame_attn.cu
@@ -323,6 +348,37 @@ def test_reward_ema_stats_on_the_simulator_match_reference_golden(on_simulator):
             vl.backward()
             for name, g in call['grads'].items():
                 torch.testing.assert_close(params[name].grad, g, atol=2e-6, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
+    finally:
+        model._release()
+
+
+def test_forward_inference_branch_on_the_simulator_matches_reference_golden(on_simulator):
+    """DynamicsWorldModel.forward (inference branch, reference dreamer4.py:6792-7295) through d4_pass_ex, and the head modules through
+    d4_head_forward, against the reference's own numbers (oracle/make_golden_forward.py): parallel 4-frame call with per-dream signal
+    levels / step sizes / actions / tasks, then the same frames one by one over the returned time cache."""
+    from dreamer4_b200 import DynamicsWorldModel
+    fx = torch.load(os.path.join(HERE, 'golden', 'forward', 'forward_inference.pt'), map_location='cpu', weights_only=False)
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    tol = dict(atol=5e-5, rtol=2e-4)
+    kw = dict(step_sizes=fx['step_sizes'], tasks=fx['tasks'], return_pred_only=True, return_intermediates=True, latent_is_noised=True)
+    try:
+        pred, (embeds, inter) = model(latents=fx['latents'], signal_levels=fx['signal_levels'], discrete_actions=fx['actions'], **kw)
+        torch.testing.assert_close(pred.flow, fx['flow'], **tol)
+        torch.testing.assert_close(embeds.agent, fx['agent'], **tol)
+        assert inter.main.token_count == fx['token_count']
+        torch.testing.assert_close(inter.main.next_kv_cache, fx['kv_cache'], **tol)
+        torch.testing.assert_close(model.policy_head(embeds.agent), fx['policy_embed'], **tol)
+        torch.testing.assert_close(model.value_head(embeds.agent), fx['value_bins'], **tol)
+        flows, agents, cache = [], [], None
+        for i in range(fx['latents'].shape[1]):
+            act = None if i == 0 else fx['actions'][:, i - 1:i]
+            p_i, (e_i, cache) = model(latents=fx['latents'][:, i:i + 1], signal_levels=fx['signal_levels'][:, i:i + 1], discrete_actions=act, time_cache=cache, **kw)
+            flows.append(p_i.flow.clone())
+            agents.append(e_i.agent.clone())
+        torch.testing.assert_close(torch.cat(flows, dim=1), fx['seq_flow'], **tol)
+        torch.testing.assert_close(torch.cat(agents, dim=1), fx['seq_agent'], **tol)
+        torch.testing.assert_close(cache.main.next_kv_cache, fx['seq_kv_cache'], **tol)
     finally:
         model._release()
 

@@ -137,7 +137,9 @@ def test_resume_across_capacity_growth_equals_one_shot():
     noise = to_cuda(make_noise(model.cfg, T, B, seed=31))
     one, tc_one = model.generate(T, batch_size=B, noise=noise, **FLAGS)
     one_kv = tc_one.main.next_kv_cache.clone()
+    model._release()                     # a context whose capacity already covers the call is reused: start over so that the 3-frame one is built
     head, tc = model.generate(P, batch_size=B, noise=noise, **FLAGS)
+    assert model._ctx_key[1] == P
     two, tc_two = model.generate(T, batch_size=B, noise=noise, time_cache=tc, prompt_latents=head.latents,
                                  prompt_discrete_actions=head.actions.discrete, prompt_rewards=head.rewards, **FLAGS)
     assert model._ctx_key[1] == 128

@@ -2,8 +2,7 @@
 chained calls against the oracle on the same injected draws; the oracle is pinned to the reference's own chained calls
 (tests/golden/cache/cache_continue.pt, tests/test_oracle_golden.py).
 
-STATUS: added after round 1's GPU budget was spent (host-side change only: the cached frames offset the cache position handed to
-d4_frame; verified on the CPU over the fake engine) - non-strict xfail until its first hardware run."""
+Green on hardware since the driver's round-1 run; strict since round 2."""
 import os
 
 import pytest
@@ -11,7 +10,7 @@ import torch
 
 from oracle import dreamer4_oracle as O
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='first hardware run pending (GPU budget of round 1 spent)')]
+pytestmark = pytest.mark.gpu
 
 
 def test_cache_continuation_matches_oracle():

@@ -1,12 +1,11 @@
 """CUDA-graph replay of frames (engine.cu: frame_impl, D4_GRAPH=1) on the GPU.
 
-STATUS: drafted in round 1 after the GPU budget was spent, never run on hardware (stream capture is outside the CPU simulator):
-non-strict xfail - it RUNS in the -m gpu suite and reports XPASS / XFAIL without gating it; the file sorts after the established
-tests.  The marker goes after the first run on a B200."""
+Strict since round 2: besides bit-equal rollouts and equal launch counts the test asserts that frames really were REPLAYED
+(d4_graph_replays), which a silent fall-back to direct launches would not satisfy."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='first hardware run pending (GPU budget of round 1 spent)')]
+pytestmark = pytest.mark.gpu
 
 
 # ------------------------------------------------------------------------------------------------ CUDA-graph replay of frames
@@ -33,6 +32,8 @@ def test_cuda_graph_replay_reproduces_direct_frames(monkeypatch):
         torch.cuda.synchronize()
         launches.append(lib.d4_launch_count() - l0)
     assert launches[0] == launches[1] == launches[2] > 0
+    # rollout 1 ran directly, rollout 2 captured each frame and replayed it, rollout 3 replayed: 2 * T graph launches
+    assert lib.d4_graph_replays(model._ctx) == 2 * T, f'{lib.d4_graph_replays(model._ctx)} graph replays, expected {2 * T}'
     for later in runs[1:]:
         assert torch.equal(later.actions.discrete, runs[0].actions.discrete)
         for name in ('latents', 'rewards', 'values', 'agent_embed'):

@@ -1,13 +1,8 @@
 """Video tokenizer on the GPU (dreamer4_b200/tokenizer.py -> d4_tf_step, frame_attn.cu, tokenizer.cu) against the reference's
 golden vectors and the CPU oracle, through the C-ABI.
 
-STATUS: drafted in round 1 after the GPU budget was spent - the CUDA side compiles for sm_100a and has never run on hardware.
-What IS verified, on the CPU: the host call sequence, the packed weights, engine.cu's d4_tf_step and the new kernels' device code
-reproduce these same golden vectors under the CUDA-thread simulator (tests/test_kernels_cusim_cpu.py); what is left for the
-hardware is the tensor-core GEMMs at the tokenizer's shapes / row maps, K1 at S = patches + latents rows, and launch limits.
-Hence the non-strict xfail: the tests RUN in the -m gpu suite and report XPASS / XFAIL without gating it; the file sorts after
-every established test (test_zy*) so that a fault here cannot take anything else with it.  The marker goes after the first run
-on a B200.
+Green on hardware since the driver's round-1 run (11 tests XPASSED first time: the CPU kernel simulator had de-risked them); strict
+since round 2.
 """
 import ctypes as C
 import glob
@@ -16,7 +11,7 @@ import os
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='first hardware run pending (GPU budget of round 1 spent)')]
+pytestmark = pytest.mark.gpu
 
 FIX = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'tokenizer', 'tokenizer_*.pt')))
 IDS = [os.path.basename(p)[:-3] for p in FIX]

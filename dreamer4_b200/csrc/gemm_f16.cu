@@ -91,7 +91,7 @@ struct EpiArgsH {
     int rs_mode, kdim;  // rs_mode 1: row_scale holds the sum of squares over kdim columns -> rsqrt(ss / kdim + eps); rows pre-scaled by 2^k
     float* ss_out;
     float w_scale;      // 1 / q of the pre-scaled weights
-    int dbg;            // ablation switches for scripts/gemm_bench.py (results are garbage when set): 1 no epilogue, 2 no split, 4 no MMA
+    int dbg;            // ablation switches for scripts/gemm_bench.py (results are garbage when set): 1 no epilogue, 2 no split, 4 no MMA, 8 / 16 same A / W tile
 };
 
 template <int BN> struct CfgH {
@@ -156,8 +156,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16x3_kernel(const __grid
         if (elect_one()) {
             uint32_t kc = 0;
             for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-                const int m0 = (t / e.n_tiles_n) * (2 * BM) + (int)rank * BM;
-                const int n0 = (t % e.n_tiles_n) * BN + (int)rank * K::BNH;
+                // dbg 8 / 16 (timing experiments): every cluster fetches the A / the W tile of tile 0 - how much of the data-movement
+                // floor is L2 slice bandwidth (identical lines requested by all SMs) and how much is delivery to the SMs
+                const int m0 = ((e.dbg & 8) ? 0 : (t / e.n_tiles_n) * (2 * BM)) + (int)rank * BM;
+                const int n0 = ((e.dbg & 16) ? 0 : (t % e.n_tiles_n) * BN) + (int)rank * K::BNH;
                 for (int kb = 0; kb < nkb; ++kb, ++kc) {
                     const int s = kc % NS; const uint32_t ph = (kc / NS) & 1;
                     mbar_wait(bar(B_EMPTY + s), ph ^ 1);
@@ -489,7 +491,7 @@ int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
 // 1 if the engine may route this GEMM here given the fp16 hi / lo arrays of its weight: the pair kernel's shapes (more rows than
 // one CTA's 128, like gemm_tc3.cu), whole 64-column K steps (K = dim, ff_inner_pad, pool width ... of every BASELINE config), and
 // the operand rules above.  g.W still points to the fp32 weight; only its leading dimension is read.
-void d4_gemm_f16_debug(int bits) { g_dbg = bits & 7; }
+void d4_gemm_f16_debug(int bits) { g_dbg = bits & 31; }
 int d4_gemm_f16x3_supported(const GemmArgs& g, const void* whi, const void* wlo) {
     return (g.M > BM && (g.K % 32) == 0 && g.K >= BK && operands_ok(g, whi, wlo)) ? 1 : 0;
 }

@@ -27,7 +27,9 @@ class MultiCategorical:
             lp = l.log_softmax(dim = -1)
             tgt = targets[..., i]
             tgt = tgt.expand(lp.shape[:-1])
-            out.append(lp.gather(-1, tgt[..., None])[..., 0])
+            # the world-model training branch hands in -1 sentinels at positions it masks out afterwards (dreamer4.py:7525, 7567): any
+            # in-range index does there, the value is discarded
+            out.append(lp.gather(-1, tgt.clamp(min = 0)[..., None])[..., 0])
         return torch.stack(out, dim = -1)
 
     def entropy(self):

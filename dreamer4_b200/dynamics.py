@@ -237,6 +237,12 @@ class DynamicsWorldModel(nn.Module):
         self.pmpo_pos_to_neg_weight, self.pmpo_reverse_kl = pmpo_pos_to_neg_weight, pmpo_reverse_kl     # reference :5227-5231
         self.pmpo_kl_div_loss_weight = pmpo_kl_div_loss_weight
         self.keep_reward_ema_stats, self.reward_ema_decay = keep_reward_ema_stats, reward_ema_decay      # reference :5238-5246
+        # knobs of the world-model training branch of forward() (reference :4698-4723, 4898, 5258-5263); forward-only here
+        self.loss_weight_fn = kwargs.get('loss_weight_fn', lambda times, slope=0.9, intercept=0.1: slope * times + intercept)     # ramp_weight (:897-899)
+        self.num_step_sizes_log2 = int(math.log2(max_steps))
+        self.prob_shortcut_train = default(kwargs.get('prob_shortcut_train'), 1. - self.num_step_sizes_log2 ** -1.)
+        self.latent_flow_loss_weight, self.shortcut_loss_weight = kwargs.get('latent_flow_loss_weight', 1.), kwargs.get('shortcut_loss_weight', 1.)
+        self._loss_weights = {k: kwargs.get(k, 1.) for k in ('reward_loss_weight', 'terminal_loss_weight', 'discrete_action_loss_weight', 'continuous_action_loss_weight')}
         self._reward_quantile_filter = tuple(float(q) for q in reward_quantile_filter)
         self.latent_shape = (num_latent_tokens, dim_latent)
         self._build_parameters()
@@ -310,7 +316,7 @@ class DynamicsWorldModel(nn.Module):
         self._reg('ema_returns_var', torch.ones(()), buffer=True)
         self._reg('reward_quantile_filter', torch.tensor(self._reward_quantile_filter), buffer=True, persistent=False)
         for name in ('reward_loss_weight', 'terminal_loss_weight', 'discrete_action_loss_weight', 'continuous_action_loss_weight'):
-            self._reg(name, torch.ones(()), buffer=True)
+            self._reg(name, torch.tensor(self._loss_weights[name], dtype=torch.float32), buffer=True)         # reference :5260-5263
         if c.same_len:          # reference dreamer4.py:4819-4834
             self._reg('latents_to_spatial_tokens.weight', _linear_w(D, Dl))
             self._reg('latents_to_spatial_tokens.bias', _linear_b(D, Dl))
@@ -572,6 +578,9 @@ class DynamicsWorldModel(nn.Module):
         Returns Predictions(flow (b, t, 1, n, d)) or (Predictions, (Embeds(agent (b, t, 1, D)), DynamicsIntermediates)).
 
         The training branch (no signal_levels: flow / shortcut / reward / action losses, :7297-7743) is a "next" row."""
+        unsupported_noise, unsupported_schedule = unsupported.pop('noise', None), unsupported.pop('train_schedule', None)      # injected draws (tests)
+        add_ar_action_loss = unsupported.pop('add_autoregressive_action_loss', True)
+        unsupported.pop('update_loss_ema', None)
         for name, v in dict(proprio=proprio, continuous_actions=continuous_actions, **unsupported).items():
             if exists(v) and v is not False:
                 raise NotImplementedError(f'forward({name}=...) is outside the B200 hot path (SURVEY.md section 8)')
@@ -579,12 +588,14 @@ class DynamicsWorldModel(nn.Module):
         if exists(video):
             assert exists(self.video_tokenizer), 'video_tokenizer must be passed in if training from raw video on dynamics model'
             latents = self.video_tokenizer.tokenize(video)
-        if not (exists(signal_levels) and (exists(step_sizes) or exists(step_sizes_log2))):
-            assert not (exists(signal_levels) ^ (exists(step_sizes) or exists(step_sizes_log2)))
-            raise NotImplementedError('forward() without signal_levels / step sizes is the world-model TRAINING branch (flow + shortcut + '
-                                      'reward / action losses, reference :7297-7743): a "next" row (SURVEY.md section 8f-4)')
-        if not (return_pred_only or latent_is_noised):
-            raise NotImplementedError('forward(return_pred_only=False, latent_is_noised=False) computes the training losses: a "next" row')
+        is_inference = exists(signal_levels)
+        assert not (exists(signal_levels) ^ (exists(step_sizes) or exists(step_sizes_log2))), 'signal_levels and a step size go together'
+        if not is_inference or not (return_pred_only or latent_is_noised):
+            return self._training_forward(latents, lens=lens, signal_levels=signal_levels, step_sizes=step_sizes, step_sizes_log2=step_sizes_log2,
+                                          tasks=tasks, rewards=rewards, terminals=terminals, discrete_actions=discrete_actions,
+                                          shift_action_tokens=shift_action_tokens, return_all_losses=return_all_losses, latent_has_view_dim=latent_has_view_dim,
+                                          agent_index=agent_index, seed=seed, noise=unsupported_noise, schedule=unsupported_schedule,
+                                          add_autoregressive_action_loss=add_ar_action_loss)
         c = self.cfg
         dev = self.device
         if latents.ndim == 5:
@@ -666,6 +677,213 @@ class DynamicsWorldModel(nn.Module):
             next_kv._d4_epoch = self._kv_epoch
         inter = DynamicsIntermediates(main=TransformerIntermediates(next_kv_cache=next_kv, token_count=t0 + T))
         return pred, (Embeds(agent=agent[:, :, None]), inter)
+
+    # ------------------------------------------------------------------ forward (training branch, forward only)
+
+    def _frames_pass(self, latents, sig, step_log2, prev, tasks, agent_index):
+        """One cache-less multi-frame forward: frames 0..T-1 of `latents` (b, t, n, d) at signal levels `sig` (b, t) through d4_pass_ex,
+        each committing its keys / values at cache position i (causal time attention = the reference's uncached parallel forward).
+        Returns (prediction (b, t, n, d), agent embeddings (b, t, D))."""
+        c = self.cfg
+        B, T = latents.shape[:2]
+        dev = self.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        lib, ctx, _ = self._adopt_time_cache(None, 0, B, T, agent_index, grow=True)
+        self._kv_epoch += 1
+        flow, agent = torch.empty(B, T, c.num_latent_tokens, c.dim_latent, **f32), torch.empty(B, T, c.dim, **f32)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        na = len(c.num_discrete_actions)
+        for i in range(T):
+            frame, s_i = latents[:, i].contiguous(), sig[:, i].contiguous()
+            pa = prev[i].contiguous() if exists(prev[i]) else None
+            pred_i, agent_i = torch.empty(B, c.num_latent_tokens, c.dim_latent, **f32), torch.empty(B, c.dim, **f32)
+            check(lib.d4_pass_ex(ctx, B, ptr(frame), ptr(s_i), ptr(step_log2), ptr(pa), na, ptr(tasks), i, 1, ptr(pred_i), ptr(agent_i), stream))
+            flow[:, i], agent[:, i] = pred_i, agent_i
+        return flow, agent
+
+    @torch.no_grad()
+    def _training_forward(self, latents, *, lens, signal_levels, step_sizes, step_sizes_log2, tasks, rewards, terminals, discrete_actions,
+                          shift_action_tokens, return_all_losses, latent_has_view_dim, agent_index, seed, noise, schedule,
+                          add_autoregressive_action_loss):
+        """World-model training losses, FORWARD ONLY (reference dreamer4.py:6963-6997, 7297-7743): flow loss with the
+        ramp weighting, shortcut (consistency) loss from two extra half-step passes, multi-token reward / discrete-action prediction
+        losses, terminal loss, and their weighted total.  The transformer passes - all of the arithmetic that matters - and the head
+        MLPs run on the native kernels (d4_pass_ex, d4_head_forward, d4_linear); the loss assembly on their (b, t, ...) outputs is a
+        handful of torch reductions.  No gradients: the returned scalars carry no autograd graph (the backward of the transformer is
+        outside this package).  `noise` / `train_schedule` (not in the reference) inject the random draws of the branch."""
+        from .experience import WorldModelLosses
+        c = self.cfg
+        dev = self.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        if latents.ndim == 5:
+            assert latent_has_view_dim and latents.shape[2] == 1, 'multi-view latents are outside the B200 hot path'
+            latents = latents[:, :, 0]
+        assert tuple(latents.shape[-2:]) == self.latent_shape, f'latents must have shape {self.latent_shape}, got {tuple(latents.shape[-2:])}'
+        latents = latents.to(**f32).contiguous()
+        B, T = latents.shape[:2]
+        N, Dl, D, na, K = c.num_latent_tokens, c.dim_latent, c.dim, len(c.num_discrete_actions), c.multi_token_pred_len
+        if exists(rewards):                                                           # reference :6897-6901
+            rewards = rewards.to(**f32)
+            if rewards.shape[1] == T - 1:
+                rewards = torch.nn.functional.pad(rewards, (1, 0), value=0.)
+            assert rewards.shape[1] == T, f'during training, rewards must perfectly align with video length {T}, got {rewards.shape[1]}'
+        if exists(terminals):
+            assert terminals.ndim == 2, 'terminals (b, t) or (b, t-1) per-frame flags (a (b,) tensor trips the reference at :6904 too)'
+            terminals = terminals.to(dev)
+            if terminals.shape[1] == T - 1:
+                terminals = torch.nn.functional.pad(terminals, (1, 0), value=False)
+        if isinstance(tasks, int):
+            tasks = torch.full((B,), tasks, device=dev, dtype=torch.long)
+        if exists(tasks):
+            tasks = tasks.to(dev, torch.long).contiguous()
+
+        # ---- signal levels and step sizes: given, injected, or drawn as the reference draws them (:6963-6979)
+        is_inference = exists(signal_levels)
+        gen = torch.Generator(device=dev).manual_seed(seed) if exists(seed) else None
+        shortcut_train = False
+        if is_inference:
+            sig = torch.as_tensor(signal_levels, device=dev)
+            sig = sig.expand(B) if sig.ndim == 0 else sig
+            sig = (sig[:, None].expand(B, T) if sig.ndim == 1 else sig).long()
+            if exists(step_sizes):
+                step_log2 = torch.log2(torch.as_tensor(step_sizes, device=dev).float()).long()
+            else:
+                step_log2 = torch.as_tensor(step_sizes_log2, device=dev).long()
+            step_log2 = step_log2.expand(B) if step_log2.ndim == 0 else step_log2
+        elif exists(schedule):
+            shortcut_train = bool(schedule['shortcut_train'])
+            step_log2, sig = schedule['step_sizes_log2'].to(dev).long(), schedule['signal_levels'].to(dev).long()
+        else:
+            shortcut_train = bool(torch.rand(1, device=dev, generator=gen).item() < self.prob_shortcut_train)
+            if shortcut_train:
+                step_log2 = torch.randint(1, self.num_step_sizes_log2, (B,), device=dev, generator=gen)
+                nss = 2 ** step_log2
+                sig = torch.randint(0, self.max_steps, (B, T), device=dev, generator=gen) // nss[:, None] * nss[:, None]
+            else:
+                step_log2 = torch.zeros(B, device=dev, dtype=torch.long)
+                sig = torch.randint(0, self.max_steps, (B, T), device=dev, generator=gen)
+        sig, step_log2 = sig.contiguous(), step_log2.contiguous()
+        times = sig.float() / self.max_steps                                           # (b, t)
+        t4 = times[..., None, None]
+        noise = noise.to(**f32) if exists(noise) else torch.randn(latents.shape, generator=gen, **f32)
+        noised = noise.lerp(latents, t4)                                               # :6995-7001
+
+        # ---- action tokens (:7088-7126) and the three passes
+        prev = [None] * T
+        acts = None
+        if exists(discrete_actions):
+            assert c.has_actions
+            acts = (discrete_actions if discrete_actions.ndim == 3 else discrete_actions[..., None]).to(dev, torch.long).contiguous()
+            alen = acts.shape[1]
+            if (alen == T and shift_action_tokens) or alen == T - 1:
+                prev = [None] + [acts[:, i] for i in range(T - 1)]
+            else:
+                assert alen == T, f'discrete_actions cover {alen} steps for {T} frames'
+                prev = [acts[:, i] for i in range(T)]
+        pred, agent = self._frames_pass(noised, sig, step_log2, prev, tasks, agent_index)
+        flow_losses = (pred - latents).square() * self.loss_weight_fn(times)[..., None, None]      # x-space: the target is the data (:7343-7350, 7413-7417)
+
+        shortcut_losses = None
+        if (not is_inference) and shortcut_train:                                       # :7354-7406
+            half_log2 = step_log2 - 1
+            half = 2 ** half_log2
+            first_pred, _ = self._frames_pass(noised, sig, half_log2, prev, tasks, agent_index)
+            first_flow = (first_pred - noised) / (1. - t4)
+            denoised = noised + first_flow * (half.float() / self.max_steps)[:, None, None, None]
+            sig2 = sig + half[:, None]
+            second_pred, _ = self._frames_pass(denoised, sig2.contiguous(), half_log2, prev, tasks, agent_index)
+            second_flow = (second_pred - denoised) / (1. - (sig2.float() / self.max_steps)[..., None, None])
+            target = (first_flow + second_flow) / 2
+            shortcut_pred = (pred - noised) / (1. - t4)
+            shortcut_losses = (shortcut_pred - target).square() * (1. - t4) ** 2
+
+        zero = torch.zeros((), **f32)
+        loss_mask = None
+        if exists(lens):                                                                # :7421-7433
+            loss_mask = torch.arange(T, device=dev)[None, :] < lens.to(dev)[:, None]
+            flow_loss = flow_losses[loss_mask].mean()
+            shortcut_loss = shortcut_losses[loss_mask].mean() if exists(shortcut_losses) else zero
+        else:
+            flow_loss = flow_losses.mean()
+            shortcut_loss = shortcut_losses.mean() if exists(shortcut_losses) else zero
+        mask_wo_last = loss_mask[:, :-1] if exists(loss_mask) else None
+
+        def mtp_targets(t, steps):                                                      # create_multi_token_prediction_targets (:530-552)
+            L = t.shape[1]
+            idx = torch.arange(L, device=dev)[:, None] + torch.arange(steps, device=dev)[None, :]
+            ok = idx < L
+            return t[:, idx.masked_fill(~ok, 0)], ok[None].expand(t.shape[0], -1, -1)
+
+        # ---- reward loss (:7447-7463): every prediction head on the agent token of the PREVIOUS frame against HL-Gauss(reward)
+        reward_loss = zero
+        if exists(rewards) and T > 1:
+            support, _ = hl_gauss_tables(*c.reward_range, c.reward_num_bins, dev)
+            sigma_sqrt2 = math.sqrt(2.) * c.hl_gauss_sigma_to_bin_ratio * (c.reward_range[1] - c.reward_range[0]) / c.reward_num_bins
+            cdf = torch.special.erf((support - rewards.clamp(*c.reward_range)[..., None]) / sigma_sqrt2)
+            two_hot = (cdf[..., 1:] - cdf[..., :-1]) / (cdf[..., -1] - cdf[..., 0]).clamp(min=c.hl_gauss_eps)[..., None]      # (b, t, bins)
+            rows = agent[:, :-1].reshape(-1, D).contiguous()
+            rstd = torch.rsqrt(rows.square().mean(dim=-1) + torch.finfo(torch.float32).eps).contiguous()
+            sd = dict(self.named_parameters())
+            logp = []
+            for e in range(K):                                                           # Ensemble of RMSNorm -> Linear (no bias), :5067-5075
+                w = (sd[f'to_reward_pred.nets.{e}.1.weight'] * sd[f'to_reward_pred.nets.{e}.0.weight'][None, :]).contiguous()
+                out = torch.empty(rows.shape[0], c.reward_num_bins, **f32)
+                check(_lib.load().d4_linear(0, rows.shape[0], c.reward_num_bins, D, ptr(rows), D, ptr(w), D, None, None, ptr(rstd), None, 0, 0, ptr(out),
+                                            c.reward_num_bins, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                logp.append(out.log_softmax(dim=-1).reshape(B, T - 1, -1))
+            logp = torch.stack(logp, dim=2)                                              # (b, t-1, mtp, bins)
+            tgt, ok = mtp_targets(two_hot[:, 1:], K)                                     # (b, t-1, mtp, bins), (b, t-1, mtp)
+            reward_losses = (-(tgt * logp).sum(dim=-1)).masked_fill(~ok, 0.)
+            reward_loss = reward_losses[mask_wo_last].mean(dim=0) if exists(loss_mask) else reward_losses.mean(dim=(0, 1))
+
+        # ---- terminal loss (:7467-7490)
+        terminal_loss = zero
+        if exists(terminals) and self.predict_terminals and T > 1:
+            pooled = latents[:, 1:].mean(dim=2)                                          # (b, t-1, d)
+            logit = self._head_forward(2, pooled)[..., 0]
+            eps_t = 1. - self.gae_discount_factor
+            tseq = terminals[:, 1:].float().clamp(min=eps_t, max=1. - eps_t)
+            tl = torch.nn.functional.binary_cross_entropy_with_logits(logit, tseq, reduction='none')
+            terminal_loss = tl[mask_wo_last].mean() if exists(loss_mask) else tl.mean()
+
+        # ---- autoregressive discrete-action loss (:7517-7590)
+        action_loss = zero
+        if exists(acts) and add_autoregressive_action_loss and T > 1 and c.num_agents == 1 and float(self.discrete_action_loss_weight.sum()) > 0:
+            padded = torch.nn.functional.pad(acts, (0, 0, 1, 0), value=-1) if shift_action_tokens else acts
+            plen = padded.shape[1]
+            num_targets = plen - 1 if shift_action_tokens else plen
+            pe = self._head_forward(0, agent[:, :num_targets])                           # (b, nt, 4D)
+            un = dict(self.named_parameters())['action_embedder.discrete_action_unembed']      # (A, mtp, 4D)
+            lib = _lib.load()
+            rows = pe.reshape(-1, pe.shape[-1]).contiguous()
+            tgt, ok = mtp_targets(padded, K)                                             # (b, plen, mtp, na)
+            if shift_action_tokens:
+                tgt, ok = tgt[:, 1:], ok[:, 1:]
+            lps = []
+            for e in range(K):
+                w = un[:, e].contiguous()
+                logits = torch.empty(rows.shape[0], c.total_actions, **f32)
+                check(lib.d4_linear(0, rows.shape[0], c.total_actions, rows.shape[1], ptr(rows), rows.shape[1], ptr(w), rows.shape[1], None, None, None, None,
+                                    0, 0, ptr(logits), c.total_actions, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                logits = logits.reshape(B, num_targets, -1)
+                per_type, off = [], 0
+                for ti, n in enumerate(c.num_discrete_actions):
+                    lp = logits[..., off:off + n].log_softmax(dim=-1)
+                    per_type.append(lp.gather(-1, tgt[:, :, e, ti].clamp(min=0)[..., None])[..., 0])
+                    off += n
+                lps.append(torch.stack(per_type, dim=-1))                                # (b, nt, na)
+            lps = torch.stack(lps, dim=0).masked_fill(~ok.permute(2, 0, 1)[..., None], 0.)      # (mtp, b, nt, na)
+            if exists(loss_mask):
+                am = mask_wo_last if plen == T - 1 else loss_mask
+                action_loss = (-lps).permute(1, 2, 3, 0)[am].mean(dim=(0, 1))
+            else:
+                action_loss = (-lps).mean(dim=(1, 2, 3))
+
+        total = (flow_loss * self.latent_flow_loss_weight + shortcut_loss * self.shortcut_loss_weight + (reward_loss * self.reward_loss_weight).sum() +
+                 terminal_loss * self.terminal_loss_weight + (action_loss * self.discrete_action_loss_weight).sum())
+        if not return_all_losses:
+            return total
+        return total, WorldModelLosses(flow_loss, shortcut_loss, reward_loss, terminal_loss, action_loss, *([zero] * 10))
 
     # ------------------------------------------------------------------ generate
 

@@ -17,6 +17,9 @@ Actions = namedtuple('Actions', ['discrete', 'continuous'])
 TransformerIntermediates = namedtuple('TransformerIntermediates', ['next_kv_cache', 'token_count'])
 DynamicsIntermediates = namedtuple('DynamicsIntermediates', ['main'])
 Predictions = namedtuple('Predictions', ['flow', 'proprioception', 'state'])              # reference dreamer4.py:128
+WorldModelLosses = namedtuple('WorldModelLosses', ('flow', 'shortcut', 'rewards', 'terminals', 'discrete_actions', 'continuous_actions', 'state_pred',
+                                                    'agent_state_pred', 'latent_ar', 'latent_ar_sigreg', 'lapo_action', 'lapo_fdm', 'lapo_raw_latent_fdm', 'tem',
+                                                    'h_net'))          # reference dreamer4.py:120
 Embeds = namedtuple('Embeds', ['agent', 'state_pred', 'actor', 'critic'], defaults=(None, None, None))    # reference dreamer4.py:130
 
 

@@ -63,7 +63,37 @@ def test_sequential_forward_over_the_time_cache_matches_parallel():
     assert torch.allclose(model.policy_head(par), model.policy_head(agent), atol=1e-4)
 
 
-def test_training_branch_is_refused_loudly():
+TRAIN = os.path.join(os.path.dirname(__file__), 'golden', 'forward', 'forward_training.pt')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('case', [0, 1, 2, 3], ids=['shortcut', 'shortcut_var_len', 'plain', 'plain_var_len'])
+def test_training_forward_losses_match_reference_golden(case, precision):
+    """The TRAINING branch of forward(), forward only (reference dreamer4.py:6963-6997, 7297-7743): flow, shortcut, multi-token reward /
+    discrete-action and terminal losses and their total against the reference's own numbers on the schedule and noise its seed produced
+    (oracle/make_golden_training_forward.py)."""
+    from dreamer4_b200 import DynamicsWorldModel
+    fx = torch.load(TRAIN, map_location='cpu', weights_only=False)
+    ref = fx['cases'][case]
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision=precision)
+    model.load_state_dict(fx['state_dict'], strict=True)
+    model = model.cuda()
+    cu = lambda t: t.cuda()
+    kw = dict(latents=cu(fx['latents']), rewards=cu(fx['rewards']), discrete_actions=cu(fx['actions']), terminals=cu(fx['terminals']), tasks=cu(fx['tasks']),
+              return_all_losses=True, noise=cu(ref['noise']),
+              train_schedule=dict(shortcut_train=ref['shortcut_train'], step_sizes_log2=cu(ref['step_sizes_log2']), signal_levels=cu(ref['signal_levels'])))
+    if ref['var_len']:
+        kw['lens'] = cu(fx['lens'])
+    total, losses = model(**kw)
+    rtol = 2e-4 if precision == 'fp32' else 1e-3
+    for name in ('flow', 'shortcut', 'rewards', 'terminals', 'discrete_actions'):
+        torch.testing.assert_close(getattr(losses, name).cpu(), ref['losses'][name], atol=5e-6, rtol=rtol, msg=lambda m, n=name: f'{n}: {m}')
+    torch.testing.assert_close(total.cpu(), ref['total'], atol=1e-5, rtol=rtol)
+
+
+def test_training_forward_draws_its_own_schedule():
+    """Without injected draws the branch samples the shortcut coin, step sizes, signal levels and noise itself (seeded): finite, repeatable."""
     fx, model = build()
-    with pytest.raises(NotImplementedError):
-        model(latents=fx['latents'].cuda())
+    kw = dict(latents=fx['latents'].cuda(), discrete_actions=fx['actions'].cuda(), tasks=fx['tasks'].cuda(), seed=7)
+    a, b = model(**kw), model(**kw)
+    assert a.ndim == 0 and bool(torch.isfinite(a)) and torch.equal(a, b)

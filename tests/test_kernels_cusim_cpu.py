@@ -383,6 +383,30 @@ def test_forward_inference_branch_on_the_simulator_matches_reference_golden(on_s
         model._release()
 
 
+@pytest.mark.parametrize('case', [0, 1, 2, 3], ids=['shortcut', 'shortcut_var_len', 'plain', 'plain_var_len'])
+def test_training_forward_losses_on_the_simulator_match_reference_golden(on_simulator, case):
+    """The TRAINING branch of DynamicsWorldModel.forward, forward only (reference dreamer4.py:6963-6997, 7297-7743): flow, shortcut,
+    multi-token reward / action and terminal losses and their total against the reference's own numbers, fed the schedule and the noise
+    the reference's seed produced (oracle/make_golden_training_forward.py)."""
+    from dreamer4_b200 import DynamicsWorldModel
+    fx = torch.load(os.path.join(HERE, 'golden', 'forward', 'forward_training.pt'), map_location='cpu', weights_only=False)
+    ref = fx['cases'][case]
+    model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+    model.load_state_dict(fx['state_dict'], strict=True)
+    try:
+        kw = dict(latents=fx['latents'], rewards=fx['rewards'], discrete_actions=fx['actions'], terminals=fx['terminals'], tasks=fx['tasks'], return_all_losses=True,
+                  noise=ref['noise'], train_schedule=dict(shortcut_train=ref['shortcut_train'], step_sizes_log2=ref['step_sizes_log2'], signal_levels=ref['signal_levels']))
+        if ref['var_len']:
+            kw['lens'] = fx['lens']
+        total, losses = model(**kw)
+    finally:
+        model._release()
+    for name in ('flow', 'shortcut', 'rewards', 'terminals', 'discrete_actions'):
+        torch.testing.assert_close(getattr(losses, name), ref['losses'][name], atol=2e-6, rtol=2e-4, msg=lambda m, n=name: f'{n}: {m}')
+    torch.testing.assert_close(total, ref['total'], atol=1e-5, rtol=1e-4)
+    assert bool(ref['shortcut_train']) == bool(float(losses.shortcut) > 0)
+
+
 def test_sim_trainer_on_the_simulator(on_simulator):
     """SimTrainer (reference trainers.py:1472-1790) end to end on the toy image env: episodes through interact_with_env (d4_observe),
     combined, replayed in shuffled minibatches through d4_learn, both heads stepped.  The first minibatch's losses equal a direct

@@ -288,19 +288,28 @@ def run_native(args):
                              note=f'{args.precision}: {terms} TF32-MMA unit(s) per algorithmic product; TF32 = half the bf16 rate')
         roof_attn = dict(bound='hbm', kernel='time_attn (K1, KV-cache decode)', achieved=attn_gbs, peak=pk['hbm'], unit='GB/s',
                          frac=attn_gbs / pk['hbm'], traffic=None, launches=int(prof[1][1]), share_of_step=shares['time_attn'],
-                         traffic_note='ncu dram bytes == algorithmic bytes at t=40 (profiles/r1a_ncu_k1_t40_raw.csv: 5.29 GB read per launch)')
-        # DRAM traffic of one representative launch of each kernel from the committed `ncu --set full` capture
+                         )
+        # DRAM traffic of one representative launch of each kernel from the committed `ncu --set full` capture (profiles/ncu_summary.json,
+        # scripts/gpu_profile_r2.sh).  The summary records the sha256 of the kernel sources it was captured from: a kernel that has
+        # changed since gets traffic = null instead of a stale number.
         summ_path = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
-        if os.path.exists(summ_path) and args.workload == 'config4' and B == WORKLOADS['config4']['batch']:
+        if os.path.exists(summ_path) and args.workload == 'config4' and B == WORKLOADS['config4']['batch'] and args.precision == 'f16x3':
+            import hashlib
             summ = json.load(open(summ_path))
-            k1 = summ['k1']
-            roof_attn.update(traffic=k1['dram_bytes'], traffic_launch=k1['launch'], traffic_algorithmic_bytes=k1['algorithmic_bytes'],
-                             traffic_source='profiles/r1_final_ncu_k1.csv')
-            ff = next((x for x in summ['gemm'] if 'feed-forward in' in x['layer']), None)
-            if ff:
+            shas = summ.get('kernel_sources_sha256', {})
+            cur = lambda rel: hashlib.sha256(open(os.path.join(ROOT, rel), 'rb').read()).hexdigest()[:16]
+            k1 = summ.get('k1')
+            if k1 and shas.get('k1') == cur('dreamer4_b200/csrc/attn_bulk.cu'):
+                roof_attn.update(traffic=k1['dram_bytes'], traffic_launch=k1['launch'], traffic_algorithmic_bytes=k1['algorithmic_bytes'],
+                                 traffic_source='profiles/r2_ncu_k1.csv')
+            else:
+                roof_attn.update(traffic_note='no ncu capture of the current attn_bulk.cu under profiles/')
+            ff = next((x for x in summ.get('gemm', []) if 'feed-forward in' in x['layer']), None)
+            if ff and shas.get('gemm') == cur('dreamer4_b200/csrc/gemm_f16.cu'):
                 roof_gemm.update(traffic=ff['dram_bytes'], traffic_launch=ff['layer'], tensor_pipe_active_pct_ncu=ff['tensor_pipe_active_pct'],
-                                 sm_clock_ghz_ncu=ff['sm_clock_ghz'], traffic_source='profiles/r1_final_ncu_gemm.csv')
-        roof_attn.pop('traffic_note', None) if roof_attn.get('traffic') else None
+                                 sm_clock_ghz_ncu=ff['sm_clock_ghz'], traffic_source='profiles/r2_ncu_gemm.csv')
+            else:
+                roof_gemm.update(traffic_note='no ncu capture of the current gemm_f16.cu under profiles/')
         line['roofline'] = roof_gemm if prof[0][0] >= prof[1][0] else roof_attn
         line['roofline_attn'] = roof_attn
         line['roofline_gemm'] = roof_gemm

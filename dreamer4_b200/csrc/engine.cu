@@ -89,6 +89,7 @@ extern "C" int d4_ctx_create(const d4_config* cfg, d4_ctx** out) {
     { const char* f = getenv("D4_GRAPH"); c->use_graphs = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_SKINNY"); c->skinny = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_GRAPH_MAX_ROWS"); if (f && atoi(f) > 0) c->graph_max_rows = atoi(f); }
+    { const char* f = getenv("D4_TRIM_FINAL"); c->trim_final = f ? atoi(f) != 0 : true; }
     d4_engine_plan(c);
     *out = c;
     return 0;
@@ -146,6 +147,8 @@ int d4_engine_plan(d4_ctx* c) {
         {&c->b.hbuf1, B * (long long)std::max(std::max(c->cfg.policy_hidden, c->cfg.value_hidden), std::max(c->cfg.terminal_hidden, 4))},
         {&c->b.logits, B * c->ldlog}, {&c->b.bins, B * (long long)std::max(std::max(c->cfg.reward_bins, c->cfg.value_bins), 4)},
         {&c->b.agent, B * c->D}, {&c->b.term_in, B * c->Dl},
+        {&c->b.fin_x, B * (long long)std::max(c->nsp, 1) * c->D}, {&c->b.fin_rstd, B * (long long)std::max(c->nsp, 1)},
+        {&c->b.fin_ctx_rs, (long long)c->n_hid * B * std::max(c->nsp, 1)},
     };
     for (auto& it : items) *it.p = reinterpret_cast<float*>(take(it.n));   // offsets for now; rebased in d4_set_buffers
     c->b.sizes_offs = reinterpret_cast<int*>(take(2 * D4_MAX_ACTION_TYPES));
@@ -435,6 +438,46 @@ int run_pool(d4_ctx* c, const PoolW& P, int M, const float* xq, const float* xq_
     return d4_engine_gemm(c, g, P.w_out, 0, s);
 }
 
+// run_pool for a SUBSET of token rows: the pool is per token (each token attends over its own history of hiddens), so a pass that
+// only reads some rows of the result - the 4 spatial tokens of every frame on a denoise pass, the agent token on the clean pass -
+// needs the keys / values of those rows only.  Rows = groups of `grp` tokens at offset `goff` of every frame; xq (B * grp, D) holds the
+// query rows compactly, the context rows are read from the snapshots through the same row map; out (B * grp, D) compact.
+int run_pool_rows(d4_ctx* c, const PoolW& P, int B, int grp, int goff, const float* xq, int ctx_ss, int n, float* out, cudaStream_t s) {
+    const int D = c->D, Dp = c->Dp, hp = c->hp, dp = c->dp, S = c->S;
+    const int Mq = B * grp;
+    const RowMap rows = rowmap(grp, S, goff);
+    D4_TRY(d4_row_rstd(xq, D, rowmap_identity(), Mq, D, c->b.fin_rstd, s));
+    SmallAttnArgs a; memset(&a, 0, sizeof(a));
+    a.nb = Mq; a.hkv = hp; a.g = 1; a.d = dp; a.nq = 1; a.n = n;
+    a.q = c->b.pool_qg; a.q_sb = c->ldpq; a.q_si = 0;
+    a.k = c->b.pool_kv; a.k_sb = 2 * Dp; a.k_sj = (long long)Mq * 2 * Dp;
+    a.v = c->b.pool_kv + Dp; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+    a.k_gamma = P.k_gamma;
+    a.out = c->b.pool_att; a.out_sb = Dp; a.out_si = 0;
+    a.scale = 1.f / sqrtf((float)dp);
+    a.gate_x = xq; a.gate_x_ld = D; a.gate_rstd = c->b.fin_rstd; a.gate_w = P.w_qg.w + (long long)Dp * D; a.gate_D = D; a.gate_rstd_is_ss = 0;
+    const bool gate_in_kernel = d4_pool_attn_ok(a) != 0;
+    if (!gate_in_kernel) {
+        a.gate_x = nullptr; a.gate_rstd = nullptr; a.gate_w = nullptr; a.gate_D = 0;
+        a.gate = c->b.pool_qg + Dp; a.gate_sb = c->ldpq; a.gate_si = 0;
+    }
+    {
+        GemmArgs g = gemm_args(xq, D, nullptr, D, c->b.pool_qg, c->ldpq, Mq, gate_in_kernel ? Dp : Dp + hp, D);
+        g.row_scale = c->b.fin_rstd;
+        D4_TRY(d4_engine_gemm(c, g, P.w_qg, 0, s));
+    }
+    {   // the statistics of the context rows, gathered next to their compact GEMM rows (row (j, b, i) of n x B x grp)
+        D4_TRY(d4_gather_rows(c->b.hid_rstd, 1, rows, (long long)n * Mq, 1, c->b.fin_ctx_rs, 1, s));
+        GemmArgs g = gemm_args(c->b.hid, D, nullptr, D, c->b.pool_kv, 2 * Dp, n * Mq, 2 * Dp, D);
+        g.amap = rows; g.row_scale = c->b.fin_ctx_rs; g.rs_mode = ctx_ss;
+        D4_TRY(d4_engine_gemm(c, g, P.w_kv, 0, s));
+    }
+    { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+    GemmArgs g = gemm_args(c->b.pool_att, Dp, nullptr, Dp, out, D, Mq, D, Dp);
+    g.residual = xq; g.ldr = D;
+    return d4_engine_gemm(c, g, P.w_out, 0, s);
+}
+
 int run_ff(d4_ctx* c, const FFW& F, int M, const float* x, long long ldx, RowMap xmap, const float* x_rstd, int x_ss, float* out, long long ldo, RowMap omap,
            float* ss_out, cudaStream_t s) {
     const int D = c->D;
@@ -445,6 +488,40 @@ int run_ff(d4_ctx* c, const FFW& F, int M, const float* x, long long ldx, RowMap
     g2.bias = F.b_out; g2.residual = x; g2.ldr = ldx; g2.cmap = omap; g2.ss_out = ss_out;
     // residual rows follow the output row map (x and out share their row layout in every use)
     return d4_engine_gemm(c, g2, F.w_out, 0, s);
+}
+
+// to_latent_pred after its first RMSNorm (the normed spatial tokens are in sp_n): Linear, or learned-query pool + Linear
+// (reference dreamer4.py:4830-4834, 7251)
+int finish_latent_pred(d4_ctx* c, int B, float* pred_out, cudaStream_t s) {
+    const int D = c->D, Dl = c->Dl, N = c->N, nsp = c->nsp, Dq = c->Dq, Dkv = c->Dkv, h = c->h, hq = c->hq, d = c->d;
+    const float att_scale = 1.f / sqrtf((float)d);
+    if (c->same_len) {
+        GemmArgs g = gemm_args(c->b.sp_n, D, nullptr, D, pred_out, Dl, B * N, Dl, D);
+        return d4_engine_gemm(c, g, c->lp_w, 0, s);
+    }
+    D4_TRY(d4_rmsnorm_rows(c->b.sp_n, D, rowmap_identity(), c->lp_norm_ctx, B * nsp, D, c->b.sp_n2, D, s));
+    GemmArgs g = gemm_args(c->b.sp_n2, D, nullptr, D, c->b.sp_kv, 2 * Dkv, B * nsp, 2 * Dkv, D);
+    D4_TRY(d4_engine_gemm(c, g, c->lp_w_kv, 0, s));
+    LpArgs pa; memset(&pa, 0, sizeof(pa));
+    pa.B = B; pa.N = N; pa.Dl = Dl; pa.nsp = nsp; pa.h = h; pa.hq = hq; pa.d = d;
+    pa.kv = c->b.sp_kv; pa.q = c->lp_q; pa.gate = c->lp_gate; pa.k_gamma = c->lp_k_gamma; pa.w_comb = c->lp_w_comb.w;
+    pa.pred = pred_out; pa.scale = att_scale;
+    if (c->fuse_pools && d4_lp_fused_supported(pa)) {
+        const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_lp_fused(pa, s); d4_prof_end(c, ph, s);
+        return rc;
+    }
+    SmallAttnArgs a; memset(&a, 0, sizeof(a));
+    a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = N; a.n = nsp;
+    a.q = c->lp_q; a.q_sb = 0; a.q_si = Dq;
+    a.k = c->b.sp_kv; a.k_sb = (long long)nsp * 2 * Dkv; a.k_sj = 2 * Dkv;
+    a.v = c->b.sp_kv + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+    a.k_gamma = c->lp_k_gamma;
+    a.gate = c->lp_gate; a.gate_sb = 0; a.gate_si = hq;
+    a.out = c->b.lp_att; a.out_sb = (long long)N * Dq; a.out_si = Dq;
+    a.scale = att_scale;
+    { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+    GemmArgs g2 = gemm_args(c->b.lp_att, Dq, nullptr, Dq, pred_out, Dl, B * N, Dl, Dq);
+    return d4_engine_gemm(c, g2, c->lp_w_comb, 0, s);
 }
 
 int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, const int64_t* prev_actions, int64_t pa_stride,
@@ -504,7 +581,11 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
     // RMS statistics.  Fused mode (CTA-pair tensor-core GEMMs, D <= 512 so a row spans at most two column tiles and the two
     // atomic partial sums commute): every GEMM that produces a residual-stream snapshot accumulates the rows' sums of squares in
     // its epilogue and every consumer turns them into rstd on the fly — no separate pass re-reads the 63 MB snapshots.
-    const int fss = (c->fuse_ss && d4_prec_split(c->cfg.precision) && M > 128 && D <= 512 && (D % 4) == 0 && d4_gemm_pair_default()) ? 1 : 0;
+    // ... which holds while the GEMMs that write D-wide rows use 256-wide tiles: small batches switch them to 128-wide tiles (four
+    // partial sums per row at D = 512, whose atomic order would make the rollout differ from run to run in the last bit) and keep the
+    // separate row passes instead.
+    const int fss = (c->fuse_ss && d4_prec_split(c->cfg.precision) && M > 128 && D <= 512 && (D % 4) == 0 && d4_gemm_pair_default() &&
+                     (D <= 256 || d4_gemm_pair_bn(M, D) == 256)) ? 1 : 0;
     auto xss = [&](int j) { return c->b.x_rstd + (long long)j * M; };
     if (fss) {
         D4_CUDA_OK(cudaMemsetAsync(hrs(1), 0, (size_t)(c->n_hid - 1) * M * 4, s));
@@ -575,6 +656,48 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
         }
     }
 
+    // ---- what follows the layers only matters for the rows a pass's outputs read: the agent token's cross attention + feed-forward
+    // and its row of the final pool on a pass that returns the agent embedding (the clean pass), the spatial tokens' rows of the
+    // final pool on a pass that returns the latent prediction (a denoise pass).  The final pool is per token and its K / V projection
+    // over all 2L+1 snapshots is the largest single GEMM of the pass (17 of the 80 pool units at depth 8): 4/15 resp. 1/15 of it.
+    const bool trim = c->trim_final && ((agent_out != nullptr) != (pred_out != nullptr));
+    if (trim && pred_out) {
+        float* xs = c->b.fin_x;
+        D4_TRY(d4_gather_rows(hid(2 * L), D, rowmap(nsp, S, 1), (long long)B * nsp, D, xs, D, s));
+        D4_TRY(run_pool_rows(c, c->pool_final, B, nsp, 1, xs, fss, c->n_hid, xs, s));
+        D4_TRY(d4_rmsnorm_rows(xs, D, rowmap_identity(), c->lp_norm0, B * nsp, D, c->b.sp_n, D, s));
+        return finish_latent_pred(c, B, pred_out, s);
+    }
+    if (trim && agent_out) {
+        float* xa = c->b.fin_x;
+        D4_TRY(d4_gather_rows(hid(2 * L), D, rowmap(1, S, S - 1), B, D, xa, D, s));
+        D4_TRY(d4_row_rstd(xa, D, rowmap_identity(), B, D, c->b.ag_rstd, s));
+        {
+            GemmArgs g = gemm_args(xa, D, nullptr, D, c->b.fa_q, c->ldfa, B, Dq + hq, D);
+            g.row_scale = c->b.ag_rstd;
+            D4_TRY(d4_engine_gemm(c, g, c->fa.w_qg, 0, s));
+            GemmArgs g2 = gemm_args(hid(2 * L), D, nullptr, D, c->b.fa_kv, 2 * Dkv, M, 2 * Dkv, D);
+            g2.row_scale = hrs(2 * L); g2.rs_mode = fss;
+            D4_TRY(d4_engine_gemm(c, g2, c->fa.w_kv, 0, s));
+            SmallAttnArgs a; memset(&a, 0, sizeof(a));
+            a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = 1; a.n = S - 1;
+            a.q = c->b.fa_q; a.q_sb = c->ldfa; a.q_si = 0;
+            a.k = c->b.fa_kv; a.k_sb = (long long)S * 2 * Dkv; a.k_sj = 2 * Dkv;
+            a.v = c->b.fa_kv + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
+            a.k_gamma = c->fa.k_gamma;
+            a.gate = c->b.fa_q + Dq; a.gate_sb = c->ldfa; a.gate_si = 0;
+            a.out = c->b.fa_att; a.out_sb = Dq; a.out_si = 0;
+            a.scale = att_scale;
+            { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+            GemmArgs g3 = gemm_args(c->b.fa_att, Dq, nullptr, Dq, xa, D, B, D, Dq);
+            g3.residual = xa; g3.ldr = D;
+            D4_TRY(d4_engine_gemm(c, g3, c->fa.w_out, 0, s));
+        }
+        D4_TRY(d4_row_rstd(xa, D, rowmap_identity(), B, D, c->b.ag_rstd, s));
+        D4_TRY(run_ff(c, c->fa_ff, B, xa, D, rowmap_identity(), c->b.ag_rstd, 0, xa, D, rowmap_identity(), nullptr, s));
+        return run_pool_rows(c, c->pool_final, B, 1, S - 1, xa, fss, c->n_hid, agent_out, s);
+    }
+
     // ---- final agent-token cross attention + feed-forward (reference dreamer4.py:3227-3238)
     float* xf = c->b.x_cur;
     D4_CUDA_OK(cudaMemcpyAsync(xf, hid(2 * L), MD * 4, cudaMemcpyDeviceToDevice, s));
@@ -611,34 +734,7 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
     if (agent_out) D4_TRY(d4_copy_rows(xf + (long long)(S - 1) * D, (long long)S * D, agent_out, D, B, D, s));
     if (pred_out) {
         D4_TRY(d4_rmsnorm_rows(xf, D, rowmap(nsp, S, 1), c->lp_norm0, B * nsp, D, c->b.sp_n, D, s));
-        if (c->same_len) {
-            GemmArgs g = gemm_args(c->b.sp_n, D, nullptr, D, pred_out, Dl, B * N, Dl, D);
-            D4_TRY(d4_engine_gemm(c, g, c->lp_w, 0, s));
-        } else {
-            D4_TRY(d4_rmsnorm_rows(c->b.sp_n, D, rowmap_identity(), c->lp_norm_ctx, B * nsp, D, c->b.sp_n2, D, s));
-            GemmArgs g = gemm_args(c->b.sp_n2, D, nullptr, D, c->b.sp_kv, 2 * Dkv, B * nsp, 2 * Dkv, D);
-            D4_TRY(d4_engine_gemm(c, g, c->lp_w_kv, 0, s));
-            LpArgs pa; memset(&pa, 0, sizeof(pa));
-            pa.B = B; pa.N = N; pa.Dl = Dl; pa.nsp = nsp; pa.h = h; pa.hq = hq; pa.d = d;
-            pa.kv = c->b.sp_kv; pa.q = c->lp_q; pa.gate = c->lp_gate; pa.k_gamma = c->lp_k_gamma; pa.w_comb = c->lp_w_comb.w;
-            pa.pred = pred_out; pa.scale = att_scale;
-            if (c->fuse_pools && d4_lp_fused_supported(pa)) {
-                const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_lp_fused(pa, s); d4_prof_end(c, ph, s); D4_TRY(rc);
-                return 0;
-            }
-            SmallAttnArgs a; memset(&a, 0, sizeof(a));
-            a.nb = B; a.hkv = h; a.g = hq / h; a.d = d; a.nq = N; a.n = nsp;
-            a.q = c->lp_q; a.q_sb = 0; a.q_si = Dq;
-            a.k = c->b.sp_kv; a.k_sb = (long long)nsp * 2 * Dkv; a.k_sj = 2 * Dkv;
-            a.v = c->b.sp_kv + Dkv; a.v_sb = a.k_sb; a.v_sj = a.k_sj;
-            a.k_gamma = c->lp_k_gamma;
-            a.gate = c->lp_gate; a.gate_sb = 0; a.gate_si = hq;
-            a.out = c->b.lp_att; a.out_sb = (long long)N * Dq; a.out_si = Dq;
-            a.scale = att_scale;
-            { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
-            GemmArgs g2 = gemm_args(c->b.lp_att, Dq, nullptr, Dq, pred_out, Dl, B * N, Dl, Dq);
-            D4_TRY(d4_engine_gemm(c, g2, c->lp_w_comb, 0, s));
-        }
+        return finish_latent_pred(c, B, pred_out, s);
     }
     return 0;
 }

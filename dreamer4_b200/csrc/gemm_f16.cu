@@ -499,14 +499,6 @@ int d4_gemm_f16x3_supported(const GemmArgs& g, const void* whi, const void* wlo)
 // g.W / g.W_lo point to fp16 arrays (N, ldw) holding hi = fp16(q W), lo = fp16(q W - hi); w_scale = 1 / q.  bn = 128 | 256 (0: by padding).
 int d4_gemm_f16x3(const GemmArgs& g, float w_scale, int bn, cudaStream_t stream) {
     if (!g.W_lo) return d4_fail("gemm_f16: needs the low fp16 words of W");
-    if (bn == 0) {
-        const long long p128 = (long long)(g.N + 127) / 128 * 128, p256 = (long long)(g.N + 255) / 256 * 256;
-        bn = (p128 * 10 < p256 * 9) ? 128 : 256;
-        // ... and when 256-wide tiles cannot even give every CTA pair one tile (small batches: M = 3840 rows at 256 dreams), as gemm_tc3.cu
-        static int clusters = 0;
-        if (!clusters) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); clusters = sms > 1 ? sms / 2 : 74; }
-        const long long mt = (g.M + 2 * BM - 1) / (2 * BM);
-        if (mt * (p256 / 256) < clusters && p128 / 128 > p256 / 256) bn = 128;
-    }
+    if (bn == 0) bn = d4_gemm_pair_bn(g.M, g.N);
     return bn == 256 ? launch_h<256>(g, w_scale, stream) : launch_h<128>(g, w_scale, stream);
 }

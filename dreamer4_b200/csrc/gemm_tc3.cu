@@ -493,19 +493,24 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
 
 }  // namespace
 
-// CTA-pair kernel entry; bn = 128 or 256 (0 = choose by padding waste)
+// The N-tile width both CTA-pair kernels (this one and gemm_f16.cu) use for an (M, N) product: 256-wide tiles unless the 128-wide one
+// saves more than 10 % of the (padded) columns (choosing 128 to smooth wave quantisation at N = 512 - 7 half-rounds instead of 4 full
+// ones - was measured SLOWER overall, 166 vs 205 TFLOP/s), and 128 when 256-wide tiles cannot even give every CTA pair one tile (small
+// batches: M = 3840 rows at 256 dreams).  The engine asks too: the fused sums of squares are only bit-reproducible while a row's
+// columns span at most TWO tiles (two atomic partial sums commute, four do not).
+int d4_gemm_pair_bn(int M, int N) {
+    const long long p128 = (long long)(N + 127) / 128 * 128, p256 = (long long)(N + 255) / 256 * 256;
+    int bn = (p128 * 10 < p256 * 9) ? 128 : 256;
+    static int clusters = 0;
+    if (!clusters) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); clusters = sms > 1 ? sms / 2 : 74; }
+    const long long mt = (M + 2 * BM - 1) / (2 * BM);
+    if (mt * (p256 / 256) < clusters && p128 / 128 > p256 / 256) bn = 128;
+    return bn;
+}
+
+// CTA-pair kernel entry; bn = 128 or 256 (0 = d4_gemm_pair_bn)
 int d4_gemm_tc3(const GemmArgs& g, int terms, int bn, cudaStream_t stream) {
-    if (bn == 0) {
-        // 256-wide tiles unless the 128-wide one saves more than 10 % of the (padded) columns.  Choosing 128 to smooth wave
-        // quantisation (N = 512: 7 half-rounds instead of 4 full ones) was measured SLOWER overall (166 vs 205 TFLOP/s).
-        const long long p128 = (long long)(g.N + 127) / 128 * 128, p256 = (long long)(g.N + 255) / 256 * 256;
-        bn = (p128 * 10 < p256 * 9) ? 128 : 256;
-        // ... and when 256-wide tiles cannot even give every CTA pair one tile (small batches: M = 3840 rows at 256 dreams)
-        static int clusters = 0;
-        if (!clusters) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); clusters = sms > 1 ? sms / 2 : 74; }
-        const long long mt = (g.M + 2 * BM - 1) / (2 * BM);
-        if (mt * (p256 / 256) < clusters && p128 / 128 > p256 / 256) bn = 128;
-    }
+    if (bn == 0) bn = d4_gemm_pair_bn(g.M, g.N);
     // K step 32 floats = one 128-byte swizzle row.  (A 16-float / SWIZZLE_64B step with twice the ring depth was measured
     // 1.9x SLOWER on every layer shape: the tensor core's operand fetch runs at half efficiency on 64-byte rows.)
     if (terms == 3) return bn == 256 ? launch3<3, 256, 32>(g, stream) : launch3<3, 128, 32>(g, stream);

@@ -11,6 +11,7 @@ int d4_gemm_skinny_supported(const GemmArgs& g);
 int d4_gemm_tc(const GemmArgs& g, int terms, cudaStream_t stream);
 int d4_gemm_tc_supported(const GemmArgs& g);
 int d4_gemm_pair_default(void);
+int d4_gemm_pair_bn(int M, int N);      // N-tile width (128 | 256) the CTA-pair kernels pick for an (M, N) product
 // persistent warp-specialised tcgen05 kernel (gemm_tc2.cu); bn = 128 / 256 / 0 (auto)
 int d4_gemm_tc2(const GemmArgs& g, int terms, int bn, cudaStream_t stream);
 // CTA-pair (cta_group::2) persistent kernel (gemm_tc3.cu): 256 x bn output tiles, bn = 128 / 256 / 0 (auto)
@@ -42,6 +43,7 @@ int d4_assemble_tokens(const AssembleArgs& a, cudaStream_t s);
 int d4_flow_step(float* x, const float* pred, long long n, float one_minus_tau, float dt, cudaStream_t s);
 int d4_store_latents(const float* x, float* out, int B, long long per_b, long long out_bstride, cudaStream_t s);
 int d4_copy_rows(const float* src, long long lds, float* dst, long long ldd, int M, int D, cudaStream_t s);
+int d4_gather_rows(const float* src, long long lds, RowMap map, long long M, int D, float* dst, long long ldd, cudaStream_t s);
 int d4_hl_gauss_decode(const float* logits, long long ld, int M, int K, const float* centers, float* out, long long out_stride, cudaStream_t s);
 int d4_sample_actions(const float* logits, long long ld, const float* u, long long ldu, int B, int na, const int* sizes_offs, float inv_temp,
                       long long* actions, long long act_stride, float* logp, long long lp_stride, cudaStream_t s);

@@ -131,6 +131,14 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long lds, f
     dst[m * ldd + c] = src[m * lds + c];
 }
 
+// dst[m, :] = src[map(m), :] (row gather through a grouped row map; D = 1 gathers a per-row statistic)
+__global__ void gather_rows_kernel(const float* __restrict__ src, long long lds, RowMap map, long long M, int D, float* __restrict__ dst, long long ldd) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * D) return;
+    const long long m = i / D, c = i % D;
+    dst[m * ldd + c] = src[map((int)m) * lds + c];
+}
+
 // HL-Gauss expectation: softmax(logits) . centers   (reference dreamer4.py:1094-1105 via hl_gauss transform_from_logits)
 __global__ void hl_gauss_decode_kernel(const float* __restrict__ logits, long long ld, int M, int K, const float* __restrict__ centers,
                                        float* __restrict__ out, long long out_stride) {
@@ -247,6 +255,11 @@ int d4_store_latents(const float* x, float* out, int B, long long per_b, long lo
 int d4_copy_rows(const float* src, long long lds, float* dst, long long ldd, int M, int D, cudaStream_t s) {
     if (M <= 0 || D <= 0) return 0;
     copy_rows_kernel<<<nblk((long long)M * D, 256), 256, 0, s>>>(src, lds, dst, ldd, M, D);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
+}
+int d4_gather_rows(const float* src, long long lds, RowMap map, long long M, int D, float* dst, long long ldd, cudaStream_t s) {
+    if (M <= 0 || D <= 0) return 0;
+    gather_rows_kernel<<<nblk(M * D, 256), 256, 0, s>>>(src, lds, map, M, D, dst, ldd);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_hl_gauss_decode(const float* logits, long long ld, int M, int K, const float* centers, float* out, long long out_stride, cudaStream_t s) {

@@ -20,6 +20,7 @@
 // Fused exactly as before: key RMS-norm (gain folded into Q), softclamp, agent-key mask, softmax, value-residual lerp, belief
 // projection out -= (out . vhat) vhat, per-head sigmoid gate.
 #include <float.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace {
@@ -57,8 +58,10 @@ __device__ __forceinline__ void load8(float (&dst)[8], const float* p, bool ok) 
     }
 }
 
-template <bool ONE_GROUP>      // one query head per kv head (no GQA): K / gain die after the scores, the compiler keeps everything in registers
-__global__ void __launch_bounds__(SPW * 32, 4) space_attn_reg_kernel(SmallAttnArgs a) {
+// ONE_GROUP: one query head per kv head (no GQA): K / gain die after the scores, the compiler keeps everything in registers.
+// MINB: resident CTAs per SM the register allocation is held to (4: 121 registers, no spills; 5: 96, 16 bytes; 6: 80, ~150 bytes).
+template <bool ONE_GROUP, int MINB>
+__global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAttnArgs a) {
     constexpr int D = 64;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * SPW + warp;
@@ -273,7 +276,12 @@ int d4_space_attn_reg_ok(const SmallAttnArgs& a) {
 int d4_space_attn_reg(const SmallAttnArgs& a, cudaStream_t s) {
     if (!d4_space_attn_reg_ok(a)) return d4_fail("space_attn_reg: shape / alignment not supported");
     const long long items = (long long)a.nb * a.hkv;
-    space_attn_reg_kernel<true><<<(unsigned)((items + SPW - 1) / SPW), SPW * 32, 0, s>>>(a);
+    static int minb = 0;
+    if (!minb) { const char* v = getenv("D4_SPACE_MINB"); minb = v ? atoi(v) : 4; }
+    const unsigned grid = (unsigned)((items + SPW - 1) / SPW);
+    if (minb == 6) space_attn_reg_kernel<true, 6><<<grid, SPW * 32, 0, s>>>(a);
+    else if (minb == 5) space_attn_reg_kernel<true, 5><<<grid, SPW * 32, 0, s>>>(a);
+    else space_attn_reg_kernel<true, 4><<<grid, SPW * 32, 0, s>>>(a);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
     return 0;
 }

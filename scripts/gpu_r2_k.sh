@@ -1,0 +1,15 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+run() { local name=$1; shift; echo "== $name"; timeout "$@" > "gpurun_out/r2k_$name.log" 2>&1; echo "rc=$? ($(tail -n 1 gpurun_out/r2k_$name.log | cut -c1-300))"; }
+run suite 900 python -m pytest tests -q -m gpu -rxXs
+run bench 500 python bench.py --no-cpu-baseline --no-profile --steps 2 --warmup 2
+export D4_TRIM_FINAL=0
+run bench_notrim 500 python bench.py --no-cpu-baseline --no-profile --steps 2 --warmup 2
+unset D4_TRIM_FINAL
+export D4_SPACE_MINB=5
+run bench_minb5 500 python bench.py --no-cpu-baseline --no-profile --steps 2 --warmup 2
+export D4_SPACE_MINB=6
+run bench_minb6 500 python bench.py --no-cpu-baseline --no-profile --steps 2 --warmup 2
+unset D4_SPACE_MINB
+run bench_b256 300 python bench.py --no-cpu-baseline --batch 256 --steps 4 --warmup 3 --no-profile

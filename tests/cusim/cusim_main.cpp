@@ -89,6 +89,7 @@ static void run(dim3 grid, dim3 block, const std::function<void()>& body) {
 // ---- tensor-core GEMMs: never reached in exact-fp32 mode
 int d4_gemm_tc_supported(const GemmArgs&) { return 0; }
 int d4_gemm_pair_default(void) { return 0; }
+int d4_gemm_pair_bn(int, int) { return 256; }
 int d4_gemm_tc(const GemmArgs&, int, cudaStream_t) { return d4_fail("cusim: tensor-core GEMM"); }
 int d4_gemm_tc2(const GemmArgs&, int, int, cudaStream_t) { return d4_fail("cusim: tensor-core GEMM"); }
 int d4_gemm_tc3(const GemmArgs&, int, int, cudaStream_t) { return d4_fail("cusim: tensor-core GEMM"); }

@@ -73,13 +73,14 @@ def test_config4_full_horizon_matches_oracle(oracle_rollout, precision):
         torch.testing.assert_close(params[k].grad.cpu(), g, msg=lambda m, n=k: f'{n}: {m}', **gtol)
 
 
-def test_full_size_rerun_is_bit_identical():
-    """The rollout is deterministic: two runs of the same 2048-dream batch on the same noise agree bit for bit in every output (the
-    only atomics on the path are the fused sums of squares, two partial sums per row that commute).  Measured on hardware in round 2
-    for tf32x3 and f16x3, with and without the fusion (scripts/determinism_check.py)."""
+@pytest.mark.parametrize('Bf,Hf', [(2048, 8), (256, 6), (40, 6)])
+def test_full_size_rerun_is_bit_identical(Bf, Hf):
+    """The rollout is deterministic: two runs of the same dream batch on the same noise agree bit for bit in every output (the only
+    atomics on the path are the fused sums of squares, two partial sums per row that commute; batches small enough for the GEMMs to
+    switch to 128-wide tiles - four partial sums per row - keep the separate row passes instead, engine.cu: fss).  Measured on hardware
+    in round 2 for tf32x3 and f16x3, with and without the fusion (scripts/determinism_check.py)."""
     from bench import WORKLOADS
     from dreamer4_b200 import DynamicsWorldModel
-    Bf, Hf = 2048, 8
     cfgm = WORKLOADS['config4']['model']
     torch.manual_seed(0)
     model = DynamicsWorldModel(**cfgm)
@@ -101,3 +102,31 @@ def test_full_size_rerun_is_bit_identical():
         assert torch.equal(keep[k], getattr(b, k)), k
     assert torch.equal(keep['actions'], b.actions.discrete) and torch.equal(keep['log_probs'], b.log_probs.discrete)
     assert torch.equal(keep['logits'], b.old_action_unembeds.discrete)
+
+
+@pytest.mark.parametrize('precision', ['tf32x3', 'f16x3'])
+def test_trimmed_final_pool_is_bit_identical_to_full(precision, monkeypatch):
+    """engine.cu computes the final attention-residual pool (the largest K / V projection of a pass) and the agent cross-attention only
+    for the token rows a pass's outputs read; the pool is per token, so the rollout must not change by a bit (D4_TRIM_FINAL=0: all rows)."""
+    from dreamer4_b200 import DynamicsWorldModel
+    kwargs = G.BASELINE_MODELS['config4_256px']
+    Tt, Bt = 4, 40
+    runs = []
+    for trim in ('1', '0'):
+        monkeypatch.setenv('D4_TRIM_FINAL', trim)
+        torch.manual_seed(21)
+        model = DynamicsWorldModel(**kwargs, precision=precision)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if 'unembed' in n:
+                    p.mul_(30.)
+        model = model.cuda()
+        noise = G.to_cuda(G.make_noise(model.cfg, Tt, Bt, seed=5))
+        e, tc = model.generate(Tt, batch_size=Bt, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True,
+                               return_time_cache=True, noise=noise)
+        runs.append((e, tc.main.next_kv_cache.clone()))
+    (a, akv), (b, bkv) = runs
+    assert torch.equal(a.actions.discrete, b.actions.discrete) and torch.equal(akv, bkv)
+    for name in ('latents', 'rewards', 'values', 'agent_embed'):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(a.old_action_unembeds.discrete, b.old_action_unembeds.discrete)

@@ -407,6 +407,31 @@ def test_training_forward_losses_on_the_simulator_match_reference_golden(on_simu
     assert bool(ref['shortcut_train']) == bool(float(losses.shortcut) > 0)
 
 
+def test_trimmed_final_pool_equals_full_on_the_simulator(on_simulator, monkeypatch):
+    """The final attention-residual pool (and the agent cross-attention) computed only for the token rows a pass's outputs read
+    (engine.cu: run_pool_rows, D4_TRIM_FINAL) gives bit-identical rollouts to computing every row - the pool is per token."""
+    from dreamer4_b200 import DynamicsWorldModel
+    fx = torch.load(GOLDEN[1], map_location='cpu', weights_only=False)
+    runs = []
+    for trim in ('1', '0'):
+        monkeypatch.setenv('D4_TRIM_FINAL', trim)
+        model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
+        model.load_state_dict(fx['state_dict'], strict=True)
+        T, B = 3, 2
+        g = torch.Generator().manual_seed(3)
+        A = sum(model.cfg.num_discrete_actions)
+        noise = dict(latent=torch.randn(T, B, model.cfg.num_latent_tokens, model.cfg.dim_latent, generator=g), action_uniform=torch.rand(T, B, A, generator=g),
+                     terminal_uniform=torch.rand(T, B, generator=g))
+        try:
+            runs.append(model.generate(T, batch_size=B, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True, noise=noise))
+        finally:
+            model._release()
+    a, b = runs
+    assert torch.equal(a.actions.discrete, b.actions.discrete)
+    for name in ('latents', 'rewards', 'values', 'agent_embed'):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
 def test_sim_trainer_on_the_simulator(on_simulator):
     """SimTrainer (reference trainers.py:1472-1790) end to end on the toy image env: episodes through interact_with_env (d4_observe),
     combined, replayed in shuffled minibatches through d4_learn, both heads stepped.  The first minibatch's losses equal a direct

@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) time_attn_bulk_kernel(TimeAttnA
 
     // producer side (lane 0): the next tile to request, as (stream, K/V phase, tile) plus its ring slot
     int p_item = first, p_ph = 0, p_ti = 0, p_slot = 0, p_idx = 0;
+    // stream -> (token, kv head): the launch may cover a subset of the token rows (a.tmap), e.g. the spatial tokens of every frame
+    auto stream_row = [&](int item) { const int mc = item / a.hkv; return (long long)a.tmap(mc) * a.hkv + (item - mc * a.hkv); };
     auto issue = [&]() {
-        const float* base = (p_ph == 0 ? a.kcache : a.vcache) + ((long long)p_item * a.Tmax + (long long)p_ti * TK) * D;
+        const float* base = (p_ph == 0 ? a.kcache : a.vcache) + (stream_row(p_item) * a.Tmax + (long long)p_ti * TK) * D;
         const uint32_t bytes = (uint32_t)min(TK, t - p_ti * TK) * D * 4;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&sm.bar[p_slot], bytes);
@@ -126,7 +128,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) time_attn_bulk_kernel(TimeAttnA
 
     using Raw = TbRaw<PPL, G>;
     auto load_raw = [&](int item, Raw& r) {
-        const int m = item / a.hkv, hk = item - m * a.hkv;
+        const int mc = item / a.hkv, hk = item - mc * a.hkv;
+        const int m = (int)a.tmap(mc);
         r.m = m; r.hk = hk;
         const float* row = a.qkvgm + (long long)m * a.ld;
         const float* v0r = a.v0 + (long long)m * a.ldv0 + hk * D;
@@ -306,8 +309,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) time_attn_bulk_kernel(TimeAttnA
             }
         }
         if (a.commit) {
-            float* kd = a.kcache + ((long long)item * a.Tmax + t) * D;
-            float* vd = a.vcache + ((long long)item * a.Tmax + t) * D;
+            float* kd = a.kcache + (((long long)m * a.hkv + hk) * a.Tmax + t) * D;
+            float* vd = a.vcache + (((long long)m * a.hkv + hk) * a.Tmax + t) * D;
 #pragma unroll
             for (int e = 0; e < PPL; ++e) {
                 const int p = lane + 32 * e;

@@ -90,6 +90,7 @@ extern "C" int d4_ctx_create(const d4_config* cfg, d4_ctx** out) {
     { const char* f = getenv("D4_SKINNY"); c->skinny = f ? atoi(f) != 0 : true; }
     { const char* f = getenv("D4_GRAPH_MAX_ROWS"); if (f && atoi(f) > 0) c->graph_max_rows = atoi(f); }
     { const char* f = getenv("D4_TRIM_FINAL"); c->trim_final = f ? atoi(f) != 0 : true; }
+    { const char* f = getenv("D4_TRIM_CONE"); c->trim_cone = f ? atoi(f) != 0 : true; }
     d4_engine_plan(c);
     *out = c;
     return 0;
@@ -148,7 +149,7 @@ int d4_engine_plan(d4_ctx* c) {
         {&c->b.logits, B * c->ldlog}, {&c->b.bins, B * (long long)std::max(std::max(c->cfg.reward_bins, c->cfg.value_bins), 4)},
         {&c->b.agent, B * c->D}, {&c->b.term_in, B * c->Dl},
         {&c->b.fin_x, B * (long long)std::max(c->nsp, 1) * c->D}, {&c->b.fin_rstd, B * (long long)std::max(c->nsp, 1)},
-        {&c->b.fin_ctx_rs, (long long)c->n_hid * B * std::max(c->nsp, 1)},
+        {&c->b.fin_ctx_rs, (long long)c->n_hid * B * std::max(c->nsp, 1)}, {&c->b.fin_rstd2, B * (long long)std::max(c->nsp, 1)},
     };
     for (auto& it : items) *it.p = reinterpret_cast<float*>(take(it.n));   // offsets for now; rebased in d4_set_buffers
     c->b.sizes_offs = reinterpret_cast<int*>(take(2 * D4_MAX_ACTION_TYPES));
@@ -440,13 +441,15 @@ int run_pool(d4_ctx* c, const PoolW& P, int M, const float* xq, const float* xq_
 
 // run_pool for a SUBSET of token rows: the pool is per token (each token attends over its own history of hiddens), so a pass that
 // only reads some rows of the result - the 4 spatial tokens of every frame on a denoise pass, the agent token on the clean pass -
-// needs the keys / values of those rows only.  Rows = groups of `grp` tokens at offset `goff` of every frame; xq (B * grp, D) holds the
-// query rows compactly, the context rows are read from the snapshots through the same row map; out (B * grp, D) compact.
-int run_pool_rows(d4_ctx* c, const PoolW& P, int B, int grp, int goff, const float* xq, int ctx_ss, int n, float* out, cudaStream_t s) {
+// needs the keys / values of those rows only.  Rows = groups of `grp` tokens at offset `goff` of every frame; the context rows are read
+// from the snapshots through that row map.  mapped = 0: xq and out hold the B * grp rows compactly; mapped = 1: xq and out are (B, S, D)
+// tensors and the rows sit at their place in them (the layers that run on a row subset, see run_pass).
+int run_pool_rows(d4_ctx* c, const PoolW& P, int B, int grp, int goff, const float* xq, int mapped, int ctx_ss, int n, float* out, cudaStream_t s) {
     const int D = c->D, Dp = c->Dp, hp = c->hp, dp = c->dp, S = c->S;
     const int Mq = B * grp;
     const RowMap rows = rowmap(grp, S, goff);
-    D4_TRY(d4_row_rstd(xq, D, rowmap_identity(), Mq, D, c->b.fin_rstd, s));
+    const RowMap io = mapped ? rows : rowmap_identity();
+    D4_TRY(d4_row_rstd(xq, D, io, Mq, D, c->b.fin_rstd, s));
     SmallAttnArgs a; memset(&a, 0, sizeof(a));
     a.nb = Mq; a.hkv = hp; a.g = 1; a.d = dp; a.nq = 1; a.n = n;
     a.q = c->b.pool_qg; a.q_sb = c->ldpq; a.q_si = 0;
@@ -456,14 +459,14 @@ int run_pool_rows(d4_ctx* c, const PoolW& P, int B, int grp, int goff, const flo
     a.out = c->b.pool_att; a.out_sb = Dp; a.out_si = 0;
     a.scale = 1.f / sqrtf((float)dp);
     a.gate_x = xq; a.gate_x_ld = D; a.gate_rstd = c->b.fin_rstd; a.gate_w = P.w_qg.w + (long long)Dp * D; a.gate_D = D; a.gate_rstd_is_ss = 0;
-    const bool gate_in_kernel = d4_pool_attn_ok(a) != 0;
+    const bool gate_in_kernel = !mapped && d4_pool_attn_ok(a) != 0;       // the in-kernel gate reads the query rows compactly
     if (!gate_in_kernel) {
         a.gate_x = nullptr; a.gate_rstd = nullptr; a.gate_w = nullptr; a.gate_D = 0;
         a.gate = c->b.pool_qg + Dp; a.gate_sb = c->ldpq; a.gate_si = 0;
     }
     {
         GemmArgs g = gemm_args(xq, D, nullptr, D, c->b.pool_qg, c->ldpq, Mq, gate_in_kernel ? Dp : Dp + hp, D);
-        g.row_scale = c->b.fin_rstd;
+        g.amap = io; g.row_scale = c->b.fin_rstd;
         D4_TRY(d4_engine_gemm(c, g, P.w_qg, 0, s));
     }
     {   // the statistics of the context rows, gathered next to their compact GEMM rows (row (j, b, i) of n x B x grp)
@@ -474,7 +477,7 @@ int run_pool_rows(d4_ctx* c, const PoolW& P, int B, int grp, int goff, const flo
     }
     { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
     GemmArgs g = gemm_args(c->b.pool_att, Dp, nullptr, Dp, out, D, Mq, D, Dp);
-    g.residual = xq; g.ldr = D;
+    g.residual = xq; g.ldr = D; g.cmap = io;          // residual rows follow the output row map
     return d4_engine_gemm(c, g, P.w_out, 0, s);
 }
 
@@ -601,25 +604,43 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
     }
 
     // ---- layers (reference dreamer4.py:3043-3223)
+    // A denoise pass returns the latent prediction only, which reads the nsp spatial tokens of the last hidden state.  Time attention,
+    // feed-forward and the attention-residual pools are per token; only space attention mixes the tokens of a frame.  So everything
+    // AFTER the attention of the last space layer `ls` is needed for the spatial rows R only: that layer's out-projection, feed-forward
+    // and pool, and every (time) layer after it completely - its fused projection, its time attention (K1 over the spatial tokens'
+    // streams only: 4/15 of the cache read) - run on B * nsp of the B * S rows, in place in the (B, S, .) buffers through row maps.  The
+    // snapshots of those steps are only valid at R, which is all the later pools read.  (The clean pass needs every row: it appends
+    // every token's keys / values and the agent token cross-attends to all of them.)
+    int ls = -1;
+    for (int i = 0; i < L; ++i) if (!c->is_time[i]) ls = i;
+    const bool cone = c->trim_final && c->trim_cone && pred_out && !agent_out && !commit && ls >= 0 && (32 % nsp) == 0 && c->cfg.time_attn_variant == 1;
+    const RowMap R = rowmap(nsp, S, 1);
+    const int Mr = B * nsp;
+    float* rs_c = c->b.fin_rstd2;                       // compact rstd of the current restricted GEMM input
+    auto stat_R = [&](const float* x, float* full) { return d4_row_stat_map(x, D, R, Mr, D, rs_c, full, fss, s); };
     const float* x_in = hid(0); const float* x_in_rstd = hrs(0);
     int ti = 0;
     for (int i = 0; i < L; ++i) {
+        const bool whole = cone && i > ls;              // the whole layer on R
+        const bool tail = cone && i >= ls;              // out-projection, feed-forward and pool on R
         {
-            GemmArgs g = gemm_args(x_in, D, nullptr, D, c->b.qkvgm, c->ldq, M, c->NQ, D);
-            g.row_scale = x_in_rstd; g.rs_mode = fss; g.bias = c->attn[i].b;
+            GemmArgs g = gemm_args(x_in, D, nullptr, D, c->b.qkvgm, c->ldq, whole ? Mr : M, c->NQ, D);
+            g.row_scale = whole ? rs_c : x_in_rstd; g.rs_mode = whole ? 0 : fss; g.bias = c->attn[i].b;
+            if (whole) { g.amap = R; g.cmap = R; }
             D4_TRY(d4_engine_gemm(c, g, c->attn[i].w, 0, s));
         }
         const int off_k = Dq, off_v = Dq + Dkv, off_g = Dq + 2 * Dkv, off_m = Dq + 2 * Dkv + hq;
         if (c->is_time[i]) {
             TimeAttnArgs a; memset(&a, 0, sizeof(a));
-            a.M = M; a.hkv = h; a.g = hq / h; a.d = d; a.t = t; a.Tmax = c->cfg.max_time;
+            a.M = whole ? Mr : M; a.hkv = h; a.g = hq / h; a.d = d; a.t = t; a.Tmax = c->cfg.max_time;
+            if (whole) a.tmap = R;
             a.qkvgm = c->b.qkvgm; a.ld = c->ldq; a.off_k = off_k; a.off_v = off_v; a.off_g = off_g; a.off_m = off_m;
             a.v0 = c->b.v0; a.ldv0 = Dkv; a.k_gamma = c->attn[i].k_gamma; a.inv_freq = c->inv_freq;
             const long long per = (long long)c->cfg.max_batch * S * h * c->cfg.max_time * d;
             a.kcache = c->kv + (long long)(ti * 2 + 0) * per; a.vcache = c->kv + (long long)(ti * 2 + 1) * per;
             a.out = c->b.attn_o; a.ldo = Dq; a.scale = att_scale; a.softclamp = c->cfg.softclamp; a.commit = commit;
             a.variant = c->cfg.time_attn_variant;
-            const double kbytes = (double)M * h * d * 4.0 * (2.0 * t + 4.0 + (commit ? 2.0 : 0.0));
+            const double kbytes = (double)a.M * h * d * 4.0 * (2.0 * t + 4.0 + (commit ? 2.0 : 0.0));
             const int ph = d4_prof_begin(c, D4_CLS_TIME_ATTN, kbytes, s);
             const int rc = d4_time_attn(a, s);
             d4_prof_end(c, ph, s);
@@ -639,6 +660,22 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
             a.scale = att_scale; a.softclamp = c->cfg.softclamp; a.mask_agent = 1; a.belief = 1;
             a.allow_tensor = (c->cfg.precision != D4_PREC_FP32) && c->space_mma;
             { const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_small_attn(a, s); d4_prof_end(c, ph, s); D4_TRY(rc); }
+        }
+        if (tail) {
+            {
+                GemmArgs g = gemm_args(c->b.attn_o, Dq, nullptr, Dq, hid(2 * i + 1), D, Mr, D, Dq);
+                g.amap = R; g.cmap = R; g.residual = x_in; g.ldr = D;
+                D4_TRY(d4_engine_gemm(c, g, c->attn[i].w_out, 0, s));
+            }
+            D4_TRY(stat_R(hid(2 * i + 1), hrs(2 * i + 1)));
+            D4_TRY(run_ff(c, c->ff[i], Mr, hid(2 * i + 1), D, R, rs_c, 0, hid(2 * i + 2), D, R, nullptr, s));
+            D4_TRY(stat_R(hid(2 * i + 2), hrs(2 * i + 2)));
+            if (i != L - 1) {
+                D4_TRY(run_pool_rows(c, c->pools[i], B, nsp, 1, hid(2 * i + 2), 1, fss, 2 * i + 3, c->b.x_cur, s));
+                D4_TRY(stat_R(c->b.x_cur, nullptr));
+                x_in = c->b.x_cur; x_in_rstd = rs_c;
+            }
+            continue;
         }
         {
             GemmArgs g = gemm_args(c->b.attn_o, Dq, nullptr, Dq, hid(2 * i + 1), D, M, D, Dq);
@@ -664,7 +701,7 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
     if (trim && pred_out) {
         float* xs = c->b.fin_x;
         D4_TRY(d4_gather_rows(hid(2 * L), D, rowmap(nsp, S, 1), (long long)B * nsp, D, xs, D, s));
-        D4_TRY(run_pool_rows(c, c->pool_final, B, nsp, 1, xs, fss, c->n_hid, xs, s));
+        D4_TRY(run_pool_rows(c, c->pool_final, B, nsp, 1, xs, 0, fss, c->n_hid, xs, s));
         D4_TRY(d4_rmsnorm_rows(xs, D, rowmap_identity(), c->lp_norm0, B * nsp, D, c->b.sp_n, D, s));
         return finish_latent_pred(c, B, pred_out, s);
     }
@@ -695,7 +732,7 @@ int run_pass(d4_ctx* c, int B, const float* latent, int signal, int step_log2, c
         }
         D4_TRY(d4_row_rstd(xa, D, rowmap_identity(), B, D, c->b.ag_rstd, s));
         D4_TRY(run_ff(c, c->fa_ff, B, xa, D, rowmap_identity(), c->b.ag_rstd, 0, xa, D, rowmap_identity(), nullptr, s));
-        return run_pool_rows(c, c->pool_final, B, 1, S - 1, xa, fss, c->n_hid, agent_out, s);
+        return run_pool_rows(c, c->pool_final, B, 1, S - 1, xa, 0, fss, c->n_hid, agent_out, s);
     }
 
     // ---- final agent-token cross attention + feed-forward (reference dreamer4.py:3227-3238)

@@ -57,7 +57,7 @@ struct d4_ctx {
     struct {
         float *lat_x, *lat_rstd, *kv_l, *att_l, *hid, *hid_rstd, *x_cur, *x_rstd, *qkvgm, *v0, *attn_o, *ff_mid,
               *pool_qg, *pool_kv, *pool_att, *fa_kv, *fa_q, *fa_att, *ag_rstd, *sp_n, *sp_n2, *sp_kv, *lp_att, *pred,
-              *hbuf0, *hbuf1, *logits, *bins, *agent, *term_in, *fin_x, *fin_rstd, *fin_ctx_rs;
+              *hbuf0, *hbuf1, *logits, *bins, *agent, *term_in, *fin_x, *fin_rstd, *fin_ctx_rs, *fin_rstd2;
         int* sizes_offs;
     } b;
     bool sizes_uploaded = false;
@@ -67,6 +67,7 @@ struct d4_ctx {
     bool fuse_ss = true;         // RMS statistics accumulated in the producing GEMM's epilogue (D4_FUSE_SS=0: separate row pass)
     bool space_mma = true;       // space attention on mma.sync 3xTF32 tiles in the tensor-core engine modes (D4_SPACE_MMA=0: FMA kernel)
     bool trim_final = true;      // final attention-residual pool (and the agent cross-attention) only for the token rows a pass's outputs read (D4_TRIM_FINAL=0: all rows)
+    bool trim_cone = true;       // denoise passes: everything after the last space layer's attention on the spatial rows only (D4_TRIM_CONE=0)
     bool skinny = true;          // GEMMs of <= 32 rows on the weight-streaming exact-fp32 kernel (gemm_skinny.cu); D4_SKINNY=0: the tile kernels
     bool fuse_pools = true;      // fused latent<->space pool kernels (fused_pools.cu); D4_FUSE_POOLS=0 keeps the GEMM + attention path
     // generic transformer context (d4_tf_create: the video tokenizer's encoder / decoder): S tokens per frame of which the last

@@ -36,6 +36,8 @@ struct AssembleArgs {
 };
 int d4_row_rstd(const float* x, long long ldx, RowMap map, int M, int D, float* out, cudaStream_t s);
 int d4_row_sumsq(const float* x, long long ldx, int M, int D, float* out, cudaStream_t s);     // out[m] = sum_d x[m][d]^2
+// rows map(0..M-1): out_c[m] = rstd (compact), out_f[map(m)] = sum of squares | rstd (full-row index); either may be null
+int d4_row_stat_map(const float* x, long long ldx, RowMap map, int M, int D, float* out_c, float* out_f, int full_is_ss, cudaStream_t s);
 int d4_rmsnorm_rows(const float* x, long long ldx, RowMap map, const float* w, int M, int D, float* out, long long ldo, cudaStream_t s);
 int d4_ln_act_rows(const float* x, long long ldx, const float* w, const float* b, int M, int D, float* out, long long ldo, int act,
                    float* save_mean, float* save_rstd, cudaStream_t s);
@@ -92,6 +94,7 @@ struct TimeAttnArgs {
     float scale, softclamp;
     int commit;
     int variant;                                   // 0 = ld.global staged, 1 = cp.async.bulk ring
+    RowMap tmap;                                   // bulk variant: stream m of the M launched covers token tmap(m) (rows of qkvgm / v0 / out and the cache); grp 0 = identity
 };
 int d4_time_attn(const TimeAttnArgs& a, cudaStream_t s);
 

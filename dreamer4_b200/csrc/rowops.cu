@@ -26,6 +26,21 @@ __global__ void row_rstd_kernel(const float* __restrict__ x, long long ldx, RowM
     if (lane == 0) out[m] = rsqrtf(ss / (float)D + D4_RMS_EPS);
 }
 
+// RMS statistic of the rows map(0..M-1) of x: rstd compactly (out_c[m]) and, for the consumers that index by the full row (the pool
+// context gather), out_f[map(m)] = the sum of squares (full_is_ss) or the rstd
+__global__ void row_stat_map_kernel(const float* __restrict__ x, long long ldx, RowMap map, int M, int D, float* __restrict__ out_c,
+                                    float* __restrict__ out_f, int full_is_ss) {
+    const int m = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const long long r = map(m);
+    const float ss = row_sumsq(x + r * ldx, D, lane);
+    if (lane == 0) {
+        const float rstd = rsqrtf(ss / (float)D + D4_RMS_EPS);
+        if (out_c) out_c[m] = rstd;
+        if (out_f) out_f[r] = full_is_ss ? ss : rstd;
+    }
+}
+
 __global__ void row_sumsq_kernel(const float* __restrict__ x, long long ldx, int M, int D, float* __restrict__ out) {
     const int m = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (m >= M) return;
@@ -222,6 +237,11 @@ inline int nblk(long long n, int per) { return (int)((n + per - 1) / per); }
 int d4_row_rstd(const float* x, long long ldx, RowMap map, int M, int D, float* out, cudaStream_t s) {
     if (M <= 0) return 0;
     row_rstd_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, map, M, D, out);
+    D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
+}
+int d4_row_stat_map(const float* x, long long ldx, RowMap map, int M, int D, float* out_c, float* out_f, int full_is_ss, cudaStream_t s) {
+    if (M <= 0) return 0;
+    row_stat_map_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, map, M, D, out_c, out_f, full_is_ss);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }
 int d4_row_sumsq(const float* x, long long ldx, int M, int D, float* out, cudaStream_t s) {

@@ -225,8 +225,9 @@ static void time_attn_host(const TimeAttnArgs& a) {
             x[c] = tmp[c] * cosf(ang) + rot * sinf(ang);
         }
     };
-    for (int m = 0; m < a.M; ++m) {
-        const float* row = a.qkvgm + (long long)m * a.ld;
+    for (int mc = 0; mc < a.M; ++mc) {
+        const long long m = a.tmap(mc);                 // the launch may cover a subset of the token rows (TimeAttnArgs::tmap)
+        const float* row = a.qkvgm + m * a.ld;
         for (int hk = 0; hk < a.hkv; ++hk) {
             const float* k = row + a.off_k + hk * d; const float* v = row + a.off_v + hk * d;
             float ss = 0.f;

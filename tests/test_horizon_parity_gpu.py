@@ -105,15 +105,20 @@ def test_full_size_rerun_is_bit_identical(Bf, Hf):
 
 
 @pytest.mark.parametrize('precision', ['tf32x3', 'f16x3'])
-def test_trimmed_final_pool_is_bit_identical_to_full(precision, monkeypatch):
-    """engine.cu computes the final attention-residual pool (the largest K / V projection of a pass) and the agent cross-attention only
-    for the token rows a pass's outputs read; the pool is per token, so the rollout must not change by a bit (D4_TRIM_FINAL=0: all rows)."""
+def test_trimmed_passes_match_untrimmed(precision, monkeypatch):
+    """engine.cu computes the final attention-residual pool and the agent cross-attention only for the token rows a pass's outputs read,
+    and on denoise passes everything after the last space layer's attention only for the spatial rows (out-projections, feed-forwards,
+    pools, the trailing time layers incl. their KV-cache reads).  Those steps are per token, so this is the same function
+    (D4_TRIM_FINAL=0 D4_TRIM_CONE=0: all rows): sampled actions identical, floats equal up to the rounding of the few places where fewer
+    rows mean another kernel (B-row GEMMs below the 128-row threshold of the CTA-pair kernels; pool gate logits from the query GEMM
+    instead of the pool kernel's own dot product).  On the CPU kernel simulator, in exact fp32, the two are bit-identical."""
     from dreamer4_b200 import DynamicsWorldModel
     kwargs = G.BASELINE_MODELS['config4_256px']
     Tt, Bt = 4, 40
     runs = []
     for trim in ('1', '0'):
         monkeypatch.setenv('D4_TRIM_FINAL', trim)
+        monkeypatch.setenv('D4_TRIM_CONE', trim)
         torch.manual_seed(21)
         model = DynamicsWorldModel(**kwargs, precision=precision)
         with torch.no_grad():
@@ -126,7 +131,9 @@ def test_trimmed_final_pool_is_bit_identical_to_full(precision, monkeypatch):
                                return_time_cache=True, noise=noise)
         runs.append((e, tc.main.next_kv_cache.clone()))
     (a, akv), (b, bkv) = runs
-    assert torch.equal(a.actions.discrete, b.actions.discrete) and torch.equal(akv, bkv)
+    assert torch.equal(a.actions.discrete, b.actions.discrete)
+    tol = dict(atol=2e-5, rtol=2e-5)
+    torch.testing.assert_close(akv, bkv, **tol)
     for name in ('latents', 'rewards', 'values', 'agent_embed'):
-        assert torch.equal(getattr(a, name), getattr(b, name)), name
-    assert torch.equal(a.old_action_unembeds.discrete, b.old_action_unembeds.discrete)
+        torch.testing.assert_close(getattr(a, name), getattr(b, name), msg=lambda m, n=name: f'{n}: {m}', **tol)
+    torch.testing.assert_close(a.old_action_unembeds.discrete, b.old_action_unembeds.discrete, **tol)

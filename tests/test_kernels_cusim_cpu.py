@@ -415,6 +415,7 @@ def test_trimmed_final_pool_equals_full_on_the_simulator(on_simulator, monkeypat
     runs = []
     for trim in ('1', '0'):
         monkeypatch.setenv('D4_TRIM_FINAL', trim)
+        monkeypatch.setenv('D4_TRIM_CONE', trim)
         model = DynamicsWorldModel(**fx['model_kwargs'], precision='fp32')
         model.load_state_dict(fx['state_dict'], strict=True)
         T, B = 3, 2

@@ -37,6 +37,28 @@ __device__ __forceinline__ float tf32_rna(float x) {
 #endif
     return __uint_as_float(r);
 }
+// The same split for the warp-level mma.sync kernels (space_attn.cu, frame_attn_mma.cu), where it is paid per fragment element: ptxas
+// expands cvt.rna.tf32.f32 into four instructions (add, Inf/NaN test, select, mask), nine per split.  Here: hi by integer rounding
+// (finite operands; ties away from zero like cvt.rna), lo = x - hi exactly, plus half a TF32 ulp so that the tensor core's truncation
+// of the 13 low operand bits rounds lo to nearest - four instructions.  hi and lo are bit patterns for the MMA operand registers.
+__device__ __forceinline__ void tf32_split_mma(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+// tanh on |x| <= 0.75 (softclamped attention scores: |s| <= 37.5 at the default clamp of 50): x + x^3 P(x^2), P a degree-5
+// least-squares fit on Chebyshev nodes; |error| <= 5.2e-8 over the interval evaluated in fp32 (under one ulp of the result near
+// the interval's end), against ~35 instructions and a branch for tanhf.  Callers fall back to tanhf when a warp holds a larger argument.
+constexpr float D4_TANH_POLY_MAX = 0.75f;
+__device__ __forceinline__ float tanh_small_(float x) {
+    const float u = x * x;
+    float q = 0.0019145376281812787f;
+    q = fmaf(q, u, -0.007940924726426601f);
+    q = fmaf(q, u, 0.02161884494125843f);
+    q = fmaf(q, u, -0.05393656715750694f);
+    q = fmaf(q, u, 0.13333185017108917f);
+    q = fmaf(q, u, -0.3333333134651184f);
+    return fmaf(x * u, q, x);
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float geluf_(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

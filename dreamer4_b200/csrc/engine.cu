@@ -1110,7 +1110,8 @@ extern "C" int d4_tf_step(d4_ctx* c, int B, const float* tokens_in, int t, float
     auto hrs = [&](int j) { return c->b.hid_rstd + (long long)j * M; };
     auto xss = [&](int j) { return c->b.x_rstd + (long long)j * M; };
     const float att_scale = 1.f / sqrtf((float)d);
-    auto attend = [&](const SmallAttnArgs& a) {
+    auto attend = [&](SmallAttnArgs a) {
+        a.allow_tensor = (c->cfg.precision != D4_PREC_FP32);          // 3xTF32 mma.sync tiles (frame_attn.cu) in the tensor-core engine modes
         const int ph = d4_prof_begin(c, D4_CLS_SMALL_ATTN, 0.0, s); const int rc = d4_frame_attn(a, s); d4_prof_end(c, ph, s); return rc;
     };
 

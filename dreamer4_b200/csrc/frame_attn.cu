@@ -7,8 +7,8 @@
 // its warps then take the queries round-robin; a query's scores live in a per-warp shared row instead of registers.
 //   a.mask_agent carries the NUMBER of special tokens here: queries i < nq - ns do not see keys j >= n - ns.
 //
-// STATUS: drafted in round 1 after the GPU budget was spent - compiles for sm_100a, not yet run on hardware.  A first, plain
-// SIMT version (exact-fp32 FMA): 4 MFLOP per (frame, head) at n = 128, d = 64 - the tokenizer's GEMMs dominate its pass.
+// This first version is exact-fp32 FMA (the `fp32` engine mode, and the shapes the tensor-core version below does not take);
+// 4 MFLOP per (frame, head) at n = 128, d = 64.
 #include "kernels.h"
 #include <float.h>
 
@@ -115,8 +115,12 @@ inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) 
 
 }  // namespace
 
+int d4_frame_attn_mma_ok(const SmallAttnArgs& a);
+int d4_frame_attn_mma(const SmallAttnArgs& a, cudaStream_t s);
+
 int d4_frame_attn(const SmallAttnArgs& a, cudaStream_t s) {
     if (a.nb <= 0 || a.nq <= 0) return 0;
+    if (d4_frame_attn_mma_ok(a)) return d4_frame_attn_mma(a, s);          // tensor-core engine modes, head dim 64, <= 128 keys
     if (a.n < 1) return d4_fail("frame_attn: no keys");
     if (a.d % 4 != 0 || a.d > 128) return d4_fail("frame_attn: head dim %d unsupported", a.d);
     if (a.belief && a.nq != a.n) return d4_fail("frame_attn: belief projection needs nq == n");

@@ -32,11 +32,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    const float h = tf32_rna(x);
-    hi = __float_as_uint(h);
-    lo = __float_as_uint(tf32_rna(x - h));
-}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) { tf32_split_mma(x, hi, lo); }
 __device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const uint32_t (&bhi)[2], const uint32_t (&blo)[2]) {
     mma_tf32(c, alo, bhi);
     mma_tf32(c, ahi, blo);
@@ -187,16 +183,37 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
         }
         if (gi == 0) fetch_vb();                      // in flight under the softmax
         // scale by the key norm, softclamp, mask, softmax over the keys of each query row (rows g: regs 0, 1; g + 8: regs 2, 3)
+        if (a.softclamp > 0.f) {          // tanh(s / c) c  (reference dreamer4.py:1723-1724)
+            const float pre = a.scale * (1.f / a.softclamp);
+            float amax = 0.f;
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { sc[n][r] = sc[n][r] * kinv[n][r & 1] * pre; amax = fmaxf(amax, fabsf(sc[n][r])); }
+            if (__all_sync(D4_FULL, amax <= D4_TANH_POLY_MAX)) {
+#pragma unroll
+                for (int n = 0; n < 2; ++n)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) sc[n][r] = tanh_small_(sc[n][r]) * a.softclamp;
+            } else {
+#pragma unroll
+                for (int n = 0; n < 2; ++n)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) sc[n][r] = tanhf(sc[n][r]) * a.softclamp;
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) sc[n][r] = sc[n][r] * kinv[n][r & 1] * a.scale;
+        }
 #pragma unroll
         for (int n = 0; n < 2; ++n)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int i = g + ((r & 2) ? 8 : 0), j = n * 8 + 2 * t + (r & 1);
-                float s = sc[n][r] * kinv[n][r & 1] * a.scale;
-                if (a.softclamp > 0.f) s = tanhf(s / a.softclamp) * a.softclamp;
-                if (a.mask_agent && i < S - 1 && j == S - 1) s = -FLT_MAX;
-                if (j >= S) s = -INFINITY;
-                sc[n][r] = s;
+                if (a.mask_agent && i < S - 1 && j == S - 1) sc[n][r] = -FLT_MAX;
+                if (j >= S) sc[n][r] = -INFINITY;
             }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -204,7 +221,7 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
             mx = fmaxf(mx, __shfl_xor_sync(D4_FULL, mx, 1)); mx = fmaxf(mx, __shfl_xor_sync(D4_FULL, mx, 2));
             float e[4], sum = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { e[q] = expf(sc[q >> 1][2 * half + (q & 1)] - mx); sum += e[q]; }
+            for (int q = 0; q < 4; ++q) { e[q] = __expf(sc[q >> 1][2 * half + (q & 1)] - mx); sum += e[q]; }
             sum += __shfl_xor_sync(D4_FULL, sum, 1); sum += __shfl_xor_sync(D4_FULL, sum, 2);
             const float inv = 1.f / sum;
 #pragma unroll

@@ -180,12 +180,19 @@ def mlp_param_names(prefix, n_layers):
 
 # ------------------------------------------------------------------------------------------------ video tokenizer
 
-def _split_all(out, split):
+def _split_all(out, split, split_f16=False):
+    """tf32 hi / lo words per GEMM weight (`split`); with `split_f16` also the fp16 words of the f16x3 mode and their 1 / q under
+    the key 'h16scales' (a {name: float} dict, not a tensor), as pack() does."""
     out = {k: v.contiguous() for k, v in out.items()}
+    names = [k for k in out if k.endswith(GEMM_WEIGHTS_SUFFIXES)]
     if split:
-        for k in list(out):
-            if k.endswith(GEMM_WEIGHTS_SUFFIXES):
-                out[k + '.hi'], out[k + '.lo'] = (t.contiguous() for t in tf32_split(out[k]))
+        for k in names:
+            out[k + '.hi'], out[k + '.lo'] = (t.contiguous() for t in tf32_split(out[k]))
+    if split_f16:
+        scales = {}
+        for k in names:
+            out[k + '.h16hi'], out[k + '.h16lo'], scales[k] = f16_split(out[k])
+        out['h16scales'] = scales
     return out
 
 
@@ -206,7 +213,7 @@ def _mlp_eval(g, p, x, act):
         i += 1
 
 
-def pack_tokenizer(sd, cfg, device, split=False):
+def pack_tokenizer(sd, cfg, device, split=False, split_f16=False):
     """Packed weights of the VideoTokenizer's inference paths (reference dreamer4.py:3686-4237, default branches), from a
     reference-layout state_dict; cfg: dreamer4_b200.tokenizer.TokenizerConfig.  Returns {'enc': {...}, 'dec': {...}, 'io': {...}}:
 
@@ -235,4 +242,4 @@ def pack_tokenizer(sd, cfg, device, split=False):
     io['lat_in.w'] = g('latents_to_decoder.weight')
     io['time_embed'] = g('time_embed.weight')
     io['to_patch.w'], io['to_patch.b'] = g('decoder.tokens_to_patch.0.weight'), g('decoder.tokens_to_patch.0.bias')
-    return dict(enc=_split_all(enc, split), dec=_split_all(dec, split), io=_split_all(io, split))
+    return dict(enc=_split_all(enc, split, split_f16), dec=_split_all(dec, split, split_f16), io=_split_all(io, split))

@@ -94,6 +94,15 @@ _TRAINING_ONLY = ('lpips_loss_weight', 'lpips_loss_network', 'encoder_add_decor_
 TokenizerTimeCache = namedtuple('TokenizerTimeCache', ['token_count', 'epoch'])
 
 
+def _register(lib, ctx, packed):
+    """Hands a packed weight dict to a native context: tensors by name, and - f16x3 mode - the 1 / q of each fp16-split weight."""
+    for name, t in packed.items():
+        if name != 'h16scales':
+            check(lib.d4_set_weight(ctx, name.encode(), ptr(t), t.numel()))
+    for name, scale in packed.get('h16scales', {}).items():
+        check(lib.d4_set_weight_scale(ctx, name.encode(), scale))
+
+
 def _records_config(init):
     @functools.wraps(init)
     def wrapped(self, *args, **kwargs):
@@ -125,7 +134,7 @@ class VideoTokenizer(nn.Module):
         assert image_height and image_width, 'image_size or image_height / image_width is required'
         assert image_height % patch_size == 0 and image_width % patch_size == 0
         assert decoder_flow_steps >= 1, 'the plain (non-flow) decoder is outside the path this package builds'
-        assert precision in ('fp32', 'tf32', 'tf32x3')
+        assert precision in ('fp32', 'tf32', 'tf32x3', 'f16x3')
         self.cfg = TokenizerConfig(dim=dim, dim_latent=dim_latent, patch_size=patch_size, image_height=image_height, image_width=image_width,
                                    num_latent_tokens=num_latent_tokens, encoder_depth=encoder_depth, decoder_depth=decoder_depth,
                                    time_block_every=time_block_every, attn_heads=attn_heads, attn_dim_head=attn_dim_head,
@@ -244,7 +253,8 @@ class VideoTokenizer(nn.Module):
         if self._packed_version != self._version():
             if self._ctx:
                 self._release()          # contexts hold pointers into the old packed tensors
-            self._packed = pack_tokenizer(self.state_dict(), self.cfg, self.device, split=self.precision == 'tf32x3')
+            self._packed = pack_tokenizer(self.state_dict(), self.cfg, self.device, split=self.precision in ('tf32x3', 'f16x3'),
+                                          split_f16=self.precision == 'f16x3')          # f16x3: odd shapes and the io GEMMs stay on 3xTF32
             self._packed_version = self._version()
         return self._packed
 
@@ -287,8 +297,7 @@ class VideoTokenizer(nn.Module):
         if old is not None:
             kv[..., :keep_frames, :] = old[2]['kv'][..., :keep_frames, :]
         check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv_bytes))
-        for name, t in packed[which].items():
-            check(lib.d4_set_weight(ctx, name.encode(), ptr(t), t.numel()))
+        _register(lib, ctx, packed[which])
         check(lib.d4_bind(ctx))
         if have is not None:
             lib.d4_ctx_destroy(have[0])
@@ -305,7 +314,7 @@ class VideoTokenizer(nn.Module):
         lo = io.get(w_name + '.lo')
         Wp = io[w_name + '.hi'] if lo is not None else W
         stream = self._stream()
-        check(lib.d4_linear_rows(_lib.PREC[self.precision], M, N, K, ptr(A), A.stride(-2), amap[0], amap[1], amap[2], ptr(Wp), K, ptr(lo),
+        check(lib.d4_linear_rows(_lib.PREC['tf32x3' if self.precision == 'f16x3' else self.precision], M, N, K, ptr(A), A.stride(-2), amap[0], amap[1], amap[2], ptr(Wp), K, ptr(lo),
                                  ptr(W), ptr(bias), ptr(out), N, stream))
         return out
 
@@ -413,7 +422,7 @@ class AxialSpaceTimeTransformer(nn.Module):
         for k, v in kwargs.items():
             if k in unsupported and v != unsupported[k]:
                 raise NotImplementedError(f'AxialSpaceTimeTransformer({k}={v!r}) is outside the path this package builds')
-        assert not attn_kwargs and precision in ('fp32', 'tf32', 'tf32x3')
+        assert not attn_kwargs and precision in ('fp32', 'tf32', 'tf32x3', 'f16x3')
         self.dim, self.depth, self.num_special_tokens, self.has_final_norm = dim, depth, num_special_tokens, final_norm
         self.precision, self.time_attn_variant = precision, time_attn_variant
         # the tokenizer config doubles as the transformer's (only the fields _reg_transformer and the context need)
@@ -463,7 +472,7 @@ class AxialSpaceTimeTransformer(nn.Module):
             out['inv_freq'] = g('time_rotary.inv_freq')
             if self.has_final_norm:
                 out['final_norm'] = g('final_norm.weight')
-            self._packed, self._packed_version = _split_all(out, self.precision == 'tf32x3'), version
+            self._packed, self._packed_version = _split_all(out, self.precision in ('tf32x3', 'f16x3'), self.precision == 'f16x3'), version
         key = (batch, tokens_per_frame, self.precision, self.time_attn_variant, dev.index)
         have = self._ctx
         if have is not None and have[1] == key and have[2]['max_time'] >= need_time:
@@ -490,8 +499,7 @@ class AxialSpaceTimeTransformer(nn.Module):
         if old is not None:
             kv[..., :keep_frames, :] = old[2]['kv'][..., :keep_frames, :]
         check(lib.d4_set_buffers(ctx, ptr(ws), ws_bytes, ptr(kv), kv_bytes))
-        for name, t in self._packed.items():
-            check(lib.d4_set_weight(ctx, name.encode(), ptr(t), t.numel()))
+        _register(lib, ctx, self._packed)
         check(lib.d4_bind(ctx))
         if have is not None:
             lib.d4_ctx_destroy(have[0])

@@ -5,10 +5,10 @@ import json
 import subprocess
 import sys
 
-POINTS = [(256, 64), (2048, 8), (2048, 64), (8192, 32)] if len(sys.argv) > 2 and sys.argv[2] == "short" else [(256, 8), (256, 64), (2048, 8), (2048, 64), (2048, 128), (8192, 8), (8192, 32)]
+POINTS = [(256, 64), (2048, 8), (2048, 64), (8192, 32)] if len(sys.argv) > 2 and sys.argv[2] == "short" else [(256, 8), (256, 64), (1024, 64), (2048, 8), (2048, 64), (2048, 128), (8192, 8), (8192, 32)]
 out = open(sys.argv[1], 'w') if len(sys.argv) > 1 else None
 for b, h in POINTS:
-    r = subprocess.run([sys.executable, 'bench.py', '--batch', str(b), '--horizon', str(h), '--steps', '1', '--warmup', '1', '--no-cpu-baseline'],
+    r = subprocess.run([sys.executable, 'bench.py', '--batch', str(b), '--horizon', str(h), '--steps', '2', '--warmup', '3', '--no-cpu-baseline'],
                        capture_output=True, text=True)
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''
     try:

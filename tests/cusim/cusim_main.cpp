@@ -149,6 +149,8 @@ static inline float lerp_t(float a, float b, float w) { const float d = b - a; r
 // ---- attn.cu's contract (SmallAttnArgs in kernels.h): softmax(q . keynorm(k) * scale [softclamp] [agent mask]) @ lerp(v, v0, sigmoid(mix)),
 // belief projection, head gate.  In-kernel gate logits (gate_w) are declined through d4_pool_attn_ok.
 int d4_pool_attn_ok(const SmallAttnArgs&) { return 0; }
+int d4_frame_attn_mma_ok(const SmallAttnArgs&) { return 0; }          // mma.sync tiles (frame_attn_mma.cu): hardware only
+int d4_frame_attn_mma(const SmallAttnArgs&, cudaStream_t) { return d4_fail("cusim: frame_attn_mma"); }
 static void small_attn_host(const SmallAttnArgs& a);
 int d4_small_attn(const SmallAttnArgs& a, cudaStream_t) {
     if (a.gate_w) return d4_fail("cusim: in-kernel gate logits");

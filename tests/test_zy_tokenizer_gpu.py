@@ -59,7 +59,7 @@ def test_frame_ops_match_torch():
     torch.testing.assert_close(Cout, want, atol=1e-4, rtol=1e-4)
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'f16x3'])
 @pytest.mark.parametrize('path', FIX, ids=IDS)
 def test_tokenize_and_decode_match_reference_golden(path, precision):
     from dreamer4_b200 import VideoTokenizer
@@ -163,7 +163,7 @@ def test_interact_with_env_through_the_attached_tokenizer(case):
         torch.testing.assert_close(getattr(exp, name).cpu(), getattr(ref, name), **TOL, msg=lambda m, n=name: f'{n}: {m}')
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'f16x3'])
 def test_axial_space_time_transformer_matches_reference_golden(precision):
     """The stand-alone transformer (d4_tf_step on caller tokens) against the reference module's own 3-frame output and time-KV cache."""
     from dreamer4_b200 import AxialSpaceTimeTransformer
@@ -179,3 +179,29 @@ def test_axial_space_time_transformer_matches_reference_golden(precision):
         o, cache = m(fx['tokens'][:, :t + 1].cuda(), cache=cache, return_intermediates=True)
         frames.append(o[:, -1])
     torch.testing.assert_close(torch.stack(frames, dim=1).cpu(), fx['out'], **TOL)
+
+
+@pytest.mark.parametrize('S,ns', [(9, 1), (33, 2), (64, 8), (72, 5), (100, 36), (128, 64)])
+def test_frame_attention_tensor_core_tiles_match_fma_kernel(S, ns):
+    """frame_attn_mma.cu (3xTF32 mma.sync tiles: the tf32x3 mode's attention inside a frame) against frame_attn.cu's exact-fp32 FMA kernel
+    (the fp32 mode, itself pinned by the reference goldens above and by the simulator tests) on the same random transformer and tokens: ragged
+    key counts (partial 8-key tiles, partial 16-query tiles), every template width (32 / 64 / 96 / 128 keys), the special-token mask, and the
+    special tokens' final cross-attention (nq = ns queries over S - ns keys)."""
+    from dreamer4_b200 import AxialSpaceTimeTransformer
+    torch.manual_seed(S * 131 + ns)
+    kw = dict(dim=128, depth=4, attn_heads=2, attn_dim_head=64, time_block_every=4, num_special_tokens=ns)
+    ref = AxialSpaceTimeTransformer(**kw, precision='fp32')
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.ndim >= 2:
+                p.normal_(0., 1.5 * p.shape[-1] ** -0.5)
+            elif p.numel() > 0:
+                p.add_(0.2 * torch.randn_like(p))
+    tc = AxialSpaceTimeTransformer(**kw, precision='tf32x3')
+    tc.load_state_dict(ref.state_dict(), strict=True)
+    ref, tc = ref.cuda(), tc.cuda()
+    tokens = torch.randn(3, 2, S, 128, device='cuda')
+    want = ref(tokens)
+    got = tc(tokens)
+    assert torch.isfinite(got).all()
+    torch.testing.assert_close(got, want, atol=5e-5, rtol=1e-4)

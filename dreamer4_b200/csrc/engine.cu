@@ -1034,7 +1034,7 @@ extern "C" int d4_tf_create(const d4_tf_config* cfg, d4_ctx** out) {
     c->cfg.pool_heads = cfg->pool_heads; c->cfg.pool_dim_head = cfg->pool_dim_head;
     c->cfg.ff_inner = cfg->ff_inner; c->cfg.ff_inner_pad = cfg->ff_inner_pad; c->cfg.ff_act = cfg->ff_act;
     c->cfg.softclamp = cfg->softclamp; c->cfg.max_batch = cfg->max_batch; c->cfg.max_time = cfg->max_time;
-    c->cfg.precision = cfg->precision == D4_PREC_F16X3 ? D4_PREC_TF32X3 : cfg->precision; c->cfg.time_attn_variant = cfg->time_attn_variant;
+    c->cfg.precision = cfg->precision; c->cfg.time_attn_variant = cfg->time_attn_variant;
     c->cfg.max_steps = 1;
     c->tf_mode = true; c->tf_ns = cfg->num_special; c->tf_final_norm = cfg->final_norm;
     c->D = cfg->dim; c->Dl = 0; c->N = 0; c->nsp = 0; c->nreg = 0; c->L = cfg->depth; c->h = cfg->heads; c->hq = cfg->query_heads; c->d = cfg->dim_head;

@@ -1,5 +1,5 @@
-// EXPERIMENTAL (not dispatched by the engine; reachable through d4_linear(precision = D4_PREC_F16X3) only, never run on
-// hardware yet): the CTA-pair tcgen05 GEMM of gemm_tc3.cu with the three split terms on kind::f16 instead of kind::tf32.
+// The dominant kernel of the `f16x3` engine mode (the bench default since round 2): the CTA-pair tcgen05 GEMM of gemm_tc3.cu with
+// the three split terms on kind::f16 instead of kind::tf32.
 //
 // Why: fp16 carries the same 11-bit significand as TF32 and kind::f16 issues at twice the TF32 rate, so
 //     D = a_hi.w_hi + a_lo.w_hi + a_hi.w_lo,   hi = fp16(x), lo = fp16(x - hi)
@@ -16,9 +16,9 @@
 //   A still arrives as fp32 through TMA (two 32-column boxes per stage); the eight splitter warps read the whole 32 KB into
 //   registers, meet at a named barrier, and write the fp16 hi tile and lo tile back IN PLACE (16 KB each) in the 128B-swizzled
 //   K-major layout; W hi / lo are fp16 in global memory and land by TMA directly;
-//   instruction descriptor a_format = b_format = F16 (0), UMMA_K = 16.
-// Roles, barriers, TMEM double buffering and the whole epilogue are those of gemm_tc3.cu (kept as a copy until this kernel
-// has been measured; the two files merge if it is adopted).
+//   instruction descriptor a_format = b_format = F16 (0), UMMA_K = 16;
+//   the residual chunk loads of the epilogue are issued early (see the epilogue).
+// Roles, barriers and TMEM double buffering are those of gemm_tc3.cu.  Measured: DESIGN.md section 5 (K5), profiles/r2_gemm_*.txt.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <string.h>
@@ -68,6 +68,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -91,7 +92,7 @@ struct EpiArgsH {
     int rs_mode, kdim;  // rs_mode 1: row_scale holds the sum of squares over kdim columns -> rsqrt(ss / kdim + eps); rows pre-scaled by 2^k
     float* ss_out;
     float w_scale;      // 1 / q of the pre-scaled weights
-    int dbg;            // ablation switches for scripts/gemm_bench.py (results are garbage when set): 1 no epilogue, 2 no split, 4 no MMA, 8 / 16 same A / W tile
+    int dbg;            // ablation switches for scripts/gemm_bench.py (results are garbage when set): 1 no epilogue, 2 no split, 4 no MMA, 8 / 16 same A / W tile; 64 residual chunk loads issued late (results stay exact), 128 no output stores
 };
 
 template <int BN> struct CfgH {
@@ -223,6 +224,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16x3_kernel(const __grid
             if (grp == 0) tma_load_2d(ebuf_u32 + buf * 4096, &maps.r, rb, col0, row0);
             else          tma_load_3d(ebuf_u32 + buf * 4096, &maps.r, rb, col0, 0, row0 / grp);
         };
+        // The residual tile is added in place in the chunk buffers (TMA load -> += -> TMA store).  With two 4 KB buffers per warp a
+        // chunk's load can only be issued once the store two chunks back has left its buffer; issued after the current chunk's
+        // store (round 1) its whole latency was exposed on every chunk, which made the epilogue of the N = 512, K = 256 / 512
+        // products (attention out, pool out) longer than their mainloop.  Now the next chunk's load is issued a quarter into the
+        // current chunk's arithmetic - the previous store has been read by then - also across the tile boundary: attention out
+        // 89 -> 79 us, pool out 87 -> 71 us at 30720 rows (profiles/r2_gemm_residual_epilogue.txt; dbg 64 restores the late issue).
+        // (Tried on top and dropped: prefetching the next tile's residual rows into L2 with cp.async.bulk.prefetch.tensor - 6-8 %
+        // slower; an epilogue without staging, every lane storing its row's 32 columns as eight 16-byte st.global and reading the
+        // residual the same way - its arithmetic is cheaper (no-store timing 141 vs 159 us on the qkv shape) but 32 half-sector
+        // stores per instruction cost far more than the TMA store: 199 vs 164 us, 30.1 k vs 32.3 k frames/s in situ.)
+        const bool res_early = has_res && !(e.dbg & 64);
+        bool pre_loaded = false;                                // lane 0: the first chunk of the coming tile is already in flight
+        auto tile_rows = [&](int tt, int& rb, int& o0) {
+            rb = (tt / e.n_tiles_n) * (2 * BM) + (int)rank * BM + quarter * 32;
+            const int nn = (tt % e.n_tiles_n) * BN;
+            o0 = glu ? (nn >> 1) : nn;
+        };
         uint32_t ac = 0;
         for (int t = cluster_id; t < total_tiles; t += n_clusters, ++ac) {
             const int m0 = (t / e.n_tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % e.n_tiles_n) * BN;
@@ -236,7 +254,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16x3_kernel(const __grid
             const uint32_t tmem_c = tmem_base + (uint32_t)(buf_acc * BN) + ((uint32_t)(quarter * 32) << 16);
             const int out0 = glu ? (n0 >> 1) : n0;
             const bool rows_ok = rbase < e.M;
-            if (has_res && rows_ok && out0 < n_out && lane == 0) { bulk_wait_read_1(); res_load(g & 1, out0, rbase); }
+            if (has_res && rows_ok && out0 < n_out && lane == 0 && !pre_loaded) { bulk_wait_read_1(); res_load(g & 1, out0, rbase); }
+            pre_loaded = false;
             mbar_wait(bar(B_TFULL + buf_acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (rows_ok && !(e.dbg & 1)) {
@@ -265,6 +284,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16x3_kernel(const __grid
                     unsigned char* rowp = ebuf + buf * 4096 + lane * 128;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
+                        if (q == 2 && res_early && lane == 0) {          // next chunk's residual: its buffer's store (the previous chunk) has been read by now
+                            const int oc_next = oc + 32;
+                            if (c0 + in_per_chunk < BN && oc_next < n_out) { bulk_wait_read_0(); res_load(buf ^ 1, oc_next, rbase); }
+                            else if (t + n_clusters < total_tiles) {
+                                int rb, o0; tile_rows(t + n_clusters, rb, o0);
+                                if (rb < e.M && o0 < n_out) { bulk_wait_read_0(); res_load(buf ^ 1, o0, rb); pre_loaded = true; }
+                            }
+                        }
                         float4 o;
                         if (!glu) {
                             const float bx = __shfl_sync(0xffffffffu, b_lo, 4 * q), by = __shfl_sync(0xffffffffu, b_lo, 4 * q + 1);
@@ -291,11 +318,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16x3_kernel(const __grid
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        if (grp == 0) tma_store_2d(&maps.c, ebuf_u32 + buf * 4096, oc, rbase);
+                        if (e.dbg & 128) {}          // timing experiment: the epilogue without its stores
+                        else if (grp == 0) tma_store_2d(&maps.c, ebuf_u32 + buf * 4096, oc, rbase);
                         else          tma_store_3d(&maps.c, ebuf_u32 + buf * 4096, oc, 0, rbase / grp);
                         bulk_commit();
                         const int oc_next = oc + 32;
-                        if (has_res && c0 + in_per_chunk < BN && oc_next < n_out) { bulk_wait_read_1(); res_load(buf ^ 1, oc_next, rbase); }
+                        if (has_res && !res_early && c0 + in_per_chunk < BN && oc_next < n_out) { bulk_wait_read_1(); res_load(buf ^ 1, oc_next, rbase); }
                     }
                     b_lo = bn_lo; b_hi = bn_hi;
                     ++g;
@@ -445,7 +473,7 @@ bool operands_ok(const GemmArgs& g, const void* whi, const void* wlo) {
     return ok;
 }
 
-int g_dbg = 0;          // d4_debug_set("gemm_f16", bits): 1 no epilogue, 2 no operand split, 4 no MMA (timing ablations only)
+int g_dbg = [] { const char* v = getenv("D4_GEMM_F16_DBG"); return v ? atoi(v) & 255 : 0; }();          // d4_debug_set("gemm_f16", bits): 1 no epilogue, 2 no operand split, 4 no MMA (timing ablations only)
 
 template <int BN>
 int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
@@ -491,7 +519,7 @@ int launch_h(const GemmArgs& g, float w_scale, cudaStream_t stream) {
 // 1 if the engine may route this GEMM here given the fp16 hi / lo arrays of its weight: the pair kernel's shapes (more rows than
 // one CTA's 128, like gemm_tc3.cu), whole 64-column K steps (K = dim, ff_inner_pad, pool width ... of every BASELINE config), and
 // the operand rules above.  g.W still points to the fp32 weight; only its leading dimension is read.
-void d4_gemm_f16_debug(int bits) { g_dbg = bits & 31; }
+void d4_gemm_f16_debug(int bits) { g_dbg = bits & 255; }
 int d4_gemm_f16x3_supported(const GemmArgs& g, const void* whi, const void* wlo) {
     return (g.M > BM && (g.K % 32) == 0 && g.K >= BK && operands_ok(g, whi, wlo)) ? 1 : 0;
 }

@@ -30,7 +30,8 @@ SHAPES = [
     ('pool kv n=9 (N=512,K=512)', 9, 512, 512, 0, False, False, 1),
     ('pool out (N=512,K=256,res)', 1, 512, 256, 0, True, False, 0),
 ]
-MODES = dict(tf32x3=(2, 0), f16x3=(3, 0), f16x3_noepi=(3, 1), f16x3_nosplit=(3, 2), f16x3_nomma=(3, 4), f16x3_only_tma=(3, 7), f16x3_only_tma_sameA=(3, 15), f16x3_only_tma_sameW=(3, 23), f16x3_only_tma_sameAW=(3, 31))
+MODES = dict(tf32x3=(2, 0), f16x3=(3, 0), f16x3_noepi=(3, 1), f16x3_nosplit=(3, 2), f16x3_nomma=(3, 4), f16x3_only_tma=(3, 7), f16x3_only_tma_sameA=(3, 15), f16x3_only_tma_sameW=(3, 23), f16x3_only_tma_sameAW=(3, 31),
+             f16x3_res_late=(3, 64), f16x3_nostore=(3, 128))          # residual chunk loads issued after the chunk's store, as before round 2's last change
 
 
 def main():

@@ -1,0 +1,7 @@
+#!/bin/bash
+# final-state evidence: whole GPU suite, ncu --set full captures (-> profiles/ncu_summary.json), the driver's round-end commands + launch list
+set -u
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+bash scripts/gpu_profile_r2.sh
+bash scripts/gpu_round_end.sh

@@ -33,6 +33,7 @@ void d4_gemm_f16_debug(int bits);
 extern "C" int d4_debug_set(const char* key, int value) {
     if (!key) return d4_fail("d4_debug_set: null key");
     if (!strcmp(key, "gemm_f16")) { d4_gemm_f16_debug(value); return 0; }
+    if (!strcmp(key, "lp_fused")) { d4_lp_fused_debug(value); return 0; }          // 1: one CTA per frame, 2: persistent (default, large batches)
     return d4_fail("d4_debug_set: unknown key '%s'", key);
 }
 extern "C" int64_t d4_graph_replays(const d4_ctx* c) { return c ? c->graph_replays : 0; }

@@ -14,6 +14,7 @@
 // Both are exact fp32 re-associations of the reference arithmetic (no reduced precision anywhere).
 #include "kernels.h"
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -28,7 +29,7 @@ __device__ __forceinline__ void l2s_mma_tf32(float (&c)[4], const uint32_t (&a)[
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-__device__ __forceinline__ void l2s_split(float x, uint32_t& hi, uint32_t& lo) {
+__device__ __forceinline__ void l2s_split(float x, uint32_t& hi, uint32_t& lo) {      // (tf32_split_mma of common.cuh was measured here: 255 vs 226 us per launch - cvt.rna kept)
     const float h = tf32_rna(x);
     hi = __float_as_uint(h);
     lo = __float_as_uint(tf32_rna(x - h));
@@ -329,6 +330,117 @@ __global__ void __launch_bounds__(256) lp_fused_kernel(LpArgs a) {
     }
 }
 
+
+// Persistent version for large batches (head dim 64, N * hq <= 512 query rows): the learned queries (N x hq*d = 128 KB) and W_comb
+// (Dl x hq*d = 64 KB) do not depend on the frame, yet lp_fused_kernel re-reads both from L2 for each of its B CTAs (393 MB of
+// L2 -> SM traffic at 2048 frames, latency-bound loads inside the dot products: 289 us per launch for 1 GFLOP).  Here one CTA per SM
+// keeps W_comb in shared memory and each thread keeps ITS query row (64 floats) in registers, then walks over its frames.  Every
+// output is accumulated in the same order as in lp_fused_kernel, so the two are bit-identical (tests/test_gpu_parity.py).
+constexpr int LPP_THREADS = 512;
+
+template <int D>
+__global__ void __launch_bounds__(LPP_THREADS, 1) lp_fused_persist_kernel(LpArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, nthr = LPP_THREADS, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    const int nsp = a.nsp, h = a.h, hq = a.hq, g = hq / h, Dkv = h * D, Dq = hq * D, N = a.N, Dl = a.Dl;
+    constexpr int dp = D + 4;
+    const int JH = nsp * hq, WP = Dq + 4;                   // W_comb row pitch: rows e, e + 1, .. of a warp start 4 banks apart
+    float* wc = smem;                                       // [Dl][WP]
+    float* ks = wc + (size_t)Dl * WP;                       // [nsp][h][dp]
+    float* vs = ks + nsp * h * dp;
+    float* ys = vs + nsp * h * dp;                          // [JH][Dl]
+    float* cf = ys + LP_MAXJH * Dl;                         // [N][JH + 1]
+
+    for (int idx = tid; idx < Dl * (Dq / 4); idx += nthr) {
+        const int e = idx / (Dq / 4), c = (idx % (Dq / 4)) * 4;
+        *reinterpret_cast<float4*>(wc + (size_t)e * WP + c) = __ldg(reinterpret_cast<const float4*>(a.w_comb + (long long)e * Dq + c));
+    }
+    // this thread's (query, query head): its row of the projected queries and its gate, for every frame
+    const int my_i = tid / hq, my_q = tid - my_i * hq, my_hk = my_q / g;
+    const bool has_pair = tid < N * hq;
+    float qreg[D];
+    float my_gate = 0.f;
+    if (has_pair) {
+        const float* qr = a.q + (long long)my_i * Dq + my_q * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+            const float4 qv = __ldg(reinterpret_cast<const float4*>(qr + c));
+            qreg[c] = qv.x; qreg[c + 1] = qv.y; qreg[c + 2] = qv.z; qreg[c + 3] = qv.w;
+        }
+        my_gate = sigmoidf_(a.gate[my_i * hq + my_q]);
+    }
+    const float sqrt_d = sqrtf((float)D);
+
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();                                    // the previous frame's cf / ys are no longer read (first pass: wc is staged)
+        const float* kvb = a.kv + (long long)b * nsp * 2 * Dkv;
+        for (int idx = tid; idx < nsp * Dkv; idx += nthr) {
+            const int j = idx / Dkv, r = idx - j * Dkv, hk = r / D, c = r - hk * D;
+            ks[(j * h + hk) * dp + c] = kvb[(long long)j * 2 * Dkv + r];
+            vs[(j * h + hk) * dp + c] = kvb[(long long)j * 2 * Dkv + Dkv + r];
+        }
+        __syncthreads();
+        for (int jh = warp; jh < nsp * h; jh += nwarps) {
+            float* kr = ks + jh * dp;
+            const int hk = jh % h;
+            float ss = 0.f;
+            for (int c = lane; c < D; c += 32) ss += kr[c] * kr[c];
+            const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), D4_L2_EPS);
+            for (int c = lane; c < D; c += 32) kr[c] = kr[c] * inv * ((a.k_gamma[hk * D + c] + 1.f) * sqrt_d);
+        }
+        for (int o = tid; o < JH * Dl; o += nthr) {
+            const int jh = o / Dl, e = o - jh * Dl, j = jh / hq, q = jh - j * hq, hk = q / g;
+            const float* w = wc + (size_t)e * WP + q * D;
+            const float* v = vs + (j * h + hk) * dp;
+            float acc = 0.f;
+            for (int c = 0; c < D; c += 4) {
+                const float4 wv = *reinterpret_cast<const float4*>(w + c);
+                const float4 vv = *reinterpret_cast<const float4*>(v + c);
+                acc = fmaf(wv.x, vv.x, acc); acc = fmaf(wv.y, vv.y, acc); acc = fmaf(wv.z, vv.z, acc); acc = fmaf(wv.w, vv.w, acc);
+            }
+            ys[jh * Dl + e] = acc;
+        }
+        __syncthreads();
+        if (has_pair) {
+            float s[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; c += 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < nsp) {
+                        const float4 kv = *reinterpret_cast<const float4*>(ks + (j * h + my_hk) * dp + c);
+                        s[j] = fmaf(qreg[c], kv.x, s[j]); s[j] = fmaf(qreg[c + 1], kv.y, s[j]); s[j] = fmaf(qreg[c + 2], kv.z, s[j]); s[j] = fmaf(qreg[c + 3], kv.w, s[j]);
+                    }
+                }
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (j < nsp) { s[j] *= a.scale; mx = fmaxf(mx, s[j]); }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (j < nsp) { s[j] = expf(s[j] - mx); sum += s[j]; }
+            const float gate = my_gate / sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (j < nsp) cf[my_i * (JH + 1) + j * hq + my_q] = s[j] * gate;
+        }
+        __syncthreads();
+        // four latent channels per thread: one broadcast coefficient + one 16-byte read per 4 FMAs (each output still sums jh ascending)
+        float* outb = a.pred + (long long)b * N * Dl;
+        for (int o4 = tid; o4 < N * (Dl / 4); o4 += nthr) {
+            const int i = o4 / (Dl / 4), e = (o4 - i * (Dl / 4)) * 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int jh = 0; jh < JH; ++jh) {
+                const float cc = cf[i * (JH + 1) + jh];
+                const float4 y = *reinterpret_cast<const float4*>(ys + jh * Dl + e);
+                acc.x = fmaf(cc, y.x, acc.x); acc.y = fmaf(cc, y.y, acc.y); acc.z = fmaf(cc, y.z, acc.z); acc.w = fmaf(cc, y.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(outb + (long long)i * Dl + e) = acc;
+        }
+    }
+}
+
 }  // namespace
 
 int d4_l2s_fused_supported(const L2sArgs& a) {
@@ -365,6 +477,9 @@ int d4_l2s_fused(const L2sArgs& a, cudaStream_t s) {
     return mma ? launch_l2s<64, true>(a, s) : launch_l2s<64, false>(a, s);
 }
 
+static int g_lp_version = [] { const char* v = getenv("D4_LP_V"); return v ? atoi(v) : 2; }();          // 1: the per-frame kernel at any batch
+void d4_lp_fused_debug(int version) { g_lp_version = version; }
+
 int d4_lp_fused_supported(const LpArgs& a) {
     return a.nsp <= 8 && a.nsp * a.hq <= LP_MAXJH && a.d % 4 == 0 && a.N * a.hq <= 4096 && (a.hq % a.h) == 0 &&
            (reinterpret_cast<uintptr_t>(a.w_comb) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0;
@@ -380,6 +495,21 @@ int d4_lp_fused(const LpArgs& a, cudaStream_t s) {
         if (smem > 200 * 1024) return d4_fail("lp_fused: %zu bytes of shared memory needed", smem);
         D4_CUDA_OK(cudaFuncSetAttribute(lp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
+    }
+    // large batches, head dim 64: the persistent kernel (queries in registers, W_comb in shared memory); D4_LP_V=1 / d4_debug_set("lp_fused", 1) keeps this one
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; D4_CUDA_OK(cudaGetDevice(&dev)); D4_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+    const int lp_v = g_lp_version;
+    const size_t smem_p = smem + sizeof(float) * (size_t)a.Dl * (a.hq * a.d + 4);
+    if (lp_v != 1 && a.d == 64 && a.N * a.hq <= LPP_THREADS && a.B > num_sms && a.Dl % 4 == 0 && (reinterpret_cast<uintptr_t>(a.pred) & 15) == 0 && smem_p <= 220 * 1024) {
+        static size_t configured_p = 0;
+        if (smem_p > configured_p) {
+            D4_CUDA_OK(cudaFuncSetAttribute(lp_fused_persist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            configured_p = smem_p;
+        }
+        lp_fused_persist_kernel<64><<<num_sms, LPP_THREADS, smem_p, s>>>(a);
+        D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+        return 0;
     }
     lp_fused_kernel<<<a.B, 256, smem, s>>>(a);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());

@@ -127,6 +127,7 @@ struct LpArgs {
 };
 int d4_lp_fused_supported(const LpArgs& a);
 int d4_lp_fused(const LpArgs& a, cudaStream_t s);
+void d4_lp_fused_debug(int version);
 
 // ---- attention within a frame of more than 64 tokens (frame_attn.cu; video tokenizer).  a.mask_agent = number of special tokens.
 int d4_frame_attn(const SmallAttnArgs& a, cudaStream_t s);

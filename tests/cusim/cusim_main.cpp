@@ -142,6 +142,7 @@ int d4_l2s_fused_supported(const L2sArgs&) { return 0; }
 int d4_l2s_fused(const L2sArgs&, cudaStream_t) { return d4_fail("cusim: fused pool"); }
 int d4_lp_fused_supported(const LpArgs&) { return 0; }
 int d4_lp_fused(const LpArgs&, cudaStream_t) { return d4_fail("cusim: fused pool"); }
+void d4_lp_fused_debug(int) {}
 
 static inline float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 static inline float lerp_t(float a, float b, float w) { const float d = b - a; return (w < 0.5f) ? a + w * d : b - d * (1.f - w); }

@@ -137,3 +137,29 @@ def test_trimmed_passes_match_untrimmed(precision, monkeypatch):
     for name in ('latents', 'rewards', 'values', 'agent_embed'):
         torch.testing.assert_close(getattr(a, name), getattr(b, name), msg=lambda m, n=name: f'{n}: {m}', **tol)
     torch.testing.assert_close(a.old_action_unembeds.discrete, b.old_action_unembeds.discrete, atol=1e-4, rtol=1e-4)      # logits of +-10 (unembedding x30): 3.8e-5 measured
+
+
+@pytest.mark.parametrize('name', ['config4_256px', 'config3_snake'])
+def test_persistent_latent_prediction_kernel_is_bit_identical(name):
+    """fused_pools.cu: above one frame per SM the space -> latent pool runs as a persistent kernel (one CTA per SM walking over its frames,
+    the learned queries in registers and W_comb in shared memory) instead of one CTA per frame; every output is accumulated in the same
+    order, so a rollout must not change by one bit (d4_debug_set('lp_fused', 1) selects the per-frame kernel at any batch)."""
+    from dreamer4_b200 import DynamicsWorldModel, _lib
+    if name not in G.BASELINE_MODELS:
+        pytest.skip(f'{name} not among the baseline models')
+    lib = _lib.load()
+    torch.manual_seed(3)
+    model = DynamicsWorldModel(**G.BASELINE_MODELS[name], precision='f16x3').cuda()
+    Tt, Bt = 3, 320          # > 2 frames per SM
+    noise = G.to_cuda(G.make_noise(model.cfg, Tt, Bt, seed=11))
+    runs = []
+    try:
+        for version in (2, 1):
+            _lib.check(lib.d4_debug_set(b'lp_fused', version))
+            e = model.generate(Tt, batch_size=Bt, return_rewards_per_frame=True, return_agent_actions=True, return_log_probs_and_values=True, noise=noise)
+            runs.append(e)
+    finally:
+        lib.d4_debug_set(b'lp_fused', 2)
+    a, b = runs
+    assert torch.equal(a.latents, b.latents) and torch.equal(a.actions.discrete, b.actions.discrete)
+    assert torch.equal(a.values, b.values) and torch.equal(a.rewards, b.rewards)

@@ -118,11 +118,47 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// A handful of output columns over many rows (the policy unembedding: N = number of actions, K = 4 D): the tile kernel above puts 64 rows
+// on a CTA - 32 CTAs and 156 us at 2048 rows.  Here a warp owns a row: coalesced 16-byte loads of the row, every lane keeps N partial
+// sums over its K slice (the N weight rows come from L1 / L2), one shuffle tree per column.  Plain products only, exact fp32.
+constexpr int RD_MAXN = 8, RD_ROWS = 8;
+__global__ void __launch_bounds__(32 * RD_ROWS) gemm_rowdot_kernel(GemmArgs g) {
+    const int m = blockIdx.x * RD_ROWS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= g.M) return;
+    const float* a = g.A + (long long)m * g.lda;
+    float acc[RD_MAXN];
+#pragma unroll
+    for (int n = 0; n < RD_MAXN; ++n) acc[n] = 0.f;
+    for (int k = lane * 4; k < g.K; k += 128) {
+        const float4 av = *reinterpret_cast<const float4*>(a + k);
+#pragma unroll
+        for (int n = 0; n < RD_MAXN; ++n) {
+            if (n < g.N) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(g.W + (long long)n * g.ldw + k));
+                acc[n] = fmaf(av.x, wv.x, acc[n]); acc[n] = fmaf(av.y, wv.y, acc[n]); acc[n] = fmaf(av.z, wv.z, acc[n]); acc[n] = fmaf(av.w, wv.w, acc[n]);
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < RD_MAXN; ++n) {
+        if (n < g.N) {
+            const float v = warp_sum(acc[n]);
+            if (lane == 0) g.C[(long long)m * g.ldc + n] = v;
+        }
+    }
+}
+
 }  // namespace
 
 int d4_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     if (g.M <= 0 || g.N <= 0) return 0;
     if (g.rs_mode || g.ss_out) return d4_fail("gemm_simt: sum-of-squares row statistics are only implemented by the CTA-pair tensor-core kernel");
+    if (g.N <= RD_MAXN && g.M >= 256 && g.K % 4 == 0 && !g.transA && !g.transW && !g.bias && !g.row_scale && !g.residual && g.act == D4_ACT_NONE &&
+        g.amap.grp == 0 && g.cmap.grp == 0 && al16(g.A) && al16(g.W) && g.lda % 4 == 0 && g.ldw % 4 == 0) {
+        gemm_rowdot_kernel<<<(g.M + RD_ROWS - 1) / RD_ROWS, 32 * RD_ROWS, 0, stream>>>(g);
+        D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN);
     // 128-bit loads need every row start 16B-aligned and the contiguous extent a multiple of 4
     const bool va = al16(g.A) && (g.lda % 4 == 0) && ((g.transA ? g.M : g.K) % 4 == 0);

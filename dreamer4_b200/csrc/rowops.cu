@@ -81,6 +81,53 @@ __global__ void ln_act_rows_kernel(const float* __restrict__ x, long long ldx, c
     if (lane == 0 && save_mean) { save_mean[m] = mean; save_rstd[m] = rstd; }
 }
 
+// The same with the row held in registers (D <= 128 * VPL, 16-byte aligned rows): one pass over memory, VPL independent 16-byte loads
+// per lane in flight instead of three dependent scalar sweeps - the head MLPs' 2048-wide rows took 39 us per launch at 2048 rows
+// against ~6 us of traffic.
+template <int VPL>
+__global__ void __launch_bounds__(32 * ROWS_PER_BLOCK) ln_act_rows_reg_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                                                              const float* __restrict__ b, int M, int D, float* __restrict__ out, long long ldo,
+                                                                              int act, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+    const int m = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)m * ldx);
+    const int n4 = D >> 2;
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int i = lane + 32 * k;
+        v[k] = (i < n4) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        if (lane + 32 * k < n4) {
+            const float tx = v[k].x - mean, ty = v[k].y - mean, tz = v[k].z - mean, tw = v[k].w - mean;
+            q += (tx * tx + ty * ty) + (tz * tz + tw * tw);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + D4_LN_EPS);
+    float4* o = reinterpret_cast<float4*>(out + (long long)m * ldo);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+        const int i = lane + 32 * k;
+        if (i < n4) {
+            const float4 ww = __ldg(w4 + i), bb = __ldg(b4 + i);
+            float4 t;
+            t.x = (v[k].x - mean) * rstd * ww.x + bb.x; t.y = (v[k].y - mean) * rstd * ww.y + bb.y;
+            t.z = (v[k].z - mean) * rstd * ww.z + bb.z; t.w = (v[k].w - mean) * rstd * ww.w + bb.w;
+            if (act == D4_ACT_SILU) { t.x = siluf_(t.x); t.y = siluf_(t.y); t.z = siluf_(t.z); t.w = siluf_(t.w); }
+            o[i] = t;
+        }
+    }
+    if (lane == 0 && save_mean) { save_mean[m] = mean; save_rstd[m] = rstd; }
+}
+
 // Non-latent tokens of the newest frame (reference dreamer4.py:7004-7010, 7101-7126, 7193-7222):
 //   s = 0                      flow token  = cat(signal_levels_embed[signal], step_size_embed[step])
 //   s = 1 .. nsp               spatial tokens (written by the latents->spatial GEMM, not here)
@@ -257,6 +304,14 @@ int d4_rmsnorm_rows(const float* x, long long ldx, RowMap map, const float* w, i
 int d4_ln_act_rows(const float* x, long long ldx, const float* w, const float* b, int M, int D, float* out, long long ldo, int act,
                    float* save_mean, float* save_rstd, cudaStream_t s) {
     if (M <= 0) return 0;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (D % 4 == 0 && D <= 2048 && ldx % 4 == 0 && ldo % 4 == 0 && al16(x) && al16(out) && al16(w) && al16(b)) {
+        const unsigned grid = (unsigned)nblk(M, ROWS_PER_BLOCK);
+        if (D <= 512)       ln_act_rows_reg_kernel<4><<<grid, 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, w, b, M, D, out, ldo, act, save_mean, save_rstd);
+        else if (D <= 1024) ln_act_rows_reg_kernel<8><<<grid, 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, w, b, M, D, out, ldo, act, save_mean, save_rstd);
+        else                ln_act_rows_reg_kernel<16><<<grid, 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, w, b, M, D, out, ldo, act, save_mean, save_rstd);
+        D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
+    }
     ln_act_rows_kernel<<<nblk(M, ROWS_PER_BLOCK), 32 * ROWS_PER_BLOCK, 0, s>>>(x, ldx, w, b, M, D, out, ldo, act, save_mean, save_rstd);
     D4_COUNT_LAUNCH(); D4_CUDA_OK(cudaGetLastError()); return 0;
 }

@@ -260,7 +260,7 @@ def run_native(args):
                             precision_note={'tf32x3': 'fp32 in / fp32 out; every dense product = 3 TF32 tensor-core MMAs (hi/lo split), fp32 accumulate: fp32-level accuracy',
                                             'fp32': 'exact fp32 FMA on CUDA cores', 'tf32': 'single-pass TF32 operands (reduced precision)',
                                             'f16x3': 'fp32 in / fp32 out; transformer dense products = 3 fp16 tensor-core MMAs (hi/lo split of power-of-two pre-scaled operands), '
-                                                     'fp32 accumulate: fp32-level accuracy, sampled actions bit-exact vs the oracle over 64 frames at this width; heads and learn on 3xTF32'}[args.precision],
+                                                     'fp32 accumulate: fp32-level accuracy, sampled actions bit-exact vs the oracle over 64 frames at this width; the update (learn_from_experience) on 3xTF32'}[args.precision],
                             time_attn_variant=args.variant,
                             parallelism=f'dp{world} (dream batch sharded, one flat gradient all-reduce)',
                             l2='inputs larger than L2 (KV cache + activations per pass >> 126 MB)' if B * H >= 4096 else 'small problem: L2 resident'),

@@ -301,6 +301,13 @@ extern "C" int d4_bind(d4_ctx* c) {
             const std::string q = p + "." + std::to_string(l);
             m.w[l] = B.get(q + ".w", (int64_t)m.dims[l + 1] * m.dims[l]); m.b[l] = B.get(q + ".b", m.dims[l + 1]);
             m.hi[l] = B.get(q + ".w.hi", (int64_t)m.dims[l + 1] * m.dims[l], true); m.lo[l] = B.get(q + ".w.lo", (int64_t)m.dims[l + 1] * m.dims[l], true);
+            m.h_hi[l] = m.h_lo[l] = nullptr; m.h_scale[l] = 1.f;
+            if (c->cfg.precision == D4_PREC_F16X3) {          // the rollout's head MLPs on the fp16 split GEMM when the caller registered the words + scale
+                const void* hh = B.get(q + ".w.h16hi", (int64_t)m.dims[l + 1] * m.dims[l], true);
+                const void* hl = B.get(q + ".w.h16lo", (int64_t)m.dims[l + 1] * m.dims[l], true);
+                auto it = c->scales.find(q + ".w");
+                if (hh && hl && it != c->scales.end()) { m.h_hi[l] = hh; m.h_lo[l] = hl; m.h_scale[l] = it->second; }
+            }
             m.wthi[l] = B.get(q + ".wt.hi", (int64_t)m.dims[l + 1] * m.dims[l], true); m.wtlo[l] = B.get(q + ".wt.lo", (int64_t)m.dims[l + 1] * m.dims[l], true);
             if (l < layers - 1) { m.lnw[l] = B.get(q + ".lnw", m.dims[l + 1]); m.lnb[l] = B.get(q + ".lnb", m.dims[l + 1]); }
             else { m.lnw[l] = m.lnb[l] = nullptr; }
@@ -392,6 +399,7 @@ int d4_mlp_forward(d4_ctx* c, const MlpW& mlp, const float* x, long long ldx, in
         GemmArgs g = gemm_args(cur, ldc, mlp.w[l], mlp.dims[l], dst, ldd, M, mlp.dims[l + 1], mlp.dims[l]);
         g.bias = mlp.b[l];
         LinW lw; lw.w = mlp.w[l]; lw.hi = mlp.hi[l]; lw.lo = mlp.lo[l];
+        if (allow_tensor) { lw.h_hi = mlp.h_hi[l]; lw.h_lo = mlp.h_lo[l]; lw.h_scale = mlp.h_scale[l]; }
         const int exact = !(allow_tensor && d4_prec_split(c->cfg.precision) && lw.hi && lw.lo);
         D4_TRY(d4_engine_gemm(c, g, lw, exact, s));
         if (!last) D4_TRY(d4_ln_act_rows(dst, ldd, mlp.lnw[l], mlp.lnb[l], M, mlp.dims[l + 1], dst, ldd, D4_ACT_SILU, nullptr, nullptr, s));

@@ -19,6 +19,7 @@ struct FFW { LinW w_in; const float* b_in; LinW w_out; const float* b_out; };
 struct PoolW { LinW w_qg; LinW w_kv; const float* k_gamma; LinW w_out; };
 struct MlpW { int layers = 0; const float* w[D4_MAX_MLP_LAYERS]; const float* b[D4_MAX_MLP_LAYERS];
               const float* hi[D4_MAX_MLP_LAYERS]; const float* lo[D4_MAX_MLP_LAYERS];   // optional tf32 split of w (tf32x3 heads)
+              const void* h_hi[D4_MAX_MLP_LAYERS]; const void* h_lo[D4_MAX_MLP_LAYERS]; float h_scale[D4_MAX_MLP_LAYERS];   // optional fp16 split of q w + 1 / q (f16x3 rollout heads)
               const float* wthi[D4_MAX_MLP_LAYERS]; const float* wtlo[D4_MAX_MLP_LAYERS]; // optional tf32 split of w^T (in, out): learn backward
               const float* lnw[D4_MAX_MLP_LAYERS]; const float* lnb[D4_MAX_MLP_LAYERS]; int dims[D4_MAX_MLP_LAYERS + 1]; };
 

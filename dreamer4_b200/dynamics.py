@@ -460,7 +460,7 @@ class DynamicsWorldModel(nn.Module):
         ver = (self._frozen_version(), agent_index)
         if self._packed_version != ver:
             sd = {k: v for k, v in self.state_dict().items()}
-            split = self.precision in ('tf32x3', 'f16x3')       # f16x3: the heads, d4_learn and odd shapes stay on 3xTF32
+            split = self.precision in ('tf32x3', 'f16x3')       # f16x3: d4_learn and odd shapes stay on 3xTF32
             self._packed = pack(sd, c, dev, agent_index=agent_index, split=split, split_f16=self.precision == 'f16x3')
             for name, scale in self._packed.pop('h16scales', {}).items():
                 check(lib.d4_set_weight_scale(self._ctx, name.encode(), scale))
@@ -481,7 +481,17 @@ class DynamicsWorldModel(nn.Module):
                         # buffers that _refresh_head_splits() rewrites in place when the parameter version moves
                         hi, lo = torch.empty_like(t), torch.empty_like(t)
                         thi, tlo = torch.empty_like(t.t().contiguous()), torch.empty_like(t.t().contiguous())     # of W^T: learn backward
-                        self._head_splits.append((t, hi, lo, thi, tlo))
+                        h16 = None
+                        if self.precision == 'f16x3':
+                            # the rollout's head MLPs also run on the fp16 split GEMM: fp16 words of q w with q a power of two fixed here
+                            # (rms(q w) ~ 1); _refresh_head_splits() re-splits with the same q and re-packs if the weights outgrow it
+                            rms = float(t.detach().float().pow(2).mean().sqrt().clamp_min(1e-30))
+                            q = 2.0 ** round(math.log2(1.0 / rms))
+                            h16 = dict(hi=torch.empty_like(t, dtype=torch.float16), lo=torch.empty_like(t, dtype=torch.float16), q=q, name=f'{short}.{pname}')
+                            for suffix, buf in (('.h16hi', h16['hi']), ('.h16lo', h16['lo'])):
+                                check(lib.d4_set_weight(self._ctx, f'{short}.{pname}{suffix}'.encode(), ptr(buf), buf.numel()))
+                            check(lib.d4_set_weight_scale(self._ctx, h16['name'].encode(), 1.0 / q))
+                        self._head_splits.append((t, hi, lo, thi, tlo, h16))
                         for suffix, buf in (('.hi', hi), ('.lo', lo)):
                             check(lib.d4_set_weight(self._ctx, f'{short}.{pname}{suffix}'.encode(), ptr(buf), buf.numel()))
                         for suffix, buf in (('.hi', thi), ('.lo', tlo)):
@@ -503,12 +513,25 @@ class DynamicsWorldModel(nn.Module):
         ver = sum(s[0]._version for s in splits)
         if ver == self._head_split_version:
             return
-        for t, hi, lo, thi, tlo in splits:
+        rebind = False
+        for t, hi, lo, thi, tlo, h16 in splits:
             h, l = tf32_split(t.detach())
             hi.copy_(h)
             lo.copy_(l)
             thi.copy_(hi.t())
             tlo.copy_(lo.t())
+            if h16 is not None:
+                wq = t.detach().float() * h16['q']
+                if float(wq.abs().max()) > 16384.:          # the weights outgrew the power of two chosen at pack time: choose again, re-bind
+                    rms = float(t.detach().float().pow(2).mean().sqrt().clamp_min(1e-30))
+                    h16['q'] = 2.0 ** round(math.log2(1.0 / rms))
+                    wq = t.detach().float() * h16['q']
+                    check(_lib.load().d4_set_weight_scale(self._ctx, h16['name'].encode(), 1.0 / h16['q']))
+                    rebind = True
+                h16['hi'].copy_(wq)
+                h16['lo'].copy_(wq - h16['hi'].float())
+        if rebind:
+            check(_lib.load().d4_bind(self._ctx))
         self._head_split_version = ver
 
     def _release(self):

@@ -493,19 +493,27 @@ int launch3(const GemmArgs& g, cudaStream_t stream) {
 
 }  // namespace
 
-// The N-tile width both CTA-pair kernels (this one and gemm_f16.cu) use for an (M, N) product: 256-wide tiles unless the 128-wide one
-// saves more than 10 % of the (padded) columns (choosing 128 to smooth wave quantisation at N = 512 - 7 half-rounds instead of 4 full
-// ones - was measured SLOWER overall, 166 vs 205 TFLOP/s), and 128 when 256-wide tiles cannot even give every CTA pair one tile (small
-// batches: M = 3840 rows at 256 dreams).  The engine asks too: the fused sums of squares are only bit-reproducible while a row's
-// columns span at most TWO tiles (two atomic partial sums commute, four do not).
+// The N-tile width both CTA-pair kernels (this one and gemm_f16.cu) use for an (M, N) product.  256-wide tiles unless the 128-wide one
+// saves more than 10 % of the (padded) columns, or wins the wave count of the persistent grid: rounds = ceil(tiles / CTA pairs), a
+// 128-wide tile costing ~ 0.7 of a 256-wide one (same A stage, half the W stage and half the epilogue).  Measured points behind the 0.7:
+// N = 512 at 30720 rows - 7 half-rounds against 4 full ones - is SLOWER on 128-wide tiles (166 vs 205 TFLOP/s); N = 1552 at 3840 rows
+// (3 half-rounds against 2 full) is slower too (19.8 k vs 20.0 k frames/s at 256 dreams); a single round stays on 256-wide tiles even
+// when they leave CTA pairs idle (64 tiles at 8192 x 512 and 2048 x 2048: + 1.6 % at 2048 dreams against 128-wide tiles), and goes to
+// 128-wide ones only when those still fit one round (30 -> 60 tiles at 3840 x 512).  D4_GEMM_PAIR_BN=128|256 pins the width.
+// The engine asks too: the fused sums of squares are only bit-reproducible while a row's columns span at most TWO tiles (two atomic
+// partial sums commute, four do not).
 int d4_gemm_pair_bn(int M, int N) {
     const long long p128 = (long long)(N + 127) / 128 * 128, p256 = (long long)(N + 255) / 256 * 256;
-    int bn = (p128 * 10 < p256 * 9) ? 128 : 256;
-    static int clusters = 0;
-    if (!clusters) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); clusters = sms > 1 ? sms / 2 : 74; }
+    static int clusters = 0, pin = 0;
+    if (!clusters) {
+        int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); clusters = sms > 1 ? sms / 2 : 74;
+        const char* e = getenv("D4_GEMM_PAIR_BN"); pin = e ? atoi(e) : 0;
+    }
+    if (pin == 128 || pin == 256) return pin;
+    if (p128 * 10 < p256 * 9) return 128;
     const long long mt = (M + 2 * BM - 1) / (2 * BM);
-    if (mt * (p256 / 256) < clusters && p128 / 128 > p256 / 256) bn = 128;
-    return bn;
+    const long long r256 = (mt * (p256 / 256) + clusters - 1) / clusters, r128 = (mt * (p128 / 128) + clusters - 1) / clusters;
+    return (r128 * 7 < r256 * 10) ? 128 : 256;
 }
 
 // CTA-pair kernel entry; bn = 128 or 256 (0 = d4_gemm_pair_bn)

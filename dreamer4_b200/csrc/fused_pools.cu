@@ -356,7 +356,9 @@ __global__ void __launch_bounds__(LPP_THREADS, 1) lp_fused_persist_kernel(LpArgs
         *reinterpret_cast<float4*>(wc + (size_t)e * WP + c) = __ldg(reinterpret_cast<const float4*>(a.w_comb + (long long)e * Dq + c));
     }
     // this thread's (query, query head): its row of the projected queries and its gate, for every frame
-    const int my_i = tid / hq, my_q = tid - my_i * hq, my_hk = my_q / g;
+    // (query head)-major: the 32 lanes of a warp share a head, so their key reads are ONE broadcast 16-byte access instead of four
+    // quarter-warp wavefronts (ncu: the first mapping spent 55 % of the shared-memory pipe's wavefronts here)
+    const int my_q = tid / N, my_i = tid - my_q * N, my_hk = my_q / g;
     const bool has_pair = tid < N * hq;
     float qreg[D];
     float my_gate = 0.f;
@@ -388,17 +390,27 @@ __global__ void __launch_bounds__(LPP_THREADS, 1) lp_fused_persist_kernel(LpArgs
             const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), D4_L2_EPS);
             for (int c = lane; c < D; c += 32) kr[c] = kr[c] * inv * ((a.k_gamma[hk * D + c] + 1.f) * sqrt_d);
         }
-        for (int o = tid; o < JH * Dl; o += nthr) {
-            const int jh = o / Dl, e = o - jh * Dl, j = jh / hq, q = jh - j * hq, hk = q / g;
+        // mixing vectors: a thread owns (query head, latent channel) and all nsp keys - its W_comb row is read once per frame instead
+        // of once per key (each output still sums c ascending)
+        for (int o = tid; o < hq * Dl; o += nthr) {
+            const int q = o / Dl, e = o - q * Dl, hk = q / g;
             const float* w = wc + (size_t)e * WP + q * D;
-            const float* v = vs + (j * h + hk) * dp;
-            float acc = 0.f;
-            for (int c = 0; c < D; c += 4) {
-                const float4 wv = *reinterpret_cast<const float4*>(w + c);
-                const float4 vv = *reinterpret_cast<const float4*>(v + c);
-                acc = fmaf(wv.x, vv.x, acc); acc = fmaf(wv.y, vv.y, acc); acc = fmaf(wv.z, vv.z, acc); acc = fmaf(wv.w, vv.w, acc);
+            for (int j0 = 0; j0 < nsp; j0 += 4) {          // four keys at a time (registers: the thread also holds its 64-float query row)
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+                for (int c = 0; c < D; c += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(w + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j0 + j < nsp) {
+                            const float4 vv = *reinterpret_cast<const float4*>(vs + ((j0 + j) * h + hk) * dp + c);
+                            acc[j] = fmaf(wv.x, vv.x, acc[j]); acc[j] = fmaf(wv.y, vv.y, acc[j]); acc[j] = fmaf(wv.z, vv.z, acc[j]); acc[j] = fmaf(wv.w, vv.w, acc[j]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j0 + j < nsp) ys[((j0 + j) * hq + q) * Dl + e] = acc[j];
             }
-            ys[jh * Dl + e] = acc;
         }
         __syncthreads();
         if (has_pair) {
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(LPP_THREADS, 1) lp_fused_persist_kernel(LpArgs
         // four latent channels per thread: one broadcast coefficient + one 16-byte read per 4 FMAs (each output still sums jh ascending)
         float* outb = a.pred + (long long)b * N * Dl;
         for (int o4 = tid; o4 < N * (Dl / 4); o4 += nthr) {
-            const int i = o4 / (Dl / 4), e = (o4 - i * (Dl / 4)) * 4;
+            const int e4 = o4 / N, i = o4 - e4 * N, e = e4 * 4;          // lanes = consecutive queries: ys is a broadcast read, cf rows are 33 floats apart
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int jh = 0; jh < JH; ++jh) {
                 const float cc = cf[i * (JH + 1) + jh];

@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lp_fused_persist -s 4 -c 1 -o gpurun_out/r2ak_lp -f \
+    python bench.py --horizon 3 --steps 1 --warmup 0 --no-cpu-baseline --no-profile --no-weak > gpurun_out/r2ak.log 2>&1; echo "rc=$?"
+ls -la gpurun_out/r2ak_lp.ncu-rep

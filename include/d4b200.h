@@ -162,7 +162,9 @@ int d4_head_forward(d4_ctx* ctx, int which, const float* x, int M, float* out, v
 
 /* ---- diagnostics (bench / profiling scripts and tests only).
  * d4_graph_replays: how many frames of this context ran as a CUDA-graph replay (0 = every frame was launched directly).
- * d4_debug_set: ablation switches of individual kernels, e.g. ("gemm_f16", bits) - results are garbage when set. */
+ * d4_debug_set: switches of individual kernels: ("gemm_f16", bits) - timing ablations of gemm_f16.cu, results are garbage for bits
+ *   1 | 2 | 4 | 8 | 16 | 128 (64 = residual chunk loads issued late: exact); ("lp_fused", 1 | 2) - per-frame / persistent space -> latent
+ *   pool kernel (bit-identical, tests/test_horizon_parity_gpu.py). */
 int64_t d4_graph_replays(const d4_ctx* ctx);
 int d4_debug_set(const char* key, int value);
 /* counters of a context: "graph_enabled", "graph_keys", "graph_captured", "graph_capture_refused"; -1 for an unknown key */

@@ -9,11 +9,12 @@
 // index itself may be permuted freely as long as A and B use the same permutation, and so may the output columns.  Chosen so that
 // every lane reads contiguous, coalesced 64-byte runs straight from global memory into its fragments:
 //   g = lane / 4, t = lane % 4
-//   Q K^T (contraction over the 64 head dims):  k-step s, fragment index t <-> head dim 16 t + 2 s,  t + 4 <-> 16 t + 2 s + 1
-//       => lane (g, t) holds dims [16 t, 16 t + 16) of query rows g, g + 8 (A) and of key rows g, g + 8 (B): 4 float4 per row
+//   Q K^T (contraction over the 64 head dims):  k-step s = 2 q + u, fragment index t <-> head dim 16 q + 4 t + 2 u,  t + 4 <-> the next one
+//       => lane (g, t) holds the four 16-byte pieces at dims 16 q + 4 t of query rows g, g + 8 (A) and of key rows g, g + 8 (B);
+//          the four lanes of a row read 64 contiguous bytes per instruction
 //   P V (contraction over the 16 keys):  k-step s, fragment index t <-> key 8 s + 2 t,  t + 4 <-> key 8 s + 2 t + 1
 //       => the score C-fragments ARE the probability A-fragments (no shuffle, no shared memory)
-//       output tile n, fragment column g <-> head dim 8 g + n
+//       output tile n, fragment column g <-> head dim 4 g + (n & 3) + 32 (n >> 2)   (was 8 g + n until the L1 sector fix below)
 //       => lane (g, t) holds dims [8 g, 8 g + 8) of value rows 2 t, 2 t + 1, 8 + 2 t, 9 + 2 t (B): 2 float4 per row, and ends up
 //          with out[g | g + 8][16 t .. 16 t + 16): 4 float4 stores per row
 // Products are 3-term TF32 splits (a_lo b_hi + a_hi b_lo + a_hi b_hi, operands rounded to nearest), fp32-accurate, as before.
@@ -53,6 +54,17 @@ __device__ __forceinline__ void load8(float (&dst)[8], const float* p, bool ok) 
         dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
     }
 }
+// Sector-friendly fragment loads (round 2, last ncu capture: the L1 data path at 68 % with every sector requested twice - a lane's
+// 16-byte pieces used to sit 64 / 32 bytes apart, so each instruction touched half-used sectors).  PIECES 16-byte pieces per lane,
+// STRIDE floats apart: in ONE instruction the lanes of a row read adjacent pieces, i.e. whole 32-byte sectors.
+template <int PIECES, int STRIDE>
+__device__ __forceinline__ void load_pieces(float (&dst)[4 * PIECES], const float* p, bool ok) {
+#pragma unroll
+    for (int q = 0; q < PIECES; ++q) {
+        const float4 v = ok ? *reinterpret_cast<const float4*>(p + STRIDE * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
+    }
+}
 
 // ONE_GROUP: one query head per kv head (no GQA): K / gain die after the scores, the compiler keeps everything in registers.
 // MINB: resident CTAs per SM the register allocation is held to (4: 121 registers, no spills; 5: 96, 16 bytes; 6: 80, ~150 bytes).
@@ -70,7 +82,7 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
     // ---- keys of rows g, g + 8, head dims [16 t, 16 t + 16); their l2 norms (summed over the four lanes t of a row)
     float kf[2][16];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) load16(kf[h], a.k + b * a.k_sb + (long long)(g + 8 * h) * a.k_sj + (long long)hk * D + 16 * t, g + 8 * h < S);
+    for (int h = 0; h < 2; ++h) load_pieces<4, 16>(kf[h], a.k + b * a.k_sb + (long long)(g + 8 * h) * a.k_sj + (long long)hk * D + 4 * t, g + 8 * h < S);
     float kinv_own[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -88,7 +100,7 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
         for (int e = 0; e < 2; ++e) kinv[n][e] = __shfl_sync(D4_FULL, kinv_own[n], 4 * (2 * t + e));
     // key-norm gain (gamma + 1) sqrt(d) of this lane's 16 head dims: folded into the queries
     float gain[16];
-    load16(gain, a.k_gamma + hk * D + 16 * t, true);
+    load_pieces<4, 16>(gain, a.k_gamma + hk * D + 4 * t, true);
 #pragma unroll
     for (int c = 0; c < 16; ++c) gain[c] = (gain[c] + 1.f) * sqrt_d;
 
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int j = 8 * (r >> 1) + 2 * t + (r & 1);
-            load8(vb[r], a.v + b * a.v_sb + (long long)j * a.v_sj + (long long)hk * D + 8 * g, j < S);
+            load_pieces<2, 32>(vb[r], a.v + b * a.v_sb + (long long)j * a.v_sj + (long long)hk * D + 4 * g, j < S);
         }
     };
     auto lerp_vb = [&]() {
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
             const int j = 8 * (r >> 1) + 2 * t + (r & 1);
             if (j < S) {
                 float r0[8];
-                load8(r0, a.v0 + b * a.v0_sb + (long long)j * a.v0_sj + (long long)hk * D + 8 * g, true);
+                load_pieces<2, 32>(r0, a.v0 + b * a.v0_sb + (long long)j * a.v0_sj + (long long)hk * D + 4 * g, true);
                 const float w = sigmoidf_(a.mix[b * a.mix_sb + (long long)j * a.mix_sj + hk]);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) vb[r][c] = lerpf_(vb[r][c], r0[c], w);
@@ -121,7 +133,13 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
     };
     auto fetch_vr = [&]() {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) load16(vr[h], a.v + b * a.v_sb + (long long)(g + 8 * h) * a.v_sj + (long long)hk * D + 16 * t, g + 8 * h < S);
+        for (int h = 0; h < 2; ++h) {
+            const float* vp = a.v + b * a.v_sb + (long long)(g + 8 * h) * a.v_sj + (long long)hk * D + 8 * t;
+            float lo8[8], hi8[8];
+            load8(lo8, vp, g + 8 * h < S); load8(hi8, vp + 32, g + 8 * h < S);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { vr[h][c] = lo8[c]; vr[h][8 + c] = hi8[c]; }
+        }
     };
     auto lerp_vr = [&]() {
         if (a.v0) {
@@ -130,7 +148,13 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
                 const int i = g + 8 * h;
                 if (i < S) {
                     float r0[16];
-                    load16(r0, a.v0 + b * a.v0_sb + (long long)i * a.v0_sj + (long long)hk * D + 16 * t, true);
+                    {
+                        const float* rp = a.v0 + b * a.v0_sb + (long long)i * a.v0_sj + (long long)hk * D + 8 * t;
+                        float lo8[8], hi8[8];
+                        load8(lo8, rp, true); load8(hi8, rp + 32, true);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) { r0[c] = lo8[c]; r0[8 + c] = hi8[c]; }
+                    }
                     const float w = sigmoidf_(a.mix[b * a.mix_sb + (long long)i * a.mix_sj + hk]);
 #pragma unroll
                     for (int c = 0; c < 16; ++c) vr[h][c] = lerpf_(vr[h][c], r0[c], w);
@@ -157,7 +181,7 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
         float qf[2][16];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            load16(qf[h], a.q + b * a.q_sb + (long long)(g + 8 * h) * a.q_si + (long long)hq * D + 16 * t, g + 8 * h < S);
+            load_pieces<4, 16>(qf[h], a.q + b * a.q_sb + (long long)(g + 8 * h) * a.q_si + (long long)hq * D + 4 * t, g + 8 * h < S);
 #pragma unroll
             for (int c = 0; c < 16; ++c) qf[h][c] *= gain[c];
         }
@@ -258,7 +282,10 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
             const int i = g + 8 * h;
             float row[16];
 #pragma unroll
-            for (int n = 0; n < 8; ++n) { row[n] = o[n][2 * h]; row[8 + n] = o[n][2 * h + 1]; }
+            for (int n = 0; n < 4; ++n) {          // tile n, columns 2 t, 2 t + 1 <-> head dims 8 t + n, 8 t + 4 + n (n < 4), + 32 for tiles 4..7
+                row[n] = o[n][2 * h]; row[4 + n] = o[n][2 * h + 1];
+                row[8 + n] = o[4 + n][2 * h]; row[12 + n] = o[4 + n][2 * h + 1];
+            }
             if (a.belief) {
                 float dot = 0.f;
 #pragma unroll
@@ -269,10 +296,10 @@ __global__ void __launch_bounds__(SPW * 32, MINB) space_attn_reg_kernel(SmallAtt
             }
             if (i < S) {
                 const float gate = a.gate ? sigmoidf_(a.gate[b * a.gate_sb + (long long)i * a.gate_si + hq]) : 1.f;
-                float* op = a.out + b * a.out_sb + (long long)i * a.out_si + (long long)hq * D + 16 * t;
+                float* op = a.out + b * a.out_sb + (long long)i * a.out_si + (long long)hq * D + 8 * t;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(op + 4 * q) = make_float4(row[4 * q] * gate, row[4 * q + 1] * gate, row[4 * q + 2] * gate, row[4 * q + 3] * gate);
+                    *reinterpret_cast<float4*>(op + 4 * (q & 1) + 32 * (q >> 1)) = make_float4(row[4 * q] * gate, row[4 * q + 1] * gate, row[4 * q + 2] * gate, row[4 * q + 3] * gate);
             }
         }
     }

@@ -275,7 +275,8 @@ int launch_fm(const SmallAttnArgs& a, cudaStream_t s) {
 
 int d4_frame_attn_mma_ok(const SmallAttnArgs& a) {
     static const bool enabled = [] { const char* e = getenv("D4_FRAME_MMA"); return !(e && e[0] == '0'); }();      // D4_FRAME_MMA=0: FMA kernel (A/B runs)
-    return enabled && a.allow_tensor && a.d == FM_D && a.n >= 1 && a.n <= FM_MAXN && a.nq >= 1 && (!a.belief || a.nq == a.n) &&
+    // (grouped queries - a.g > 1 - are written out in the kernel but no test reaches them: they stay on the FMA kernel, which the simulator covers)
+    return enabled && a.allow_tensor && a.g == 1 && a.d == FM_D && a.n >= 1 && a.n <= FM_MAXN && a.nq >= 1 && (!a.belief || a.nq == a.n) &&
            ((a.q_sb | a.q_si | a.k_sb | a.k_sj | a.v_sb | a.v_sj | a.v0_sb | a.v0_sj) & 3) == 0 && ((a.out_sb | a.out_si) & 1) == 0 &&
            (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.k) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.v) & 15) == 0 &&
            (!a.v0 || ((reinterpret_cast<uintptr_t>(a.v0) & 15) == 0 && a.mix)) && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0 ? 1 : 0;

@@ -275,6 +275,12 @@ static void time_attn_host(const TimeAttnArgs& a) {
 }
 
 // ---- a direct entry for the one simulated kernel the C-ABI does not expose on its own
+// rowops.cu's LayerNorm + activation rows (head MLP hidden layers) for the unit test: register-resident and scalar variants by shape
+extern "C" int sim_ln_act_rows(const float* x, long long ldx, const float* w, const float* b, int M, int D, float* out, long long ldo, int act,
+                               float* save_mean, float* save_rstd) {
+    return d4_ln_act_rows(x, ldx, w, b, M, D, out, ldo, act, save_mean, save_rstd, nullptr);
+}
+
 extern "C" int sim_frame_attn(int nb, int hkv, int g, int d, int nq, int n, const float* q, long long q_sb, long long q_si, const float* k,
                               long long k_sb, long long k_sj, const float* v, long long v_sb, long long v_sj, const float* k_gamma, const float* v0,
                               long long v0_sb, long long v0_sj, const float* mix, long long mix_sb, long long mix_sj, const float* gate,

@@ -99,6 +99,35 @@ def test_skinny_gemm_on_the_simulator(simlib, M, N, K, act, res):
     torch.testing.assert_close(Cc.double(), ref, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize('M,N,K', [(256, 4, 128), (300, 8, 64), (257, 1, 36)])
+def test_rowdot_gemm_on_the_simulator(simlib, M, N, K):
+    """d4_linear(fp32) with many rows and at most 8 output columns, no epilogue (the policy unembedding) takes gemm_simt.cu's
+    one-warp-per-row kernel: ragged row count, K not a multiple of the 128-float lane stride."""
+    torch.manual_seed(M + N)
+    A, W = torch.randn(M, K), torch.randn(N, K) / K ** 0.5
+    Cc = torch.full((M, N), float('nan'))
+    rc = simlib.d4_linear(0, M, N, K, p(A), K, p(W), K, None, None, None, None, N, 0, p(Cc), N, None)
+    assert rc == 0, simlib.d4_last_error()
+    torch.testing.assert_close(Cc.double(), A.double() @ W.double().T, atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize('M,D', [(9, 512), (5, 2048), (3, 100), (4, 2052)])
+def test_layernorm_silu_rows_on_the_simulator(simlib, M, D):
+    """d4_mlp-style hidden layer rows: LayerNorm + SiLU with the row held in registers (D <= 2048, D % 4 == 0) and the scalar fallback."""
+    if not hasattr(simlib, 'sim_ln_act_rows'):
+        pytest.skip('simulator build without the ln_act_rows entry point')
+    torch.manual_seed(D)
+    x, w, b = torch.randn(M, D) * 3 + 1, torch.randn(D), torch.randn(D)
+    out, mean, rstd = torch.empty(M, D), torch.empty(M), torch.empty(M)
+    f = simlib.sim_ln_act_rows
+    f.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
+    f.restype = C.c_int
+    assert f(p(x), D, p(w), p(b), M, D, p(out), D, 3, p(mean), p(rstd)) == 0
+    ref = torch.nn.functional.silu(torch.nn.functional.layer_norm(x.double(), (D,), w.double(), b.double(), 1e-5))
+    torch.testing.assert_close(out.double(), ref, atol=2e-5, rtol=2e-5)
+    torch.testing.assert_close(mean.double(), x.double().mean(1), atol=1e-5, rtol=1e-5)
+
+
 # ------------------------------------------------------------------------------------------------ frame_attn.cu
 
 def frame_attn(sim, q, k, v, k_gamma, scale, v0=None, mix=None, gate=None, softclamp=0., num_special=0, belief=False):

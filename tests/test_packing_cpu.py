@@ -152,6 +152,14 @@ def test_library_exports_every_declared_symbol():
     assert lib.d4_last_error() is not None
 
 
+def test_integration_md_names_every_entry_point():
+    """INTEGRATION.md says, per exported entry point, which reference interface it replaces (file:line): none may be missing."""
+    root = os.path.dirname(os.path.dirname(__file__))
+    declared = set(re.findall(r'\b(d4_[a-z0-9_]+)\s*\(', open(os.path.join(root, 'include', 'd4b200.h')).read()))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    assert not sorted(sym for sym in declared if sym not in text)
+
+
 def test_ctypes_structs_mirror_the_header(tmp_path):
     """Every field of every struct the C-ABI passes by pointer sits at the offset gcc gives it from include/d4b200.h."""
     import ctypes
